@@ -1,0 +1,640 @@
+// gt16_capi.cu -- extern "C" layer of libgt16.so (include/gt16.h): context, table prefill,
+// the reference's operator seam, and the fused snapshot -> called-sites path with a copy
+// stream that feeds HBM while the previous block is being classified.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+#include "gt16_kernels.cuh"
+
+using namespace gt16;
+
+static std::string g_createError;
+
+struct gt16_ctx {
+  int device = 0;
+  cudaStream_t compute = nullptr, copy = nullptr;
+  std::string err;
+  // tables
+  double *tabOwned[10] = {nullptr};
+  int nOwned = 0;
+  double *tab[10] = {nullptr};
+  double *ycsq = nullptr, *prior = nullptr;
+  uint32_t *g2i = nullptr;
+  float *lnfact = nullptr;
+  uint32_t *s1 = nullptr, *s2p = nullptr, *s2q = nullptr, *g4 = nullptr;
+  uint32_t *errWord = nullptr, *dTotal = nullptr;
+  uint32_t *hPinned = nullptr;          // [0] total, [1] error word
+  bool havePrefill = false, haveDecisions = false, useDecisions = true;
+  double balance = 0.01, unbalance = 0.005;
+  float prefillMs = 0.f, decisionMs = 0.f;
+  uint32_t launches = 0;
+};
+
+struct gt16_dev_snapshot {
+  SnapView v;
+  void *counters = nullptr, *invalid = nullptr, *ovf = nullptr, *ovfBase = nullptr, *pool = nullptr, *ref = nullptr;
+};
+
+struct gt16_calls {
+  std::vector<gt16_called_site> sites;
+};
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char b_[512];                                                                                \
+      snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      ctx->err = b_;                                                                               \
+      return GT16_ECUDA;                                                                           \
+    }                                                                                              \
+  } while (0)
+
+static int fail(gt16_ctx *ctx, int code, const char *msg) { if (ctx) ctx->err = msg; return code; }
+
+static EvalParams eval_params(const gt16_ctx *ctx) {
+  EvalParams P;
+  for (int k = 0; k < 10; ++k) P.lh.t[k] = ctx->tab[k];
+  P.lh.ycsq = ctx->ycsq;
+  P.lh.p_err_s = ctx->balance / 4;        // FisherExactTest.cpp:298
+  P.lh.p_err_i = ctx->unbalance / 2;      // :299
+  P.prior = ctx->prior;
+  P.g2i = ctx->g2i;
+  P.lnfact.tab = ctx->lnfact;
+  P.lnfact.size = kLnFactTab;
+  return P;
+}
+
+extern "C" {
+
+const char *gt16_last_error(const gt16_ctx *ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int gt16_create_snp_prior(double out256[256]) {
+  if (!out256) return GT16_EINVAL;
+  make_prior(out256);
+  return GT16_OK;
+}
+
+int gt16_ctx_create(int device, gt16_ctx **out) {
+  if (!out) return GT16_EINVAL;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_createError = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libgt16 has no CPU path)";
+    (void) cudaGetLastError();
+    return GT16_ENODEVICE;
+  }
+  if (device < 0 || device >= n) { g_createError = "device index out of range"; return GT16_EINVAL; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+    g_createError = "device is not Blackwell-class (kernels are built for sm_100a only)";
+    return GT16_ENODEVICE;
+  }
+  gt16_ctx *ctx = new gt16_ctx();
+  ctx->device = device;
+  auto bail = [&](const char *what, cudaError_t ce) {
+    g_createError = std::string(what) + ": " + cudaGetErrorString(ce);
+    delete ctx;
+    return GT16_ECUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaMalloc(&ctx->prior, 256 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->g2i, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->ycsq, kYcsqN * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->lnfact, (size_t) kLnFactTab * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->errWord, 2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+  ctx->dTotal = ctx->errWord + 1;
+  if ((e = cudaHostAlloc(&ctx->hPinned, 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  if ((e = cudaMemset(ctx->errWord, 0, 2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+  // defaults of selectPossibleSNPs (VariantCaller.cpp:506-513)
+  const unsigned g2i[16] = {0, 1, 2, 3, 9, 10, 11, 18, 19, 27, 4, 12, 20, 28, 36, 37};
+  double prior[256];
+  make_prior(prior);
+  if ((e = cudaMemcpy(ctx->g2i, g2i, sizeof(g2i), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+  if ((e = cudaMemcpy(ctx->prior, prior, sizeof(prior), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+  // float log-factorial table: lnfactC(n) = lgammaf((float)(n+1)) from the host libm, i.e. the
+  // very function the reference calls (SNPFunctions.cpp:82-84) -- a constant table, like the prior
+  {
+    std::vector<float> tab(kLnFactTab);
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() { for (uint32_t k = t; k < kLnFactTab; k += nt) tab[k] = lgammaf((float) (k + 1)); });
+    for (auto &x : th) x.join();
+    if ((e = cudaMemcpy(ctx->lnfact, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail("cudaMemcpy", e);
+  }
+  *out = ctx;
+  return GT16_OK;
+}
+
+void gt16_ctx_destroy(gt16_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int k = 0; k < ctx->nOwned; ++k) cudaFree(ctx->tabOwned[k]);
+  cudaFree(ctx->ycsq); cudaFree(ctx->prior); cudaFree(ctx->g2i); cudaFree(ctx->lnfact);
+  cudaFree(ctx->s1); cudaFree(ctx->s2p); cudaFree(ctx->s2q); cudaFree(ctx->g4);
+  cudaFree(ctx->errWord);
+  cudaFreeHost(ctx->hPinned);
+  cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
+  delete ctx;
+}
+
+int gt16_copy_genotype_table(gt16_ctx *ctx, const unsigned int g2i[16]) {
+  if (!ctx || !g2i) return GT16_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpy(ctx->g2i, g2i, 16 * sizeof(unsigned), cudaMemcpyHostToDevice));
+  ctx->haveDecisions = false;             // decision bitmaps were built for the previous table
+  return GT16_OK;
+}
+
+int gt16_copy_snp_prior(gt16_ctx *ctx, const double prior[256]) {
+  if (!ctx || !prior) return GT16_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpy(ctx->prior, prior, 256 * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->haveDecisions = false;
+  return GT16_OK;
+}
+
+int gt16_prefill_likelihood_cache(gt16_ctx *ctx, float b_err, float ub_err, void *lc_host) {
+  if (!ctx) return GT16_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  ErrFractions ef = err_fractions(b_err, ub_err);
+  for (int k = 0; k < ctx->nOwned; ++k) { cudaFree(ctx->tabOwned[k]); ctx->tabOwned[k] = nullptr; }
+  ctx->nOwned = 0;
+  ctx->havePrefill = false; ctx->haveDecisions = false;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, ctx->compute));
+  const size_t bytes = (size_t) kFisherN * kFisherN * sizeof(double);
+  for (int k = 0; k < 10; ++k) {
+    int same = -1;
+    for (int j = 0; j < k; ++j) if (memcmp(&ef.e[j], &ef.e[k], sizeof(float)) == 0) { same = j; break; }
+    if (same >= 0) { ctx->tab[k] = ctx->tab[same]; continue; }   // identical error fraction -> identical table
+    double *d = nullptr;
+    CU(cudaMalloc(&d, bytes));
+    ctx->tabOwned[ctx->nOwned++] = d;
+    ctx->tab[k] = d;
+    launch_build_table(d, ef.e[k], ctx->compute);
+    ctx->launches++;
+  }
+  launch_build_ycsq(ctx->ycsq, ctx->compute);
+  ctx->launches++;
+  CU(cudaEventRecord(e1, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  CU(cudaGetLastError());
+  CU(cudaEventElapsedTime(&ctx->prefillMs, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  ctx->havePrefill = true;
+  if (lc_host) {                                  // LikelihoodCache layout, likelihood_cache.h:13-31
+    char *dst = (char *) lc_host;
+    for (int k = 0; k < 10; ++k) CU(cudaMemcpy(dst + (size_t) k * bytes, ctx->tab[k], bytes, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(dst + 10 * bytes, ctx->ycsq, kYcsqN * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return GT16_OK;
+}
+
+int gt16_configure(gt16_ctx *ctx, double balance_sub_error, double unbalance_sub_error, int use_decision_tables) {
+  if (!ctx) return GT16_EINVAL;
+  ctx->balance = balance_sub_error;
+  ctx->unbalance = unbalance_sub_error;
+  ctx->useDecisions = use_decision_tables != 0;
+  // snapshotSnpcaller.cpp:230-231 passes the ini doubles through float parameters
+  int rc = gt16_prefill_likelihood_cache(ctx, (float) balance_sub_error, (float) unbalance_sub_error, nullptr);
+  if (rc != GT16_OK) return rc;
+  if (!ctx->useDecisions) return GT16_OK;
+  if (!ctx->s1) {
+    CU(cudaMalloc(&ctx->s1, kS1Words * 4)); CU(cudaMalloc(&ctx->s2p, kS2Words * 4));
+    CU(cudaMalloc(&ctx->s2q, kS2Words * 4)); CU(cudaMalloc(&ctx->g4, kG4Words * 4));
+  }
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, ctx->compute));
+  launch_build_decisions(eval_params(ctx), ctx->s1, ctx->s2p, ctx->s2q, ctx->g4, ctx->compute);
+  ctx->launches++;
+  CU(cudaEventRecord(e1, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  CU(cudaGetLastError());
+  CU(cudaEventElapsedTime(&ctx->decisionMs, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  ctx->haveDecisions = true;
+  return GT16_OK;
+}
+
+int gt16_setup_times(const gt16_ctx *ctx, float *prefill_ms, float *decision_ms) {
+  if (!ctx) return GT16_EINVAL;
+  if (prefill_ms) *prefill_ms = ctx->prefillMs;
+  if (decision_ms) *decision_ms = ctx->decisionMs;
+  return GT16_OK;
+}
+
+// ---- operator seam ------------------------------------------------------------------------
+int gt16_compute_genotype_likelihood(gt16_ctx *ctx, const void *w, size_t in_stride, const void *ref_char,
+                                     size_t ref_stride, double *lh, uint32_t n, double balance, double unbalance) {
+  if (!ctx || !w || !ref_char || !lh || in_stride < 24 || ref_stride < 1) return GT16_EINVAL;
+  if (!ctx->havePrefill) return fail(ctx, GT16_ESTATE, "likelihood cache not prefilled");
+  if (!n) return GT16_OK;
+  CU(cudaSetDevice(ctx->device));
+  ctx->balance = balance; ctx->unbalance = unbalance;
+  // only W[0..5] and refChar are read by the operator: gather them on the host side of the copy
+  std::vector<uint32_t> wbuf((size_t) n * 6);
+  std::vector<uint8_t> rbuf(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    memcpy(&wbuf[(size_t) i * 6], (const char *) w + (size_t) i * in_stride, 24);
+    rbuf[i] = *((const uint8_t *) ref_char + (size_t) i * ref_stride);
+  }
+  uint32_t *dW = nullptr; uint8_t *dR = nullptr; double *dL = nullptr;
+  CU(cudaMalloc(&dW, wbuf.size() * 4)); CU(cudaMalloc(&dR, n)); CU(cudaMalloc(&dL, (size_t) n * 128));
+  CU(cudaMemcpyAsync(dW, wbuf.data(), wbuf.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemcpyAsync(dR, rbuf.data(), n, cudaMemcpyHostToDevice, ctx->compute));
+  launch_op_likelihood(eval_params(ctx), (const uint8_t *) dW, 24, dR, 1, dL, n, ctx->compute);
+  ctx->launches++;
+  CU(cudaMemcpyAsync(lh, dL, (size_t) n * 128, cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  CU(cudaGetLastError());
+  cudaFree(dW); cudaFree(dR); cudaFree(dL);
+  return GT16_OK;
+}
+
+int gt16_compute_genotype(gt16_ctx *ctx, const unsigned char *ref_char, const double *lh, void *info,
+                          size_t info_stride, uint32_t n) {
+  if (!ctx || !ref_char || !lh || !info || info_stride < 160) return GT16_EINVAL;
+  if (!n) return GT16_OK;
+  CU(cudaSetDevice(ctx->device));
+  uint8_t *dR = nullptr, *dI = nullptr; double *dL = nullptr;
+  const size_t dStride = 160;   // pD, genotype(+pad), flh[16], bestD, secondD
+  CU(cudaMalloc(&dR, n)); CU(cudaMalloc(&dL, (size_t) n * 128)); CU(cudaMalloc(&dI, (size_t) n * dStride));
+  CU(cudaMemcpyAsync(dR, ref_char, n, cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemcpyAsync(dL, lh, (size_t) n * 128, cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemsetAsync(dI, 0, (size_t) n * dStride, ctx->compute));
+  launch_op_genotype(eval_params(ctx), dR, dL, dI, dStride, n, ctx->compute);
+  ctx->launches++;
+  std::vector<uint8_t> hI((size_t) n * dStride);
+  CU(cudaMemcpyAsync(hI.data(), dI, hI.size(), cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  CU(cudaGetLastError());
+  for (uint32_t i = 0; i < n; ++i) {          // scatter into SnpCallingInfo (SNP_Meta.h:115-125)
+    char *d = (char *) info + (size_t) i * info_stride;
+    const uint8_t *s = &hI[(size_t) i * dStride];
+    memcpy(d + 0, s + 0, 8);                  // pD
+    memcpy(d + 8, s + 8, 4);                  // genotype (secondGenotype @12 untouched)
+    memcpy(d + 16, s + 16, 128);              // flh
+    memcpy(d + 144, s + 144, 16);             // bestD, secondD (rfProb/rfMode untouched)
+  }
+  cudaFree(dR); cudaFree(dL); cudaFree(dI);
+  return GT16_OK;
+}
+
+int gt16_compute_bias(gt16_ctx *ctx, const void *w, const void *f, const void *r, size_t stride, uint32_t n,
+                      float *sb, float *bqb) {
+  if (!ctx || !w || !f || !r || !sb || !bqb || stride < 16) return GT16_EINVAL;
+  if (!n) return GT16_OK;
+  CU(cudaSetDevice(ctx->device));
+  std::vector<uint32_t> buf((size_t) n * 12);
+  for (uint32_t i = 0; i < n; ++i) {
+    memcpy(&buf[(size_t) i * 12 + 0], (const char *) w + (size_t) i * stride, 16);
+    memcpy(&buf[(size_t) i * 12 + 4], (const char *) f + (size_t) i * stride, 16);
+    memcpy(&buf[(size_t) i * 12 + 8], (const char *) r + (size_t) i * stride, 16);
+  }
+  uint8_t *d = nullptr; float *dS = nullptr, *dB = nullptr;
+  CU(cudaMalloc(&d, buf.size() * 4)); CU(cudaMalloc(&dS, (size_t) n * 16)); CU(cudaMalloc(&dB, (size_t) n * 16));
+  CU(cudaMemcpyAsync(d, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
+  launch_op_bias(eval_params(ctx), d, d + 16, d + 32, 48, n, dS, dB, ctx->compute);
+  ctx->launches++;
+  CU(cudaMemcpyAsync(sb, dS, (size_t) n * 16, cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaMemcpyAsync(bqb, dB, (size_t) n * 16, cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  CU(cudaGetLastError());
+  cudaFree(d); cudaFree(dS); cudaFree(dB);
+  return GT16_OK;
+}
+
+// ---- fused path -----------------------------------------------------------------------------
+static const uint32_t kCopyChunkSites = 1u << 22;     // 32 MiB of counters per cudaMemcpyAsync
+
+static int alloc_snapshot(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot *ds,
+                          std::vector<uint32_t> &ovfBase) {
+  const uint32_t L = view->text_length;
+  size_t nOvf = 0;
+  ovfBase.assign(view->n_overflow_regions + 1, 0);
+  for (uint32_t r = 0; r < view->n_overflow_regions; ++r) { ovfBase[r] = (uint32_t) nOvf; nOvf += view->overflow_size[r]; }
+  ovfBase[view->n_overflow_regions] = (uint32_t) nOvf;
+  CU(cudaMalloc(&ds->counters, (size_t) L * 8 + 16));
+  CU(cudaMalloc(&ds->ovf, nOvf * 32 + 32));
+  CU(cudaMalloc(&ds->ovfBase, ovfBase.size() * 4));
+  CU(cudaMalloc(&ds->pool, (size_t) view->pool_bytes + 16));
+  CU(cudaMalloc(&ds->ref, (size_t) view->packed_ref_words * 4 + 16));
+  if (view->invalid_bitmap) CU(cudaMalloc(&ds->invalid, (((size_t) L + 31) >> 5) * 4 + 4));
+  SnapView &v = ds->v;
+  v.counters = (const uint64_t *) ds->counters;
+  v.invalid = (const uint32_t *) ds->invalid;
+  v.ovf = (const uint8_t *) ds->ovf;
+  v.ovfBase = (const uint32_t *) ds->ovfBase;
+  v.pool = (const uint8_t *) ds->pool;
+  v.packedRef = (const uint32_t *) ds->ref;
+  v.L = L;
+  v.nOvfRegions = view->n_overflow_regions;
+  v.poolBytes = view->pool_bytes;
+  v.refWords = view->packed_ref_words;
+  return GT16_OK;
+}
+
+// everything except the counters (small: 0.375 B/site + overflow records + pool)
+static int upload_aux(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot *ds,
+                      const std::vector<uint32_t> &ovfBase, cudaStream_t s) {
+  const uint32_t L = view->text_length;
+  for (uint32_t r = 0; r < view->n_overflow_regions; ++r)
+    if (view->overflow_size[r])
+      CU(cudaMemcpyAsync((char *) ds->ovf + (size_t) ovfBase[r] * 32, view->overflow[r], (size_t) view->overflow_size[r] * 32,
+                         cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ds->ovfBase, ovfBase.data(), ovfBase.size() * 4, cudaMemcpyHostToDevice, s));
+  if (view->pool_bytes) CU(cudaMemcpyAsync(ds->pool, view->pool, view->pool_bytes, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ds->ref, view->packed_ref, (size_t) view->packed_ref_words * 4, cudaMemcpyHostToDevice, s));
+  if (view->invalid_bitmap)
+    CU(cudaMemcpyAsync(ds->invalid, view->invalid_bitmap, (((size_t) L + 31) >> 5) * 4, cudaMemcpyHostToDevice, s));
+  return GT16_OK;
+}
+
+static int check_view(gt16_ctx *ctx, const gt16_snapshot_view *v) {
+  if (!v || !v->counters || !v->text_length || !v->packed_ref || !v->n_overflow_regions || !v->overflow_size ||
+      !v->overflow)
+    return fail(ctx, GT16_EINVAL, "incomplete snapshot view");
+  if ((size_t) v->packed_ref_words * 16 < v->text_length) return fail(ctx, GT16_EINVAL, "packed reference shorter than the snapshot");
+  return GT16_OK;
+}
+
+void gt16_snapshot_release(gt16_ctx *ctx, gt16_dev_snapshot *ds) {
+  if (!ds) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(ds->counters); cudaFree(ds->invalid); cudaFree(ds->ovf); cudaFree(ds->ovfBase); cudaFree(ds->pool); cudaFree(ds->ref);
+  delete ds;
+}
+
+int gt16_snapshot_upload(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot **out) {
+  if (!ctx || !out) return GT16_EINVAL;
+  int rc = check_view(ctx, view);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  gt16_dev_snapshot *ds = new gt16_dev_snapshot();
+  std::vector<uint32_t> ovfBase;
+  rc = alloc_snapshot(ctx, view, ds, ovfBase);
+  if (rc == GT16_OK) rc = upload_aux(ctx, view, ds, ovfBase, ctx->copy);
+  if (rc == GT16_OK) {
+    const uint32_t L = view->text_length;
+    for (uint64_t a = 0; a < L && rc == GT16_OK; a += kCopyChunkSites) {
+      uint64_t b = std::min<uint64_t>(a + kCopyChunkSites, L);
+      if (cudaMemcpyAsync((char *) ds->counters + a * 8, view->counters + a, (b - a) * 8, cudaMemcpyHostToDevice, ctx->copy) != cudaSuccess)
+        rc = fail(ctx, GT16_ECUDA, "counter upload failed");
+    }
+  }
+  if (rc == GT16_OK && cudaStreamSynchronize(ctx->copy) != cudaSuccess) rc = fail(ctx, GT16_ECUDA, "upload synchronize failed");
+  if (rc != GT16_OK) { gt16_snapshot_release(ctx, ds); return rc; }
+  *out = ds;
+  return GT16_OK;
+}
+
+namespace {
+
+struct RegionPlan {
+  std::vector<uint32_t> start;
+  std::vector<uint64_t> first;      // nRegions + 1
+  bool ascending = true;
+  uint32_t *dStart = nullptr;
+  uint64_t *dFirst = nullptr;
+  DevSiteMap map;
+  uint32_t pos_of(uint64_t i) const {
+    size_t lo = 0, hi = start.size();
+    while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (first[mid] <= i) lo = mid; else hi = mid; }
+    return start[lo] + (uint32_t) (i - first[lo]);
+  }
+};
+
+int make_plan(gt16_ctx *ctx, uint32_t L, const gt16_region *regions, uint32_t nRegions, RegionPlan &pl) {
+  gt16_region whole = {0, L};
+  if (!regions || !nRegions) { regions = &whole; nRegions = 1; }
+  uint64_t acc = 0;
+  for (uint32_t r = 0; r < nRegions; ++r) {
+    if (regions[r].start >= L || regions[r].end > L)       // VariantCaller.cpp:623-627
+      return fail(ctx, GT16_EINVAL, "[Error] Positions in exome region are incompatible with the index, please generate the exome list with the correct index.");
+    if (regions[r].end <= regions[r].start) continue;      // empty loop body in the reference
+    if (!pl.start.empty() && regions[r].start < pl.start.back()) pl.ascending = false;
+    pl.start.push_back(regions[r].start);
+    pl.first.push_back(acc);
+    acc += regions[r].end - regions[r].start;
+  }
+  if (pl.start.empty()) { pl.start.push_back(0); pl.first.push_back(0); }
+  pl.first.push_back(acc);
+  CU(cudaMalloc(&pl.dStart, pl.start.size() * 4));
+  CU(cudaMalloc(&pl.dFirst, pl.first.size() * 8));
+  CU(cudaMemcpyAsync(pl.dStart, pl.start.data(), pl.start.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
+  CU(cudaMemcpyAsync(pl.dFirst, pl.first.data(), pl.first.size() * 8, cudaMemcpyHostToDevice, ctx->compute));
+  pl.map.m.regStart = pl.dStart;
+  pl.map.m.regFirst = pl.dFirst;
+  pl.map.m.nRegions = (uint32_t) pl.start.size();
+  pl.map.totalSites = acc;
+  return GT16_OK;
+}
+
+struct Work {       // device scratch of one call
+  uint32_t *mask = nullptr, *counts = nullptr, *listA = nullptr, *mask2 = nullptr, *counts2 = nullptr, *listB = nullptr;
+  gt16_called_site *recs = nullptr;
+  void release() { cudaFree(mask); cudaFree(counts); cudaFree(listA); cudaFree(mask2); cudaFree(counts2); cudaFree(listB); cudaFree(recs); }
+};
+
+// ordered compaction of `mask` over nItems -> list (allocated here); returns count
+int compact(gt16_ctx *ctx, const uint32_t *mask, uint32_t nItems, uint32_t *counts, const uint32_t *values,
+            uint32_t offset, uint32_t **list, uint32_t *count) {
+  launch_mask_count(mask, nItems, counts, ctx->compute);
+  launch_scan_counts(counts, scan_blocks(nItems), ctx->dTotal, ctx->compute);
+  ctx->launches += 2;
+  CU(cudaMemcpyAsync(ctx->hPinned, ctx->dTotal, 4, cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  *count = ctx->hPinned[0];
+  CU(cudaMalloc(list, (size_t) (*count ? *count : 1) * 4));
+  launch_mask_scatter(mask, nItems, counts, values, offset, *list, ctx->compute);
+  ctx->launches++;
+  return GT16_OK;
+}
+
+float ms_between(cudaEvent_t a, cudaEvent_t b) { float m = 0.f; cudaEventElapsedTime(&m, a, b); return m; }
+
+// stages after the streaming pass: compaction, exact evaluation, candidate records, D2H
+int finish_call(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t begin, uint32_t n, bool usedTables,
+                Work &wk, cudaEvent_t *ev /*[6]*/, gt16_calls *calls, gt16_stats *st) {
+  EvalParams P = eval_params(ctx);
+  uint32_t nA = 0, nB = 0;
+  int rc = compact(ctx, wk.mask, n, wk.counts, nullptr, 0, &wk.listA, &nA);
+  if (rc) return rc;
+  CU(cudaEventRecord(ev[2], ctx->compute));
+  const uint32_t *finalList = wk.listA;
+  nB = nA;
+  if (usedTables) {
+    CU(cudaMalloc(&wk.mask2, ((size_t) (nA + 31) / 32 + 1) * 4));
+    CU(cudaMalloc(&wk.counts2, ((size_t) scan_blocks(nA) + 1) * 4));
+    launch_eval_list(V, pl.map, begin, wk.listA, nA, P, wk.mask2, ctx->errWord, ctx->compute);
+    ctx->launches++;
+    CU(cudaEventRecord(ev[3], ctx->compute));
+    if (nA) {
+      rc = compact(ctx, wk.mask2, nA, wk.counts2, wk.listA, 0, &wk.listB, &nB);
+      if (rc) return rc;
+    } else nB = 0;
+    finalList = wk.listB;
+  } else {
+    CU(cudaEventRecord(ev[3], ctx->compute));
+  }
+  CU(cudaMalloc(&wk.recs, (size_t) (nB ? nB : 1) * sizeof(gt16_called_site)));
+  launch_candidates(V, pl.map, begin, finalList, nB, P, wk.recs, ctx->errWord, ctx->compute);
+  ctx->launches++;
+  CU(cudaEventRecord(ev[4], ctx->compute));
+  calls->sites.resize(nB);
+  if (nB) CU(cudaMemcpyAsync(calls->sites.data(), wk.recs, (size_t) nB * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaMemcpyAsync(ctx->hPinned + 1, ctx->errWord, 4, cudaMemcpyDeviceToHost, ctx->compute));
+  CU(cudaEventRecord(ev[5], ctx->compute));
+  CU(cudaStreamSynchronize(ctx->compute));
+  CU(cudaGetLastError());
+  uint32_t errw = ctx->hPinned[1];
+  CU(cudaMemset(ctx->errWord, 0, 4));
+  if (errw & kErrBadSnapshot) return fail(ctx, GT16_EDATA, "snapshot refers to an overflow record or pool range that does not exist");
+  if (errw & kErrGenotype) return fail(ctx, GT16_EGENOTYPE, "Error in selecting Genotype");
+  if (st) { st->flagged = nA; st->called = nB; }
+  return GT16_OK;
+}
+
+}  // namespace
+
+static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const gt16_dev_snapshot *resident,
+                       const gt16_region *regions, uint32_t nRegions, uint64_t begin, uint64_t end,
+                       gt16_calls **out, gt16_stats *stats) {
+  if (!ctx || !out) return GT16_EINVAL;
+  if (!ctx->havePrefill) return fail(ctx, GT16_ESTATE, "gt16_configure / gt16_prefill_likelihood_cache must run first");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t L = resident ? resident->v.L : hostView->text_length;
+  RegionPlan pl;
+  int rc = make_plan(ctx, L, regions, nRegions, pl);
+  if (rc) return rc;
+  if (end > pl.map.totalSites) end = pl.map.totalSites;
+  if (begin > end) begin = end;
+  if (begin % kBatch) { cudaFree(pl.dStart); cudaFree(pl.dFirst); return fail(ctx, GT16_EINVAL, "site_begin must be a multiple of GT16_BATCH_SITES"); }
+  if (end - begin >= 0xFFFFFFFFull) { cudaFree(pl.dStart); cudaFree(pl.dFirst); return fail(ctx, GT16_EINVAL, "range too long"); }
+  const uint32_t n = (uint32_t) (end - begin);
+  const uint32_t launches0 = ctx->launches;
+  const bool useTables = ctx->useDecisions && ctx->haveDecisions;
+  DecisionTables D = {ctx->s1, ctx->s2p, ctx->s2q, ctx->g4};
+  EvalParams P = eval_params(ctx);
+
+  gt16_calls *calls = new gt16_calls();
+  gt16_stats st;
+  memset(&st, 0, sizeof(st));
+  st.sites = n;
+  Work wk;
+  gt16_dev_snapshot *streamed = nullptr;
+  cudaEvent_t ev[6];
+  for (int k = 0; k < 6; ++k) cudaEventCreate(&ev[k]);
+  std::vector<cudaEvent_t> chunkEv;
+  auto cleanup = [&]() {
+    wk.release(); cudaFree(pl.dStart); cudaFree(pl.dFirst);
+    for (int k = 0; k < 6; ++k) cudaEventDestroy(ev[k]);
+    for (auto e : chunkEv) cudaEventDestroy(e);
+    if (streamed) gt16_snapshot_release(ctx, streamed);
+  };
+#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); delete calls; return GT16_ECUDA; } } while (0)
+
+  if (n == 0) { cleanup(); *out = calls; if (stats) *stats = st; return GT16_OK; }
+  CUX(cudaMalloc(&wk.mask, ((size_t) (n + 31) / 32 + 1) * 4));
+  CUX(cudaMalloc(&wk.counts, ((size_t) scan_blocks(n) + 1) * 4));
+  CUX(cudaEventRecord(ev[0], ctx->compute));
+
+  if (resident) {
+    launch_stream(resident->v, pl.map, begin, n, useTables, D, P, wk.mask, ctx->errWord, ctx->compute);
+    ctx->launches++;
+    CUX(cudaEventRecord(ev[1], ctx->compute));
+    rc = finish_call(ctx, resident->v, pl, begin, n, useTables, wk, ev, calls, &st);
+  } else {
+    // counters stream in on the copy stream in genome order; the classification of block k only
+    // waits for the chunk that holds its last needed position (+1 look-ahead, +355 for windows)
+    streamed = new gt16_dev_snapshot();
+    std::vector<uint32_t> ovfBase;
+    rc = alloc_snapshot(ctx, hostView, streamed, ovfBase);
+    if (rc == GT16_OK) rc = upload_aux(ctx, hostView, streamed, ovfBase, ctx->copy);
+    if (rc != GT16_OK) { cleanup(); delete calls; return rc; }
+    const uint32_t loPos = pl.ascending ? pl.pos_of(begin) : 0;
+    const uint32_t hiPos = pl.ascending ? pl.pos_of(end - 1) : L - 1;
+    const uint64_t copyLo = loPos > 512 ? ((loPos - 512) / kCopyChunkSites) * (uint64_t) kCopyChunkSites : 0;
+    const uint64_t copyHi = std::min<uint64_t>((uint64_t) hiPos + 1024, L);
+    size_t nChunks = (size_t) ((copyHi - copyLo + kCopyChunkSites - 1) / kCopyChunkSites);
+    chunkEv.resize(nChunks);
+    for (size_t c = 0; c < nChunks; ++c) {
+      uint64_t a = copyLo + c * (uint64_t) kCopyChunkSites, b = std::min<uint64_t>(a + kCopyChunkSites, copyHi);
+      bool needed = true;
+      if (pl.ascending && pl.start.size() > 1) {         // sparse targets: skip chunks no region touches
+        needed = false;
+        size_t lo = 0, hi = pl.start.size();
+        while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if ((uint64_t) pl.start[mid] <= a + 0) lo = mid; else hi = mid; }
+        for (size_t r = lo; r < pl.start.size(); ++r) {
+          uint64_t rs = pl.start[r], re = rs + (pl.first[r + 1] - pl.first[r]);
+          if (rs > b + 512) break;
+          if (re + 512 > a && rs < b + 512) { needed = true; break; }
+        }
+      }
+      if (needed)
+        CUX(cudaMemcpyAsync((char *) streamed->counters + a * 8, hostView->counters + a, (b - a) * 8, cudaMemcpyHostToDevice, ctx->copy));
+      else
+        CUX(cudaMemsetAsync((char *) streamed->counters + a * 8, 0, (b - a) * 8, ctx->copy));
+      CUX(cudaEventCreateWithFlags(&chunkEv[c], cudaEventDisableTiming));
+      CUX(cudaEventRecord(chunkEv[c], ctx->copy));
+    }
+    for (uint64_t a = begin; a < end; a += kBatch) {
+      uint64_t b = std::min<uint64_t>(a + kBatch, end);
+      uint64_t need = pl.ascending ? std::min<uint64_t>((uint64_t) pl.pos_of(b - 1) + 2, copyHi) : copyHi;
+      size_t c = (size_t) ((need - 1 - copyLo) / kCopyChunkSites);
+      CUX(cudaStreamWaitEvent(ctx->compute, chunkEv[std::min(c, nChunks - 1)], 0));
+      launch_stream(streamed->v, pl.map, a, (uint32_t) (b - a), useTables, D, P, wk.mask + (a - begin) / 32, ctx->errWord, ctx->compute);
+      ctx->launches++;
+    }
+    CUX(cudaStreamWaitEvent(ctx->compute, chunkEv[nChunks - 1], 0));
+    CUX(cudaEventRecord(ev[1], ctx->compute));
+    rc = finish_call(ctx, streamed->v, pl, begin, n, useTables, wk, ev, calls, &st);
+  }
+  if (rc != GT16_OK) { cleanup(); delete calls; return rc; }
+  st.ms_stream = ms_between(ev[0], ev[1]);
+  st.ms_scan = ms_between(ev[1], ev[2]);
+  st.ms_eval = ms_between(ev[2], ev[3]);
+  st.ms_candidates = ms_between(ev[3], ev[4]);
+  st.ms_d2h = ms_between(ev[4], ev[5]);
+  st.ms_total_device = ms_between(ev[0], ev[5]);
+  st.kernel_launches = ctx->launches - launches0;
+  cleanup();
+#undef CUX
+  *out = calls;
+  if (stats) *stats = st;
+  return GT16_OK;
+}
+
+int gt16_call_sites(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
+                    uint64_t site_begin, uint64_t site_end, gt16_calls **out, gt16_stats *stats) {
+  if (!snap) return GT16_EINVAL;
+  return call_common(ctx, nullptr, snap, regions, n_regions, site_begin, site_end, out, stats);
+}
+
+int gt16_call_sites_host(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt16_region *regions,
+                         uint32_t n_regions, uint64_t site_begin, uint64_t site_end, gt16_calls **out,
+                         gt16_stats *stats) {
+  if (!ctx) return GT16_EINVAL;
+  int rc = check_view(ctx, view);
+  if (rc) return rc;
+  return call_common(ctx, view, nullptr, regions, n_regions, site_begin, site_end, out, stats);
+}
+
+uint64_t gt16_calls_count(const gt16_calls *c) { return c ? c->sites.size() : 0; }
+const gt16_called_site *gt16_calls_data(const gt16_calls *c) { return c && !c->sites.empty() ? c->sites.data() : nullptr; }
+void gt16_calls_free(gt16_calls *c) { delete c; }
+
+}  // extern "C"

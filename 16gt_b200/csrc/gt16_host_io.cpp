@@ -1,0 +1,343 @@
+// gt16_host_io.cpp -- host-side formats on either side of the hot path: snapshot container
+// reader, packed-reference index reader, coordinate translation and the .txt row printer.
+// Plain C++ in the reference's own style; no CUDA here except optional page-locking of the
+// big buffers (so cudaMemcpyAsync from them is truly asynchronous).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+#include <cuda_runtime_api.h>
+#include "../../include/gt16.h"
+
+namespace {
+
+void set_err(char *err, size_t n, const char *fmt, ...) {
+  if (!err || !n) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err, n, fmt, ap);
+  va_end(ap);
+}
+
+// big host buffer, page-locked on request
+struct HostBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  bool pinned = false;
+  bool alloc(size_t n, bool pin) {
+    bytes = n ? n : 1;
+    if (pin && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) { pinned = true; return true; }
+    (void) cudaGetLastError();
+    pinned = false;
+    p = malloc(bytes);
+    return p != nullptr;
+  }
+  void release() {
+    if (!p) return;
+    if (pinned) cudaFreeHost(p); else free(p);
+    p = nullptr;
+  }
+};
+
+bool read_at(FILE *f, uint64_t off, void *dst, size_t n) {
+  if (fseeko(f, (off_t) off, SEEK_SET) != 0) return false;
+  return fread(dst, 1, n, f) == n;
+}
+
+}  // namespace
+
+struct gt16_host_snapshot {
+  uint32_t textLength = 0;
+  uint32_t nRegions = 0;
+  HostBuf counters, invalid, pool, ovfAll;
+  bool hasInvalid = false;
+  uint32_t poolBytes = 0;
+  std::vector<const void *> ovfPtr;
+  std::vector<uint32_t> ovfSize;
+};
+
+struct gt16_index {
+  uint32_t length = 0;
+  std::vector<uint32_t> packed;            // 16 bases per word, MSB first (HSP.packedDNA)
+  std::vector<std::string> names;          // annotation[i].text
+  struct Tr { uint32_t startPos; uint16_t chrID; uint32_t correction; };
+  std::vector<Tr> translate;               // HSP.translate
+};
+
+extern "C" {
+
+// ---- snapshot container (SnapshotHandler.cpp:238-347) -----------------------------------
+int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, char *err, size_t errLen) {
+  if (!path || !out) return GT16_EINVAL;
+  FILE *f = fopen(path, "rb");
+  if (!f) { set_err(err, errLen, "Error opening %s", path); return GT16_EIO; }
+  gt16_host_snapshot *hs = new gt16_host_snapshot();
+  int rc = GT16_OK;
+  uint8_t hdr[4 + 5 * 16];
+  uint64_t start[5], len[5];
+  do {
+    if (!read_at(f, 0, hdr, sizeof(hdr))) { set_err(err, errLen, "%s: short header", path); rc = GT16_EIO; break; }
+    for (int i = 0; i < 5; ++i) { memcpy(&start[i], hdr + 4 + 16 * i, 8); memcpy(&len[i], hdr + 12 + 16 * i, 8); }
+    // subfile 1: counters (dense mode 1, sparse mode 2)
+    uint8_t head[5];
+    if (!read_at(f, start[1], head, 5)) { set_err(err, errLen, "%s: no counter subfile", path); rc = GT16_EIO; break; }
+    char mode = (char) head[0];
+    memcpy(&hs->textLength, head + 1, 4);
+    const uint32_t L = hs->textLength;
+    if (!L) { set_err(err, errLen, "%s: empty snapshot", path); rc = GT16_EDATA; break; }
+    if (!hs->counters.alloc((size_t) L * 8 + 16, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
+    if (mode & 1) {
+      if (fread(hs->counters.p, 8, L, f) != L) { set_err(err, errLen, "%s: truncated counters", path); rc = GT16_EIO; break; }
+      memset((char *) hs->counters.p + (size_t) L * 8, 0, 16);
+    } else if (mode & 2) {
+      memset(hs->counters.p, 0, (size_t) L * 8 + 16);
+      uint64_t n = len[1] / 12;
+      std::vector<uint8_t> buf((size_t) 12 << 16);
+      uint64_t done = 0;
+      bool ok = true;
+      while (done < n && ok) {
+        size_t chunk = (size_t) ((n - done) < (1u << 16) ? (n - done) : (1u << 16));
+        if (fread(buf.data(), 12, chunk, f) != chunk) { ok = false; break; }
+        for (size_t k = 0; k < chunk; ++k) {
+          uint32_t pos; memcpy(&pos, &buf[k * 12], 4);
+          if (pos >= L) { ok = false; break; }
+          memcpy((char *) hs->counters.p + (size_t) pos * 8, &buf[k * 12 + 4], 8);
+        }
+        done += chunk;
+      }
+      if (!ok) { set_err(err, errLen, "%s: bad sparse counter subfile", path); rc = GT16_EDATA; break; }
+    } else { set_err(err, errLen, "%s: unknown counter mode %d", path, (int) mode); rc = GT16_EDATA; break; }
+    // subfile 2: overflow arrays
+    if (!read_at(f, start[2], &hs->nRegions, 4) || hs->nRegions == 0 || hs->nRegions > 4096) {
+      set_err(err, errLen, "%s: bad overflow subfile", path); rc = GT16_EDATA; break;
+    }
+    {
+      std::vector<std::vector<uint8_t> > tmp(hs->nRegions);
+      size_t total = 0;
+      bool ok = true;
+      for (uint32_t r = 0; r < hs->nRegions && ok; ++r) {
+        uint32_t sz, lim;
+        if (fread(&sz, 4, 1, f) != 1 || fread(&lim, 4, 1, f) != 1) { ok = false; break; }
+        hs->ovfSize.push_back(sz);
+        if (lim == 0) continue;                       // SnapshotHandler.cpp:313
+        tmp[r].resize((size_t) sz * 32);
+        if (sz && fread(tmp[r].data(), 32, sz, f) != sz) { ok = false; break; }
+        total += (size_t) sz * 32;
+      }
+      if (!ok) { set_err(err, errLen, "%s: truncated overflow arrays", path); rc = GT16_EIO; break; }
+      if (!hs->ovfAll.alloc(total + 32, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
+      size_t off = 0;
+      for (uint32_t r = 0; r < hs->nRegions; ++r) {
+        hs->ovfPtr.push_back((char *) hs->ovfAll.p + off);
+        if (!tmp[r].empty()) memcpy((char *) hs->ovfAll.p + off, tmp[r].data(), tmp[r].size());
+        off += tmp[r].size();
+      }
+    }
+    // subfile 3: invalid bitmap (absent in sparse snapshots)
+    size_t bmWords = ((size_t) L + 31) >> 5;
+    if (!hs->invalid.alloc(bmWords * 4 + 4, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
+    if (len[3]) {
+      if (!read_at(f, start[3], hs->invalid.p, bmWords * 4)) { set_err(err, errLen, "%s: truncated bitmap", path); rc = GT16_EIO; break; }
+      hs->hasInvalid = true;
+    } else {
+      memset(hs->invalid.p, 0, bmWords * 4);
+    }
+    // subfile 0: memory pool; only the first curPtr bytes carry data
+    uint8_t ph[12];
+    if (!read_at(f, start[0], ph, 12)) { set_err(err, errLen, "%s: no pool subfile", path); rc = GT16_EIO; break; }
+    uint32_t curPtr; uint64_t capacity;
+    memcpy(&curPtr, ph, 4); memcpy(&capacity, ph + 4, 8);
+    if (curPtr > capacity) { set_err(err, errLen, "%s: pool pointer beyond capacity", path); rc = GT16_EDATA; break; }
+    hs->poolBytes = curPtr;
+    if (!hs->pool.alloc((size_t) curPtr + 16, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
+    if (curPtr && fread(hs->pool.p, 1, curPtr, f) != curPtr) { set_err(err, errLen, "%s: truncated pool", path); rc = GT16_EIO; break; }
+  } while (0);
+  fclose(f);
+  if (rc != GT16_OK) { gt16_snapshot_free(hs); return rc; }
+  *out = hs;
+  return GT16_OK;
+}
+
+void gt16_snapshot_view_of(const gt16_host_snapshot *hs, gt16_snapshot_view *v) {
+  memset(v, 0, sizeof(*v));
+  v->counters = (const uint64_t *) hs->counters.p;
+  v->text_length = hs->textLength;
+  v->invalid_bitmap = hs->hasInvalid ? (const uint32_t *) hs->invalid.p : nullptr;
+  v->n_overflow_regions = hs->nRegions;
+  v->overflow = hs->ovfPtr.data();
+  v->overflow_size = hs->ovfSize.data();
+  v->pool = (const uint8_t *) hs->pool.p;
+  v->pool_bytes = hs->poolBytes;
+}
+
+void gt16_snapshot_free(gt16_host_snapshot *hs) {
+  if (!hs) return;
+  hs->counters.release(); hs->invalid.release(); hs->pool.release(); hs->ovfAll.release();
+  delete hs;
+}
+
+// ---- index files (.pac/.ann/.tra) -----------------------------------------------------
+int gt16_index_read(const char *prefix, gt16_index **out, char *err, size_t errLen) {
+  if (!prefix || !out) return GT16_EINVAL;
+  std::string pre(prefix);
+  gt16_index *ix = new gt16_index();
+  int rc = GT16_OK;
+  do {
+    // .ann: "%u %d %u" then per sequence "%u %s" (gi, name up to end of line) and "%u %u %d" (readIndex.cpp:96-115)
+    FILE *f = fopen((pre + ".ann").c_str(), "r");
+    if (!f) { set_err(err, errLen, "Cannot open %s.ann", prefix); rc = GT16_EIO; break; }
+    unsigned len = 0, seed = 0; int nSeq = 0;
+    if (fscanf(f, "%u %d %u", &len, &nSeq, &seed) != 3 || nSeq <= 0) { fclose(f); set_err(err, errLen, "%s.ann: bad header", prefix); rc = GT16_EDATA; break; }
+    ix->length = len;
+    char line[4096];
+    if (!fgets(line, sizeof(line), f)) { fclose(f); rc = GT16_EDATA; break; }   // rest of header line
+    bool ok = true;
+    for (int i = 0; i < nSeq; ++i) {
+      if (!fgets(line, sizeof(line), f)) { ok = false; break; }
+      char *sp = strchr(line, ' ');
+      std::string name = sp ? std::string(sp + 1) : std::string(line);
+      while (!name.empty() && (name.back() == '\n' || name.back() == '\r')) name.pop_back();
+      ix->names.push_back(name);
+      if (!fgets(line, sizeof(line), f)) { ok = false; break; }
+    }
+    fclose(f);
+    if (!ok) { set_err(err, errLen, "%s.ann: truncated", prefix); rc = GT16_EDATA; break; }
+    // .tra: "%u %d %d %u" header, gridEntries lines, then translate entries (readIndex.cpp:24-60)
+    f = fopen((pre + ".tra").c_str(), "r");
+    if (!f) { set_err(err, errLen, "Cannot open %s.tra", prefix); rc = GT16_EIO; break; }
+    unsigned tl = 0, grid = 0; int ns = 0, removed = 0;
+    if (fscanf(f, "%u %d %d %u", &tl, &ns, &removed, &grid) != 4) { fclose(f); set_err(err, errLen, "%s.tra: bad header", prefix); rc = GT16_EDATA; break; }
+    for (unsigned g = 0; g < grid; ++g) { unsigned v; if (fscanf(f, "%u", &v) != 1) { ok = false; break; } }
+    int nTr = ns + removed;
+    for (int i = 0; i < nTr && ok; ++i) {
+      unsigned sp, corr; unsigned short chr;
+      if (fscanf(f, "%u %hu %u", &sp, &chr, &corr) != 3) { ok = false; break; }
+      gt16_index::Tr t; t.startPos = sp; t.chrID = chr; t.correction = corr;
+      ix->translate.push_back(t);
+    }
+    fclose(f);
+    if (!ok || ix->translate.empty()) { set_err(err, errLen, "%s.tra: truncated", prefix); rc = GT16_EDATA; break; }
+    // .pac: 4 bases / byte, first base in bits 7..6; trailing byte = length % 4
+    f = fopen((pre + ".pac").c_str(), "rb");
+    if (!f) { set_err(err, errLen, "Cannot open %s.pac", prefix); rc = GT16_EIO; break; }
+    size_t nBytes = ((size_t) len + 3) / 4;
+    std::vector<uint8_t> bytes(nBytes + 8, 0);
+    size_t got = fread(bytes.data(), 1, nBytes, f);
+    fclose(f);
+    if (got != nBytes) { set_err(err, errLen, "%s.pac: truncated", prefix); rc = GT16_EIO; break; }
+    size_t nWords = ((size_t) len + 15) / 16 + 2;
+    ix->packed.assign(nWords, 0);
+    for (size_t w = 0; w * 4 < nBytes; ++w)
+      ix->packed[w] = ((uint32_t) bytes[w * 4] << 24) | ((uint32_t) bytes[w * 4 + 1] << 16) |
+                      ((uint32_t) bytes[w * 4 + 2] << 8) | (uint32_t) bytes[w * 4 + 3];
+    // clear bits beyond the last base so reads past the end see 'A' like a zeroed trailer
+    if (len % 16) ix->packed[len / 16] &= ~0u << (32 - 2 * (len % 16));
+  } while (0);
+  if (rc != GT16_OK) { delete ix; return rc; }
+  *out = ix;
+  return GT16_OK;
+}
+
+uint32_t gt16_index_length(const gt16_index *ix) { return ix->length; }
+const uint32_t *gt16_index_packed(const gt16_index *ix, uint32_t *nWords) {
+  if (nWords) *nWords = (uint32_t) ix->packed.size();
+  return ix->packed.data();
+}
+
+// getChrAndPos: last translate entry starting at or before amb; position = amb - correction
+const char *gt16_index_translate(const gt16_index *ix, uint32_t amb, uint32_t *chrPos) {
+  size_t lo = 0, hi = ix->translate.size();
+  while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (ix->translate[mid].startPos <= amb) lo = mid; else hi = mid; }
+  const gt16_index::Tr &t = ix->translate[lo];
+  if (chrPos) *chrPos = amb - t.correction;      // low 32 bits, printed with %u (interpreter.cpp:116)
+  size_t c = (size_t) t.chrID - 1;
+  return c < ix->names.size() ? ix->names[c].c_str() : "?";
+}
+
+void gt16_index_free(gt16_index *ix) { delete ix; }
+
+// ---- .txt emitter (interpreter.cpp:5-156) ---------------------------------------------
+static const char kGenotypeString[][4] = {"AA", "AC", "AG", "AT", "CC", "CG", "CT", "GG", "GT", "TT",
+                                          "AX", "CX", "GX", "TX", "XX", "XY", "NN"};
+static const char kSym[] = {'A', 'C', 'G', 'T', 'X', 'Y', 'N'};
+
+static void print_indel(FILE *f, const gt16_indel &d) {
+  if (d.type == '*') { fputs("*\t*\t*\t*\t", f); return; }
+  fprintf(f, "%u%c\t", (unsigned) d.len, (char) d.type);
+  for (unsigned i = 0; i < d.len; ++i) fputc(kSym[(d.seq[i >> 2] >> ((i & 3) << 1)) & 3], f);
+  fprintf(f, "\t%u\t%u\t", (unsigned) d.hq, (unsigned) d.lq);
+}
+
+int gt16_write_txt(const char *path, const gt16_index *ix, const gt16_called_site *sites, uint64_t n, int append,
+                   float *carry) {
+  FILE *f = fopen(path, append ? "a" : "w");
+  if (!f) return GT16_EIO;
+  std::vector<char> big(1 << 20);
+  setvbuf(f, big.data(), _IOFBF, big.size());
+  if (!append) {
+    fputs("Chr\tPos\tRef\tPreBase\t"
+          "pAA\tpAC\tpAG\tpAT\tpCC\tpCG\tpCT\tpGG\tpGT\tpTT\tpAX\tpCX\tpGX\tpTX\tpXX\tpXY\t"
+          "GT\tOptb\tSuboptb\tpD\t"
+          "rfProb\trfMode\t"
+          "optIn/Del\tPatt\tHQ\tLQ\t"
+          "suboptIn/Del\tPatt\tHQ\tLQ\t"
+          "Depth\tA\tC\tG\tT\tA+\tA-\tC+\tC-\tG+\tG-\tT+\tT-\t"
+          "AA\tAC\tAG\tAT\tCC\tCG\tCT\tGG\tGT\tTT\tAX\tCX\tGX\tTX\tXX\tXY\t"
+          "SB-A\tSB-C\tSB-G\tSB-T\t"
+          "SB1-A\tSB1-C\tSB1-G\tSB1-T\t"
+          "SB2-A\tSB2-C\tSB2-G\tSB2-T\t"
+          "BQB-A\tBQB-C\tBQB-G\tBQB-T\t"
+          "BQB1-A\tBQB1-C\tBQB1-G\tBQB1-T\t"
+          "BQB2-A\tBQB2-C\tBQB2-G\tBQB2-T\t"
+          "RPB\t"
+          "LGC\tRGC\t"
+          "LG\tRG\t"
+          "ASC\t"
+          "LQ\tRQ\t"
+          "polyrun\t"
+          "totalHQ\ttotalLQ\n", f);
+  }
+  float lq = carry ? carry[0] : 0.0f, rq = carry ? carry[1] : 0.0f;
+  for (uint64_t k = 0; k < n; ++k) {
+    const gt16_called_site &s = sites[k];
+    uint32_t chrPos = 0;
+    const char *chr = gt16_index_translate(ix, s.amb, &chrPos);
+    fprintf(f, "%s\t%u\t%c\t", chr, chrPos, kSym[s.ref]);
+    if (s.is_indel) fprintf(f, "%c\t", kSym[s.ref]); else fputs("*\t", f);
+    for (int g = 0; g < 16; ++g) fprintf(f, "%.4e\t", s.flh[g]);
+    fprintf(f, "%s\t", kGenotypeString[s.genotype <= 16 ? s.genotype : 16]);
+    fprintf(f, "%.4e\t%.4e\t%.4e\t", s.bestD, s.secondD, s.pD);
+    fprintf(f, "%.4e\t%d\t", 0.0, 0);                               // rfProb, rfMode (SNP_Caller.cpp:583-584)
+    print_indel(f, s.indel[0]);
+    print_indel(f, s.indel[1]);
+    fprintf(f, "%u\t", s.W[0] + s.W[1] + s.W[2] + s.W[3]);
+    for (int b = 0; b < 4; ++b) fprintf(f, "%hu\t", (unsigned short) s.W[b]);
+    for (int b = 0; b < 4; ++b) fprintf(f, "%hu\t%hu\t", (unsigned short) s.F[b], (unsigned short) s.R[b]);
+    for (int g = 0; g < 16; ++g) fprintf(f, "%.4e\t", s.lh[g]);
+    if (s.is_indel) {
+      for (int k3 = 0; k3 < 3; ++k3) for (int b = 0; b < 4; ++b) fprintf(f, "%.4e\t", s.sb[k3][b]);
+      for (int k3 = 0; k3 < 3; ++k3) for (int b = 0; b < 4; ++b) fprintf(f, "%.4e\t", s.bqb[k3][b]);
+    } else {
+      for (int b = 0; b < 4; ++b) fprintf(f, "%.4e\t", s.sb[0][b]);
+      fputs("*\t*\t*\t*\t*\t*\t*\t*\t", f);
+      for (int b = 0; b < 4; ++b) fprintf(f, "%.4e\t", s.bqb[0][b]);
+      fputs("*\t*\t*\t*\t*\t*\t*\t*\t", f);
+    }
+    if (s.rq_assigned) { lq = s.lq; rq = s.rq; }                    // else: previous row's values survive
+    fprintf(f, "%.4f\t", s.rpb);
+    fprintf(f, "%.4f\t%.4f\t", s.lgc, s.rgc);
+    fprintf(f, "%u\t%u\t", (unsigned) s.lg, (unsigned) s.rg);
+    fprintf(f, "%.4f\t", s.asc);
+    fprintf(f, "%.4f\t%.4f\t", lq, rq);
+    fprintf(f, "%hu\t", s.polyrun);
+    fprintf(f, "%u\t%u\n", s.total_hq, s.total_lq);
+  }
+  if (carry) { carry[0] = lq; carry[1] = rq; }
+  int bad = ferror(f);
+  if (fclose(f) != 0 || bad) return GT16_EIO;
+  return GT16_OK;
+}
+
+}  // extern "C"

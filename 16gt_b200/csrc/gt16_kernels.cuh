@@ -1,0 +1,59 @@
+// gt16_kernels.cuh -- launch-side declarations shared by gt16_kernels.cu and gt16_capi.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gt16_core.cuh"
+#include "../../include/gt16.h"
+
+namespace gt16 {
+
+// decision-table geometry (see DESIGN.md "exact memoised fast path")
+constexpr int kS1Bits = 16384;                 // (Wr,0,0,0), Wr < 16384 (14-bit compact weight)
+constexpr int kS2R = 1024, kS2A = 64;          // (Wr,Wp,0,0) and (Wr,0,Wq,0): Wr < 1024, alt < 64
+constexpr int kG4R = 1024, kG4A = 32;          // (Wr,Wp,Wq1,Wq3): Wr < 1024, each alt < 32
+constexpr size_t kS1Words = kS1Bits / 32;
+constexpr size_t kS2Words = (size_t) kS2R * kS2A / 32;
+constexpr size_t kG4Words = (size_t) kG4R * kG4A * kG4A * kG4A / 32;
+
+struct DecisionTables {
+  const uint32_t *s1;    // bit = 1: needs exact evaluation
+  const uint32_t *s2p;   // index Wp * kS2R + Wr
+  const uint32_t *s2q;   // index Wq * kS2R + Wr
+  const uint32_t *g4;    // index ((Wq3 * kG4A + Wq1) * kG4A + Wp) * kG4R + Wr
+};
+
+void launch_build_table(double *out, float err, cudaStream_t s);
+void launch_build_ycsq(double *out, cudaStream_t s);
+void launch_build_decisions(const EvalParams &P, uint32_t *s1, uint32_t *s2p, uint32_t *s2q, uint32_t *g4,
+                            cudaStream_t s);
+
+// streaming classification of processed sites [first, first+n): bit i of mask = site first+i must be
+// evaluated exactly (useTables) / is a candidate (exact inline mode)
+void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint32_t n, bool useTables,
+                   const DecisionTables &D, const EvalParams &P, uint32_t *mask, uint32_t *errWord,
+                   cudaStream_t s);
+// exact predicate for listed sites: bit j of mask = list[j] is a candidate
+void launch_eval_list(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
+                      const EvalParams &P, uint32_t *mask, uint32_t *errWord, cudaStream_t s);
+
+// ordered compaction of a bit mask over nItems items
+constexpr int kScanBlock = 256;                       // mask words per block
+inline uint32_t scan_blocks(uint32_t nItems) { return ((nItems + 31) / 32 + kScanBlock - 1) / kScanBlock; }
+void launch_mask_count(const uint32_t *mask, uint32_t nItems, uint32_t *blockCounts, cudaStream_t s);
+void launch_scan_counts(uint32_t *blockCounts, uint32_t nBlocks, uint32_t *total, cudaStream_t s);
+// out[k] = (values ? values[i] : i + offset) for the k-th set bit i
+void launch_mask_scatter(const uint32_t *mask, uint32_t nItems, const uint32_t *blockOffsets,
+                         const uint32_t *values, uint32_t offset, uint32_t *out, cudaStream_t s);
+
+void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
+                       const EvalParams &P, gt16_called_site *out, uint32_t *errWord, cudaStream_t s);
+
+// operator seam kernels
+void launch_op_likelihood(const EvalParams &P, const uint8_t *w, size_t wStride, const uint8_t *ref,
+                          size_t refStride, double *lh, uint32_t n, cudaStream_t s);
+void launch_op_genotype(const EvalParams &P, const uint8_t *ref, const double *lh, uint8_t *info,
+                        size_t infoStride, uint32_t n, cudaStream_t s);
+void launch_op_bias(const EvalParams &P, const uint8_t *w, const uint8_t *f, const uint8_t *r, size_t stride,
+                    uint32_t n, float *sb, float *bqb, cudaStream_t s);
+
+}  // namespace gt16

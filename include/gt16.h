@@ -1,0 +1,194 @@
+/* gt16.h -- C ABI of libgt16.so: the B200 (sm_100a) implementation of 16GT's calling hot
+ * path (per-site 16-genotype likelihood, posterior, candidate selection, strand / base-quality
+ * bias, window features).  Plain pointers and sizes only; every entry point returns 0 on
+ * success or a negative GT16_E* code, and gt16_last_error() gives the text.
+ *
+ * There is NO CPU implementation behind these calls: gt16_ctx_create() fails with
+ * GT16_ENODEVICE when no CUDA device is usable, and every compute entry needs a context.
+ *
+ * Two levels, mirroring SURVEY.md 8(b):
+ *   (1) operator seam  -- the five functions of the reference's vestigial GPU seam
+ *       (FisherExactTest.h:10-23), so the reference harness can be A/B-tested by swapping
+ *       FisherExactTest.cpp for a 40-line shim;
+ *   (2) fused path     -- raw snapshot blocks in, called sites out; this is what the
+ *       snapshotSnpcaller drop-in binary and bench.py use.
+ */
+#ifndef GT16_H_
+#define GT16_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GT16_OK 0
+#define GT16_EINVAL (-1)     /* bad argument */
+#define GT16_ENODEVICE (-2)  /* no usable CUDA device / wrong architecture */
+#define GT16_ECUDA (-3)      /* CUDA runtime error (text in gt16_last_error) */
+#define GT16_EIO (-4)        /* file could not be read / written / parsed */
+#define GT16_EDATA (-5)      /* snapshot is internally inconsistent */
+#define GT16_ESTATE (-6)     /* call order violated (e.g. compute before prefill) */
+#define GT16_EGENOTYPE (-7)  /* "Error in selecting Genotype" (SNP_Caller.cpp:235-239) */
+
+#define GT16_BATCH_SITES 8388608u   /* VariantCaller.cpp:526-528 */
+
+typedef struct gt16_ctx gt16_ctx;
+
+/* ---- context ------------------------------------------------------------------------ */
+int gt16_ctx_create(int device, gt16_ctx **out);
+void gt16_ctx_destroy(gt16_ctx *ctx);
+const char *gt16_last_error(const gt16_ctx *ctx);   /* ctx may be NULL: last create error */
+
+/* ---- (1) operator seam --------------------------------------------------------------- */
+
+/* copyGenotypeTableToGPU(unsigned int *genotype2int)            FisherExactTest.h:10, .cpp:19-21 */
+int gt16_copy_genotype_table(gt16_ctx *ctx, const unsigned int genotype2int[16]);
+/* copySnpPriorToGPU(double *snpPrior)                           FisherExactTest.h:12, .cpp:23-25 */
+int gt16_copy_snp_prior(gt16_ctx *ctx, const double snp_prior[256]);
+/* createSnpPriorArray()                                         SNPFunctions.cpp:13-70 */
+int gt16_create_snp_prior(double out256[256]);
+
+/* prefill_likelihood_cache_with_p_err(LikelihoodCache *lc, float b_err, float ub_err)
+ *                                                               FisherExactTest.h:23, .cpp:61-92
+ * Builds the ten 2000x2000 error tables and the 15000-entry chi-square table in HBM.  If
+ * lc_host is non-NULL it must point to sizeof(LikelihoodCache) = 10*2000*2000*8 + 15000*8
+ * bytes (likelihood_cache.h:13-31) and receives a copy in the reference's layout. */
+int gt16_prefill_likelihood_cache(gt16_ctx *ctx, float b_err, float ub_err, void *lc_host);
+
+/* Start-up of the fused path = what main + selectPossibleSNPs do before the position loop
+ * (snapshotSnpcaller.cpp:229-231, VariantCaller.cpp:506-513): prefill with the ini's
+ * BalanceSubError / UnbalanceSubError (passed through float like the reference does), default
+ * genotype2int + prior, and -- when use_decision_tables != 0 -- the exact memoised decision
+ * bitmaps the streaming kernel consults (built on the device by the same evaluator). */
+int gt16_configure(gt16_ctx *ctx, double balance_sub_error, double unbalance_sub_error, int use_decision_tables);
+/* device milliseconds spent by the last prefill / decision-table build */
+int gt16_setup_times(const gt16_ctx *ctx, float *prefill_ms, float *decision_ms);
+
+/* computeGenotypeLikelihoodWrapper(InputStat *in, MetaReference *reference, GenotypeLikelihood *lh,
+ *                                  IniParams ini, unsigned n, LikelihoodCache *lc)
+ *                                                               FisherExactTest.h:14, .cpp:291-301
+ * w points at in[0].W (6 x u32 per site, stride in_stride bytes = sizeof(InputStat) = 144);
+ * ref_char points at reference[0].refChar (stride sizeof(MetaReference) = 270);
+ * lh receives n x 16 doubles (GenotypeLikelihood, 128 B).  balance/unbalance are
+ * ini.Ini_BalanceSubError / Ini_UnbalanceSubError. */
+int gt16_compute_genotype_likelihood(gt16_ctx *ctx, const void *w, size_t in_stride, const void *ref_char,
+                                     size_t ref_stride, double *lh, uint32_t n, double balance_sub_error,
+                                     double unbalance_sub_error);
+
+/* computeGenotypeWrapper(unsigned char *refChar, GenotypeLikelihood *lh, SnpCallingInfo *info,
+ *                        IniParams ini, unsigned n)            FisherExactTest.h:17, .cpp:511-521
+ * info points at n SnpCallingInfo records of info_stride bytes (168): pD @0, genotype @8,
+ * flh[16] @16, bestD @144, secondD @152 are written; the other fields are left untouched. */
+int gt16_compute_genotype(gt16_ctx *ctx, const unsigned char *ref_char, const double *lh, void *info,
+                          size_t info_stride, uint32_t n);
+
+/* computeStrandBias / computeBaseQualityBias (SNPFunctions.cpp:145-159) for n sites:
+ * w,f,r point at 4 x u32 per site with the given stride; sb and bqb receive n x 4 floats. */
+int gt16_compute_bias(gt16_ctx *ctx, const void *w, const void *f, const void *r, size_t stride, uint32_t n,
+                      float *sb, float *bqb);
+
+/* ---- (2) fused path ------------------------------------------------------------------- */
+
+/* Host-side view of one snapshot (what readSnpInfoSnapshot fills, SnapshotHandler.cpp:259-347)
+ * plus the packed reference (HSP.packedDNA). */
+typedef struct gt16_snapshot_view {
+  const uint64_t *counters;        /* SnpCounter[text_length], 8 bytes each (coreStruct.h:10-30) */
+  uint32_t text_length;            /* dnaLength */
+  const uint32_t *invalid_bitmap;  /* (text_length+31)>>5 words, bit 31-(p&31); NULL = none */
+  uint32_t n_overflow_regions;     /* numOfCPUThreads stored in the snapshot */
+  const void *const *overflow;     /* per region: SnpOverflowCounter[] (32 B each) */
+  const uint32_t *overflow_size;   /* per region: number of records */
+  const uint8_t *pool;             /* memory pool bytes */
+  uint32_t pool_bytes;             /* curPtr: bytes in use */
+  const uint32_t *packed_ref;      /* 16 bases / word, first base in bits 31..30 */
+  uint32_t packed_ref_words;
+} gt16_snapshot_view;
+
+typedef struct gt16_region { uint32_t start, end; } gt16_region;   /* [start,end), struct.h:5-13 */
+
+typedef struct gt16_indel {
+  uint8_t type;      /* 'I', 'D' or '*' */
+  uint8_t len;
+  uint16_t hq, lq;
+  uint8_t seq[64];   /* 2-bit bases, interpreter.cpp:85-87 order */
+} gt16_indel;
+
+/* One called site = everything one row of <prefix>.txt needs (interpreter.cpp:107-156),
+ * i.e. the payload of the reference's packed .tmpresult record (SNP_Caller.cpp:101-209). */
+typedef struct gt16_called_site {
+  uint32_t amb;            /* concatenated-coordinate position */
+  uint8_t ref;             /* 0..3 */
+  uint8_t is_indel;        /* 0, 2 or 3 (isValid of an indel genotype row) */
+  uint8_t genotype;        /* 0..15 */
+  uint8_t rq_assigned;     /* 0: reference prints the previous row's LQ/RQ (SNP_Caller.cpp:338-353) */
+  uint32_t W[6], F[6], R[6];
+  double lh[16];           /* GenotypeLikelihood */
+  double flh[16];          /* SnpCallingInfo.flh */
+  double pD, bestD, secondD;
+  float sb[3][4], bqb[3][4];
+  float rpb, lgc, rgc, asc, lq, rq;
+  uint8_t lg, rg;
+  uint16_t polyrun;
+  uint32_t total_hq, total_lq;
+  gt16_indel indel[2];
+} gt16_called_site;
+
+typedef struct gt16_dev_snapshot gt16_dev_snapshot;
+typedef struct gt16_calls gt16_calls;
+
+typedef struct gt16_stats {
+  uint64_t sites;              /* processed positions */
+  uint64_t flagged;            /* sites the streaming kernel sent to exact evaluation */
+  uint64_t called;             /* Called Entries */
+  uint32_t kernel_launches;    /* kernels of this library launched by the call */
+  float ms_h2d, ms_stream, ms_scan, ms_eval, ms_candidates, ms_d2h, ms_total_device;
+} gt16_stats;
+
+/* Copy a snapshot to HBM (pinned staging + cudaMemcpyAsync on the copy stream). */
+int gt16_snapshot_upload(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot **out);
+void gt16_snapshot_release(gt16_ctx *ctx, gt16_dev_snapshot *snap);
+
+/* Call every site of the processed-order range [site_begin, site_end) of the concatenated
+ * region list (regions == NULL: the single region [0,text_length), snapshotSnpcaller.cpp
+ * default).  site_begin must be a multiple of GT16_BATCH_SITES so that the reference's
+ * per-batch window semantics are reproduced.  Requires a prior
+ * gt16_prefill_likelihood_cache().  Results are ordered by processed index. */
+int gt16_call_sites(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
+                    uint64_t site_begin, uint64_t site_end, gt16_calls **out, gt16_stats *stats);
+
+/* Same, from HOST buffers: counter blocks are streamed into HBM on the copy stream while the
+ * previous block is being evaluated; includes the device->host copy of the calls. */
+int gt16_call_sites_host(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt16_region *regions,
+                         uint32_t n_regions, uint64_t site_begin, uint64_t site_end, gt16_calls **out,
+                         gt16_stats *stats);
+
+uint64_t gt16_calls_count(const gt16_calls *calls);
+const gt16_called_site *gt16_calls_data(const gt16_calls *calls);
+void gt16_calls_free(gt16_calls *calls);
+
+/* ---- host-side formats (the callers / data formats on either side of the path) ---------- */
+typedef struct gt16_host_snapshot gt16_host_snapshot;
+/* readSnpInfoSnapshot (SnapshotHandler.cpp:259-347); buffers are page-locked when pinned != 0 */
+int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, char *err, size_t err_len);
+void gt16_snapshot_view_of(const gt16_host_snapshot *hs, gt16_snapshot_view *view);  /* packed_ref left NULL */
+void gt16_snapshot_free(gt16_host_snapshot *hs);
+
+typedef struct gt16_index gt16_index;
+/* <prefix>.pac/.ann/.tra as HSPLoad reads them (readIndex.cpp:24-60,96-115) */
+int gt16_index_read(const char *prefix, gt16_index **out, char *err, size_t err_len);
+uint32_t gt16_index_length(const gt16_index *ix);
+const uint32_t *gt16_index_packed(const gt16_index *ix, uint32_t *n_words);
+/* getChrAndPos (HSP.h:273-275): concatenated position -> (sequence name, 1-based position) */
+const char *gt16_index_translate(const gt16_index *ix, uint32_t amb, uint32_t *chr_pos);
+void gt16_index_free(gt16_index *ix);
+
+/* printHeader + printPossibleSNP (interpreter.cpp:8-31,107-156): byte-identical layout */
+int gt16_write_txt(const char *path, const gt16_index *ix, const gt16_called_site *sites, uint64_t n, int append,
+                   float *lq_rq_carry /* [2] in/out, may be NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GT16_H_ */
