@@ -63,14 +63,14 @@ def build(force=False, verbose=True):
             _run([NVCC] + NVCC_FLAGS + ["-x", "cu", "-c", src, "-o", obj], log=obj + ".log")
     if force or not _newer(lib, objs):
         _run([NVCC, "-shared", "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a"] + objs +
-             ["-o", lib, "-lcudart", "-lpthread"])
+             ["-o", lib, "-cudart", "static", "-lpthread", "-ldl", "-lrt"])
     # drop-in CLI
     cli_src = os.path.join(PKG, "host", "snapshotSnpcaller.cpp")
     cli = os.path.join(PKG, "bin", "snapshotSnpcaller")
     if os.path.exists(cli_src) and (force or not _newer(cli, [cli_src, lib] + hdrs)):
         _run([HOST_CXX, "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), cli_src, "-o", cli,
               "-L", os.path.join(PKG, "lib"), "-lgt16", "-Wl,-rpath,$ORIGIN/../lib",
-              "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lcudart", "-lpthread"])
+              "-Wl,-rpath-link,/usr/local/cuda/lib64", "-lpthread"])
         shutil.copyfile(os.path.join(PKG, "host", "snapshotSnpcaller.ini"), cli + ".ini")
     # synthetic data generator
     synth_src = os.path.join(ROOT, "tools", "gt16_synth.cpp")

@@ -80,6 +80,13 @@ int gt16_create_snp_prior(double out256[256]) {
   return GT16_OK;
 }
 
+int gt16_device_count(int *n) {
+  if (!n) return GT16_EINVAL;
+  *n = 0;
+  if (cudaGetDeviceCount(n) != cudaSuccess) { (void) cudaGetLastError(); *n = 0; return GT16_ENODEVICE; }
+  return GT16_OK;
+}
+
 int gt16_ctx_create(int device, gt16_ctx **out) {
   if (!out) return GT16_EINVAL;
   int n = 0;

@@ -37,6 +37,7 @@ extern "C" {
 typedef struct gt16_ctx gt16_ctx;
 
 /* ---- context ------------------------------------------------------------------------ */
+int gt16_device_count(int *n);                      /* usable sm_100 devices */
 int gt16_ctx_create(int device, gt16_ctx **out);
 void gt16_ctx_destroy(gt16_ctx *ctx);
 const char *gt16_last_error(const gt16_ctx *ctx);   /* ctx may be NULL: last create error */
