@@ -1,0 +1,50 @@
+"""Small parity configs shared by tests/golden/make_golden.py (which runs the UNMODIFIED reference
+objects in oracle/_ref on them, here, where /root/reference exists) and by the tests (which
+regenerate the same inputs with tools/gt16_synth -- a pure function of its arguments -- and
+compare against the committed reference outputs in tests/golden/).
+
+Each entry mirrors one of BASELINE.json's configs at a size the reference finishes in seconds:
+  wgs_small    config 1/2: 30x WGS, planted SNPs/indels, two contigs
+  exome_small  config 4  : -e region.bin, sparse (mode 2) snapshot, 150x targets
+  stress_small config 5  : 60x, dense indels with multi-pattern (pooled) lists, long indels,
+                           depth hotspots (overflow promotion, W >= 2000 -> chi-square fallback,
+                           invalid bits), odd number of overflow regions, coverage gaps
+  two_batch    config 3  : > 8,388,608 sites, so the per-batch window reset and the batch-aligned
+                           sharding of SURVEY 8(e) are exercised
+"""
+
+CONFIGS = {
+    "wgs_small": dict(
+        synth=["--contigs", "chrA:180000,chrB:70000", "--seed", "7"], exome=False),
+    "exome_small": dict(
+        synth=["--genome-len", "3000000", "--n-contigs", "3", "--exome", "300:300", "--depth", "150",
+               "--seed", "11"], exome=True),
+    "stress_small": dict(
+        synth=["--genome-len", "400000", "--n-contigs", "2", "--depth", "60", "--indel-rate", "2e-3",
+               "--multi-pattern-frac", "0.5", "--long-indel-frac", "0.1", "--hotspot-rate", "2e-4",
+               "--hotspot-depth", "1500", "--invalid-rate", "1e-3", "--ovf-regions", "7", "--gaps", "2:5000",
+               "--seed", "13"], exome=False),
+    "two_batch": dict(
+        synth=["--genome-len", "8600000", "--n-contigs", "2", "--snp-rate", "4e-5", "--indel-rate", "1e-5",
+               "--seed", "17"], exome=False),
+}
+
+# BASELINE.json configs[1] at FULL size (what bench.py times).  The reference's .txt is 47 MB, so only
+# a digest of its call-set columns is committed (tests/golden/MANIFEST.json: callset_sha256).
+FULL_CONFIGS = {
+    "chr20_full": dict(synth=["--contigs", "chr20:64444167", "--seed", "1"], exome=False),
+}
+CONFIGS_ALL = dict(CONFIGS, **FULL_CONFIGS)
+
+
+def synth_command(synth_bin, name, workdir):
+    """argv that regenerates config `name` under workdir; returns (argv, index_prefix, out_prefix, region_bin)"""
+    import os
+    cfg = CONFIGS_ALL[name]
+    idx = os.path.join(workdir, name + ".idx")
+    out = os.path.join(workdir, name)
+    region = os.path.join(workdir, name + ".region.bin") if cfg["exome"] else None
+    argv = [synth_bin, "--index", idx, "--snapshot", out] + cfg["synth"]
+    if region:
+        argv += ["--region-out", region]
+    return argv, idx, out, region

@@ -1,0 +1,95 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (and through the drop-in
+snapshotSnpcaller binary), against the UNMODIFIED reference's output for the same input
+(tests/golden/*.txt.gz, made by tests/golden/make_golden.py from oracle/_ref/ref_caller).
+
+Bar (BASELINE.json north_star): identical called positions, genotypes, alleles, indel patterns,
+counts and integer features (byte-identical columns); likelihood / posterior / bias columns equal
+to 1e-6 relative (they are printed with 5 significant digits, so at most the last printed digit
+may differ by one unit; the number of such fields is reported and bounded)."""
+import os
+import subprocess
+
+import pytest
+
+import gt16_testlib as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", list(T.CONFIGS))
+@pytest.mark.parametrize("mode", ["host_stream", "resident"])
+def test_fused_path_matches_reference(gpu_caller, tmp_path, name, mode):
+    idx, out, region = T.regenerate(name, tmp_path)
+    inp = T.LoadedInput(idx, out + ".snapshot", region)
+    try:
+        st = T.call_to_txt(gpu_caller, inp, out + ".txt", resident=(mode == "resident"))
+    finally:
+        inp.close()
+    got = open(out + ".txt", "rb").read()
+    want = T.golden_txt(name)
+    nonident = T.compare_txt(got, want)
+    rows = T.manifest()[name]["rows"]
+    assert sum(s.called for s in st) == rows
+    assert sum(s.kernel_launches for s in st) > 0
+    assert nonident <= max(2, rows * 98 // 1000), "too many fields differ in the last digit: %d" % nonident
+
+
+@pytest.mark.parametrize("name", ["wgs_small", "two_batch"])
+def test_exact_inline_mode_matches_reference(tmp_path, name):
+    """DecisionTables=0: every site goes through the exact evaluator in the streaming kernel."""
+    idx, out, region = T.regenerate(name, tmp_path)
+    with T.Caller(0, decision_tables=False) as c:
+        inp = T.LoadedInput(idx, out + ".snapshot", region)
+        st = T.call_to_txt(c, inp, out + ".txt")
+        inp.close()
+    T.compare_txt(open(out + ".txt", "rb").read(), T.golden_txt(name))
+    assert st[0].flagged == st[0].called       # inline mode: the mask IS the candidate set
+
+
+def test_shards_are_invisible(gpu_caller, tmp_path):
+    """N batch-aligned shards (what N GPUs would each do) concatenate to the same bytes."""
+    idx, out, region = T.regenerate("two_batch", tmp_path)
+    inp = T.LoadedInput(idx, out + ".snapshot", region)
+    T.call_to_txt(gpu_caller, inp, out + ".1.txt", shards=1)
+    T.call_to_txt(gpu_caller, inp, out + ".2.txt", shards=2)
+    inp.close()
+    a, b = open(out + ".1.txt", "rb").read(), open(out + ".2.txt", "rb").read()
+    assert a == b
+    T.compare_txt(a, T.golden_txt("two_batch"))
+
+
+@pytest.mark.parametrize("name", ["wgs_small", "exome_small"])
+def test_dropin_binary(tmp_path, name):
+    """The drop-in CLI: same flags, same <prefix>.snapshot -> <prefix>.txt, same stdout protocol."""
+    idx, out, region = T.regenerate(name, tmp_path)
+    cmd = [T.CLI, "-i", idx, "-o", out, "-v"] + (["-e", region] if region else [])
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    for marker in ("Loading reference index...", "Reference sequence length:", "Reading snapshot...",
+                   "Handling SNP Counter Result", "Writing variants to", "Called Entries : %d" % T.manifest()[name]["rows"],
+                   "Total Running Time:"):
+        assert marker in r.stdout, marker
+    T.compare_txt(open(out + ".txt", "rb").read(), T.golden_txt(name))
+
+
+def test_dropin_binary_errors(tmp_path):
+    r = subprocess.run([T.CLI], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Usage:" in r.stderr
+    r = subprocess.run([T.CLI, "-i", str(tmp_path / "nope"), "-o", str(tmp_path / "x")], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1
+
+
+def test_full_size_chr20_callset_digest(gpu_caller, tmp_path):
+    """BASELINE.json configs[1] at full size (64,444,167 sites, what bench.py times): the call-set
+    columns of all 72,171 rows hash to the digest of the reference's own .txt for this snapshot."""
+    idx, out, region = T.regenerate("chr20_full", tmp_path)
+    inp = T.LoadedInput(idx, out + ".snapshot", region)
+    try:
+        st = T.call_to_txt(gpu_caller, inp, out + ".txt", shards=3)
+    finally:
+        inp.close()
+    m = T.manifest()["chr20_full"]
+    digest, rows = T.callset_digest(open(out + ".txt", "rb").read())
+    assert rows == m["rows"] == sum(s.called for s in st)
+    assert digest == m["callset_sha256"]
