@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -14,6 +16,51 @@
 using namespace gt16;
 
 static std::string g_createError;
+
+namespace {
+
+// grow-only device buffer: the fused path allocates nothing in steady state
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// page-locked result buffers are recycled between calls (cudaHostAlloc of tens of MB costs milliseconds);
+// gt16_calls objects hold a reference, so they may outlive the context
+struct PinPool {
+  std::mutex mu;
+  std::vector<std::pair<void *, size_t> > free_;
+  void *take(size_t bytes, size_t *cap) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (size_t k = 0; k < free_.size(); ++k)
+        if (free_[k].second >= bytes) { void *p = free_[k].first; *cap = free_[k].second; free_.erase(free_.begin() + k); return p; }
+    }
+    size_t want = bytes + bytes / 4 + 4096;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { (void) cudaGetLastError(); return nullptr; }
+    *cap = want;
+    return p;
+  }
+  void give(void *p, size_t cap) {
+    std::lock_guard<std::mutex> g(mu);
+    if (free_.size() >= 4) { cudaFreeHost(p); return; }
+    free_.push_back(std::make_pair(p, cap));
+  }
+  ~PinPool() { for (auto &f : free_) cudaFreeHost(f.first); }
+};
+
+}  // namespace
 
 struct gt16_ctx {
   int device = 0;
@@ -33,15 +80,26 @@ struct gt16_ctx {
   double balance = 0.01, unbalance = 0.005;
   float prefillMs = 0.f, decisionMs = 0.f;
   uint32_t launches = 0;
+  int numSMs = 148;
+  // persistent scratch of the fused path
+  DevBuf mask, counts, listA, listB, recs, planStart, planFirst;
+  DevBuf sCounters, sInvalid, sOvf, sOvfBase, sPool, sRef;      // streamed (host-fed) snapshot
+  std::vector<cudaEvent_t> evPool;
+  std::shared_ptr<PinPool> pins = std::make_shared<PinPool>();
 };
 
 struct gt16_dev_snapshot {
   SnapView v;
   void *counters = nullptr, *invalid = nullptr, *ovf = nullptr, *ovfBase = nullptr, *pool = nullptr, *ref = nullptr;
+  bool borrowed = false;      // buffers belong to the context's streaming arena
 };
 
 struct gt16_calls {
-  std::vector<gt16_called_site> sites;
+  std::shared_ptr<PinPool> pins;
+  gt16_called_site *sites = nullptr;
+  size_t cap = 0;
+  uint64_t n = 0;
+  ~gt16_calls() { if (sites && pins) pins->give(sites, cap); }
 };
 
 #define CU(call)                                                                                   \
@@ -104,6 +162,7 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   }
   gt16_ctx *ctx = new gt16_ctx();
   ctx->device = device;
+  ctx->numSMs = prop.multiProcessorCount;
   auto bail = [&](const char *what, cudaError_t ce) {
     g_createError = std::string(what) + ": " + cudaGetErrorString(ce);
     delete ctx;
@@ -151,6 +210,9 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   cudaFree(ctx->s1); cudaFree(ctx->s2p); cudaFree(ctx->s2q); cudaFree(ctx->g4);
   cudaFree(ctx->errWord);
   cudaFreeHost(ctx->hPinned);
+  for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->listA, &ctx->listB, &ctx->recs, &ctx->planStart, &ctx->planFirst,
+                    &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
+  for (auto e : ctx->evPool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
   delete ctx;
 }
@@ -324,22 +386,61 @@ int gt16_compute_bias(gt16_ctx *ctx, const void *w, const void *f, const void *r
   return GT16_OK;
 }
 
-// ---- fused path -----------------------------------------------------------------------------
-static const uint32_t kCopyChunkSites = 1u << 22;     // 32 MiB of counters per cudaMemcpyAsync
+}  // extern "C"
 
+// ---- fused path -----------------------------------------------------------------------------
+// A context is driven by one host thread at a time; all scratch is owned by the context and only grows.
+static const uint32_t kCopyChunkSites = 1u << 22;     // 32 MiB of counters per cudaMemcpyAsync
+static const uint32_t kCandSlice = 8192;              // candidate records per kernel launch / D2H copy
+
+#define CUF(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char b_[512];                                                                                \
+      snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      ctx->err = b_;                                                                               \
+      (void) cudaGetLastError();                                                                   \
+      return GT16_ECUDA;                                                                           \
+    }                                                                                              \
+  } while (0)
+
+static int get_event(gt16_ctx *ctx, size_t k, cudaEvent_t *out) {
+  while (ctx->evPool.size() <= k) {
+    cudaEvent_t e;
+    CUF(cudaEventCreate(&e));
+    ctx->evPool.push_back(e);
+  }
+  *out = ctx->evPool[k];
+  return GT16_OK;
+}
+
+// Device arrays of one snapshot.  Every array is over-allocated by kStreamPadSites positions so that the
+// TMA streaming kernel may copy whole tiles; counters[L] duplicates counters[L-1] (the reference clamps the
+// indel look-ahead of the last position, see decode_indel_refs).
 static int alloc_snapshot(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot *ds,
-                          std::vector<uint32_t> &ovfBase) {
+                          std::vector<uint32_t> &ovfBase, bool arena) {
   const uint32_t L = view->text_length;
   size_t nOvf = 0;
   ovfBase.assign(view->n_overflow_regions + 1, 0);
   for (uint32_t r = 0; r < view->n_overflow_regions; ++r) { ovfBase[r] = (uint32_t) nOvf; nOvf += view->overflow_size[r]; }
   ovfBase[view->n_overflow_regions] = (uint32_t) nOvf;
-  CU(cudaMalloc(&ds->counters, (size_t) L * 8 + 16));
-  CU(cudaMalloc(&ds->ovf, nOvf * 32 + 32));
-  CU(cudaMalloc(&ds->ovfBase, ovfBase.size() * 4));
-  CU(cudaMalloc(&ds->pool, (size_t) view->pool_bytes + 16));
-  CU(cudaMalloc(&ds->ref, (size_t) view->packed_ref_words * 4 + 16));
-  if (view->invalid_bitmap) CU(cudaMalloc(&ds->invalid, (((size_t) L + 31) >> 5) * 4 + 4));
+  const size_t bC = ((size_t) L + kStreamPadSites) * 8, bO = nOvf * 32 + 32, bB = ovfBase.size() * 4,
+               bP = (size_t) view->pool_bytes + 16,
+               bR = ((size_t) view->packed_ref_words + kStreamPadSites / 16 + 4) * 4,
+               bI = ((((size_t) L + 31) >> 5) + kStreamPadSites / 32 + 4) * 4;
+  ds->borrowed = arena;
+  if (arena) {
+    CUF(ctx->sCounters.ensure(bC)); CUF(ctx->sOvf.ensure(bO)); CUF(ctx->sOvfBase.ensure(bB)); CUF(ctx->sPool.ensure(bP));
+    CUF(ctx->sRef.ensure(bR));
+    if (view->invalid_bitmap) CUF(ctx->sInvalid.ensure(bI));
+    ds->counters = ctx->sCounters.p; ds->ovf = ctx->sOvf.p; ds->ovfBase = ctx->sOvfBase.p; ds->pool = ctx->sPool.p;
+    ds->ref = ctx->sRef.p; ds->invalid = view->invalid_bitmap ? ctx->sInvalid.p : nullptr;
+  } else {
+    CUF(cudaMalloc(&ds->counters, bC)); CUF(cudaMalloc(&ds->ovf, bO)); CUF(cudaMalloc(&ds->ovfBase, bB));
+    CUF(cudaMalloc(&ds->pool, bP)); CUF(cudaMalloc(&ds->ref, bR));
+    if (view->invalid_bitmap) CUF(cudaMalloc(&ds->invalid, bI));
+  }
   SnapView &v = ds->v;
   v.counters = (const uint64_t *) ds->counters;
   v.invalid = (const uint32_t *) ds->invalid;
@@ -354,19 +455,32 @@ static int alloc_snapshot(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_de
   return GT16_OK;
 }
 
-// everything except the counters (small: 0.375 B/site + overflow records + pool)
+// everything except the counters (small: 0.375 B/site + overflow records + pool), plus the padding
 static int upload_aux(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot *ds,
                       const std::vector<uint32_t> &ovfBase, cudaStream_t s) {
   const uint32_t L = view->text_length;
   for (uint32_t r = 0; r < view->n_overflow_regions; ++r)
     if (view->overflow_size[r])
-      CU(cudaMemcpyAsync((char *) ds->ovf + (size_t) ovfBase[r] * 32, view->overflow[r], (size_t) view->overflow_size[r] * 32,
-                         cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(ds->ovfBase, ovfBase.data(), ovfBase.size() * 4, cudaMemcpyHostToDevice, s));
-  if (view->pool_bytes) CU(cudaMemcpyAsync(ds->pool, view->pool, view->pool_bytes, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(ds->ref, view->packed_ref, (size_t) view->packed_ref_words * 4, cudaMemcpyHostToDevice, s));
-  if (view->invalid_bitmap)
-    CU(cudaMemcpyAsync(ds->invalid, view->invalid_bitmap, (((size_t) L + 31) >> 5) * 4, cudaMemcpyHostToDevice, s));
+      CUF(cudaMemcpyAsync((char *) ds->ovf + (size_t) ovfBase[r] * 32, view->overflow[r], (size_t) view->overflow_size[r] * 32,
+                          cudaMemcpyHostToDevice, s));
+  CUF(cudaMemcpyAsync(ds->ovfBase, ovfBase.data(), ovfBase.size() * 4, cudaMemcpyHostToDevice, s));
+  if (view->pool_bytes) CUF(cudaMemcpyAsync(ds->pool, view->pool, view->pool_bytes, cudaMemcpyHostToDevice, s));
+  CUF(cudaMemcpyAsync(ds->ref, view->packed_ref, (size_t) view->packed_ref_words * 4, cudaMemcpyHostToDevice, s));
+  CUF(cudaMemsetAsync((char *) ds->ref + (size_t) view->packed_ref_words * 4, 0, (kStreamPadSites / 16 + 4) * 4, s));
+  if (view->invalid_bitmap) {
+    const size_t w = ((size_t) L + 31) >> 5;
+    CUF(cudaMemcpyAsync(ds->invalid, view->invalid_bitmap, w * 4, cudaMemcpyHostToDevice, s));
+    CUF(cudaMemsetAsync((char *) ds->invalid + w * 4, 0, (kStreamPadSites / 32 + 4) * 4, s));
+  }
+  CUF(cudaMemsetAsync((char *) ds->counters + (size_t) L * 8, 0, kStreamPadSites * 8, s));
+  return GT16_OK;
+}
+
+// after the counter element L-1 has been copied: counters[L] = counters[L-1]
+static int finish_counters(gt16_ctx *ctx, gt16_dev_snapshot *ds, cudaStream_t s) {
+  const uint32_t L = ds->v.L;
+  CUF(cudaMemcpyAsync((char *) ds->counters + (size_t) L * 8, (char *) ds->counters + (size_t) (L - 1) * 8, 8,
+                      cudaMemcpyDeviceToDevice, s));
   return GT16_OK;
 }
 
@@ -378,21 +492,23 @@ static int check_view(gt16_ctx *ctx, const gt16_snapshot_view *v) {
   return GT16_OK;
 }
 
-void gt16_snapshot_release(gt16_ctx *ctx, gt16_dev_snapshot *ds) {
+extern "C" void gt16_snapshot_release(gt16_ctx *ctx, gt16_dev_snapshot *ds) {
   if (!ds) return;
   if (ctx) cudaSetDevice(ctx->device);
-  cudaFree(ds->counters); cudaFree(ds->invalid); cudaFree(ds->ovf); cudaFree(ds->ovfBase); cudaFree(ds->pool); cudaFree(ds->ref);
+  if (!ds->borrowed) {
+    cudaFree(ds->counters); cudaFree(ds->invalid); cudaFree(ds->ovf); cudaFree(ds->ovfBase); cudaFree(ds->pool); cudaFree(ds->ref);
+  }
   delete ds;
 }
 
-int gt16_snapshot_upload(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot **out) {
+extern "C" int gt16_snapshot_upload(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot **out) {
   if (!ctx || !out) return GT16_EINVAL;
   int rc = check_view(ctx, view);
   if (rc) return rc;
   CU(cudaSetDevice(ctx->device));
   gt16_dev_snapshot *ds = new gt16_dev_snapshot();
   std::vector<uint32_t> ovfBase;
-  rc = alloc_snapshot(ctx, view, ds, ovfBase);
+  rc = alloc_snapshot(ctx, view, ds, ovfBase, false);
   if (rc == GT16_OK) rc = upload_aux(ctx, view, ds, ovfBase, ctx->copy);
   if (rc == GT16_OK) {
     const uint32_t L = view->text_length;
@@ -402,6 +518,7 @@ int gt16_snapshot_upload(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev
         rc = fail(ctx, GT16_ECUDA, "counter upload failed");
     }
   }
+  if (rc == GT16_OK) rc = finish_counters(ctx, ds, ctx->copy);
   if (rc == GT16_OK && cudaStreamSynchronize(ctx->copy) != cudaSuccess) rc = fail(ctx, GT16_ECUDA, "upload synchronize failed");
   if (rc != GT16_OK) { gt16_snapshot_release(ctx, ds); return rc; }
   *out = ds;
@@ -414,8 +531,6 @@ struct RegionPlan {
   std::vector<uint32_t> start;
   std::vector<uint64_t> first;      // nRegions + 1
   bool ascending = true;
-  uint32_t *dStart = nullptr;
-  uint64_t *dFirst = nullptr;
   DevSiteMap map;
   uint32_t pos_of(uint64_t i) const {
     size_t lo = 0, hi = start.size();
@@ -439,76 +554,102 @@ int make_plan(gt16_ctx *ctx, uint32_t L, const gt16_region *regions, uint32_t nR
   }
   if (pl.start.empty()) { pl.start.push_back(0); pl.first.push_back(0); }
   pl.first.push_back(acc);
-  CU(cudaMalloc(&pl.dStart, pl.start.size() * 4));
-  CU(cudaMalloc(&pl.dFirst, pl.first.size() * 8));
-  CU(cudaMemcpyAsync(pl.dStart, pl.start.data(), pl.start.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
-  CU(cudaMemcpyAsync(pl.dFirst, pl.first.data(), pl.first.size() * 8, cudaMemcpyHostToDevice, ctx->compute));
-  pl.map.m.regStart = pl.dStart;
-  pl.map.m.regFirst = pl.dFirst;
+  CUF(ctx->planStart.ensure(pl.start.size() * 4));
+  CUF(ctx->planFirst.ensure(pl.first.size() * 8));
+  CUF(cudaMemcpyAsync(ctx->planStart.p, pl.start.data(), pl.start.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
+  CUF(cudaMemcpyAsync(ctx->planFirst.p, pl.first.data(), pl.first.size() * 8, cudaMemcpyHostToDevice, ctx->compute));
+  CUF(cudaStreamSynchronize(ctx->compute));     // the host vectors may be pageable
+  pl.map.m.regStart = (const uint32_t *) ctx->planStart.p;
+  pl.map.m.regFirst = (const uint64_t *) ctx->planFirst.p;
   pl.map.m.nRegions = (uint32_t) pl.start.size();
   pl.map.totalSites = acc;
   return GT16_OK;
 }
 
-struct Work {       // device scratch of one call
-  uint32_t *mask = nullptr, *counts = nullptr, *listA = nullptr, *mask2 = nullptr, *counts2 = nullptr, *listB = nullptr;
-  gt16_called_site *recs = nullptr;
-  void release() { cudaFree(mask); cudaFree(counts); cudaFree(listA); cudaFree(mask2); cudaFree(counts2); cudaFree(listB); cudaFree(recs); }
-};
-
-// ordered compaction of `mask` over nItems -> list (allocated here); returns count
-int compact(gt16_ctx *ctx, const uint32_t *mask, uint32_t nItems, uint32_t *counts, const uint32_t *values,
-            uint32_t offset, uint32_t **list, uint32_t *count) {
+// ordered compaction of the site mask over nItems -> list (grown on demand); returns the count
+int compact(gt16_ctx *ctx, const uint32_t *mask, uint32_t nItems, DevBuf &list, uint32_t *count) {
+  uint32_t *counts = (uint32_t *) ctx->counts.p;
   launch_mask_count(mask, nItems, counts, ctx->compute);
   launch_scan_counts(counts, scan_blocks(nItems), ctx->dTotal, ctx->compute);
   ctx->launches += 2;
-  CU(cudaMemcpyAsync(ctx->hPinned, ctx->dTotal, 4, cudaMemcpyDeviceToHost, ctx->compute));
-  CU(cudaStreamSynchronize(ctx->compute));
+  CUF(cudaMemcpyAsync(ctx->hPinned, ctx->dTotal, 4, cudaMemcpyDeviceToHost, ctx->compute));
+  CUF(cudaStreamSynchronize(ctx->compute));
   *count = ctx->hPinned[0];
-  CU(cudaMalloc(list, (size_t) (*count ? *count : 1) * 4));
-  launch_mask_scatter(mask, nItems, counts, values, offset, *list, ctx->compute);
+  CUF(list.ensure((size_t) (*count ? *count : 1) * 4));
+  launch_mask_scatter(mask, nItems, counts, nullptr, 0, (uint32_t *) list.p, ctx->compute);
   ctx->launches++;
   return GT16_OK;
 }
 
 float ms_between(cudaEvent_t a, cudaEvent_t b) { float m = 0.f; cudaEventElapsedTime(&m, a, b); return m; }
 
-// stages after the streaming pass: compaction, exact evaluation, candidate records, D2H
+// can [pos(begin), pos(end)) go through the TMA-staged kernel?
+bool tma_eligible(const gt16_ctx *ctx, const RegionPlan &pl, uint64_t begin, bool useTables) {
+  return useTables && pl.start.size() == 1 && ((pl.start[0] + (begin - pl.first[0])) % 128) == 0 && ctx->s1 != nullptr;
+}
+
+void stream_range(gt16_ctx *ctx, const SnapView &V, const RegionPlan &pl, uint64_t a, uint64_t b, bool useTables,
+                  const DecisionTables &D, const EvalParams &P, uint32_t *mask) {
+  if (tma_eligible(ctx, pl, a, useTables)) {
+    uint32_t pBeg = pl.start[0] + (uint32_t) (a - pl.first[0]);
+    launch_stream_tma(V, pBeg, pBeg + (uint32_t) (b - a), D, mask, ctx->numSMs, ctx->compute);
+  } else {
+    launch_stream(V, pl.map, a, (uint32_t) (b - a), useTables, D, P, mask, ctx->errWord, ctx->compute);
+  }
+  ctx->launches++;
+}
+
+// stages after the streaming pass: compaction, exact evaluation, second compaction, candidate records
+// written slice by slice while the previous slice travels to the host on the copy stream
 int finish_call(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t begin, uint32_t n, bool usedTables,
-                Work &wk, cudaEvent_t *ev /*[6]*/, gt16_calls *calls, gt16_stats *st) {
+                const DecisionTables &D, cudaEvent_t *ev /*[8]*/, size_t evBase, gt16_calls *calls, gt16_stats *st) {
   EvalParams P = eval_params(ctx);
+  uint32_t *mask = (uint32_t *) ctx->mask.p;
   uint32_t nA = 0, nB = 0;
-  int rc = compact(ctx, wk.mask, n, wk.counts, nullptr, 0, &wk.listA, &nA);
+  int rc = compact(ctx, mask, n, ctx->listA, &nA);
   if (rc) return rc;
-  CU(cudaEventRecord(ev[2], ctx->compute));
-  const uint32_t *finalList = wk.listA;
+  CUF(cudaEventRecord(ev[2], ctx->compute));
+  const uint32_t *finalList = (const uint32_t *) ctx->listA.p;
   nB = nA;
   if (usedTables) {
-    CU(cudaMalloc(&wk.mask2, ((size_t) (nA + 31) / 32 + 1) * 4));
-    CU(cudaMalloc(&wk.counts2, ((size_t) scan_blocks(nA) + 1) * 4));
-    launch_eval_list(V, pl.map, begin, wk.listA, nA, P, wk.mask2, ctx->errWord, ctx->compute);
+    launch_eval_list(V, pl.map, begin, (const uint32_t *) ctx->listA.p, nA, true, D, P, mask, ctx->errWord, ctx->compute);
     ctx->launches++;
-    CU(cudaEventRecord(ev[3], ctx->compute));
-    if (nA) {
-      rc = compact(ctx, wk.mask2, nA, wk.counts2, wk.listA, 0, &wk.listB, &nB);
-      if (rc) return rc;
-    } else nB = 0;
-    finalList = wk.listB;
+    CUF(cudaEventRecord(ev[3], ctx->compute));
+    rc = compact(ctx, mask, n, ctx->listB, &nB);
+    if (rc) return rc;
+    finalList = (const uint32_t *) ctx->listB.p;
   } else {
-    CU(cudaEventRecord(ev[3], ctx->compute));
+    CUF(cudaEventRecord(ev[3], ctx->compute));
   }
-  CU(cudaMalloc(&wk.recs, (size_t) (nB ? nB : 1) * sizeof(gt16_called_site)));
-  launch_candidates(V, pl.map, begin, finalList, nB, P, wk.recs, ctx->errWord, ctx->compute);
-  ctx->launches++;
-  CU(cudaEventRecord(ev[4], ctx->compute));
-  calls->sites.resize(nB);
-  if (nB) CU(cudaMemcpyAsync(calls->sites.data(), wk.recs, (size_t) nB * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->compute));
-  CU(cudaMemcpyAsync(ctx->hPinned + 1, ctx->errWord, 4, cudaMemcpyDeviceToHost, ctx->compute));
-  CU(cudaEventRecord(ev[5], ctx->compute));
-  CU(cudaStreamSynchronize(ctx->compute));
-  CU(cudaGetLastError());
+  CUF(ctx->recs.ensure((size_t) (nB ? nB : 1) * sizeof(gt16_called_site)));
+  calls->n = nB;
+  if (nB) {
+    calls->sites = (gt16_called_site *) ctx->pins->take((size_t) nB * sizeof(gt16_called_site), &calls->cap);
+    if (!calls->sites) return fail(ctx, GT16_ECUDA, "cudaHostAlloc of the result buffer failed");
+  }
+  CUF(cudaEventRecord(ev[4], ctx->compute));
+  gt16_called_site *recs = (gt16_called_site *) ctx->recs.p;
+  size_t slice = 0;
+  for (uint32_t off = 0; off < nB; off += kCandSlice, ++slice) {
+    uint32_t cnt = std::min<uint32_t>(kCandSlice, nB - off);
+    launch_candidates(V, pl.map, begin, finalList + off, cnt, P, recs + off, ctx->errWord, ctx->compute);
+    ctx->launches++;
+    cudaEvent_t se;
+    rc = get_event(ctx, evBase + slice, &se);
+    if (rc) return rc;
+    CUF(cudaEventRecord(se, ctx->compute));
+    CUF(cudaStreamWaitEvent(ctx->copy, se, 0));
+    CUF(cudaMemcpyAsync(calls->sites + off, recs + off, (size_t) cnt * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->copy));
+  }
+  CUF(cudaEventRecord(ev[5], ctx->compute));
+  CUF(cudaEventRecord(ev[6], ctx->copy));
+  CUF(cudaStreamWaitEvent(ctx->compute, ev[6], 0));
+  CUF(cudaMemcpyAsync(ctx->hPinned + 1, ctx->errWord, 4, cudaMemcpyDeviceToHost, ctx->compute));
+  CUF(cudaEventRecord(ev[7], ctx->compute));
+  CUF(cudaStreamSynchronize(ctx->compute));
+  CUF(cudaGetLastError());
   uint32_t errw = ctx->hPinned[1];
-  CU(cudaMemset(ctx->errWord, 0, 4));
+  if (errw) CUF(cudaMemset(ctx->errWord, 0, 4));
   if (errw & kErrBadSnapshot) return fail(ctx, GT16_EDATA, "snapshot refers to an overflow record or pool range that does not exist");
   if (errw & kErrGenotype) return fail(ctx, GT16_EGENOTYPE, "Error in selecting Genotype");
   if (st) { st->flagged = nA; st->called = nB; }
@@ -529,55 +670,50 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   if (rc) return rc;
   if (end > pl.map.totalSites) end = pl.map.totalSites;
   if (begin > end) begin = end;
-  if (begin % kBatch) { cudaFree(pl.dStart); cudaFree(pl.dFirst); return fail(ctx, GT16_EINVAL, "site_begin must be a multiple of GT16_BATCH_SITES"); }
-  if (end - begin >= 0xFFFFFFFFull) { cudaFree(pl.dStart); cudaFree(pl.dFirst); return fail(ctx, GT16_EINVAL, "range too long"); }
+  if (begin % kBatch) return fail(ctx, GT16_EINVAL, "site_begin must be a multiple of GT16_BATCH_SITES");
+  if (end - begin >= 0xFFFFFFFFull) return fail(ctx, GT16_EINVAL, "range too long");
   const uint32_t n = (uint32_t) (end - begin);
   const uint32_t launches0 = ctx->launches;
   const bool useTables = ctx->useDecisions && ctx->haveDecisions;
   DecisionTables D = {ctx->s1, ctx->s2p, ctx->s2q, ctx->g4};
   EvalParams P = eval_params(ctx);
 
-  gt16_calls *calls = new gt16_calls();
+  std::unique_ptr<gt16_calls> calls(new gt16_calls());
+  calls->pins = ctx->pins;
   gt16_stats st;
   memset(&st, 0, sizeof(st));
   st.sites = n;
-  Work wk;
-  gt16_dev_snapshot *streamed = nullptr;
-  cudaEvent_t ev[6];
-  for (int k = 0; k < 6; ++k) cudaEventCreate(&ev[k]);
-  std::vector<cudaEvent_t> chunkEv;
-  auto cleanup = [&]() {
-    wk.release(); cudaFree(pl.dStart); cudaFree(pl.dFirst);
-    for (int k = 0; k < 6; ++k) cudaEventDestroy(ev[k]);
-    for (auto e : chunkEv) cudaEventDestroy(e);
-    if (streamed) gt16_snapshot_release(ctx, streamed);
-  };
-#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); delete calls; return GT16_ECUDA; } } while (0)
+  if (n == 0) { *out = calls.release(); if (stats) *stats = st; return GT16_OK; }
 
-  if (n == 0) { cleanup(); *out = calls; if (stats) *stats = st; return GT16_OK; }
-  CUX(cudaMalloc(&wk.mask, ((size_t) (n + 31) / 32 + 1) * 4));
-  CUX(cudaMalloc(&wk.counts, ((size_t) scan_blocks(n) + 1) * 4));
-  CUX(cudaEventRecord(ev[0], ctx->compute));
+  cudaEvent_t ev[8];
+  for (int k = 0; k < 8; ++k) { rc = get_event(ctx, k, &ev[k]); if (rc) return rc; }
+  size_t evNext = 8;
+  CUF(ctx->mask.ensure(((size_t) (n + 31) / 32 + 64) * 4));
+  CUF(ctx->counts.ensure(((size_t) scan_blocks(n) + 1) * 4));
+  uint32_t *mask = (uint32_t *) ctx->mask.p;
+  CUF(cudaEventRecord(ev[0], ctx->compute));
 
+  gt16_dev_snapshot streamed;
+  const SnapView *V = nullptr;
   if (resident) {
-    launch_stream(resident->v, pl.map, begin, n, useTables, D, P, wk.mask, ctx->errWord, ctx->compute);
-    ctx->launches++;
-    CUX(cudaEventRecord(ev[1], ctx->compute));
-    rc = finish_call(ctx, resident->v, pl, begin, n, useTables, wk, ev, calls, &st);
+    V = &resident->v;
+    stream_range(ctx, *V, pl, begin, end, useTables, D, P, mask);
+    CUF(cudaEventRecord(ev[1], ctx->compute));
   } else {
-    // counters stream in on the copy stream in genome order; the classification of block k only
-    // waits for the chunk that holds its last needed position (+1 look-ahead, +355 for windows)
-    streamed = new gt16_dev_snapshot();
+    // counters stream in on the copy stream in genome order; the classification of batch k only waits for
+    // the chunk that holds its last needed position (+1 look-ahead); windows are read after the last chunk
     std::vector<uint32_t> ovfBase;
-    rc = alloc_snapshot(ctx, hostView, streamed, ovfBase);
-    if (rc == GT16_OK) rc = upload_aux(ctx, hostView, streamed, ovfBase, ctx->copy);
-    if (rc != GT16_OK) { cleanup(); delete calls; return rc; }
+    rc = alloc_snapshot(ctx, hostView, &streamed, ovfBase, true);
+    if (rc == GT16_OK) rc = upload_aux(ctx, hostView, &streamed, ovfBase, ctx->copy);
+    if (rc != GT16_OK) return rc;
+    V = &streamed.v;
     const uint32_t loPos = pl.ascending ? pl.pos_of(begin) : 0;
     const uint32_t hiPos = pl.ascending ? pl.pos_of(end - 1) : L - 1;
     const uint64_t copyLo = loPos > 512 ? ((loPos - 512) / kCopyChunkSites) * (uint64_t) kCopyChunkSites : 0;
     const uint64_t copyHi = std::min<uint64_t>((uint64_t) hiPos + 1024, L);
-    size_t nChunks = (size_t) ((copyHi - copyLo + kCopyChunkSites - 1) / kCopyChunkSites);
-    chunkEv.resize(nChunks);
+    const size_t nChunks = (size_t) ((copyHi - copyLo + kCopyChunkSites - 1) / kCopyChunkSites);
+    const size_t chunkEv0 = evNext;
+    evNext += nChunks;
     for (size_t c = 0; c < nChunks; ++c) {
       uint64_t a = copyLo + c * (uint64_t) kCopyChunkSites, b = std::min<uint64_t>(a + kCopyChunkSites, copyHi);
       bool needed = true;
@@ -592,38 +728,40 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
         }
       }
       if (needed)
-        CUX(cudaMemcpyAsync((char *) streamed->counters + a * 8, hostView->counters + a, (b - a) * 8, cudaMemcpyHostToDevice, ctx->copy));
+        CUF(cudaMemcpyAsync((char *) streamed.counters + a * 8, hostView->counters + a, (b - a) * 8, cudaMemcpyHostToDevice, ctx->copy));
       else
-        CUX(cudaMemsetAsync((char *) streamed->counters + a * 8, 0, (b - a) * 8, ctx->copy));
-      CUX(cudaEventCreateWithFlags(&chunkEv[c], cudaEventDisableTiming));
-      CUX(cudaEventRecord(chunkEv[c], ctx->copy));
+        CUF(cudaMemsetAsync((char *) streamed.counters + a * 8, 0, (b - a) * 8, ctx->copy));
+      if (c + 1 == nChunks && copyHi == L) { rc = finish_counters(ctx, &streamed, ctx->copy); if (rc) return rc; }
+      cudaEvent_t ce;
+      rc = get_event(ctx, chunkEv0 + c, &ce);
+      if (rc) return rc;
+      CUF(cudaEventRecord(ce, ctx->copy));
     }
     for (uint64_t a = begin; a < end; a += kBatch) {
       uint64_t b = std::min<uint64_t>(a + kBatch, end);
       uint64_t need = pl.ascending ? std::min<uint64_t>((uint64_t) pl.pos_of(b - 1) + 2, copyHi) : copyHi;
-      size_t c = (size_t) ((need - 1 - copyLo) / kCopyChunkSites);
-      CUX(cudaStreamWaitEvent(ctx->compute, chunkEv[std::min(c, nChunks - 1)], 0));
-      launch_stream(streamed->v, pl.map, a, (uint32_t) (b - a), useTables, D, P, wk.mask + (a - begin) / 32, ctx->errWord, ctx->compute);
-      ctx->launches++;
+      size_t c = std::min((size_t) ((need - 1 - copyLo) / kCopyChunkSites), nChunks - 1);
+      CUF(cudaStreamWaitEvent(ctx->compute, ctx->evPool[chunkEv0 + c], 0));
+      stream_range(ctx, *V, pl, a, b, useTables, D, P, mask + (a - begin) / 32);
     }
-    CUX(cudaStreamWaitEvent(ctx->compute, chunkEv[nChunks - 1], 0));
-    CUX(cudaEventRecord(ev[1], ctx->compute));
-    rc = finish_call(ctx, streamed->v, pl, begin, n, useTables, wk, ev, calls, &st);
+    CUF(cudaStreamWaitEvent(ctx->compute, ctx->evPool[chunkEv0 + nChunks - 1], 0));
+    CUF(cudaEventRecord(ev[1], ctx->compute));
   }
-  if (rc != GT16_OK) { cleanup(); delete calls; return rc; }
+  rc = finish_call(ctx, *V, pl, begin, n, useTables, D, ev, evNext, calls.get(), &st);
+  if (rc != GT16_OK) return rc;
   st.ms_stream = ms_between(ev[0], ev[1]);
-  st.ms_scan = ms_between(ev[1], ev[2]);
+  st.ms_scan = ms_between(ev[1], ev[2]) + ms_between(ev[3], ev[4]);
   st.ms_eval = ms_between(ev[2], ev[3]);
-  st.ms_candidates = ms_between(ev[3], ev[4]);
-  st.ms_d2h = ms_between(ev[4], ev[5]);
-  st.ms_total_device = ms_between(ev[0], ev[5]);
+  st.ms_candidates = ms_between(ev[4], ev[5]);
+  st.ms_d2h = ms_between(ev[5], ev[7]);
+  st.ms_total_device = ms_between(ev[0], ev[7]);
   st.kernel_launches = ctx->launches - launches0;
-  cleanup();
-#undef CUX
-  *out = calls;
+  *out = calls.release();
   if (stats) *stats = st;
   return GT16_OK;
 }
+
+extern "C" {
 
 int gt16_call_sites(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
                     uint64_t site_begin, uint64_t site_end, gt16_calls **out, gt16_stats *stats) {
@@ -640,8 +778,8 @@ int gt16_call_sites_host(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt
   return call_common(ctx, view, nullptr, regions, n_regions, site_begin, site_end, out, stats);
 }
 
-uint64_t gt16_calls_count(const gt16_calls *c) { return c ? c->sites.size() : 0; }
-const gt16_called_site *gt16_calls_data(const gt16_calls *c) { return c && !c->sites.empty() ? c->sites.data() : nullptr; }
+uint64_t gt16_calls_count(const gt16_calls *c) { return c ? c->n : 0; }
+const gt16_called_site *gt16_calls_data(const gt16_calls *c) { return c && c->n ? c->sites : nullptr; }
 void gt16_calls_free(gt16_calls *c) { delete c; }
 
 }  // extern "C"

@@ -181,12 +181,11 @@ GT16_HD double lh_het(const LhTables &T, const uint32_t *W, int x, int y, int wt
   return scale_back(ret);
 }
 
-// W[6] = A,C,G,T,deepest indel,second indel weighted counts; ref in 0..3; lh[16] out (:249-289)
-GT16_HDN void genotype_likelihood16(const LhTables &T, const uint32_t *Win, int ref, double *lh) {
-  uint32_t W[6];
+// ref-weight penalty when indel evidence is present (:251-260) and W_total (:262-266)
+GT16_HD int penalised_weights(const uint32_t *Win, int ref, uint32_t *W) {
   for (int i = 0; i < 6; ++i) W[i] = Win[i];
   uint32_t indelCount = W[4] + W[5];
-  if (indelCount) {                                                   // ref-weight penalty :254-260
+  if (indelCount) {
     double tmp = (double) indelCount * (1.375f) + 0.5f;
     tmp = W[ref] - tmp;
     if (tmp <= 0) tmp = 0;
@@ -194,18 +193,34 @@ GT16_HDN void genotype_likelihood16(const LhTables &T, const uint32_t *Win, int 
   }
   int wt = 0;
   for (int i = 0; i < 6; ++i) wt += (int) W[i];
+  return wt;
+}
+
+// likelihood of genotype g (0..9 = AA,AC,AG,AT,CC,CG,CT,GG,GT,TT; 10..13 = AX,CX,GX,TX; 14 = XX;
+// 15 = XY) from the penalised weights (:268-284)
+GT16_HDN double genotype_lh_one(const LhTables &T, const uint32_t *W, int wt, int g) {
   const double ps = T.p_err_s, pi = T.p_err_i;
-  const double p_hom_base = 3 * ps + 2 * pi, p_hom_indel = 4 * ps + pi, p_het_base = 2 * ps + 2 * pi,
-               p_het_bi = 3 * ps + pi, p_het_ii = 4 * ps;
-  int g = 0;
-  for (int i = 0; i < 4; ++i)
-    for (int j = i; j < 4; ++j) {
-      double v = (i == j) ? lh_hom(T, W, i, wt, p_hom_base, 0, 1) : lh_het(T, W, i, j, wt, p_het_base, 4, 4, 5);
-      lh[g++] = fmin(1.0, v);
-    }
-  for (int b = 0; b < 4; ++b) lh[g++] = fmin(1.0, lh_het(T, W, b, 4, wt, p_het_bi, 6, 8, 7));   // AX CX GX TX
-  lh[g++] = fmin(1.0, lh_hom(T, W, 4, wt, p_hom_indel, 2, 3));                                   // XX
-  lh[g++] = fmin(1.0, lh_het(T, W, 5, 4, wt, p_het_ii, 8, 8, 9));                                // XY
+  double v;
+  if (g < 10) {
+    int i = 0, rem = g;                       // (i, j) of the g-th pair in the i <= j enumeration
+    while (rem >= 4 - i) { rem -= 4 - i; ++i; }
+    int j = i + rem;
+    v = (i == j) ? lh_hom(T, W, i, wt, 3 * ps + 2 * pi, 0, 1) : lh_het(T, W, i, j, wt, 2 * ps + 2 * pi, 4, 4, 5);
+  } else if (g < 14) {
+    v = lh_het(T, W, g - 10, 4, wt, 3 * ps + pi, 6, 8, 7);
+  } else if (g == 14) {
+    v = lh_hom(T, W, 4, wt, 4 * ps + pi, 2, 3);
+  } else {
+    v = lh_het(T, W, 5, 4, wt, 4 * ps, 8, 8, 9);
+  }
+  return fmin(1.0, v);
+}
+
+// W[6] = A,C,G,T,deepest indel,second indel weighted counts; ref in 0..3; lh[16] out (:249-289)
+GT16_HDN void genotype_likelihood16(const LhTables &T, const uint32_t *Win, int ref, double *lh) {
+  uint32_t W[6];
+  int wt = penalised_weights(Win, ref, W);
+  for (int g = 0; g < 16; ++g) lh[g] = genotype_lh_one(T, W, wt, g);
 }
 
 // ------------------------------------------------------------------------------------
@@ -475,9 +490,11 @@ GT16_HDN void materialise(const SnapView &V, const PatRef &p, IndelPat *o) {
   }
 }
 
-// insertion/deletion lists of position+1 (VariantCaller.cpp:125-488).  pats may be null.
-GT16_HDN void decode_indels(const SnapView &V, uint32_t p, IndelInfo &o, IndelPat *pats /*[2] or null*/) {
+// insertion/deletion lists of position+1 (VariantCaller.cpp:125-488); d0 / d1 receive references to
+// the deepest / second-deepest pattern (type 0 = none)
+GT16_HDN void decode_indel_refs(const SnapView &V, uint32_t p, IndelInfo &o, PatRef &d0, PatRef &d1) {
   o.W4 = o.F4 = o.R4 = o.W5 = o.F5 = o.R5 = 0; o.hqTotal = o.lqTotal = 0; o.isValidPlus = 0; o.bad = 0;
+  d0.type = d1.type = 0; d0.len = d1.len = 0; d0.hq = d0.lq = d1.hq = d1.lq = 0; d0.seq = d1.seq = nullptr; d0.delPos = d1.delPos = 0;
   uint32_t q = p + 1;
   if (q >= V.L) q = V.L - 1;
   uint64_t c = V.counters[q];
@@ -487,8 +504,7 @@ GT16_HDN void decode_indels(const SnapView &V, uint32_t p, IndelInfo &o, IndelPa
   // quirk kept: the region is that of `p`, not of p+1 (:47,150,268)
   const uint8_t *r = ovf_record(V, ovf_region(V, p), (uint32_t) (c >> 32));
   if (!r) { o.bad = 1; return; }
-  PatRef d0, d1, cur;
-  d0.type = d1.type = 0; d0.len = d1.len = 0; d0.hq = d0.lq = d1.hq = d1.lq = 0; d0.seq = d1.seq = nullptr; d0.delPos = d1.delPos = 0;
+  PatRef cur;
   if (w1 & 0x2000) {
     if (w1 & 0x1000) {                                       // pooled pattern list :147-210
       uint32_t size = w1 & 0xFFF, ptr = rd32(r + 24), i = 0;
@@ -529,6 +545,12 @@ GT16_HDN void decode_indels(const SnapView &V, uint32_t p, IndelInfo &o, IndelPa
   o.W5 = (uint32_t) d1.hq * 4; o.F5 = d1.hq; o.R5 = d1.lq;
   if (d1.hq | d1.lq) o.isValidPlus = 2;                       // return 3 (:436-478)
   else if (d0.hq | d0.lq) o.isValidPlus = 1;                  // return 2 (:481-487)
+}
+
+// same, materialising the two pattern records when pats != null
+GT16_HDN void decode_indels(const SnapView &V, uint32_t p, IndelInfo &o, IndelPat *pats /*[2] or null*/) {
+  PatRef d0, d1;
+  decode_indel_refs(V, p, o, d0, d1);
   if (pats) {
     pats[0].type = pats[1].type = 0;
     if (o.isValidPlus >= 1) materialise(V, d0, &pats[0]);

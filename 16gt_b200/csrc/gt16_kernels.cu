@@ -95,6 +95,141 @@ __device__ __forceinline__ bool lookup_needs_exact(const DecisionTables &D, uint
   return true;
 }
 
+// ---- TMA bulk-copy + mbarrier primitives (PTX ISA 8.x; SASS: UBLKCP / SYNCS) ---------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > (1u << 24)) __trap();          // a lost bulk copy must not hang the device
+}
+
+// Streaming classification of a dense, single-region range of positions [pBeg, pEnd) -- the HBM-bound
+// pass of the path.  Persistent CTAs (one per SM); each walks tiles of kTile positions that an elected
+// thread stages into shared memory with three 1-D TMA bulk copies per tile (counters + one look-ahead
+// entry, packed reference, invalid bitmap) through a kStages-deep mbarrier ring, so ~100 KB per SM is
+// in flight independent of the warps' progress.  The decision bitmaps for the two most common site
+// shapes (only the reference allele seen / reference + one other allele) live in shared memory.
+// Per site: ~45 instructions, no divergent path.  Sites whose counter is of overflow type, whose
+// successor carries indel records, or whose (role-indexed) weights the bitmaps do not certify as
+// hom-ref are flagged for the exact evaluator (k_eval_list).
+// Requires pBeg % 128 == 0 (16-byte alignment of all three sources) and arrays padded by one tile.
+struct StreamSmem {
+  uint64_t counters[kStreamStages][kStreamTile + 2];
+  uint32_t ref[kStreamStages][kStreamTile / 16];
+  uint32_t bm[kStreamStages][kStreamTile / 32];
+  uint32_t tab[kS1Words + 2 * kS2Words];
+  uint64_t full[kStreamStages];
+};
+static_assert(sizeof(uint64_t) * (kStreamTile + 2) % 16 == 0, "bulk copy sizes must be multiples of 16 bytes");
+
+__global__ void __launch_bounds__(kStreamThreads, 1)
+k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__ packedRef,
+             const uint32_t *__restrict__ invalid, uint32_t pBeg, uint32_t pEnd, DecisionTables D,
+             uint32_t *__restrict__ mask) {
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  StreamSmem &S = *reinterpret_cast<StreamSmem *>(smemRaw);
+  const uint32_t nTiles = (pEnd - pBeg + kStreamTile - 1) / kStreamTile;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr uint32_t kBytesC = sizeof(uint64_t) * (kStreamTile + 2), kBytesR = kStreamTile / 4, kBytesB = kStreamTile / 8;
+  const uint32_t txBytes = kBytesC + kBytesR + (invalid ? kBytesB : 0);
+
+  auto issue = [&](uint32_t stage, uint32_t tile) {        // elected thread only
+    const uint32_t pT = pBeg + tile * kStreamTile;
+    mbar_expect_tx(&S.full[stage], txBytes);
+    bulk_g2s(S.counters[stage], counters + pT, kBytesC, &S.full[stage]);
+    bulk_g2s(S.ref[stage], packedRef + (pT >> 4), kBytesR, &S.full[stage]);
+    if (invalid) bulk_g2s(S.bm[stage], invalid + (pT >> 5), kBytesB, &S.full[stage]);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < kStreamStages; ++s) mbar_init(&S.full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (uint32_t k = tid; k < kS1Words + 2 * kS2Words; k += kStreamThreads)
+    S.tab[k] = k < kS1Words ? __ldg(D.s1 + k) : k < kS1Words + kS2Words ? __ldg(D.s2p + (k - kS1Words)) : __ldg(D.s2q + (k - kS1Words - kS2Words));
+  if (!invalid)
+    for (uint32_t k = tid; k < kStreamStages * (kStreamTile / 32); k += kStreamThreads) (&S.bm[0][0])[k] = 0;
+  __syncthreads();
+  if (tid == 0)
+    for (uint32_t s = 0; s < (uint32_t) kStreamStages; ++s) {
+      uint32_t t = blockIdx.x + s * gridDim.x;
+      if (t < nTiles) issue(s, t);
+    }
+
+  uint32_t k = 0;
+  for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++k) {
+    const uint32_t stage = k % kStreamStages, parity = (k / kStreamStages) & 1;
+    mbar_wait(&S.full[stage], parity);
+    const uint2 *sc = reinterpret_cast<const uint2 *>(S.counters[stage]);
+    const uint32_t *sr = S.ref[stage], *sb = S.bm[stage];
+    const uint32_t pT = pBeg + tile * kStreamTile;
+    constexpr int kRows = kStreamTile / kStreamThreads;      // 32-site rows per warp
+    uint2 c[kRows]; uint32_t nlo[kRows], rw[kRows], bw[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const uint32_t site = warp * (32 * kRows) + 32 * r + lane;
+      c[r] = sc[site]; nlo[r] = sc[site + 1].x; rw[r] = sr[site >> 4]; bw[r] = sb[site >> 5];
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const uint32_t site = warp * (32 * kRows) + 32 * r + lane;
+      const uint32_t p = pT + site;
+      const uint32_t ref = (rw[r] >> (30 - ((site & 15) << 1))) & 3;
+      const bool ok = p < pEnd && !((bw[r] >> (31 - lane)) & 1);
+      const uint32_t x = c[r].x, y = c[r].y;
+      const bool special = ((x & (x >> 16) & 0xC000u) == 0xC000u) |                                    // overflow-type site
+                           (((nlo[r] & (nlo[r] >> 16) & 0xC000u) == 0xC000u) & (((nlo[r] | (nlo[r] >> 16)) & 0x2000u) != 0));
+      uint32_t v1 = (y & 0xFFFFu) ? (x & 0x3FFFu) : 0u, v2 = (y >> 16) ? ((x >> 16) & 0x3FFFu) : 0u;
+      const uint32_t r1 = ((x >> 14) & 3u) ^ ref, r2 = (x >> 30) ^ ref;
+      if (r1 == r2 && (y >> 16)) v1 = 0;                       // the second slot overwrites the first
+      const uint32_t wr = (r1 == 0 ? v1 : 0u) | (r2 == 0 ? v2 : 0u);
+      const uint32_t a1 = r1 ? v1 : 0u, a2 = r2 ? v2 : 0u, alt = a1 | a2, ar = a1 ? r1 : r2;
+      const bool outside = (a1 && a2) | (alt != 0 && (wr >= (uint32_t) kS2R || alt >= (uint32_t) kS2A));
+      uint32_t idx = alt == 0 ? wr : (uint32_t) kS1Bits + (ar == 2 ? 0u : (uint32_t) (kS2R * kS2A)) + alt * kS2R + wr;
+      if (outside) idx = 0;
+      const bool bit = (S.tab[idx >> 5] >> (idx & 31)) & 1u;
+      const bool flag = ok & (special | outside | bit);
+      const uint32_t word = __ballot_sync(0xffffffffu, flag);
+      const uint32_t rowBase = pT + warp * (32 * kRows) + 32 * r;
+      if (lane == 0 && rowBase < pEnd) mask[(rowBase - pBeg) >> 5] = word;
+    }
+    __syncthreads();                                           // every warp is done with this stage
+    if (tid == 0) {
+      const uint32_t nt = tile + kStreamStages * gridDim.x;
+      if (nt < nTiles) issue(stage, nt);
+    }
+  }
+}
+
+void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t *mask,
+                       int numSMs, cudaStream_t s) {
+  if (pEnd <= pBeg) return;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_stream_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmem));
+    configured = true;
+  }
+  uint32_t nTiles = (pEnd - pBeg + kStreamTile - 1) / kStreamTile;
+  unsigned grid = nTiles < (uint32_t) numSMs ? nTiles : (unsigned) numSMs;
+  k_stream_tma<<<grid, kStreamThreads, sizeof(StreamSmem), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, mask);
+}
+
 template <bool kUseTables>
 __global__ void __launch_bounds__(256) k_stream(SnapView V, DevSiteMap M, uint64_t first, uint32_t n,
                                                 DecisionTables D, EvalParams P, uint32_t *__restrict__ mask,
@@ -152,23 +287,53 @@ void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint3
   else k_stream<false><<<grid, 256, 0, s>>>(V, M, first, n, D, P, mask, errWord);
 }
 
+// Exact predicate for the flagged sites.  Sites flagged only because their counter is of overflow type
+// first get the decision-bitmap test the streaming kernel could not do without the gather; the rest
+// run the full evaluator.  A site that is NOT a candidate has its bit cleared in the site mask, so that
+// one more ordered compaction of the mask yields the candidate list.
 __global__ void __launch_bounds__(128) k_eval_list(SnapView V, DevSiteMap M, uint64_t base,
-                                                   const uint32_t *__restrict__ list, uint32_t n, EvalParams P,
-                                                   uint32_t *__restrict__ mask, uint32_t *errWord) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  bool flag = false;
-  if (j < n) {
+                                                   const uint32_t *__restrict__ list, uint32_t n, bool useTables,
+                                                   DecisionTables D, EvalParams P, uint32_t *__restrict__ siteMask,
+                                                   uint32_t *errWord) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint32_t i = list[j];
+    const uint32_t p = site_pos(M, base + i);
     uint32_t e = 0;
-    flag = site_is_candidate(V, P, site_pos(M, base + list[j]), e);
+    bool cand = false;
+    BaseCounts bc;
+    decode_bases(V, p, bc);
+    if (bc.bad) e |= kErrBadSnapshot;
+    else if (bc.valid) {
+      IndelInfo ii; PatRef d0, d1;
+      decode_indel_refs(V, p, ii, d0, d1);
+      if (ii.bad) e |= kErrBadSnapshot;
+      else {
+        const int ref = (int) ref_base(V, p);
+        bool full = true;
+        if (useTables && (ii.W4 | ii.W5) == 0)
+          full = lookup_needs_exact(D, bc.W[ref], bc.W[ref ^ 2], bc.W[ref ^ 1], bc.W[ref ^ 3]);
+        if (full) {
+          uint32_t W[6] = {bc.W[0], bc.W[1], bc.W[2], bc.W[3], ii.W4, ii.W5};
+          double lh[16];
+          genotype_likelihood16(P.lh, W, ref, lh);
+          Posterior po;
+          select_genotype(ref, lh, P.prior, P.g2i, po);
+          if (po.genotype > 9 && ii.isValidPlus == 0) e |= kErrGenotype;   // SNP_Caller.cpp:235-239
+          cand = po.genotype != hom_ref_genotype(ref);
+        }
+      }
+    }
     if (e) atomicOr(errWord, e);
+    if (!cand) atomicAnd(siteMask + (i >> 5), ~(1u << (i & 31)));
   }
-  uint32_t word = __ballot_sync(0xffffffffu, flag);
-  if ((threadIdx.x & 31) == 0 && j < n) mask[j >> 5] = word;
 }
 void launch_eval_list(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
-                      const EvalParams &P, uint32_t *mask, uint32_t *errWord, cudaStream_t s) {
+                      bool useTables, const DecisionTables &D, const EvalParams &P, uint32_t *siteMask,
+                      uint32_t *errWord, cudaStream_t s) {
   if (!n) return;
-  k_eval_list<<<(n + 127) / 128, 128, 0, s>>>(V, M, base, list, n, P, mask, errWord);
+  unsigned grid = (n + 127) / 128;
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_eval_list<<<grid, 128, 0, s>>>(V, M, base, list, n, useTables, D, P, siteMask, errWord);
 }
 
 // ------------------------------------------------------------------------------ ordered compaction
@@ -253,19 +418,182 @@ void launch_mask_scatter(const uint32_t *mask, uint32_t nItems, const uint32_t *
 }
 
 // ------------------------------------------------------------------------------ candidates
-__global__ void __launch_bounds__(64) k_candidates(SnapView V, DevSiteMap M, uint64_t base,
-                                                   const uint32_t *__restrict__ list, uint32_t n, EvalParams P,
-                                                   gt16_called_site *__restrict__ out, uint32_t *errWord) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  uint32_t e = 0;
-  build_called_site(V, M, base + list[j], P, out[j], e);
-  if (e) atomicOr(errWord, e);
+// One WARP per called site (computeMeta + outputPossibleSNPs, SNP_Caller.cpp:101-393).  The work of a
+// record is a few hundred dependent gathers (two 101-entry windows of decoded counters) plus up to 24
+// serial float Fisher recurrences; spread over the lanes it becomes: one genotype likelihood per lane
+// (16), one strand / base-quality test per lane (8 or 24), four window entries per lane and side, and
+// warp reductions for the window sums.  Every leaf routine is the one the serial build_called_site()
+// uses, so the bits are the same.
+constexpr int kCandThreads = 128;
+struct CandWarpSmem {
+  double lh[16];
+  uint32_t sc[2][kWindow + 4];
+  uint32_t w[2][kWindow + 4];
+  uint8_t fl[2][kWindow + 4];      // bit0 valid, bit1 gc
+};
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kCandThreads) k_candidates(SnapView V, DevSiteMap M, uint64_t base,
+                                                             const uint32_t *__restrict__ list, uint32_t n,
+                                                             EvalParams P, gt16_called_site *__restrict__ out,
+                                                             uint32_t *errWord) {
+  __shared__ CandWarpSmem smAll[kCandThreads / 32];
+  CandWarpSmem &sm = smAll[threadIdx.x >> 5];
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warpsTotal = gridDim.x * (kCandThreads / 32);
+  for (uint32_t j = blockIdx.x * (kCandThreads / 32) + (threadIdx.x >> 5); j < n; j += warpsTotal) {
+    const uint64_t i = base + list[j];
+    const uint32_t p = site_pos(M, i);
+    gt16_called_site &o = out[j];
+    uint32_t err = 0;
+    // -- decode (uniform across the warp: broadcast loads)
+    BaseCounts bc;
+    decode_bases(V, p, bc);
+    IndelInfo ii; PatRef d0, d1;
+    decode_indel_refs(V, p, ii, d0, d1);
+    if (bc.bad || ii.bad) err |= kErrBadSnapshot;
+    const int ref = (int) ref_base(V, p);
+    const uint32_t W[6] = {bc.W[0], bc.W[1], bc.W[2], bc.W[3], ii.W4, ii.W5};
+    // -- 16 genotype likelihoods, one per lane
+    {
+      uint32_t Wp[6];
+      const int wt = penalised_weights(W, ref, Wp);
+      if (lane < 16) sm.lh[lane] = genotype_lh_one(P.lh, Wp, wt, (int) lane);
+    }
+    __syncwarp();
+    double lh[16];
+#pragma unroll
+    for (int g = 0; g < 16; ++g) lh[g] = sm.lh[g];
+    Posterior po;
+    select_genotype(ref, lh, P.prior, P.g2i, po);
+    const uint8_t isValid = (uint8_t) (1 + ii.isValidPlus);
+    uint8_t isIndel = 0, nextBp = 0;
+    if (po.genotype > 9) {                                              // SNP_Caller.cpp:228-239
+      if (isValid >= 2) { isIndel = isValid; if (d0.type == 'D') nextBp = d0.len; }
+      else err |= kErrGenotype;
+    }
+    BatchGeom B;
+    B.first = (i / kBatch) * (uint64_t) kBatch;
+    const uint64_t left = M.totalSites - B.first;
+    B.n = left < kBatch ? (uint32_t) left : kBatch;
+    B.amb0 = site_pos(M, B.first);
+    B.ambLast = site_pos(M, B.first + B.n - 1);
+    const uint32_t idx = (uint32_t) (i - B.first);
+
+    // -- strand / base-quality bias: lane t -> (site k, kind, base)                     :248-274
+    if (lane < 24) {
+      const uint32_t k = lane >> 3, kind = (lane >> 2) & 1, b = lane & 3;
+      float v = 0.f;
+      bool have; uint64_t si = i;
+      if (isIndel) {
+        if (k == 0) { have = idx != 0; si = i - 1; }
+        else if (k == 1) { have = idx + nextBp < B.n; si = i + nextBp; }
+        else have = true;
+      } else have = (k == 0);
+      if (have) {
+        BaseCounts nb;
+        if (si == i) nb = bc; else decode_bases(V, site_pos(M, si), nb);
+        v = kind ? base_quality_bias(P.lnfact, nb.W[b], nb.F[b], nb.R[b]) : strand_bias(P.lnfact, nb.F[b], nb.R[b]);
+      }
+      if (kind) o.bqb[k][b] = v; else o.sb[k][b] = v;
+    }
+
+    // -- windows (reference's un-offset mwInfo indexing)                                 :276-367
+    const bool haveLeft = idx >= (uint32_t) kWindow;
+    for (uint32_t t = lane; t <= (uint32_t) kWindow; t += 32) {
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        if (side == 0 && !haveLeft) continue;
+        const uint64_t k0 = side == 0 ? (uint64_t) idx - kWindow : (uint64_t) idx + nextBp;
+        WinEntry e = window_entry(V, M.m, B, k0 + t);
+        sm.sc[side][t] = e.sc; sm.w[side][t] = e.w; sm.fl[side][t] = (uint8_t) (e.valid | (e.gc << 1));
+      }
+    }
+    __syncwarp();
+    int strandSum[2] = {0, 0}, deltaSum[2] = {0, 0}, depthSum[2] = {0, 0}, gcSum[2] = {0, 0}, validSum[2] = {0, 0};
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      if (side == 0 && !haveLeft) continue;
+      int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+      for (uint32_t t = lane; t < (uint32_t) kWindow; t += 32) {
+        const uint32_t f = sm.fl[side][t];
+        if (f & 1) {
+          const uint32_t sc = sm.sc[side][t], sn = sm.sc[side][t + 1];
+          a0 += (int) sc; a1 += (int) sm.w[side][t]; a2 += (int) ((f >> 1) & 1); a3 += 1;
+          if (sm.fl[side][t + 1] & 1) a4 += (int) (sc > sn ? sc - sn : sn - sc);
+        }
+      }
+      strandSum[side] = warp_sum(a0); depthSum[side] = warp_sum(a1); gcSum[side] = warp_sum(a2) & 0xFF;
+      validSum[side] = warp_sum(a3) & 0xFF; deltaSum[side] = warp_sum(a4);
+    }
+    __syncwarp();
+    // G counts of the three sites before / after                                        :355-367
+    bool gbit = false;
+    if (lane < 3) { if (idx >= 3) { WinEntry e = window_entry(V, M.m, B, (uint64_t) idx - 3 + lane); gbit = e.valid && e.g; } }
+    else if (lane < 6) { WinEntry e = window_entry(V, M.m, B, (uint64_t) idx + nextBp + (lane - 3)); gbit = e.valid && e.g; }
+    const uint32_t gb = __ballot_sync(0xffffffffu, gbit);
+    const uint32_t run = polyrun(V, p);
+
+    // -- record
+    if (lane < 16) { o.lh[lane] = lh[lane]; o.flh[lane] = po.flh[lane]; }
+    if (lane < 6) {
+      o.W[lane] = lane < 4 ? bc.W[lane] : (lane == 4 ? ii.W4 : ii.W5);
+      o.F[lane] = lane < 4 ? bc.F[lane] : (lane == 4 ? ii.F4 : ii.F5);
+      o.R[lane] = lane < 4 ? bc.R[lane] : (lane == 4 ? ii.R4 : ii.R5);
+    }
+    for (int k = 0; k < 2; ++k) {                                       // indel pattern bytes, two per lane
+      gt16_indel &d = o.indel[k];
+      const PatRef &pr = k ? d1 : d0;
+      const bool have = isIndel && (k == 0 || isIndel == 3);
+      const uint32_t nb = ((uint32_t) pr.len + 3) / 4;
+      for (uint32_t bIdx = lane; bIdx < 64; bIdx += 32) {
+        uint8_t v = 0;
+        if (have && bIdx < nb) {
+          if (pr.type == 'I') v = pr.seq[bIdx];
+          else for (uint32_t q = bIdx * 4; q < bIdx * 4 + 4 && q < pr.len; ++q) v |= (uint8_t) (ref_base(V, pr.delPos + q) << ((q & 3) << 1));
+        }
+        d.seq[bIdx] = v;
+      }
+      if (lane == 0) { d.type = have ? pr.type : (uint8_t) '*'; d.len = have ? pr.len : 0; d.hq = have ? pr.hq : 0; d.lq = have ? pr.lq : 0; }
+    }
+    if (lane == 0) {
+      o.amb = p; o.ref = (uint8_t) ref; o.genotype = (uint8_t) po.genotype; o.is_indel = isIndel;
+      o.pD = po.pD; o.bestD = po.bestD; o.secondD = po.secondD;
+      float avgSC[2] = {0.f, 0.f}, avgD[2] = {0.f, 0.f};
+      if (deltaSum[0] | deltaSum[1]) o.rpb = (deltaSum[0] - deltaSum[1] + 0.0f) / (deltaSum[0] + deltaSum[1]);
+      else o.rpb = 0.0f;
+      if (validSum[0]) { o.lgc = (gcSum[0] + 0.0f) / validSum[0]; avgSC[0] = (strandSum[0] + 0.0f) / validSum[0]; avgD[0] = (depthSum[0] + 0.0f) / validSum[0]; }
+      else o.lgc = 0.0f;
+      if (validSum[1]) { o.rgc = (gcSum[1] + 0.0f) / validSum[1]; avgSC[1] = (strandSum[1] + 0.0f) / validSum[1]; avgD[1] = (depthSum[1] + 0.0f) / validSum[1]; }
+      else o.rgc = 0.0f;
+      o.lq = 0.f; o.rq = 0.f; o.rq_assigned = 0;
+      if (fabsf(avgSC[0] + avgSC[1]) > FLT_EPSILON) {
+        o.asc = (avgSC[0] - avgSC[1]) / (avgSC[0] + avgSC[1]);
+        o.lq = fabsf(avgSC[0]) > FLT_EPSILON ? avgD[0] / avgSC[0] : 0.0f;
+        o.rq = fabsf(avgSC[1]) > FLT_EPSILON ? avgD[1] / avgSC[1] : 0.0f;
+        o.rq_assigned = 1;
+      } else {
+        o.asc = 0.0f;
+      }
+      o.lg = (uint8_t) __popc(gb & 0x7u); o.rg = (uint8_t) __popc(gb & 0x38u);
+      o.polyrun = (uint16_t) run;
+      o.total_hq = ii.hqTotal; o.total_lq = ii.lqTotal;
+      if (err) atomicOr(errWord, err);
+    }
+    __syncwarp();
+  }
 }
 void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
                        const EvalParams &P, gt16_called_site *out, uint32_t *errWord, cudaStream_t s) {
   if (!n) return;
-  k_candidates<<<(n + 63) / 64, 64, 0, s>>>(V, M, base, list, n, P, out, errWord);
+  unsigned grid = (n + (kCandThreads / 32) - 1) / (kCandThreads / 32);
+  if (grid > 148 * 32) grid = 148 * 32;
+  k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, list, n, P, out, errWord);
 }
 
 // ------------------------------------------------------------------------------ operator seam

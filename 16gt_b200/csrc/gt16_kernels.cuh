@@ -22,6 +22,13 @@ struct DecisionTables {
   const uint32_t *g4;    // index ((Wq3 * kG4A + Wq1) * kG4A + Wp) * kG4R + Wr
 };
 
+// TMA-staged streaming kernel geometry
+constexpr int kStreamTile = 4096;      // positions per tile (32 KB of counters)
+constexpr int kStreamStages = 4;       // mbarrier ring depth
+constexpr int kStreamThreads = 1024;
+// bytes by which every streamed array must be over-allocated so that full tiles can be copied
+constexpr size_t kStreamPadSites = kStreamTile + 64;
+
 void launch_build_table(double *out, float err, cudaStream_t s);
 void launch_build_ycsq(double *out, cudaStream_t s);
 void launch_build_decisions(const EvalParams &P, uint32_t *s1, uint32_t *s2p, uint32_t *s2q, uint32_t *g4,
@@ -32,9 +39,14 @@ void launch_build_decisions(const EvalParams &P, uint32_t *s1, uint32_t *s2p, ui
 void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint32_t n, bool useTables,
                    const DecisionTables &D, const EvalParams &P, uint32_t *mask, uint32_t *errWord,
                    cudaStream_t s);
-// exact predicate for listed sites: bit j of mask = list[j] is a candidate
+// same contract for a dense single-region range of positions [pBeg,pEnd), pBeg % 128 == 0, arrays padded
+// by kStreamPadSites: persistent CTAs, TMA bulk copies into a shared-memory ring
+void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t *mask,
+                       int numSMs, cudaStream_t s);
+// exact predicate for the listed (flagged) sites: clears bit list[j] of siteMask unless the site is a candidate
 void launch_eval_list(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
-                      const EvalParams &P, uint32_t *mask, uint32_t *errWord, cudaStream_t s);
+                      bool useTables, const DecisionTables &D, const EvalParams &P, uint32_t *siteMask,
+                      uint32_t *errWord, cudaStream_t s);
 
 // ordered compaction of a bit mask over nItems items
 constexpr int kScanBlock = 256;                       // mask words per block
