@@ -125,6 +125,8 @@ static EvalParams eval_params(const gt16_ctx *ctx) {
   P.g2i = ctx->g2i;
   P.lnfact.tab = ctx->lnfact;
   P.lnfact.size = kLnFactTab;
+  P.lnfact.far = nullptr;
+  P.lnfact.farSize = 0;
   return P;
 }
 
@@ -391,7 +393,9 @@ int gt16_compute_bias(gt16_ctx *ctx, const void *w, const void *f, const void *r
 // ---- fused path -----------------------------------------------------------------------------
 // A context is driven by one host thread at a time; all scratch is owned by the context and only grows.
 static const uint32_t kCopyChunkSites = 1u << 22;     // 32 MiB of counters per cudaMemcpyAsync
-static const uint32_t kCandSlice = 8192;              // candidate records per kernel launch / D2H copy
+// candidate records per kernel launch / D2H copy: a small first slice starts the device->host stream early,
+// later slices double up to kCandSliceMax so the kernels run at full occupancy
+static const uint32_t kCandSliceFirst = 4096, kCandSliceMax = 32768;
 
 #define CUF(call)                                                                                  \
   do {                                                                                             \
@@ -630,10 +634,12 @@ int finish_call(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t begin
   CUF(cudaEventRecord(ev[4], ctx->compute));
   gt16_called_site *recs = (gt16_called_site *) ctx->recs.p;
   size_t slice = 0;
-  for (uint32_t off = 0; off < nB; off += kCandSlice, ++slice) {
-    uint32_t cnt = std::min<uint32_t>(kCandSlice, nB - off);
+  uint32_t sliceLen = kCandSliceFirst;
+  for (uint32_t off = 0, cnt = 0; off < nB; off += cnt, ++slice, sliceLen = std::min(sliceLen * 2, kCandSliceMax)) {
+    cnt = std::min<uint32_t>(sliceLen, nB - off);
     launch_candidates(V, pl.map, begin, finalList + off, cnt, P, recs + off, ctx->errWord, ctx->compute);
-    ctx->launches++;
+    launch_bias(V, pl.map, begin, finalList + off, cnt, P, recs + off, ctx->compute);
+    ctx->launches += 2;
     cudaEvent_t se;
     rc = get_event(ctx, evBase + slice, &se);
     if (rc) return rc;

@@ -330,11 +330,14 @@ GT16_HDN float expf_glibc(float x) {
 }
 
 struct LnFact {
-  const float *tab;   // tab[n] = lgammaf((float)(n+1)), n < size
+  const float *tab;   // tab[n] = lgammaf((float)(n+1)), n < size  (the Fisher kernel points this at shared memory)
   uint32_t size;
+  const float *far;   // continuation of the same table in global memory, n < farSize (may be null)
+  uint32_t farSize;
 };
 GT16_HD float lnfactC(const LnFact &L, int n) {
   if ((uint32_t) n < L.size) return L.tab[n];
+  if ((uint32_t) n < L.farSize) return L.far[n];
   return lgammaf((float) (n + 1));  // beyond 2^21: documented tolerance path (depth > 130k)
 }
 GT16_HD float lnbicoC(const LnFact &L, int n, int k) { return (lnfactC(L, n) - lnfactC(L, k) - lnfactC(L, n - k)); }
@@ -348,6 +351,10 @@ GT16_HDN float fisher2tailC(const LnFact &L, int n11, int n1_, int n_1, int n) {
   float two = 0;
   two += poa;
   const float poa_e = poa * 1.000000001f;
+  // Once a tail term has underflowed to zero every later term of that tail is zero too and adds
+  // nothing, so the walk may stop there -- provided the integer products below cannot wrap (then
+  // every factor is a positive finite float); for deeper tables the full walk is kept.
+  const bool stopAtZero = n <= 46340;
   int lo = 0;
   if (n1_ + n_1 - n > 0) lo = n1_ + n_1 - n;
   for (int x = n11; x > lo; --x) {
@@ -355,6 +362,7 @@ GT16_HDN float fisher2tailC(const LnFact &L, int n11, int n1_, int n_1, int n) {
     int den = (int) ((uint32_t) (n1_ - x + 1) * (uint32_t) (n_1 - x + 1));
     pox = pox * (float) num / den;
     two += pox * (pox < poa_e);
+    if (stopAtZero && pox == 0.0f) break;
   }
   int hi = n_1;
   if (n1_ < n_1) hi = n1_;
@@ -363,6 +371,7 @@ GT16_HDN float fisher2tailC(const LnFact &L, int n11, int n1_, int n_1, int n) {
     int den = (int) ((uint32_t) (n + x - n1_ - n_1) * (uint32_t) x);
     pox = pox * (float) (n1_ - (x - 1)) * (n_1 - (x - 1)) / den;
     two += pox * (pox < poa_e);
+    if (stopAtZero && pox == 0.0f) break;
   }
   return two;
 }

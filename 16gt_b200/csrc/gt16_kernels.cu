@@ -120,23 +120,48 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 // Streaming classification of a dense, single-region range of positions [pBeg, pEnd) -- the HBM-bound
-// pass of the path.  Persistent CTAs (one per SM); each walks tiles of kTile positions that an elected
-// thread stages into shared memory with three 1-D TMA bulk copies per tile (counters + one look-ahead
-// entry, packed reference, invalid bitmap) through a kStages-deep mbarrier ring, so ~100 KB per SM is
-// in flight independent of the warps' progress.  The decision bitmaps for the two most common site
-// shapes (only the reference allele seen / reference + one other allele) live in shared memory.
-// Per site: ~45 instructions, no divergent path.  Sites whose counter is of overflow type, whose
-// successor carries indel records, or whose (role-indexed) weights the bitmaps do not certify as
-// hom-ref are flagged for the exact evaluator (k_eval_list).
+// pass of the path.  Persistent CTAs (one per SM); each walks tiles of kStreamTile positions that an
+// elected thread stages into shared memory with three 1-D TMA bulk copies per tile (counters + one
+// look-ahead entry, packed reference, invalid bitmap) through a kStreamStages-deep mbarrier ring, so
+// ~100 KB per SM is in flight independent of the warps' progress.
+//
+// The integer ALU pipe is what bounds this kernel once the loads are asynchronous (every LOP3/SHF/ISETP
+// occupies it for two cycles per warp), so the per-site work is split by how common the site shape is:
+//   simple  (~90 %): no coverage, or only the reference allele seen with a compact counter -> one byte
+//                    lookup in a 16 KB shared-memory table indexed by the weight (~25 ALU ops);
+//   special (~0.4 %): overflow-type counter, or the successor carries indel records -> flagged for
+//                    the exact evaluator without further work;
+//   complex (~9 %) : anything else (a non-reference allele in a compact counter).  The lane parks the
+//                    counter in a per-warp shared-memory queue; whenever 32 are parked the whole warp
+//                    runs the general role-indexed bitmap test, one site per lane, and ORs the verdicts
+//                    into the mask words the warp wrote earlier.
 // Requires pBeg % 128 == 0 (16-byte alignment of all three sources) and arrays padded by one tile.
+struct StreamQueueEntry { uint32_t x, y, bit, ref; };
 struct StreamSmem {
   uint64_t counters[kStreamStages][kStreamTile + 2];
   uint32_t ref[kStreamStages][kStreamTile / 16];
   uint32_t bm[kStreamStages][kStreamTile / 32];
-  uint32_t tab[kS1Words + 2 * kS2Words];
+  uint8_t s1[kS1Bits];                                   // byte per weight: 1 = needs exact evaluation
+  uint32_t s2[2 * kS2Words];                             // bitmaps (Wr, Wp) and (Wr, Wq)
+  StreamQueueEntry queue[kStreamThreads / 32][64];
   uint64_t full[kStreamStages];
 };
 static_assert(sizeof(uint64_t) * (kStreamTile + 2) % 16 == 0, "bulk copy sizes must be multiples of 16 bytes");
+static_assert(sizeof(StreamSmem) <= 227 * 1024, "shared memory budget");
+
+// general role-indexed test of one compact (non-overflow) counter; same verdict as lookup_needs_exact
+__device__ __forceinline__ bool compact_needs_exact(const uint32_t *__restrict__ s2, const uint8_t *__restrict__ s1,
+                                                    uint32_t x, uint32_t y, uint32_t ref) {
+  uint32_t v1 = (y & 0xFFFFu) ? (x & 0x3FFFu) : 0u, v2 = (y >> 16) ? ((x >> 16) & 0x3FFFu) : 0u;
+  const uint32_t r1 = ((x >> 14) & 3u) ^ ref, r2 = (x >> 30) ^ ref;
+  if (r1 == r2 && (y >> 16)) v1 = 0;                       // the second slot overwrites the first
+  const uint32_t wr = (r1 == 0 ? v1 : 0u) | (r2 == 0 ? v2 : 0u);
+  const uint32_t a1 = r1 ? v1 : 0u, a2 = r2 ? v2 : 0u, alt = a1 | a2, ar = a1 ? r1 : r2;
+  if (alt == 0) return s1[wr] != 0;
+  if ((a1 && a2) || wr >= (uint32_t) kS2R || alt >= (uint32_t) kS2A) return true;
+  const uint32_t idx = (ar == 2 ? 0u : (uint32_t) (kS2R * kS2A)) + alt * kS2R + wr;
+  return (s2[idx >> 5] >> (idx & 31)) & 1u;
+}
 
 __global__ void __launch_bounds__(kStreamThreads, 1)
 k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__ packedRef,
@@ -161,8 +186,12 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
     for (int s = 0; s < kStreamStages; ++s) mbar_init(&S.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (uint32_t k = tid; k < kS1Words + 2 * kS2Words; k += kStreamThreads)
-    S.tab[k] = k < kS1Words ? __ldg(D.s1 + k) : k < kS1Words + kS2Words ? __ldg(D.s2p + (k - kS1Words)) : __ldg(D.s2q + (k - kS1Words - kS2Words));
+  for (uint32_t k = tid; k < (uint32_t) kS1Bits / 4; k += kStreamThreads) {     // expand the s1 bitmap to bytes
+    const uint32_t bits = (__ldg(D.s1 + (k >> 3)) >> ((k & 7) << 2)) & 0xFu;
+    reinterpret_cast<uint32_t *>(S.s1)[k] = (bits & 1u) | ((bits & 2u) << 7) | ((bits & 4u) << 14) | ((bits & 8u) << 21);
+  }
+  for (uint32_t k = tid; k < 2 * kS2Words; k += kStreamThreads)
+    S.s2[k] = k < kS2Words ? __ldg(D.s2p + k) : __ldg(D.s2q + (k - kS2Words));
   if (!invalid)
     for (uint32_t k = tid; k < kStreamStages * (kStreamTile / 32); k += kStreamThreads) (&S.bm[0][0])[k] = 0;
   __syncthreads();
@@ -172,6 +201,17 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
       if (t < nTiles) issue(s, t);
     }
 
+  StreamQueueEntry *q = S.queue[warp];
+  uint32_t qlen = 0;
+  auto drain = [&](uint32_t count) {                        // lanes < count run one parked site each
+    if (lane < count) {
+      const StreamQueueEntry e = q[lane];
+      if (compact_needs_exact(S.s2, S.s1, e.x, e.y, e.ref)) atomicOr(mask + (e.bit >> 5), 1u << (e.bit & 31));
+    }
+  };
+  const uint32_t sh = 30u - ((lane & 15u) << 1), laneBit = 0x80000000u >> lane, ltMask = (1u << lane) - 1u;
+  constexpr int kRows = kStreamTile / kStreamThreads;      // 32-site rows per warp and tile
+
   uint32_t k = 0;
   for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++k) {
     const uint32_t stage = k % kStreamStages, parity = (k / kStreamStages) & 1;
@@ -179,7 +219,7 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
     const uint2 *sc = reinterpret_cast<const uint2 *>(S.counters[stage]);
     const uint32_t *sr = S.ref[stage], *sb = S.bm[stage];
     const uint32_t pT = pBeg + tile * kStreamTile;
-    constexpr int kRows = kStreamTile / kStreamThreads;      // 32-site rows per warp
+    const uint32_t lim = (pEnd - pT) < (uint32_t) kStreamTile ? pEnd - pT : (uint32_t) kStreamTile;
     uint2 c[kRows]; uint32_t nlo[kRows], rw[kRows], bw[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
@@ -188,26 +228,39 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
     }
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
-      const uint32_t site = warp * (32 * kRows) + 32 * r + lane;
-      const uint32_t p = pT + site;
-      const uint32_t ref = (rw[r] >> (30 - ((site & 15) << 1))) & 3;
-      const bool ok = p < pEnd && !((bw[r] >> (31 - lane)) & 1);
-      const uint32_t x = c[r].x, y = c[r].y;
-      const bool special = ((x & (x >> 16) & 0xC000u) == 0xC000u) |                                    // overflow-type site
-                           (((nlo[r] & (nlo[r] >> 16) & 0xC000u) == 0xC000u) & (((nlo[r] | (nlo[r] >> 16)) & 0x2000u) != 0));
-      uint32_t v1 = (y & 0xFFFFu) ? (x & 0x3FFFu) : 0u, v2 = (y >> 16) ? ((x >> 16) & 0x3FFFu) : 0u;
-      const uint32_t r1 = ((x >> 14) & 3u) ^ ref, r2 = (x >> 30) ^ ref;
-      if (r1 == r2 && (y >> 16)) v1 = 0;                       // the second slot overwrites the first
-      const uint32_t wr = (r1 == 0 ? v1 : 0u) | (r2 == 0 ? v2 : 0u);
-      const uint32_t a1 = r1 ? v1 : 0u, a2 = r2 ? v2 : 0u, alt = a1 | a2, ar = a1 ? r1 : r2;
-      const bool outside = (a1 && a2) | (alt != 0 && (wr >= (uint32_t) kS2R || alt >= (uint32_t) kS2A));
-      uint32_t idx = alt == 0 ? wr : (uint32_t) kS1Bits + (ar == 2 ? 0u : (uint32_t) (kS2R * kS2A)) + alt * kS2R + wr;
-      if (outside) idx = 0;
-      const bool bit = (S.tab[idx >> 5] >> (idx & 31)) & 1u;
-      const bool flag = ok & (special | outside | bit);
+      const uint32_t rowSite = warp * (32 * kRows) + 32 * r, site = rowSite + lane;
+      const uint32_t x = c[r].x, y = c[r].y, n = nlo[r];
+      const uint32_t refx = rw[r] >> sh;
+      const bool isRef1 = (((x >> 14) ^ refx) & 3u) == 0;
+      const bool oneSlot = (y - 1u) < 0xFFFFu;                 // slot 1 live, slot 2 dead
+      const bool dead = y == 0;
+      const bool special = ((x & 0xC000C000u) == 0xC000C000u) |
+                           (((n & 0xC000C000u) == 0xC000C000u) & ((n & 0x20002000u) != 0));
+      const bool valid = (site < lim) & ((bw[r] & laneBit) == 0);
+      const bool simple = dead | (oneSlot & isRef1);
+      const uint32_t idx = dead ? 0u : (x & 0x3FFFu);
+      const bool bit = S.s1[idx] != 0;
+      const bool flag = valid & (special | (simple & bit));
+      const bool cplx = valid & !special & !simple;
       const uint32_t word = __ballot_sync(0xffffffffu, flag);
-      const uint32_t rowBase = pT + warp * (32 * kRows) + 32 * r;
-      if (lane == 0 && rowBase < pEnd) mask[(rowBase - pBeg) >> 5] = word;
+      const uint32_t cw = __ballot_sync(0xffffffffu, cplx);
+      if (lane == 0 && rowSite < lim) mask[(pT - pBeg + rowSite) >> 5] = word;
+      if (cw) {
+        if (cplx) {
+          StreamQueueEntry e; e.x = x; e.y = y; e.bit = pT - pBeg + site; e.ref = refx & 3u;
+          q[qlen + __popc(cw & ltMask)] = e;
+        }
+        qlen += __popc(cw);
+        __syncwarp();
+        if (qlen >= 32) {
+          const StreamQueueEntry keep = q[32 + lane];
+          drain(32);
+          __syncwarp();
+          qlen -= 32;
+          if (lane < qlen) q[lane] = keep;
+          __syncwarp();
+        }
+      }
     }
     __syncthreads();                                           // every warp is done with this stage
     if (tid == 0) {
@@ -215,6 +268,8 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
       if (nt < nTiles) issue(stage, nt);
     }
   }
+  __syncwarp();
+  drain(qlen);
 }
 
 void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t *mask,
@@ -287,53 +342,92 @@ void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint3
   else k_stream<false><<<grid, 256, 0, s>>>(V, M, first, n, D, P, mask, errWord);
 }
 
-// Exact predicate for the flagged sites.  Sites flagged only because their counter is of overflow type
-// first get the decision-bitmap test the streaming kernel could not do without the gather; the rest
-// run the full evaluator.  A site that is NOT a candidate has its bit cleared in the site mask, so that
-// one more ordered compaction of the mask yields the candidate list.
-__global__ void __launch_bounds__(128) k_eval_list(SnapView V, DevSiteMap M, uint64_t base,
-                                                   const uint32_t *__restrict__ list, uint32_t n, bool useTables,
-                                                   DecisionTables D, EvalParams P, uint32_t *__restrict__ siteMask,
-                                                   uint32_t *errWord) {
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    const uint32_t i = list[j];
-    const uint32_t p = site_pos(M, base + i);
-    uint32_t e = 0;
-    bool cand = false;
-    BaseCounts bc;
-    decode_bases(V, p, bc);
-    if (bc.bad) e |= kErrBadSnapshot;
-    else if (bc.valid) {
-      IndelInfo ii; PatRef d0, d1;
-      decode_indel_refs(V, p, ii, d0, d1);
-      if (ii.bad) e |= kErrBadSnapshot;
-      else {
-        const int ref = (int) ref_base(V, p);
-        bool full = true;
-        if (useTables && (ii.W4 | ii.W5) == 0)
-          full = lookup_needs_exact(D, bc.W[ref], bc.W[ref ^ 2], bc.W[ref ^ 1], bc.W[ref ^ 3]);
-        if (full) {
-          uint32_t W[6] = {bc.W[0], bc.W[1], bc.W[2], bc.W[3], ii.W4, ii.W5};
-          double lh[16];
-          genotype_likelihood16(P.lh, W, ref, lh);
-          Posterior po;
-          select_genotype(ref, lh, P.prior, P.g2i, po);
-          if (po.genotype > 9 && ii.isValidPlus == 0) e |= kErrGenotype;   // SNP_Caller.cpp:235-239
-          cand = po.genotype != hom_ref_genotype(ref);
+// Exact predicate for the flagged sites.  Lane phase: every lane decodes one listed site (overflow
+// gather, indel lists of position+1) and, when the site carries no indel evidence, asks the decision
+// bitmaps (the test the streaming kernel could not do for overflow-type sites).  Warp phase: the sites
+// that still need the full evaluator are taken two at a time; each half-warp computes the 16 genotype
+// likelihoods of one site in parallel (one genotype per lane), one lane runs the posterior / argmax.
+// A site that is NOT a candidate has its bit cleared in the site mask, so that one more ordered
+// compaction of the mask yields the candidate list.
+constexpr int kEvalThreads = 128;
+__global__ void __launch_bounds__(kEvalThreads) k_eval_list(SnapView V, DevSiteMap M, uint64_t base,
+                                                            const uint32_t *__restrict__ list, uint32_t n, bool useTables,
+                                                            DecisionTables D, EvalParams P, uint32_t *__restrict__ siteMask,
+                                                            uint32_t *errWord) {
+  __shared__ double lhS[kEvalThreads / 32][2][16];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, g = lane & 15;
+  const uint32_t warpsTotal = gridDim.x * (kEvalThreads / 32);
+  for (uint32_t j0 = (blockIdx.x * (kEvalThreads / 32) + warp) * 32u; j0 < n; j0 += warpsTotal * 32u) {
+    const uint32_t j = j0 + lane;
+    uint32_t e = 0, i = 0;
+    bool cand = false, full = false;
+    uint32_t W[6] = {0, 0, 0, 0, 0, 0};
+    int ref = 0; uint32_t validPlus = 0;
+    if (j < n) {
+      i = list[j];
+      const uint32_t p = site_pos(M, base + i);
+      BaseCounts bc;
+      decode_bases(V, p, bc);
+      if (bc.bad) e |= kErrBadSnapshot;
+      else if (bc.valid) {
+        IndelInfo ii; PatRef d0, d1;
+        decode_indel_refs(V, p, ii, d0, d1);
+        if (ii.bad) e |= kErrBadSnapshot;
+        else {
+          ref = (int) ref_base(V, p);
+          W[0] = bc.W[0]; W[1] = bc.W[1]; W[2] = bc.W[2]; W[3] = bc.W[3]; W[4] = ii.W4; W[5] = ii.W5;
+          validPlus = ii.isValidPlus;
+          full = true;
+          if (useTables && (ii.W4 | ii.W5) == 0) {
+            const uint32_t wr = ref == 0 ? W[0] : ref == 1 ? W[1] : ref == 2 ? W[2] : W[3];
+            const uint32_t wp = ref == 0 ? W[2] : ref == 1 ? W[3] : ref == 2 ? W[0] : W[1];
+            const uint32_t wq1 = ref == 0 ? W[1] : ref == 1 ? W[0] : ref == 2 ? W[3] : W[2];
+            const uint32_t wq3 = ref == 0 ? W[3] : ref == 1 ? W[2] : ref == 2 ? W[1] : W[0];
+            full = lookup_needs_exact(D, wr, wp, wq1, wq3);
+          }
         }
       }
     }
+    uint32_t todo = __ballot_sync(0xffffffffu, full);
+    while (todo) {
+      // the two lowest pending lanes -> half-warps 0 and 1
+      const int src0 = __ffs(todo) - 1;
+      uint32_t rest = todo & (todo - 1);
+      const int src1 = rest ? __ffs(rest) - 1 : src0;
+      rest = rest ? rest & (rest - 1) : 0;
+      const int src = half ? src1 : src0;
+      uint32_t Ws[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Ws[k] = __shfl_sync(0xffffffffu, W[k], src);
+      const int refS = __shfl_sync(0xffffffffu, ref, src);
+      const uint32_t vpS = __shfl_sync(0xffffffffu, validPlus, src);
+      uint32_t Wp[6];
+      const int wt = penalised_weights(Ws, refS, Wp);
+      lhS[warp][half][g] = genotype_lh_one(P.lh, Wp, wt, (int) g);
+      __syncwarp();
+      int res = 0;                                    // bit0 candidate, bit1 genotype error
+      if (g == 0) {
+        Posterior po;
+        select_genotype(refS, lhS[warp][half], P.prior, P.g2i, po);
+        res = (po.genotype != hom_ref_genotype(refS) ? 1 : 0) | ((po.genotype > 9 && vpS == 0) ? 2 : 0);   // SNP_Caller.cpp:235-239
+      }
+      const int res0 = __shfl_sync(0xffffffffu, res, 0), res1 = __shfl_sync(0xffffffffu, res, 16);
+      if ((int) lane == src0) { cand = res0 & 1; if (res0 & 2) e |= kErrGenotype; }
+      if ((int) lane == src1 && src1 != src0) { cand = res1 & 1; if (res1 & 2) e |= kErrGenotype; }
+      todo = rest;
+      __syncwarp();
+    }
     if (e) atomicOr(errWord, e);
-    if (!cand) atomicAnd(siteMask + (i >> 5), ~(1u << (i & 31)));
+    if (j < n && !cand) atomicAnd(siteMask + (i >> 5), ~(1u << (i & 31)));
   }
 }
 void launch_eval_list(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
                       bool useTables, const DecisionTables &D, const EvalParams &P, uint32_t *siteMask,
                       uint32_t *errWord, cudaStream_t s) {
   if (!n) return;
-  unsigned grid = (n + 127) / 128;
+  unsigned grid = (n + kEvalThreads - 1) / kEvalThreads;
   if (grid > 148 * 16) grid = 148 * 16;
-  k_eval_list<<<grid, 128, 0, s>>>(V, M, base, list, n, useTables, D, P, siteMask, errWord);
+  k_eval_list<<<grid, kEvalThreads, 0, s>>>(V, M, base, list, n, useTables, D, P, siteMask, errWord);
 }
 
 // ------------------------------------------------------------------------------ ordered compaction
@@ -421,8 +515,8 @@ void launch_mask_scatter(const uint32_t *mask, uint32_t nItems, const uint32_t *
 // One WARP per called site (computeMeta + outputPossibleSNPs, SNP_Caller.cpp:101-393).  The work of a
 // record is a few hundred dependent gathers (two 101-entry windows of decoded counters) plus up to 24
 // serial float Fisher recurrences; spread over the lanes it becomes: one genotype likelihood per lane
-// (16), one strand / base-quality test per lane (8 or 24), four window entries per lane and side, and
-// warp reductions for the window sums.  Every leaf routine is the one the serial build_called_site()
+// (16), four window entries per lane and side, and warp reductions for the window sums; the Fisher
+// tests of the record are done by k_bias.  Every leaf routine is the one the serial build_called_site()
 // uses, so the bits are the same.
 constexpr int kCandThreads = 128;
 struct CandWarpSmem {
@@ -484,24 +578,6 @@ __global__ void __launch_bounds__(kCandThreads) k_candidates(SnapView V, DevSite
     B.amb0 = site_pos(M, B.first);
     B.ambLast = site_pos(M, B.first + B.n - 1);
     const uint32_t idx = (uint32_t) (i - B.first);
-
-    // -- strand / base-quality bias: lane t -> (site k, kind, base)                     :248-274
-    if (lane < 24) {
-      const uint32_t k = lane >> 3, kind = (lane >> 2) & 1, b = lane & 3;
-      float v = 0.f;
-      bool have; uint64_t si = i;
-      if (isIndel) {
-        if (k == 0) { have = idx != 0; si = i - 1; }
-        else if (k == 1) { have = idx + nextBp < B.n; si = i + nextBp; }
-        else have = true;
-      } else have = (k == 0);
-      if (have) {
-        BaseCounts nb;
-        if (si == i) nb = bc; else decode_bases(V, site_pos(M, si), nb);
-        v = kind ? base_quality_bias(P.lnfact, nb.W[b], nb.F[b], nb.R[b]) : strand_bias(P.lnfact, nb.F[b], nb.R[b]);
-      }
-      if (kind) o.bqb[k][b] = v; else o.sb[k][b] = v;
-    }
 
     // -- windows (reference's un-offset mwInfo indexing)                                 :276-367
     const bool haveLeft = idx >= (uint32_t) kWindow;
@@ -594,6 +670,117 @@ void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, co
   unsigned grid = (n + (kCandThreads / 32) - 1) / (kCandThreads / 32);
   if (grid > 148 * 32) grid = 148 * 32;
   k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, list, n, P, out, errWord);
+}
+
+// ------------------------------------------------------------------------------ Fisher tests of the candidates
+// Strand bias and base-quality bias (computeStrandBias / computeBaseQualityBias, SNPFunctions.cpp:137-159)
+// of every called site: SB and BQB for the four bases of the site itself (SNP rows) or of the three sites
+// {index-1, index+nextBp, index} (indel rows, SNP_Caller.cpp:248-274).  A test is a serial float
+// recurrence of ~(W + 4*depth) steps that cannot be split without changing its rounding, and most
+// (site, base) slots are empty (a base that was never seen), so a slot-per-lane mapping would leave
+// ~85 % of the lanes idle.  Each warp therefore scans slots 32 at a time, answers the empty ones on the
+// spot and queues the non-empty ones in shared memory; whenever 32 are queued every lane runs one test.
+// The log-factorial table lnfactC(n) = lgammaf(n+1) for n < kLnSmem is staged in shared memory.
+constexpr int kBiasThreads = 256;
+constexpr int kLnSmem = 4096;
+constexpr int kBiasQueue = 96;
+struct BiasTask { uint32_t W, F, R, dst; };      // dst = record * 12 + k * 4 + base, bit 31 = base-quality test
+
+__device__ __forceinline__ void run_bias_task(const LnFact &L, const BiasTask &t, gt16_called_site *out) {
+  const uint32_t d = t.dst & 0x7FFFFFFFu;
+  gt16_called_site &o = out[d / 12];
+  const uint32_t k = (d % 12) >> 2, b = d & 3;
+  if (t.dst >> 31) o.bqb[k][b] = base_quality_bias(L, t.W, t.F, t.R);
+  else o.sb[k][b] = strand_bias(L, t.F, t.R);
+}
+
+__global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M, uint64_t base,
+                                                       const uint32_t *__restrict__ list, uint32_t n, LnFact G,
+                                                       gt16_called_site *__restrict__ out) {
+  __shared__ float lnS[kLnSmem];
+  __shared__ BiasTask queue[kBiasThreads / 32][2][kBiasQueue];     // [warp][0 = short walks, 1 = long walks]
+  const uint32_t nS = G.size < (uint32_t) kLnSmem ? G.size : (uint32_t) kLnSmem;
+  for (uint32_t k = threadIdx.x; k < nS; k += kBiasThreads) lnS[k] = G.tab[k];
+  __syncthreads();
+  LnFact L;
+  L.tab = lnS; L.size = nS; L.far = G.tab; L.farSize = G.size;
+  const float sbEmpty = strand_bias(L, 0, 0), bqbEmpty = base_quality_bias(L, 0, 0, 0);   // a base that was never seen
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
+  uint32_t qlen[2] = {0, 0};
+  auto drain = [&](int cls, uint32_t count) {
+    if (lane < count) run_bias_task(L, queue[warp][cls][lane], out);
+  };
+  auto push = [&](int cls, bool want, const BiasTask &t) {
+    BiasTask *q = queue[warp][cls];
+    const uint32_t bal = __ballot_sync(0xffffffffu, want);
+    if (!bal) return;
+    if (want) q[qlen[cls] + __popc(bal & ltMask)] = t;
+    qlen[cls] += __popc(bal);
+    __syncwarp();
+    while (qlen[cls] >= 32) {
+      drain(cls, 32);
+      __syncwarp();
+      const uint32_t restN = qlen[cls] - 32;
+      BiasTask keep[2];
+      keep[0] = q[32 + lane]; keep[1] = q[64 + lane];
+      __syncwarp();
+      if (lane < restN) q[lane] = keep[0];
+      if (32 + lane < restN) q[32 + lane] = keep[1];
+      qlen[cls] = restN;
+      __syncwarp();
+    }
+  };
+  const uint32_t nSlots = n * 12u, warpsTotal = gridDim.x * (kBiasThreads / 32);
+  for (uint32_t chunk = blockIdx.x * (kBiasThreads / 32) + warp; chunk * 32u < nSlots; chunk += warpsTotal) {
+    const uint32_t slot = chunk * 32u + lane;
+    bool pending = false;
+    BiasTask t; t.W = t.F = t.R = 0; t.dst = slot;
+    if (slot < nSlots) {
+      const uint32_t j = slot / 12, k = (slot % 12) >> 2, b = slot & 3;
+      const gt16_called_site &o = out[j];
+      const uint32_t isIndel = o.is_indel;
+      const uint32_t nextBp = (isIndel && o.indel[0].type == 'D') ? o.indel[0].len : 0;
+      const uint64_t i = base + list[j];
+      const uint64_t bFirst = (i / kBatch) * (uint64_t) kBatch;
+      const uint64_t left = M.totalSites - bFirst;
+      const uint32_t bn = left < kBatch ? (uint32_t) left : kBatch, idx = (uint32_t) (i - bFirst);
+      bool have; uint64_t si = i;
+      if (isIndel) {
+        if (k == 0) { have = idx != 0; si = i - 1; }
+        else if (k == 1) { have = idx + nextBp < bn; si = i + nextBp; }
+        else have = true;
+      } else have = (k == 0);
+      float sbv = 0.f, bqv = 0.f;
+      if (have) {
+        BaseCounts nb;
+        decode_bases(V, site_pos(M, si), nb);
+        t.W = b == 0 ? nb.W[0] : b == 1 ? nb.W[1] : b == 2 ? nb.W[2] : nb.W[3];
+        t.F = b == 0 ? nb.F[0] : b == 1 ? nb.F[1] : b == 2 ? nb.F[2] : nb.F[3];
+        t.R = b == 0 ? nb.R[0] : b == 1 ? nb.R[1] : b == 2 ? nb.R[2] : nb.R[3];
+        pending = (t.W | t.F | t.R) != 0;
+        sbv = sbEmpty; bqv = bqbEmpty;
+      }
+      if (!pending) { out[j].sb[k][b] = sbv; out[j].bqb[k][b] = bqv; }
+    }
+    // strand test: ~(F+R) steps; base-quality test: ~(W + 4(F+R)) steps
+    const uint32_t costS = t.F + t.R, costB = t.W + 4u * (t.F + t.R);
+    BiasTask tb = t; tb.dst |= 0x80000000u;
+    push(0, pending && costS < 96u, t);
+    push(1, pending && costS >= 96u, t);
+    push(0, pending && costB < 96u, tb);
+    push(1, pending && costB >= 96u, tb);
+  }
+  drain(0, qlen[0]);
+  drain(1, qlen[1]);
+}
+void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
+                 const EvalParams &P, gt16_called_site *out, cudaStream_t s) {
+  if (!n) return;
+  const uint32_t chunks = (n * 12u + 31) / 32, perBlock = kBiasThreads / 32;
+  unsigned grid = (chunks + perBlock * 4 - 1) / (perBlock * 4);     // >= 4 chunks (128 slots) per warp
+  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid < 1) grid = 1;
+  k_bias<<<grid, kBiasThreads, 0, s>>>(V, M, base, list, n, P.lnfact, out);
 }
 
 // ------------------------------------------------------------------------------ operator seam

@@ -60,6 +60,10 @@ void launch_mask_scatter(const uint32_t *mask, uint32_t nItems, const uint32_t *
 void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
                        const EvalParams &P, gt16_called_site *out, uint32_t *errWord, cudaStream_t s);
 
+// strand-bias / base-quality-bias Fisher tests of the records written by launch_candidates (same list)
+void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
+                 const EvalParams &P, gt16_called_site *out, cudaStream_t s);
+
 // operator seam kernels
 void launch_op_likelihood(const EvalParams &P, const uint8_t *w, size_t wStride, const uint8_t *ref,
                           size_t refStride, double *lh, uint32_t n, cudaStream_t s);

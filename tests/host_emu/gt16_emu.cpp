@@ -16,7 +16,7 @@ static const LnFact &lnfact_table() {
   if (g_lnfact.empty()) {
     g_lnfact.resize(1u << 16);
     for (uint32_t k = 0; k < g_lnfact.size(); ++k) g_lnfact[k] = lgammaf((float) (k + 1));
-    L.tab = g_lnfact.data(); L.size = (uint32_t) g_lnfact.size();
+    L.tab = g_lnfact.data(); L.size = (uint32_t) g_lnfact.size(); L.far = nullptr; L.farSize = 0;
   }
   return L;
 }
