@@ -189,11 +189,9 @@ class LoadedInput:
 def call_to_txt(caller, inp, txt_path, shards=1, resident=False):
     """Run the fused path over all processed sites in `shards` batch-aligned shards and write .txt."""
     L = caller.L
-    B = BATCH_SITES
-    total = inp.total_sites
-    nb = (total + B - 1) // B
-    shards = max(1, min(shards, nb if nb else 1))
-    cuts = [min(total, (nb * d // shards) * B) for d in range(shards)] + [total]
+    from .sharding import shard_cuts
+    cuts = shard_cuts(inp.total_sites, shards)
+    shards = len(cuts) - 1
     carry = (ctypes.c_float * 2)(0.0, 0.0)
     stats_all = []
     dev = ctypes.c_void_p()

@@ -137,6 +137,11 @@ struct LhTables {
   double p_err_i;        // Ini_UnbalanceSubError / 2  (:299)
 };
 
+// test builds (tests/host_emu) may route table reads through a lazily filled table
+#ifndef GT16_TABLE_READ
+#define GT16_TABLE_READ(T, k, w_total, w_target) ((T).t[k][(w_total) * kFisherN + (w_target)])
+#endif
+
 GT16_HD double table_lookup(const LhTables &T, int k, int w_target, int err, int w_total) {
   if (w_target >= kFisherN || w_total >= kFisherN) {            // likelihood_cache.cpp:70-72
     double dist = chi2_uniform_distance(w_target, w_total, err, w_total);
@@ -144,7 +149,7 @@ GT16_HD double table_lookup(const LhTables &T, int k, int w_target, int err, int
     if (di >= kYcsqN) di = kYcsqN - 1;
     return T.ycsq[di];
   }
-  return T.t[k][w_total * kFisherN + w_target];
+  return GT16_TABLE_READ(T, k, w_total, w_target);
 }
 
 GT16_HD double scale_back(double ret) {  // checkOverflowAndReturn, FisherExactTest.cpp:101-114

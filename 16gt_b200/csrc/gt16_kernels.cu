@@ -675,30 +675,75 @@ void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, co
 // ------------------------------------------------------------------------------ Fisher tests of the candidates
 // Strand bias and base-quality bias (computeStrandBias / computeBaseQualityBias, SNPFunctions.cpp:137-159)
 // of every called site: SB and BQB for the four bases of the site itself (SNP rows) or of the three sites
-// {index-1, index+nextBp, index} (indel rows, SNP_Caller.cpp:248-274).  A test is a serial float
-// recurrence of ~(W + 4*depth) steps that cannot be split without changing its rounding, and most
-// (site, base) slots are empty (a base that was never seen), so a slot-per-lane mapping would leave
-// ~85 % of the lanes idle.  Each warp therefore scans slots 32 at a time, answers the empty ones on the
-// spot and queues the non-empty ones in shared memory; whenever 32 are queued every lane runs one test.
-// The log-factorial table lnfactC(n) = lgammaf(n+1) for n < kLnSmem is staged in shared memory.
+// {index-1, index+nextBp, index} (indel rows, SNP_Caller.cpp:248-274).
+//
+// A test (fisher2tailC, SNPFunctions.cpp:94-135) is a serial float recurrence -- a left and a right walk
+// over the hypergeometric support, a few to several hundred steps -- that cannot be split or reordered
+// without changing its rounding, and most (site, base) slots are empty (a base that was never seen).  A
+// slot-per-lane mapping leaves ~80 % of the lanes idle, so the kernel runs the walks as per-lane state
+// machines: a warp decodes 32 slots at a time and queues the non-empty tests in shared memory; every lane
+// owns one test at a time and advances it by one step per iteration of a warp-uniform loop (both walks
+// share one step body: the left walk's single factor is multiplied by an exact 1.0f), and a lane that
+// finishes takes the next queued test at the next refill point.  lnfactC(n) = lgammaf(n+1) for
+// n < kLnSmem is staged in shared memory.
 constexpr int kBiasThreads = 256;
 constexpr int kLnSmem = 4096;
-constexpr int kBiasQueue = 96;
+constexpr int kBiasQueue = 128;
+constexpr int kBiasStepsPerRefill = 12;
 struct BiasTask { uint32_t W, F, R, dst; };      // dst = record * 12 + k * 4 + base, bit 31 = base-quality test
 
-__device__ __forceinline__ void run_bias_task(const LnFact &L, const BiasTask &t, gt16_called_site *out) {
-  const uint32_t d = t.dst & 0x7FFFFFFFu;
-  gt16_called_site &o = out[d / 12];
-  const uint32_t k = (d % 12) >> 2, b = d & 3;
-  if (t.dst >> 31) o.bqb[k][b] = base_quality_bias(L, t.W, t.F, t.R);
-  else o.sb[k][b] = strand_bias(L, t.F, t.R);
+struct FisherWalk {                               // state of one fisher2tailC evaluation
+  int n1_, n_1, n, x, lo, hi, n11;
+  float pox, poa, poa_e, two;
+  uint32_t dst;
+  int phase;                                      // 0 idle, 1 left walk, 2 right walk
+  bool stopAtZero;
+};
+
+// fisher2tailC(n11, n1_, n_1, n) up to the start of the left walk (same expressions, same order)
+__device__ __forceinline__ void walk_begin(const LnFact &L, FisherWalk &w, int n11, int n1_, int n_1, int n, uint32_t dst) {
+  n += n11 + n1_ + n_1;
+  n1_ += n11;
+  n_1 += n11;
+  const float poa = expf_glibc(lnbicoC(L, n1_, n11) + lnbicoC(L, n - n1_, n_1 - n11) - lnbicoC(L, n, n_1));
+  w.n11 = n11; w.n1_ = n1_; w.n_1 = n_1; w.n = n; w.dst = dst;
+  w.poa = poa; w.pox = poa; w.two = 0; w.two += poa; w.poa_e = poa * 1.000000001f;
+  w.stopAtZero = n <= 46340;
+  w.lo = (n1_ + n_1 - n > 0) ? n1_ + n_1 - n : 0;
+  w.hi = (n1_ < n_1) ? n1_ : n_1;
+  w.x = n11;
+  w.phase = 1;
+  if (!(w.x > w.lo)) { w.phase = 2; w.x = n11 + 1; w.pox = poa; if (!(w.x <= w.hi)) w.phase = 3; }
+}
+// one step of whichever walk the lane is in; phase 3 = finished (result in w.two)
+__device__ __forceinline__ void walk_step(FisherWalk &w) {
+  if (w.phase != 1 && w.phase != 2) return;
+  const bool left = w.phase == 1;
+  const int x = w.x;
+  const int a = left ? (int) ((uint32_t) x * (uint32_t) (w.n + x - w.n1_ - w.n_1)) : w.n1_ - (x - 1);
+  const int b = left ? 1 : w.n_1 - (x - 1);
+  const int den = left ? (int) ((uint32_t) (w.n1_ - x + 1) * (uint32_t) (w.n_1 - x + 1))
+                       : (int) ((uint32_t) (w.n + x - w.n1_ - w.n_1) * (uint32_t) x);
+  float pox = w.pox * (float) a;
+  pox = pox * (float) b;                          // left walk: times 1.0f, exact
+  pox = pox / (float) den;
+  w.pox = pox;
+  w.two += pox * (pox < w.poa_e);
+  const bool zero = w.stopAtZero && pox == 0.0f;
+  if (left) {
+    w.x = x - 1;
+    if (zero || !(w.x > w.lo)) { w.phase = 2; w.x = w.n11 + 1; w.pox = w.poa; if (!(w.x <= w.hi)) w.phase = 3; }
+  } else {
+    w.x = x + 1;
+    if (zero || !(w.x <= w.hi)) w.phase = 3;
+  }
 }
 
 __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M, uint64_t base,
                                                        const uint32_t *__restrict__ list, uint32_t n, LnFact G,
                                                        gt16_called_site *__restrict__ out) {
   __shared__ float lnS[kLnSmem];
-  __shared__ BiasTask queue[kBiasThreads / 32][2][kBiasQueue];     // [warp][0 = short walks, 1 = long walks]
+  __shared__ BiasTask queue[kBiasThreads / 32][kBiasQueue];
   const uint32_t nS = G.size < (uint32_t) kLnSmem ? G.size : (uint32_t) kLnSmem;
   for (uint32_t k = threadIdx.x; k < nS; k += kBiasThreads) lnS[k] = G.tab[k];
   __syncthreads();
@@ -706,30 +751,41 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
   L.tab = lnS; L.size = nS; L.far = G.tab; L.farSize = G.size;
   const float sbEmpty = strand_bias(L, 0, 0), bqbEmpty = base_quality_bias(L, 0, 0, 0);   // a base that was never seen
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
-  uint32_t qlen[2] = {0, 0};
-  auto drain = [&](int cls, uint32_t count) {
-    if (lane < count) run_bias_task(L, queue[warp][cls][lane], out);
+  BiasTask *q = queue[warp];
+  uint32_t qhead = 0, qtail = 0;                   // ring indices (monotonic), entries live in q[i % kBiasQueue]
+  FisherWalk w;
+  w.phase = 0;
+
+  auto store_result = [&]() {                      // min(1, two) into the record (computeStrandBias / ...BaseQualityBias)
+    const uint32_t d = w.dst & 0x7FFFFFFFu;
+    gt16_called_site &o = out[d / 12];
+    const uint32_t k = (d % 12) >> 2, b = d & 3;
+    const float v = fminf(1.0f, w.two);
+    if (w.dst >> 31) o.bqb[k][b] = v; else o.sb[k][b] = v;
   };
-  auto push = [&](int cls, bool want, const BiasTask &t) {
-    BiasTask *q = queue[warp][cls];
-    const uint32_t bal = __ballot_sync(0xffffffffu, want);
-    if (!bal) return;
-    if (want) q[qlen[cls] + __popc(bal & ltMask)] = t;
-    qlen[cls] += __popc(bal);
-    __syncwarp();
-    while (qlen[cls] >= 32) {
-      drain(cls, 32);
-      __syncwarp();
-      const uint32_t restN = qlen[cls] - 32;
-      BiasTask keep[2];
-      keep[0] = q[32 + lane]; keep[1] = q[64 + lane];
-      __syncwarp();
-      if (lane < restN) q[lane] = keep[0];
-      if (32 + lane < restN) q[32 + lane] = keep[1];
-      qlen[cls] = restN;
-      __syncwarp();
+  auto refill = [&]() {                            // finished lanes store; idle lanes take queued tests
+    if (w.phase == 3) { store_result(); w.phase = 0; }
+    const uint32_t idle = __ballot_sync(0xffffffffu, w.phase == 0);
+    const uint32_t avail = qtail - qhead;
+    if (idle && avail) {
+      const uint32_t rank = __popc(idle & ltMask);
+      if (w.phase == 0 && rank < avail) {
+        const BiasTask t = q[(qhead + rank) % kBiasQueue];
+        if (t.dst >> 31) { const int S = (int) ((t.F + t.R) * 4); walk_begin(L, w, (int) t.W, S, S, S, t.dst); }      // getBaseQualityBias
+        else { const int S = (int) (t.F + t.R); walk_begin(L, w, (int) t.F, (int) t.R, (int) (S * 0.5), (int) (S * 0.5), t.dst); }  // getStrandBiasC
+      }
+      const uint32_t taken = __popc(idle) < avail ? __popc(idle) : avail;
+      qhead += taken;
     }
+    __syncwarp();
   };
+  auto push = [&](bool want, const BiasTask &t) {
+    const uint32_t bal = __ballot_sync(0xffffffffu, want);
+    if (want) q[(qtail + __popc(bal & ltMask)) % kBiasQueue] = t;
+    qtail += __popc(bal);
+    __syncwarp();
+  };
+
   const uint32_t nSlots = n * 12u, warpsTotal = gridDim.x * (kBiasThreads / 32);
   for (uint32_t chunk = blockIdx.x * (kBiasThreads / 32) + warp; chunk * 32u < nSlots; chunk += warpsTotal) {
     const uint32_t slot = chunk * 32u + lane;
@@ -762,22 +818,30 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
       }
       if (!pending) { out[j].sb[k][b] = sbv; out[j].bqb[k][b] = bqv; }
     }
-    // strand test: ~(F+R) steps; base-quality test: ~(W + 4(F+R)) steps
-    const uint32_t costS = t.F + t.R, costB = t.W + 4u * (t.F + t.R);
     BiasTask tb = t; tb.dst |= 0x80000000u;
-    push(0, pending && costS < 96u, t);
-    push(1, pending && costS >= 96u, t);
-    push(0, pending && costB < 96u, tb);
-    push(1, pending && costB >= 96u, tb);
+    push(pending, t);                               // strand test
+    push(pending, tb);                              // base-quality test
+    // keep room for the next chunk's (up to 64) tests
+    while (qtail - qhead > (uint32_t) (kBiasQueue - 64)) {
+      refill();
+#pragma unroll 1
+      for (int it = 0; it < kBiasStepsPerRefill; ++it) walk_step(w);
+    }
   }
-  drain(0, qlen[0]);
-  drain(1, qlen[1]);
+  while (true) {                                    // drain
+    refill();
+    if (!__any_sync(0xffffffffu, w.phase != 0)) break;
+#pragma unroll 1
+    for (int it = 0; it < kBiasStepsPerRefill; ++it) walk_step(w);
+  }
 }
 void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
                  const EvalParams &P, gt16_called_site *out, cudaStream_t s) {
   if (!n) return;
   const uint32_t chunks = (n * 12u + 31) / 32, perBlock = kBiasThreads / 32;
-  unsigned grid = (chunks + perBlock * 4 - 1) / (perBlock * 4);     // >= 4 chunks (128 slots) per warp
+  // the walks are long dependent chains: what matters is how many run at once, so spread the chunks
+  // over as many resident warps as the device holds (4 blocks of 8 warps per SM)
+  unsigned grid = (chunks + perBlock - 1) / perBlock;
   if (grid > 148 * 4) grid = 148 * 4;
   if (grid < 1) grid = 1;
   k_bias<<<grid, kBiasThreads, 0, s>>>(V, M, base, list, n, P.lnfact, out);

@@ -189,6 +189,7 @@ def main():
         torch.cuda.synchronize()
 
     capi = importlib.import_module("16gt_b200.capi")
+    sharding = importlib.import_module("16gt_b200.sharding")
     L = capi.capi()
     wd = tempfile.mkdtemp(prefix="gt16_bench_%d_" % rank)
     try:
@@ -229,10 +230,7 @@ def main():
             barrier()
             dt = time.perf_counter() - t0
             clocks = sampler.stop() if sampler else None
-            if world > 1:
-                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
+            dt = sharding.max_over_ranks(dt, dist if world > 1 else None, "cuda")
             return dt, stats, clocks
 
         dt, stats, clocks = timed(step_resident, args.warmup, args.steps, rank == 0)

@@ -6,9 +6,25 @@
 #include <string.h>
 #include <vector>
 #include <string>
+// Table reads go through emu_lazy_entry(): a null table pointer means "evaluate the entry on first use
+// with the product's own table builder (table_entry) and memoise it", so the emulation needs no 320 MB
+// prefill; a non-null pointer is read directly (LikelihoodCache layout).
+static double emu_lazy_entry(const double *tab, int k, int w_total, int w_target);
+#define GT16_TABLE_READ(T, k, w_total, w_target) emu_lazy_entry((T).t[k], k, w_total, w_target)
 #include "../../16gt_b200/csrc/gt16_core.cuh"
 
 using namespace gt16;
+
+static ErrFractions g_lazyErr;
+static std::vector<std::vector<double> > g_lazyRows[10];
+static double emu_lazy_entry(const double *tab, int k, int w_total, int w_target) {
+  if (tab) return tab[(size_t) w_total * kFisherN + w_target];
+  if (g_lazyRows[k].empty()) g_lazyRows[k].resize(kFisherN);
+  std::vector<double> &row = g_lazyRows[k][w_total];
+  if (row.empty()) row.assign(kFisherN, -1.0);
+  if (row[w_target] < 0) row[w_target] = table_entry(w_total, w_target, g_lazyErr.e[k]);
+  return row[w_target];
+}
 
 static std::vector<float> g_lnfact;
 static const LnFact &lnfact_table() {
@@ -24,8 +40,14 @@ static const LnFact &lnfact_table() {
 static EvalParams make_params(const double *lc, double balance, double unbalance, double *prior, uint32_t *g2i) {
   static const uint32_t kG2I[16] = {0, 1, 2, 3, 9, 10, 11, 18, 19, 27, 4, 12, 20, 28, 36, 37};
   EvalParams P;
-  for (int k = 0; k < 10; ++k) P.lh.t[k] = lc + (size_t) k * kFisherN * kFisherN;
-  P.lh.ycsq = lc + (size_t) 10 * kFisherN * kFisherN;
+  static std::vector<double> ycsq;
+  if (!lc) {                                   // lazy tables built by the product's own routines
+    ErrFractions e = err_fractions((float) balance, (float) unbalance);
+    if (memcmp(&e, &g_lazyErr, sizeof(e)) != 0) { g_lazyErr = e; for (auto &t : g_lazyRows) t.clear(); }
+    if (ycsq.empty()) { ycsq.resize(kYcsqN); for (int i = 0; i < kYcsqN; ++i) ycsq[i] = chisqr1(i / 10.0); }
+  }
+  for (int k = 0; k < 10; ++k) P.lh.t[k] = lc ? lc + (size_t) k * kFisherN * kFisherN : nullptr;
+  P.lh.ycsq = lc ? lc + (size_t) 10 * kFisherN * kFisherN : ycsq.data();
   P.lh.p_err_s = balance / 4; P.lh.p_err_i = unbalance / 2;
   make_prior(prior);
   memcpy(g2i, kG2I, sizeof(kG2I));

@@ -1,0 +1,89 @@
+"""CPU tests of the drop-in boundary: libgt16.so loads and exports every symbol include/gt16.h declares,
+refuses to compute without a GPU (there is no CPU path), and its host-side format code (index reader,
+coordinate translation, snapshot reader, prior table) behaves like the reference's."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import gt16_testlib as T
+
+
+def have_gpu():
+    n = ctypes.c_int()
+    return T.capi().gt16_device_count(ctypes.byref(n)) == 0 and n.value > 0
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(T.ROOT, "include", "gt16.h")).read()
+    declared = sorted(set(re.findall(r"\b(gt16_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 28
+    lib = ctypes.CDLL(T.LIB)
+    for name in declared:
+        assert hasattr(lib, name), "libgt16.so does not export " + name
+    bound = set(T.capi()._signatures)
+    assert bound == set(declared), "ctypes binding and header disagree: %s" % (bound ^ set(declared))
+
+
+def test_no_cpu_fallback():
+    if have_gpu():
+        pytest.skip("a GPU is present")
+    L = T.capi()
+    ctx = ctypes.c_void_p()
+    assert L.gt16_ctx_create(0, ctypes.byref(ctx)) == -2          # GT16_ENODEVICE
+    assert b"no CPU path" in L.gt16_last_error(None)
+    r = subprocess.run([T.CLI, "-i", "/nonexistent/x", "-o", "/tmp/y"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1
+
+
+def test_prior_table_matches_reference():
+    g = np.load(os.path.join(T.GOLDEN, "operator_vectors.npz"))
+    prior = np.zeros(256)
+    assert T.capi().gt16_create_snp_prior(prior.ctypes.data) == 0
+    assert np.array_equal(prior, g["prior"])
+
+
+def test_index_and_snapshot_readers(tmp_path):
+    idx, out, region = T.regenerate("stress_small", tmp_path)
+    inp = T.LoadedInput(idx, out + ".snapshot", None, pinned=0)
+    try:
+        L = T.capi()
+        n = L.gt16_index_length(inp.ix)
+        assert n == inp.view.text_length == 400000
+        assert inp.view.n_overflow_regions == 7
+        # coordinate translation: contig boundaries, 1-based positions (getChrAndPos)
+        pos = ctypes.c_uint32()
+        assert L.gt16_index_translate(inp.ix, 0, ctypes.byref(pos)) == b"chr1" and pos.value == 1
+        ann = open(idx + ".ann").read().split("\n")
+        start2 = int(ann[4].split()[0])
+        assert L.gt16_index_translate(inp.ix, start2 - 1, ctypes.byref(pos)) == b"chr1" and pos.value == start2
+        assert L.gt16_index_translate(inp.ix, start2, ctypes.byref(pos)) == b"chr2" and pos.value == 1
+        # packed reference equals the .pac bytes re-packed 16 bases per word
+        nw = ctypes.c_uint32()
+        ptr = L.gt16_index_packed(inp.ix, ctypes.byref(nw))
+        words = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint32)), (nw.value,))
+        pac = np.fromfile(idx + ".pac", dtype=np.uint8)[:(n + 3) // 4]
+        pad = np.zeros((-len(pac)) % 4, dtype=np.uint8)
+        want = np.concatenate([pac, pad]).reshape(-1, 4).astype(np.uint32)
+        want = (want[:, 0] << 24) | (want[:, 1] << 16) | (want[:, 2] << 8) | want[:, 3]
+        assert np.array_equal(words[:len(want)], want)
+    finally:
+        inp.close()
+    err = ctypes.create_string_buffer(256)
+    hs = ctypes.c_void_p()
+    assert T.capi().gt16_snapshot_read(b"/nonexistent.snapshot", 0, ctypes.byref(hs), err, 256) == -4
+    assert b"Error opening" in err.value
+
+
+def test_cli_usage_errors():
+    r = subprocess.run([T.CLI], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Usage:" in r.stderr and "-e <Exome Region Index>" in r.stderr
+    r = subprocess.run([T.CLI, "-i", "a", "-i", "b"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Multiple indexes" in r.stderr
+    r = subprocess.run([T.CLI, "-o", "x"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Missing index" in r.stderr
+    r = subprocess.run([T.CLI, "-q"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Invalid arguments" in r.stderr

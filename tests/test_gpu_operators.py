@@ -1,0 +1,149 @@
+"""GPU tests of the operator seam (the five entry points that replace FisherExactTest.h:10-23) and of the
+device-built tables, through the C ABI, against the reference's golden vectors.
+
+Tolerances (BASELINE.json north_star): genotypes identical; likelihood / posterior values within 1e-6
+relative in log space (the device's log/exp differ from glibc's in the last ulp, so table entries -- and
+everything derived from them -- are not bit-identical); SB / BQB (float) within 1e-6 relative."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import gt16_testlib as T
+
+pytestmark = pytest.mark.gpu
+N = 2000
+LC_BYTES = 10 * N * N * 8 + 15000 * 8
+
+
+def log_close(a, b, rel=1e-6):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert np.array_equal(a == 0, b == 0), "zero / non-zero pattern differs (txt2vcf.pl drops zero Optb rows)"
+    nz = b != 0
+    la, lb = np.log(a[nz]), np.log(b[nz])
+    tol = rel * np.maximum(1.0, np.abs(lb))
+    bad = np.abs(la - lb) > tol
+    assert not bad.any(), "max log error %.3g" % np.max(np.abs(la - lb) / np.maximum(1.0, np.abs(lb)))
+
+
+def run_operator_seam(c, g):
+    L = c.L
+    n = len(g["ref"])
+    # the reference's AoS layout: InputStat (144 B: W @0, F @24, R @48 ...), MetaReference.refChar, SnpCallingInfo (168 B)
+    istat = np.zeros((n, 36), dtype=np.uint32)
+    istat[:, :6] = g["W"]
+    mref = np.zeros((n, 270), dtype=np.uint8)
+    REFCHAR_OFF = 257
+    mref[:, REFCHAR_OFF] = g["ref"]
+    lh = np.zeros((n, 16))
+    c.check(L.gt16_compute_genotype_likelihood(c.ctx, istat.ctypes.data, 144, mref.ctypes.data + REFCHAR_OFF, 270,
+                                               lh.ctypes.data, n, 0.01, 0.005))
+    info = np.full((n, 168), 0xAB, dtype=np.uint8)
+    ref = np.ascontiguousarray(g["ref"])
+    c.check(L.gt16_compute_genotype(c.ctx, ref.ctypes.data, lh.ctypes.data, info.ctypes.data, 168, n))
+    pD = info[:, 0:8].copy().view(np.float64)[:, 0]
+    gt = info[:, 8:12].copy().view(np.int32)[:, 0]
+    flh = info[:, 16:144].copy().view(np.float64)
+    best = info[:, 144:152].copy().view(np.float64)[:, 0]
+    second = info[:, 152:160].copy().view(np.float64)[:, 0]
+    assert (info[:, 12:16] == 0xAB).all() and (info[:, 160:168] == 0xAB).all()     # secondGenotype, rfProb/rfMode untouched
+    return lh, flh, pD, best, second, gt
+
+
+def test_device_tables_match_reference_prefill(gpu_caller):
+    g = np.load(os.path.join(T.GOLDEN, "lc_samples.npz"))
+    buf = np.zeros(LC_BYTES // 8)
+    gpu_caller.check(gpu_caller.L.gt16_prefill_likelihood_cache(gpu_caller.ctx, 0.01, 0.005, buf.ctypes.data))
+    got = buf[(g["k"].astype(np.int64) - 1) * N * N + g["i"].astype(np.int64) * N + g["j"]]
+    np.testing.assert_allclose(got, g["value"], rtol=1e-11, atol=0)
+    assert np.array_equal(got == 0, g["value"] == 0)
+    np.testing.assert_allclose(buf[10 * N * N:], g["ycsq"], rtol=1e-12)
+    # rebuild the decision bitmaps the fixture's context had
+    gpu_caller.check(gpu_caller.L.gt16_configure(gpu_caller.ctx, 0.01, 0.005, 1))
+
+
+def test_operator_seam_matches_reference(gpu_caller):
+    g = np.load(os.path.join(T.GOLDEN, "operator_vectors.npz"))
+    lh, flh, pD, best, second, gt = run_operator_seam(gpu_caller, g)
+    assert np.array_equal(gt, g["genotype"])
+    for got, name in ((lh, "lh"), (flh, "flh"), (pD, "pD"), (best, "bestD"), (second, "secondD")):
+        log_close(got, g[name])
+
+
+def test_bias_operator_matches_reference(gpu_caller):
+    g = np.load(os.path.join(T.GOLDEN, "operator_vectors.npz"))
+    m = len(g["bias_W"])
+    W, F, R = (np.ascontiguousarray(g[x]) for x in ("bias_W", "bias_F", "bias_R"))
+    sb = np.zeros((m, 4), dtype=np.float32); bqb = np.zeros((m, 4), dtype=np.float32)
+    gpu_caller.check(gpu_caller.L.gt16_compute_bias(gpu_caller.ctx, W.ctypes.data, F.ctypes.data, R.ctypes.data, 16, m,
+                                                    sb.ctypes.data, bqb.ctypes.data))
+    # float path: table of the host's lgammaf + re-implemented glibc expf -> expected bit-identical
+    assert np.array_equal(sb.view(np.uint32), g["sb"].view(np.uint32))
+    assert np.array_equal(bqb.view(np.uint32), g["bqb"].view(np.uint32))
+
+
+def test_custom_prior_and_genotype_table(gpu_caller):
+    """copySnpPriorToGPU / copyGenotypeTableToGPU are honoured (flat prior -> argmax of the likelihood)"""
+    L = gpu_caller.L
+    g = np.load(os.path.join(T.GOLDEN, "operator_vectors.npz"))
+    flat = np.ones(256)
+    gpu_caller.check(L.gt16_copy_snp_prior(gpu_caller.ctx, flat.ctypes.data))
+    try:
+        lh, flh, pD, best, second, gt = run_operator_seam(gpu_caller, g)
+        nz = pD > 0
+        assert np.array_equal(gt[nz], np.argmax(flh[nz], axis=1))
+        np.testing.assert_allclose(flh[nz], lh[nz] / pD[nz, None], rtol=1e-15)
+    finally:
+        gpu_caller.check(L.gt16_copy_snp_prior(gpu_caller.ctx, np.ascontiguousarray(g["prior"]).ctypes.data))
+        gpu_caller.check(L.gt16_copy_genotype_table(gpu_caller.ctx, T.G2I.ctypes.data))
+        gpu_caller.check(L.gt16_configure(gpu_caller.ctx, 0.01, 0.005, 1))
+
+
+def test_called_site_records_against_oracle(gpu_caller, tmp_path):
+    """the raw records behind the .txt rows: doubles within 1e-6 in log space of the C oracle's operator outputs
+    for the same W vectors, integer fields consistent"""
+    O = ctypes.CDLL(T.ORACLE_LIB)
+    vp = ctypes.c_void_p
+    O.oracle_call.argtypes = [ctypes.c_double, ctypes.c_double, vp, vp, ctypes.c_uint] + [vp] * 6
+    idx, out, region = T.regenerate("stress_small", tmp_path)
+    inp = T.LoadedInput(idx, out + ".snapshot", region)
+    L = gpu_caller.L
+    calls = ctypes.c_void_p(); st = T.Stats()
+    gpu_caller.check(L.gt16_call_sites_host(gpu_caller.ctx, ctypes.byref(inp.view), None, 0, 0, inp.total_sites,
+                                            ctypes.byref(calls), ctypes.byref(st)))
+    recs = T.capi_mod.calls_array(L, calls)
+    L.gt16_calls_free(calls)
+    inp.close()
+    n = len(recs)
+    assert n == T.manifest()["stress_small"]["rows"]
+    W = np.ascontiguousarray(recs["W"]); ref = np.ascontiguousarray(recs["ref"])
+    lh = np.zeros((n, 16)); flh = np.zeros((n, 16)); pD = np.zeros(n); b = np.zeros(n); s = np.zeros(n)
+    gt = np.zeros(n, dtype=np.int32)
+    O.oracle_call(0.01, 0.005, W.ctypes.data, ref.ctypes.data, n, lh.ctypes.data, flh.ctypes.data, pD.ctypes.data,
+                  b.ctypes.data, s.ctypes.data, gt.ctypes.data)
+    assert np.array_equal(recs["genotype"], gt)
+    log_close(recs["lh"], lh); log_close(recs["flh"], flh); log_close(recs["pD"], pD)
+    log_close(recs["bestD"], b); log_close(recs["secondD"], s)
+    assert (np.diff(recs["amb"].astype(np.int64)) > 0).all()            # ordered by position
+    assert ((recs["is_indel"] > 0) == (recs["genotype"] > 9)).all()
+
+
+def smoke_check():
+    """operator-level part of __graft_entry__.smoke(): a handful of sites through the GPU seam vs the C oracle"""
+    O = ctypes.CDLL(T.ORACLE_LIB)
+    vp = ctypes.c_void_p
+    O.oracle_call.argtypes = [ctypes.c_double, ctypes.c_double, vp, vp, ctypes.c_uint] + [vp] * 6
+    g = np.load(os.path.join(T.GOLDEN, "operator_vectors.npz"))
+    sub = {k: g[k][:256] for k in ("W", "ref")}
+    n = 256
+    lh = np.zeros((n, 16)); flh = np.zeros((n, 16)); pD = np.zeros(n); b = np.zeros(n); s = np.zeros(n)
+    gt = np.zeros(n, dtype=np.int32)
+    W = np.ascontiguousarray(sub["W"]); ref = np.ascontiguousarray(sub["ref"])
+    O.oracle_call(0.01, 0.005, W.ctypes.data, ref.ctypes.data, n, lh.ctypes.data, flh.ctypes.data, pD.ctypes.data,
+                  b.ctypes.data, s.ctypes.data, gt.ctypes.data)
+    with T.Caller(0) as c:
+        glh, gflh, gpD, gb, gs, ggt = run_operator_seam(c, sub)
+    assert np.array_equal(ggt, gt)
+    log_close(glh, lh); log_close(gflh, flh); log_close(gpD, pD)
+    print("smoke: operator seam on %d sites matches the oracle (genotypes identical, likelihoods within 1e-6 in log space)" % n)
