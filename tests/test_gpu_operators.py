@@ -56,8 +56,11 @@ def test_device_tables_match_reference_prefill(gpu_caller):
     buf = np.zeros(LC_BYTES // 8)
     gpu_caller.check(gpu_caller.L.gt16_prefill_likelihood_cache(gpu_caller.ctx, 0.01, 0.005, buf.ctypes.data))
     got = buf[(g["k"].astype(np.int64) - 1) * N * N + g["i"].astype(np.int64) * N + g["j"]]
-    np.testing.assert_allclose(got, g["value"], rtol=1e-11, atol=0)
-    assert np.array_equal(got == 0, g["value"] == 0)
+    # device exp/log differ from glibc's in the last ulp: 1e-11 relative on normal values; entries that
+    # underflow into the subnormal range (< 2.2e-308) may land one subnormal step apart, including the
+    # step between 4.9e-324 and 0 (DESIGN.md "known deviations"); bound how often that happens
+    np.testing.assert_allclose(got, g["value"], rtol=1e-11, atol=2e-323)
+    assert ((got == 0) != (g["value"] == 0)).sum() <= 3
     np.testing.assert_allclose(buf[10 * N * N:], g["ycsq"], rtol=1e-12)
     # rebuild the decision bitmaps the fixture's context had
     gpu_caller.check(gpu_caller.L.gt16_configure(gpu_caller.ctx, 0.01, 0.005, 1))
@@ -95,7 +98,8 @@ def test_custom_prior_and_genotype_table(gpu_caller):
         assert np.array_equal(gt[nz], np.argmax(flh[nz], axis=1))
         np.testing.assert_allclose(flh[nz], lh[nz] / pD[nz, None], rtol=1e-15)
     finally:
-        gpu_caller.check(L.gt16_copy_snp_prior(gpu_caller.ctx, np.ascontiguousarray(g["prior"]).ctypes.data))
+        prior = np.ascontiguousarray(g["prior"])          # keep the array alive across the call
+        gpu_caller.check(L.gt16_copy_snp_prior(gpu_caller.ctx, prior.ctypes.data))
         gpu_caller.check(L.gt16_copy_genotype_table(gpu_caller.ctx, T.G2I.ctypes.data))
         gpu_caller.check(L.gt16_configure(gpu_caller.ctx, 0.01, 0.005, 1))
 
