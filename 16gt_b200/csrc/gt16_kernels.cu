@@ -115,8 +115,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity))
-    if (++spins > (1u << 24)) __trap();          // a lost bulk copy must not hang the device
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);                             // waiting warps must not take issue slots from working ones
+    if (++spins > (1u << 22)) __trap();          // a lost bulk copy must not hang the device
+  }
 }
 
 // Streaming classification of a dense, single-region range of positions [pBeg, pEnd) -- the HBM-bound
@@ -144,7 +146,8 @@ struct StreamSmem {
   uint8_t s1[kS1Bits];                                   // byte per weight: 1 = needs exact evaluation
   uint32_t s2[2 * kS2Words];                             // bitmaps (Wr, Wp) and (Wr, Wq)
   StreamQueueEntry queue[kStreamThreads / 32][64];
-  uint64_t full[kStreamStages];
+  uint64_t full[kStreamStages];                          // TMA bytes have landed
+  uint32_t released[kStreamStages];                      // warps that are done reading the stage
 };
 static_assert(sizeof(uint64_t) * (kStreamTile + 2) % 16 == 0, "bulk copy sizes must be multiples of 16 bytes");
 static_assert(sizeof(StreamSmem) <= 227 * 1024, "shared memory budget");
@@ -183,7 +186,7 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
   };
 
   if (tid == 0) {
-    for (int s = 0; s < kStreamStages; ++s) mbar_init(&S.full[s], 1);
+    for (int s = 0; s < kStreamStages; ++s) { mbar_init(&S.full[s], 1); S.released[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (uint32_t k = tid; k < (uint32_t) kS1Bits / 4; k += kStreamThreads) {     // expand the s1 bitmap to bytes
@@ -201,34 +204,37 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
       if (t < nTiles) issue(s, t);
     }
 
+  // per-warp ring of parked (complex) sites
   StreamQueueEntry *q = S.queue[warp];
-  uint32_t qlen = 0;
+  uint32_t qhead = 0, qtail = 0;
   auto drain = [&](uint32_t count) {                        // lanes < count run one parked site each
     if (lane < count) {
-      const StreamQueueEntry e = q[lane];
+      const StreamQueueEntry e = q[(qhead + lane) & 63u];
       if (compact_needs_exact(S.s2, S.s1, e.x, e.y, e.ref)) atomicOr(mask + (e.bit >> 5), 1u << (e.bit & 31));
     }
+    qhead += count;
   };
+  constexpr int kRows = kStreamTile / kStreamThreads;       // 32-site rows per warp and tile
   const uint32_t sh = 30u - ((lane & 15u) << 1), laneBit = 0x80000000u >> lane, ltMask = (1u << lane) - 1u;
-  constexpr int kRows = kStreamTile / kStreamThreads;      // 32-site rows per warp and tile
+  const uint32_t site0 = warp * (32 * kRows) + lane;        // this lane's site in row 0 of a tile
+  const uint32_t refIdx0 = site0 >> 4, bmIdx0 = warp * kRows;
+  const bool deadBit = S.s1[0] != 0;                        // verdict for a position without coverage
 
   uint32_t k = 0;
   for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++k) {
     const uint32_t stage = k % kStreamStages, parity = (k / kStreamStages) & 1;
     mbar_wait(&S.full[stage], parity);
-    const uint2 *sc = reinterpret_cast<const uint2 *>(S.counters[stage]);
-    const uint32_t *sr = S.ref[stage], *sb = S.bm[stage];
+    const uint2 *sc = reinterpret_cast<const uint2 *>(S.counters[stage]) + site0;
+    const uint32_t *sr = S.ref[stage] + refIdx0, *sb = S.bm[stage] + bmIdx0;
     const uint32_t pT = pBeg + tile * kStreamTile;
     const uint32_t lim = (pEnd - pT) < (uint32_t) kStreamTile ? pEnd - pT : (uint32_t) kStreamTile;
     uint2 c[kRows]; uint32_t nlo[kRows], rw[kRows], bw[kRows];
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const uint32_t site = warp * (32 * kRows) + 32 * r + lane;
-      c[r] = sc[site]; nlo[r] = sc[site + 1].x; rw[r] = sr[site >> 4]; bw[r] = sb[site >> 5];
-    }
+    for (int r = 0; r < kRows; ++r) { c[r] = sc[32 * r]; nlo[r] = sc[32 * r + 1].x; rw[r] = sr[2 * r]; bw[r] = sb[r]; }
+    uint32_t *mw = mask + ((pT - pBeg) >> 5) + warp * kRows;
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
-      const uint32_t rowSite = warp * (32 * kRows) + 32 * r, site = rowSite + lane;
+      const uint32_t site = site0 + 32 * r;
       const uint32_t x = c[r].x, y = c[r].y, n = nlo[r];
       const uint32_t refx = rw[r] >> sh;
       const bool isRef1 = (((x >> 14) ^ refx) & 3u) == 0;
@@ -237,39 +243,38 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
       const bool special = ((x & 0xC000C000u) == 0xC000C000u) |
                            (((n & 0xC000C000u) == 0xC000C000u) & ((n & 0x20002000u) != 0));
       const bool valid = (site < lim) & ((bw[r] & laneBit) == 0);
-      const bool simple = dead | (oneSlot & isRef1);
-      const uint32_t idx = dead ? 0u : (x & 0x3FFFu);
-      const bool bit = S.s1[idx] != 0;
-      const bool flag = valid & (special | (simple & bit));
-      const bool cplx = valid & !special & !simple;
+      const bool simple1 = oneSlot & isRef1;
+      const bool bit = S.s1[x & 0x3FFFu] != 0;
+      const bool flag = valid & (special | (simple1 & bit) | (dead & deadBit));
+      const bool cplx = valid & !special & !simple1 & !dead;
       const uint32_t word = __ballot_sync(0xffffffffu, flag);
       const uint32_t cw = __ballot_sync(0xffffffffu, cplx);
-      if (lane == 0 && rowSite < lim) mask[(pT - pBeg + rowSite) >> 5] = word;
+      if (lane == 0 && site < lim) mw[r] = word;              // lane 0: site == first site of the row
       if (cw) {
         if (cplx) {
           StreamQueueEntry e; e.x = x; e.y = y; e.bit = pT - pBeg + site; e.ref = refx & 3u;
-          q[qlen + __popc(cw & ltMask)] = e;
+          q[(qtail + __popc(cw & ltMask)) & 63u] = e;
         }
-        qlen += __popc(cw);
-        __syncwarp();
-        if (qlen >= 32) {
-          const StreamQueueEntry keep = q[32 + lane];
-          drain(32);
-          __syncwarp();
-          qlen -= 32;
-          if (lane < qlen) q[lane] = keep;
-          __syncwarp();
-        }
+        qtail += __popc(cw);
+        __syncwarp();                                         // entries and the row's mask word are visible to the warp
+        if (qtail - qhead >= 32u) { drain(32); __syncwarp(); }
       }
     }
-    __syncthreads();                                           // every warp is done with this stage
-    if (tid == 0) {
-      const uint32_t nt = tile + kStreamStages * gridDim.x;
-      if (nt < nTiles) issue(stage, nt);
+    __syncwarp();
+    // This warp no longer reads the stage.  The LAST warp to say so refills it (no producer warp, nobody waits
+    // for a release): the stage's next tile is kStreamStages rounds ahead.
+    if (lane == 0) {
+      __threadfence_block();
+      if (atomicAdd(&S.released[stage], 1u) == kStreamThreads / 32 - 1) {
+        S.released[stage] = 0;
+        __threadfence_block();
+        const uint32_t nt = tile + kStreamStages * gridDim.x;
+        if (nt < nTiles) issue(stage, nt);
+      }
     }
   }
   __syncwarp();
-  drain(qlen);
+  drain(qtail - qhead);
 }
 
 void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t *mask,
