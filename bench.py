@@ -121,7 +121,7 @@ def reference_arm(args):
     if rank != 0:
         return 0
     if not os.path.exists(REF_CALLER):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_caller not built"}))
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_caller not built"}), flush=True)
         return 0
     wd = tempfile.mkdtemp(prefix="gt16_refarm_")
     try:
@@ -152,13 +152,17 @@ def reference_arm(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     finally:
         shutil.rmtree(wd, ignore_errors=True)
     return 0
 
 
 def main():
+    # exactly ONE line on stdout: libraries (NCCL's version banner, ...) that print to fd 1 are sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -308,7 +312,7 @@ def main():
         inp.close()
         caller.close()
         if rank == 0:
-            print(json.dumps(line))
+            print(json.dumps(line), flush=True)
     finally:
         shutil.rmtree(wd, ignore_errors=True)
         if world > 1:
