@@ -33,6 +33,15 @@ CONFIGS = {
 # a digest of its call-set columns is committed (tests/golden/MANIFEST.json: callset_sha256).
 FULL_CONFIGS = {
     "chr20_full": dict(synth=["--contigs", "chr20:64444167", "--seed", "1"], exome=False),
+    # config 5 flavour at chr20 size: 60x, indels 1/500 with pooled multi-pattern lists, depth hotspots
+    # (overflow promotion, chi-square fallback), invalid bits, coverage gaps; 8 batches
+    "stress_full": dict(synth=["--contigs", "chrS:64444167", "--depth", "60", "--indel-rate", "2e-3",
+                               "--multi-pattern-frac", "0.4", "--long-indel-frac", "0.05", "--hotspot-rate", "2e-5",
+                               "--hotspot-depth", "1500", "--invalid-rate", "1e-4", "--gaps", "6:100000",
+                               "--seed", "5"], exome=False),
+    # config 4 flavour: 20,000 targets of ~300 bp at 150x on a 256 Mb genome, sparse (mode 2) snapshot, -e region.bin
+    "exome_mid": dict(synth=["--genome-len", "256000000", "--n-contigs", "8", "--exome", "20000:300", "--depth", "150",
+                             "--seed", "4"], exome=True),
 }
 CONFIGS_ALL = dict(CONFIGS, **FULL_CONFIGS)
 

@@ -80,16 +80,23 @@ def test_dropin_binary_errors(tmp_path):
     assert r.returncode == 1
 
 
-def test_full_size_chr20_callset_digest(gpu_caller, tmp_path):
-    """BASELINE.json configs[1] at full size (64,444,167 sites, what bench.py times): the call-set
-    columns of all 72,171 rows hash to the digest of the reference's own .txt for this snapshot."""
-    idx, out, region = T.regenerate("chr20_full", tmp_path)
+@pytest.mark.parametrize("name,shards", [("chr20_full", 3), ("stress_full", 2), ("exome_mid", 1)])
+def test_full_size_callset_digest(gpu_caller, tmp_path, name, shards):
+    """Full-size configs (chr20_full is what bench.py times; stress_full is the config-5 flavour with 189,080
+    rows; exome_mid the config-4 flavour with a sparse snapshot and 20,000 regions): the call-set columns of
+    every row hash to the digest of the reference's own .txt for the same snapshot, and the number of rows
+    whose floating-point columns print differently is bounded."""
+    import hashlib
+    idx, out, region = T.regenerate(name, tmp_path)
     inp = T.LoadedInput(idx, out + ".snapshot", region)
     try:
-        st = T.call_to_txt(gpu_caller, inp, out + ".txt", shards=3)
+        st = T.call_to_txt(gpu_caller, inp, out + ".txt", shards=shards)
     finally:
         inp.close()
-    m = T.manifest()["chr20_full"]
-    digest, rows = T.callset_digest(open(out + ".txt", "rb").read())
+    m = T.manifest()[name]
+    txt = open(out + ".txt", "rb").read()
+    digest, rows = T.callset_digest(txt)
     assert rows == m["rows"] == sum(s.called for s in st)
     assert digest == m["callset_sha256"]
+    print("%s: whole .txt %s the reference's" % (name, "IDENTICAL to" if hashlib.sha256(txt).hexdigest() == m["txt_sha256"]
+                                                  else "differs (floating-point columns only) from"))
