@@ -232,8 +232,7 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
 #pragma unroll
     for (int r = 0; r < kRows; ++r) { c[r] = sc[32 * r]; nlo[r] = sc[32 * r + 1].x; rw[r] = sr[2 * r]; bw[r] = sb[r]; }
     uint32_t *mw = mask + ((pT - pBeg) >> 5) + warp * kRows;
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
+    auto row = [&](int r, bool partial) {                      // partial: the range ends inside this tile
       const uint32_t site = site0 + 32 * r;
       const uint32_t x = c[r].x, y = c[r].y, n = nlo[r];
       const uint32_t refx = rw[r] >> sh;
@@ -242,14 +241,15 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
       const bool dead = y == 0;
       const bool special = ((x & 0xC000C000u) == 0xC000C000u) |
                            (((n & 0xC000C000u) == 0xC000C000u) & ((n & 0x20002000u) != 0));
-      const bool valid = (site < lim) & ((bw[r] & laneBit) == 0);
+      bool valid = (bw[r] & laneBit) == 0;
+      if (partial) valid &= site < lim;
       const bool simple1 = oneSlot & isRef1;
       const bool bit = S.s1[x & 0x3FFFu] != 0;
       const bool flag = valid & (special | (simple1 & bit) | (dead & deadBit));
       const bool cplx = valid & !special & !simple1 & !dead;
       const uint32_t word = __ballot_sync(0xffffffffu, flag);
       const uint32_t cw = __ballot_sync(0xffffffffu, cplx);
-      if (lane == 0 && site < lim) mw[r] = word;              // lane 0: site == first site of the row
+      if (lane == 0 && (!partial || site < lim)) mw[r] = word; // lane 0: site == first site of the row
       if (cw) {
         if (cplx) {
           StreamQueueEntry e; e.x = x; e.y = y; e.bit = pT - pBeg + site; e.ref = refx & 3u;
@@ -259,6 +259,13 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
         __syncwarp();                                         // entries and the row's mask word are visible to the warp
         if (qtail - qhead >= 32u) { drain(32); __syncwarp(); }
       }
+    };
+    if (lim == (uint32_t) kStreamTile) {                       // all tiles but the last: no per-site range test
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) row(r, false);
+    } else {
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) row(r, true);
     }
     __syncwarp();
     // This warp no longer reads the stage.  The LAST warp to say so refills it (no producer warp, nobody waits
