@@ -64,7 +64,7 @@ struct PinPool {
 
 struct gt16_ctx {
   int device = 0;
-  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaStream_t compute = nullptr, copy = nullptr, d2h = nullptr;   // kernels / host->device / device->host
   std::string err;
   // tables
   double *tabOwned[10] = {nullptr};
@@ -82,7 +82,7 @@ struct gt16_ctx {
   uint32_t launches = 0;
   int numSMs = 148;
   // persistent scratch of the fused path
-  DevBuf mask, counts, listA, listB, recs, planStart, planFirst;
+  DevBuf mask, counts, listA, listB, recs, recs2, planStart, planFirst;
   DevBuf sCounters, sInvalid, sOvf, sOvfBase, sPool, sRef;      // streamed (host-fed) snapshot
   std::vector<cudaEvent_t> evPool;
   std::shared_ptr<PinPool> pins = std::make_shared<PinPool>();
@@ -173,6 +173,7 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaMalloc(&ctx->prior, 256 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->g2i, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->ycsq, kYcsqN * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -212,10 +213,10 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   cudaFree(ctx->s1); cudaFree(ctx->s2p); cudaFree(ctx->s2q); cudaFree(ctx->g4);
   cudaFree(ctx->errWord);
   cudaFreeHost(ctx->hPinned);
-  for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->listA, &ctx->listB, &ctx->recs, &ctx->planStart, &ctx->planFirst,
+  for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->listA, &ctx->listB, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst,
                     &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
   for (auto e : ctx->evPool) cudaEventDestroy(e);
-  cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
+  cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy); cudaStreamDestroy(ctx->d2h);
   delete ctx;
 }
 
@@ -396,6 +397,7 @@ static const uint32_t kCopyChunkSites = 1u << 22;     // 32 MiB of counters per 
 // candidate records per kernel launch / D2H copy: a small first slice starts the device->host stream early,
 // later slices double up to kCandSliceMax so the kernels run at full occupancy
 static const uint32_t kCandSliceFirst = 4096, kCandSliceMax = 32768;
+static const uint32_t kSegBatches = 2;                // batches per segment of a host-fed range
 
 #define CUF(call)                                                                                  \
   do {                                                                                             \
@@ -570,8 +572,8 @@ int make_plan(gt16_ctx *ctx, uint32_t L, const gt16_region *regions, uint32_t nR
   return GT16_OK;
 }
 
-// ordered compaction of the site mask over nItems -> list (grown on demand); returns the count
-int compact(gt16_ctx *ctx, const uint32_t *mask, uint32_t nItems, DevBuf &list, uint32_t *count) {
+// ordered compaction of mask bits [0, nItems) -> list of (bit index + offset), grown on demand; returns the count
+int compact(gt16_ctx *ctx, const uint32_t *mask, uint32_t nItems, uint32_t offset, DevBuf &list, uint32_t *count) {
   uint32_t *counts = (uint32_t *) ctx->counts.p;
   launch_mask_count(mask, nItems, counts, ctx->compute);
   launch_scan_counts(counts, scan_blocks(nItems), ctx->dTotal, ctx->compute);
@@ -580,7 +582,7 @@ int compact(gt16_ctx *ctx, const uint32_t *mask, uint32_t nItems, DevBuf &list, 
   CUF(cudaStreamSynchronize(ctx->compute));
   *count = ctx->hPinned[0];
   CUF(list.ensure((size_t) (*count ? *count : 1) * 4));
-  launch_mask_scatter(mask, nItems, counts, nullptr, 0, (uint32_t *) list.p, ctx->compute);
+  launch_mask_scatter(mask, nItems, counts, nullptr, offset, (uint32_t *) list.p, ctx->compute);
   ctx->launches++;
   return GT16_OK;
 }
@@ -603,62 +605,90 @@ void stream_range(gt16_ctx *ctx, const SnapView &V, const RegionPlan &pl, uint64
   ctx->launches++;
 }
 
-// stages after the streaming pass: compaction, exact evaluation, second compaction, candidate records
-// written slice by slice while the previous slice travels to the host on the copy stream
-int finish_call(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t begin, uint32_t n, bool usedTables,
-                const DecisionTables &D, cudaEvent_t *ev /*[8]*/, size_t evBase, gt16_calls *calls, gt16_stats *st) {
+// make room for `need` more records in the pinned result buffer of `calls` (contents are preserved)
+int reserve_results(gt16_ctx *ctx, gt16_calls *calls, uint64_t need, uint64_t hint) {
+  const uint64_t want = calls->n + need;
+  if (want * sizeof(gt16_called_site) <= calls->cap) return GT16_OK;
+  const uint64_t target = std::max<uint64_t>(want + want / 2, hint);
+  size_t cap = 0;
+  gt16_called_site *fresh = (gt16_called_site *) ctx->pins->take((size_t) target * sizeof(gt16_called_site), &cap);
+  if (!fresh) return fail(ctx, GT16_ECUDA, "cudaHostAlloc of the result buffer failed");
+  if (calls->sites) {
+    CUF(cudaStreamSynchronize(ctx->d2h));                  // copies into the old buffer must have landed
+    memcpy(fresh, calls->sites, (size_t) calls->n * sizeof(gt16_called_site));
+    ctx->pins->give(calls->sites, calls->cap);
+  }
+  calls->sites = fresh;
+  calls->cap = cap;
+  return GT16_OK;
+}
+
+struct SegTimes { float stream = 0, scan = 0, eval = 0, cand = 0; };
+
+// One segment [a, b) of the processed range after its streaming pass: compaction, exact evaluation (clears
+// bits), compaction, then candidate records slice by slice (k_candidates + k_bias) while the previous slice
+// travels to the host on the d2h stream.  `mask` is the flag bitmap of the whole call (bit 0 = site `begin`).
+int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t begin, uint64_t a, uint64_t b,
+                   bool usedTables, const DecisionTables &D, size_t &evNext, uint32_t seg, gt16_calls *calls,
+                   gt16_stats *st, uint64_t resultHint, cudaEvent_t evStream0, cudaEvent_t evStream1, cudaEvent_t haloReady,
+                   std::vector<cudaEvent_t> &timing, std::vector<cudaEvent_t> &segCopied) {
   EvalParams P = eval_params(ctx);
-  uint32_t *mask = (uint32_t *) ctx->mask.p;
+  uint32_t *mask = (uint32_t *) ctx->mask.p + (a - begin) / 32;
+  const uint32_t n = (uint32_t) (b - a), off = (uint32_t) (a - begin);
+  cudaEvent_t ev[4];
+  for (int k = 0; k < 4; ++k) { int rc = get_event(ctx, evNext++, &ev[k]); if (rc) return rc; }
   uint32_t nA = 0, nB = 0;
-  int rc = compact(ctx, mask, n, ctx->listA, &nA);
+  int rc = compact(ctx, mask, n, off, ctx->listA, &nA);
   if (rc) return rc;
-  CUF(cudaEventRecord(ev[2], ctx->compute));
+  CUF(cudaEventRecord(ev[0], ctx->compute));
   const uint32_t *finalList = (const uint32_t *) ctx->listA.p;
   nB = nA;
   if (usedTables) {
-    launch_eval_list(V, pl.map, begin, (const uint32_t *) ctx->listA.p, nA, true, D, P, mask, ctx->errWord, ctx->compute);
+    launch_eval_list(V, pl.map, begin, (const uint32_t *) ctx->listA.p, nA, true, D, P, (uint32_t *) ctx->mask.p, ctx->errWord, ctx->compute);
     ctx->launches++;
-    CUF(cudaEventRecord(ev[3], ctx->compute));
-    rc = compact(ctx, mask, n, ctx->listB, &nB);
+    CUF(cudaEventRecord(ev[1], ctx->compute));
+    rc = compact(ctx, mask, n, off, ctx->listB, &nB);
     if (rc) return rc;
     finalList = (const uint32_t *) ctx->listB.p;
   } else {
-    CUF(cudaEventRecord(ev[3], ctx->compute));
+    CUF(cudaEventRecord(ev[1], ctx->compute));
   }
-  CUF(ctx->recs.ensure((size_t) (nB ? nB : 1) * sizeof(gt16_called_site)));
-  calls->n = nB;
-  if (nB) {
-    calls->sites = (gt16_called_site *) ctx->pins->take((size_t) nB * sizeof(gt16_called_site), &calls->cap);
-    if (!calls->sites) return fail(ctx, GT16_ECUDA, "cudaHostAlloc of the result buffer failed");
-  }
-  CUF(cudaEventRecord(ev[4], ctx->compute));
-  gt16_called_site *recs = (gt16_called_site *) ctx->recs.p;
-  size_t slice = 0;
+  // candidate records of this segment: device buffers alternate between segments so that a segment's copies
+  // may still be in flight while the next one is being written
+  DevBuf &rb = (seg & 1) ? ctx->recs2 : ctx->recs;
+  CUF(rb.ensure((size_t) (nB ? nB : 1) * sizeof(gt16_called_site)));
+  rc = reserve_results(ctx, calls, nB, resultHint);
+  if (rc) return rc;
+  if (haloReady) CUF(cudaStreamWaitEvent(ctx->compute, haloReady, 0));   // windows reach up to 355 positions past b
+  if (seg >= 2) CUF(cudaStreamWaitEvent(ctx->compute, segCopied[seg - 2], 0));   // this record buffer's previous contents are on the host
+  CUF(cudaEventRecord(ev[2], ctx->compute));
+  gt16_called_site *recs = (gt16_called_site *) rb.p;
   uint32_t sliceLen = kCandSliceFirst;
-  for (uint32_t off = 0, cnt = 0; off < nB; off += cnt, ++slice, sliceLen = std::min(sliceLen * 2, kCandSliceMax)) {
-    cnt = std::min<uint32_t>(sliceLen, nB - off);
-    launch_candidates(V, pl.map, begin, finalList + off, cnt, P, recs + off, ctx->errWord, ctx->compute);
-    launch_bias(V, pl.map, begin, finalList + off, cnt, P, recs + off, ctx->compute);
+  for (uint32_t o = 0, cnt = 0; o < nB; o += cnt, sliceLen = std::min(sliceLen * 2, kCandSliceMax)) {
+    cnt = std::min<uint32_t>(sliceLen, nB - o);
+    launch_candidates(V, pl.map, begin, finalList + o, cnt, P, recs + o, ctx->errWord, ctx->compute);
+    launch_bias(V, pl.map, begin, finalList + o, cnt, P, recs + o, ctx->compute);
     ctx->launches += 2;
     cudaEvent_t se;
-    rc = get_event(ctx, evBase + slice, &se);
+    rc = get_event(ctx, evNext++, &se);
     if (rc) return rc;
     CUF(cudaEventRecord(se, ctx->compute));
-    CUF(cudaStreamWaitEvent(ctx->copy, se, 0));
-    CUF(cudaMemcpyAsync(calls->sites + off, recs + off, (size_t) cnt * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->copy));
+    CUF(cudaStreamWaitEvent(ctx->d2h, se, 0));
+    CUF(cudaMemcpyAsync(calls->sites + calls->n + o, recs + o, (size_t) cnt * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->d2h));
   }
-  CUF(cudaEventRecord(ev[5], ctx->compute));
-  CUF(cudaEventRecord(ev[6], ctx->copy));
-  CUF(cudaStreamWaitEvent(ctx->compute, ev[6], 0));
-  CUF(cudaMemcpyAsync(ctx->hPinned + 1, ctx->errWord, 4, cudaMemcpyDeviceToHost, ctx->compute));
-  CUF(cudaEventRecord(ev[7], ctx->compute));
-  CUF(cudaStreamSynchronize(ctx->compute));
-  CUF(cudaGetLastError());
-  uint32_t errw = ctx->hPinned[1];
-  if (errw) CUF(cudaMemset(ctx->errWord, 0, 4));
-  if (errw & kErrBadSnapshot) return fail(ctx, GT16_EDATA, "snapshot refers to an overflow record or pool range that does not exist");
-  if (errw & kErrGenotype) return fail(ctx, GT16_EGENOTYPE, "Error in selecting Genotype");
-  if (st) { st->flagged = nA; st->called = nB; }
+  CUF(cudaEventRecord(ev[3], ctx->compute));
+  {
+    cudaEvent_t done;
+    rc = get_event(ctx, evNext++, &done);
+    if (rc) return rc;
+    CUF(cudaEventRecord(done, ctx->d2h));
+    segCopied.push_back(done);
+  }
+  calls->n += nB;
+  st->flagged += nA;
+  st->called += nB;
+  timing.push_back(evStream0); timing.push_back(evStream1);
+  for (int k = 0; k < 4; ++k) timing.push_back(ev[k]);
   return GT16_OK;
 }
 
@@ -691,23 +721,28 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   st.sites = n;
   if (n == 0) { *out = calls.release(); if (stats) *stats = st; return GT16_OK; }
 
-  cudaEvent_t ev[8];
-  for (int k = 0; k < 8; ++k) { rc = get_event(ctx, k, &ev[k]); if (rc) return rc; }
-  size_t evNext = 8;
+  size_t evNext = 0;
+  cudaEvent_t evBegin, evEnd;
+  if ((rc = get_event(ctx, evNext++, &evBegin)) || (rc = get_event(ctx, evNext++, &evEnd))) return rc;
   CUF(ctx->mask.ensure(((size_t) (n + 31) / 32 + 64) * 4));
-  CUF(ctx->counts.ensure(((size_t) scan_blocks(n) + 1) * 4));
+  // A resident range is one segment (one streaming launch, D2H overlapped by slicing).  A host-fed range is
+  // cut into segments of kSegBatches batches so that everything after the streaming pass -- including the
+  // records' trip back -- runs while later counter chunks are still on the bus.
+  const uint64_t segSites = resident ? (uint64_t) n : (uint64_t) kSegBatches * kBatch;
+  CUF(ctx->counts.ensure(((size_t) scan_blocks((uint32_t) std::min<uint64_t>(segSites, n)) + 1) * 4));
   uint32_t *mask = (uint32_t *) ctx->mask.p;
-  CUF(cudaEventRecord(ev[0], ctx->compute));
+  const uint64_t resultHint = std::max<uint64_t>(4096, (uint64_t) n / 512);
+  std::vector<cudaEvent_t> timing, segCopied;
+  CUF(cudaEventRecord(evBegin, ctx->compute));
 
   gt16_dev_snapshot streamed;
   const SnapView *V = nullptr;
+  uint64_t copyLo = 0, copyHi = 0;
+  size_t nChunks = 0, chunkEv0 = 0;
   if (resident) {
     V = &resident->v;
-    stream_range(ctx, *V, pl, begin, end, useTables, D, P, mask);
-    CUF(cudaEventRecord(ev[1], ctx->compute));
   } else {
-    // counters stream in on the copy stream in genome order; the classification of batch k only waits for
-    // the chunk that holds its last needed position (+1 look-ahead); windows are read after the last chunk
+    // counters stream in on the copy stream in genome order (32 MiB chunks, all queued up front)
     std::vector<uint32_t> ovfBase;
     rc = alloc_snapshot(ctx, hostView, &streamed, ovfBase, true);
     if (rc == GT16_OK) rc = upload_aux(ctx, hostView, &streamed, ovfBase, ctx->copy);
@@ -715,10 +750,10 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     V = &streamed.v;
     const uint32_t loPos = pl.ascending ? pl.pos_of(begin) : 0;
     const uint32_t hiPos = pl.ascending ? pl.pos_of(end - 1) : L - 1;
-    const uint64_t copyLo = loPos > 512 ? ((loPos - 512) / kCopyChunkSites) * (uint64_t) kCopyChunkSites : 0;
-    const uint64_t copyHi = std::min<uint64_t>((uint64_t) hiPos + 1024, L);
-    const size_t nChunks = (size_t) ((copyHi - copyLo + kCopyChunkSites - 1) / kCopyChunkSites);
-    const size_t chunkEv0 = evNext;
+    copyLo = loPos > 512 ? ((loPos - 512) / kCopyChunkSites) * (uint64_t) kCopyChunkSites : 0;
+    copyHi = std::min<uint64_t>((uint64_t) hiPos + 1024, L);
+    nChunks = (size_t) ((copyHi - copyLo + kCopyChunkSites - 1) / kCopyChunkSites);
+    chunkEv0 = evNext;
     evNext += nChunks;
     for (size_t c = 0; c < nChunks; ++c) {
       uint64_t a = copyLo + c * (uint64_t) kCopyChunkSites, b = std::min<uint64_t>(a + kCopyChunkSites, copyHi);
@@ -743,24 +778,56 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
       if (rc) return rc;
       CUF(cudaEventRecord(ce, ctx->copy));
     }
-    for (uint64_t a = begin; a < end; a += kBatch) {
-      uint64_t b = std::min<uint64_t>(a + kBatch, end);
-      uint64_t need = pl.ascending ? std::min<uint64_t>((uint64_t) pl.pos_of(b - 1) + 2, copyHi) : copyHi;
-      size_t c = std::min((size_t) ((need - 1 - copyLo) / kCopyChunkSites), nChunks - 1);
-      CUF(cudaStreamWaitEvent(ctx->compute, ctx->evPool[chunkEv0 + c], 0));
-      stream_range(ctx, *V, pl, a, b, useTables, D, P, mask + (a - begin) / 32);
-    }
-    CUF(cudaStreamWaitEvent(ctx->compute, ctx->evPool[chunkEv0 + nChunks - 1], 0));
-    CUF(cudaEventRecord(ev[1], ctx->compute));
   }
-  rc = finish_call(ctx, *V, pl, begin, n, useTables, D, ev, evNext, calls.get(), &st);
-  if (rc != GT16_OK) return rc;
-  st.ms_stream = ms_between(ev[0], ev[1]);
-  st.ms_scan = ms_between(ev[1], ev[2]) + ms_between(ev[3], ev[4]);
-  st.ms_eval = ms_between(ev[2], ev[3]);
-  st.ms_candidates = ms_between(ev[4], ev[5]);
-  st.ms_d2h = ms_between(ev[5], ev[7]);
-  st.ms_total_device = ms_between(ev[0], ev[7]);
+  // event of the chunk that holds position `need - 1` (host-fed ranges only)
+  auto chunk_event = [&](uint64_t need) -> cudaEvent_t {
+    if (resident) return nullptr;
+    if (!pl.ascending) return ctx->evPool[chunkEv0 + nChunks - 1];
+    need = std::min<uint64_t>(std::max<uint64_t>(need, copyLo + 1), copyHi);
+    return ctx->evPool[chunkEv0 + std::min((size_t) ((need - 1 - copyLo) / kCopyChunkSites), nChunks - 1)];
+  };
+
+  uint32_t seg = 0;
+  for (uint64_t a = begin; a < end; a += segSites, ++seg) {
+    const uint64_t b = std::min<uint64_t>(a + segSites, end);
+    cudaEvent_t es0, es1;
+    if ((rc = get_event(ctx, evNext++, &es0)) || (rc = get_event(ctx, evNext++, &es1))) return rc;
+    CUF(cudaEventRecord(es0, ctx->compute));
+    for (uint64_t c = a; c < b; c += kBatch) {           // classification of a batch waits for the chunk with its last position + 1
+      const uint64_t d = std::min<uint64_t>(c + kBatch, b);
+      if (!resident) CUF(cudaStreamWaitEvent(ctx->compute, chunk_event(pl.ascending ? (uint64_t) pl.pos_of(d - 1) + 2 : copyHi), 0));
+      if (resident) { stream_range(ctx, *V, pl, a, b, useTables, D, P, mask + (a - begin) / 32); break; }
+      stream_range(ctx, *V, pl, c, d, useTables, D, P, mask + (c - begin) / 32);
+    }
+    CUF(cudaEventRecord(es1, ctx->compute));
+    cudaEvent_t halo = resident ? nullptr : chunk_event(pl.ascending ? (uint64_t) pl.pos_of(b - 1) + 600 : copyHi);
+    rc = finish_segment(ctx, *V, pl, begin, a, b, useTables, D, evNext, seg, calls.get(), &st, resultHint, es0, es1, halo, timing, segCopied);
+    if (rc != GT16_OK) return rc;
+  }
+  // drain: results on the host, error word
+  cudaEvent_t evD2H;
+  if ((rc = get_event(ctx, evNext++, &evD2H))) return rc;
+  CUF(cudaEventRecord(evD2H, ctx->d2h));
+  CUF(cudaStreamWaitEvent(ctx->compute, evD2H, 0));
+  if (!resident) CUF(cudaStreamWaitEvent(ctx->compute, ctx->evPool[chunkEv0 + nChunks - 1], 0));
+  CUF(cudaMemcpyAsync(ctx->hPinned + 1, ctx->errWord, 4, cudaMemcpyDeviceToHost, ctx->compute));
+  CUF(cudaEventRecord(evEnd, ctx->compute));
+  CUF(cudaStreamSynchronize(ctx->compute));
+  CUF(cudaGetLastError());
+  const uint32_t errw = ctx->hPinned[1];
+  if (errw) CUF(cudaMemset(ctx->errWord, 0, 4));
+  if (errw & kErrBadSnapshot) return fail(ctx, GT16_EDATA, "snapshot refers to an overflow record or pool range that does not exist");
+  if (errw & kErrGenotype) return fail(ctx, GT16_EGENOTYPE, "Error in selecting Genotype");
+  float lastCand = 0.f;
+  for (size_t k = 0; k + 6 <= timing.size(); k += 6) {
+    st.ms_stream += ms_between(timing[k], timing[k + 1]);
+    st.ms_scan += ms_between(timing[k + 1], timing[k + 2]) + ms_between(timing[k + 3], timing[k + 4]);
+    st.ms_eval += ms_between(timing[k + 2], timing[k + 3]);
+    st.ms_candidates += ms_between(timing[k + 4], timing[k + 5]);
+    lastCand = ms_between(evBegin, timing[k + 5]);
+  }
+  st.ms_total_device = ms_between(evBegin, evEnd);
+  st.ms_d2h = st.ms_total_device - lastCand;            // tail after the last candidate slice was written
   st.kernel_launches = ctx->launches - launches0;
   *out = calls.release();
   if (stats) *stats = st;
