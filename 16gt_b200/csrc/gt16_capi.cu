@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <memory>
@@ -397,7 +398,7 @@ static const uint32_t kCopyChunkSites = 1u << 22;     // 32 MiB of counters per 
 // candidate records per kernel launch / D2H copy: a small first slice starts the device->host stream early,
 // later slices double up to kCandSliceMax so the kernels run at full occupancy
 static const uint32_t kCandSliceFirst = 4096, kCandSliceMax = 32768;
-static const uint32_t kSegBatches = 2;                // batches per segment of a host-fed range
+static const uint32_t kSegBatchesDefault = 2;         // batches per segment of a host-fed range (GT16_SEG_BATCHES overrides)
 
 #define CUF(call)                                                                                  \
   do {                                                                                             \
@@ -728,7 +729,9 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   // A resident range is one segment (one streaming launch, D2H overlapped by slicing).  A host-fed range is
   // cut into segments of kSegBatches batches so that everything after the streaming pass -- including the
   // records' trip back -- runs while later counter chunks are still on the bus.
-  const uint64_t segSites = resident ? (uint64_t) n : (uint64_t) kSegBatches * kBatch;
+  uint32_t segBatches = kSegBatchesDefault;
+  if (const char *e = getenv("GT16_SEG_BATCHES")) { int v = atoi(e); if (v >= 1 && v <= 64) segBatches = (uint32_t) v; }
+  const uint64_t segSites = resident ? (uint64_t) n : (uint64_t) segBatches * kBatch;
   CUF(ctx->counts.ensure(((size_t) scan_blocks((uint32_t) std::min<uint64_t>(segSites, n)) + 1) * 4));
   uint32_t *mask = (uint32_t *) ctx->mask.p;
   const uint64_t resultHint = std::max<uint64_t>(4096, (uint64_t) n / 512);
