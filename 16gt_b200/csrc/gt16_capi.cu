@@ -65,7 +65,7 @@ struct PinPool {
 
 struct gt16_ctx {
   int device = 0;
-  cudaStream_t compute = nullptr, copy = nullptr, d2h = nullptr;   // kernels / host->device / device->host
+  cudaStream_t compute = nullptr, aux = nullptr, copy = nullptr, d2h = nullptr;   // kernels / Fisher-test kernels / host->device / device->host
   std::string err;
   // tables
   double *tabOwned[10] = {nullptr};
@@ -175,6 +175,7 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaMalloc(&ctx->prior, 256 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->g2i, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->ycsq, kYcsqN * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -217,7 +218,7 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->listA, &ctx->listB, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst,
                     &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
   for (auto e : ctx->evPool) cudaEventDestroy(e);
-  cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy); cudaStreamDestroy(ctx->d2h);
+  cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy); cudaStreamDestroy(ctx->d2h); cudaStreamDestroy(ctx->aux);
   delete ctx;
 }
 
@@ -667,15 +668,24 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
   uint32_t sliceLen = kCandSliceFirst;
   for (uint32_t o = 0, cnt = 0; o < nB; o += cnt, sliceLen = std::min(sliceLen * 2, kCandSliceMax)) {
     cnt = std::min<uint32_t>(sliceLen, nB - o);
+    // records of slice k on the compute stream, their Fisher tests on the aux stream (both kernels are
+    // latency-bound at low occupancy, so slice k's tests run beside slice k+1's records), then the copy home
     launch_candidates(V, pl.map, begin, finalList + o, cnt, P, recs + o, ctx->errWord, ctx->compute);
-    launch_bias(V, pl.map, begin, finalList + o, cnt, P, recs + o, ctx->compute);
     ctx->launches += 2;
-    cudaEvent_t se;
-    rc = get_event(ctx, evNext++, &se);
-    if (rc) return rc;
+    cudaEvent_t se, be;
+    if ((rc = get_event(ctx, evNext++, &se)) || (rc = get_event(ctx, evNext++, &be))) return rc;
     CUF(cudaEventRecord(se, ctx->compute));
-    CUF(cudaStreamWaitEvent(ctx->d2h, se, 0));
+    CUF(cudaStreamWaitEvent(ctx->aux, se, 0));
+    launch_bias(V, pl.map, begin, finalList + o, cnt, P, recs + o, ctx->aux);
+    CUF(cudaEventRecord(be, ctx->aux));
+    CUF(cudaStreamWaitEvent(ctx->d2h, be, 0));
     CUF(cudaMemcpyAsync(calls->sites + calls->n + o, recs + o, (size_t) cnt * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->d2h));
+  }
+  {                                                          // the segment's timing ends when its last tests are done
+    cudaEvent_t auxDone;
+    if ((rc = get_event(ctx, evNext++, &auxDone))) return rc;
+    CUF(cudaEventRecord(auxDone, ctx->aux));
+    CUF(cudaStreamWaitEvent(ctx->compute, auxDone, 0));
   }
   CUF(cudaEventRecord(ev[3], ctx->compute));
   {
