@@ -37,6 +37,15 @@ LIBS="$REF/lib/lib.a -lpthread -lm -lz"
 
 $CXX $CF -no-pie "$HERE/ref_drivers/ref_caller_main.cpp" $CALLER_OBJS $LIBS -o "$OUT/ref_caller"
 install -m 644 "$REF/snapshotSnpcaller.ini" "$OUT/ref_caller.ini"          # config, not source
+# the same driver with FisherExactTest.o replaced by the libgt16 shim: the
+# reference's own loop / consumer thread / writer around the GPU operators.  Needs 16gt_b200/lib/libgt16.so.
+GT16LIB=$HERE/../16gt_b200/lib
+if [ -f "$GT16LIB/libgt16.so" ]; then
+  SHIM_OBJS="$O/SNP.o $O/SAMhandler.o $O/VariantCaller.o $O/SnapshotHandler.o $O/fisher.o $O/likelihood_cache.o $O/ycsq.o $O/SNP_Caller.o $O/SNPFunctions.o $O/interpreter.o"
+  $CXX $CF -no-pie -I"$HERE/../include" "$HERE/ref_drivers/ref_caller_main.cpp" "$HERE/ref_drivers/gt16_shim.cpp" $SHIM_OBJS $LIBS \
+       -L"$GT16LIB" -lgt16 -Wl,-rpath,'$ORIGIN/../../16gt_b200/lib' -Wl,-rpath-link,/usr/local/cuda/lib64 -o "$OUT/ref_caller_gt16"
+  install -m 644 "$REF/snapshotSnpcaller.ini" "$OUT/ref_caller_gt16.ini"
+fi
 $CXX $CF -no-pie "$HERE/ref_drivers/ref_mkindex_main.cpp" $LIBS -o "$OUT/ref_mkindex"
 $CXX $CF -no-pie $O/bam2snapshot.o $O/SAMhandler.o $O/SNP.o $O/CounterReader.o $O/SnapshotHandler.o \
      $O/indexFunction.o $O/readIndex.o $LIBS -o "$OUT/ref_bam2snapshot"

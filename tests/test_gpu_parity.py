@@ -100,3 +100,19 @@ def test_full_size_callset_digest(gpu_caller, tmp_path, name, shards):
     assert digest == m["callset_sha256"]
     print("%s: whole .txt %s the reference's" % (name, "IDENTICAL to" if hashlib.sha256(txt).hexdigest() == m["txt_sha256"]
                                                   else "differs (floating-point columns only) from"))
+
+
+@pytest.mark.parametrize("name", ["wgs_small", "stress_small"])
+def test_reference_harness_with_gt16_operator_shim(tmp_path, name):
+    """Drop-in at operator level: the UNMODIFIED reference objects -- its producer loop,
+    consumer thread, window code and .txt writer -- linked with oracle/ref_drivers/gt16_shim.cpp in place of
+    FisherExactTest.o, so that prefill / likelihood / posterior run in libgt16.so on the GPU."""
+    exe = os.path.join(T.REF_DIR, "ref_caller_gt16")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_caller_gt16 not built (needs /root/reference at build time)")
+    idx, out, region = T.regenerate(name, tmp_path)
+    r = subprocess.run([exe, idx, out] + ([region] if region else []), stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Called Entries : %d" % T.manifest()[name]["rows"] in r.stdout
+    T.compare_txt(open(out + ".txt", "rb").read(), T.golden_txt(name))
