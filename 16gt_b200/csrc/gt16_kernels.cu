@@ -284,14 +284,14 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
   drain(qtail - qhead);
 }
 
+// function attributes are per device: called once per context, with its device current
+cudaError_t configure_kernels() {
+  return cudaFuncSetAttribute(k_stream_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmem));
+}
+
 void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t *mask,
                        int numSMs, cudaStream_t s) {
   if (pEnd <= pBeg) return;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_stream_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmem));
-    configured = true;
-  }
   uint32_t nTiles = (pEnd - pBeg + kStreamTile - 1) / kStreamTile;
   unsigned grid = nTiles < (uint32_t) numSMs ? nTiles : (unsigned) numSMs;
   k_stream_tma<<<grid, kStreamThreads, sizeof(StreamSmem), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, mask);

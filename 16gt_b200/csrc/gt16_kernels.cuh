@@ -29,6 +29,7 @@ constexpr int kStreamThreads = 1024;
 // bytes by which every streamed array must be over-allocated so that full tiles can be copied
 constexpr size_t kStreamPadSites = kStreamTile + 64;
 
+cudaError_t configure_kernels();   // per-device kernel attributes (dynamic shared memory opt-in)
 void launch_build_table(double *out, float err, cudaStream_t s);
 void launch_build_ycsq(double *out, cudaStream_t s);
 void launch_build_decisions(const EvalParams &P, uint32_t *s1, uint32_t *s2p, uint32_t *s2q, uint32_t *g4,

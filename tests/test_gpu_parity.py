@@ -72,6 +72,18 @@ def test_dropin_binary(tmp_path, name):
     T.compare_txt(open(out + ".txt", "rb").read(), T.golden_txt(name))
 
 
+def test_dropin_binary_multi_shard(tmp_path):
+    """the drop-in's multi-GPU path (one thread + context per shard, batch-aligned cuts, ordered gather) with two
+    shards on whatever GPUs are visible (GT16_SHARDS): byte-identical to the single-shard output"""
+    idx, out, region = T.regenerate("two_batch", tmp_path)
+    env = dict(os.environ, GT16_SHARDS="2")
+    r = subprocess.run([T.CLI, "-i", idx, "-o", out, "-v"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("[GT16] GPU") == 2
+    T.compare_txt(open(out + ".txt", "rb").read(), T.golden_txt("two_batch"))
+
+
 def test_dropin_binary_errors(tmp_path):
     r = subprocess.run([T.CLI], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "Usage:" in r.stderr
