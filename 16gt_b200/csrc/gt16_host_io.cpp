@@ -6,7 +6,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 #include <cuda_runtime_api.h>
 #include "../../include/gt16.h"
@@ -44,6 +48,39 @@ struct HostBuf {
 bool read_at(FILE *f, uint64_t off, void *dst, size_t n) {
   if (fseeko(f, (off_t) off, SEEK_SET) != 0) return false;
   return fread(dst, 1, n, f) == n;
+}
+
+unsigned io_threads() {
+  unsigned n = std::thread::hardware_concurrency();
+  return std::max(1u, std::min(16u, n ? n : 4u));
+}
+
+// big contiguous read: the range is cut into slices that worker threads pread() concurrently
+// (snapshot ingest is row (f)1 of SURVEY 8: it bounds the drop-in once the kernels are fast)
+bool pread_parallel(const char *path, uint64_t off, void *dst, size_t n) {
+  if (n < (8u << 20)) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return false;
+    size_t done = 0;
+    while (done < n) { ssize_t k = pread(fd, (char *) dst + done, n - done, (off_t) (off + done)); if (k <= 0) break; done += (size_t) k; }
+    close(fd);
+    return done == n;
+  }
+  const unsigned nt = io_threads();
+  const size_t slice = ((n + nt - 1) / nt + 4095) & ~(size_t) 4095;
+  std::vector<char> ok(nt, 1);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() {
+    size_t a = (size_t) t * slice, b = std::min(n, a + slice);
+    if (a >= b) return;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { ok[t] = 0; return; }
+    while (a < b) { ssize_t k = pread(fd, (char *) dst + a, b - a, (off_t) (off + a)); if (k <= 0) { ok[t] = 0; break; } a += (size_t) k; }
+    close(fd);
+  });
+  for (auto &x : th) x.join();
+  for (char c : ok) if (!c) return false;
+  return true;
 }
 
 }  // namespace
@@ -89,7 +126,7 @@ int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, c
     if (!L) { set_err(err, errLen, "%s: empty snapshot", path); rc = GT16_EDATA; break; }
     if (!hs->counters.alloc((size_t) L * 8 + 16, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
     if (mode & 1) {
-      if (fread(hs->counters.p, 8, L, f) != L) { set_err(err, errLen, "%s: truncated counters", path); rc = GT16_EIO; break; }
+      if (!pread_parallel(path, start[1] + 5, hs->counters.p, (size_t) L * 8)) { set_err(err, errLen, "%s: truncated counters", path); rc = GT16_EIO; break; }
       memset((char *) hs->counters.p + (size_t) L * 8, 0, 16);
     } else if (mode & 2) {
       memset(hs->counters.p, 0, (size_t) L * 8 + 16);
@@ -139,7 +176,7 @@ int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, c
     size_t bmWords = ((size_t) L + 31) >> 5;
     if (!hs->invalid.alloc(bmWords * 4 + 4, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
     if (len[3]) {
-      if (!read_at(f, start[3], hs->invalid.p, bmWords * 4)) { set_err(err, errLen, "%s: truncated bitmap", path); rc = GT16_EIO; break; }
+      if (!pread_parallel(path, start[3], hs->invalid.p, bmWords * 4)) { set_err(err, errLen, "%s: truncated bitmap", path); rc = GT16_EIO; break; }
       hs->hasInvalid = true;
     } else {
       memset(hs->invalid.p, 0, bmWords * 4);
@@ -263,19 +300,70 @@ static const char kGenotypeString[][4] = {"AA", "AC", "AG", "AT", "CC", "CG", "C
                                           "AX", "CX", "GX", "TX", "XX", "XY", "NN"};
 static const char kSym[] = {'A', 'C', 'G', 'T', 'X', 'Y', 'N'};
 
-static void print_indel(FILE *f, const gt16_indel &d) {
-  if (d.type == '*') { fputs("*\t*\t*\t*\t", f); return; }
-  fprintf(f, "%u%c\t", (unsigned) d.len, (char) d.type);
-  for (unsigned i = 0; i < d.len; ++i) fputc(kSym[(d.seq[i >> 2] >> ((i & 3) << 1)) & 3], f);
-  fprintf(f, "\t%u\t%u\t", (unsigned) d.hq, (unsigned) d.lq);
+// one row of the .txt (printPossibleSNP, interpreter.cpp:107-156) appended to `out`; lq / rq are the values the
+// reference would print for this row (its ReadQuality variable survives rows that do not assign it)
+namespace {
+struct RowBuf {
+  std::string &s;
+  char tmp[96];
+  explicit RowBuf(std::string &str) : s(str) {}
+  void e4(double v) { s.append(tmp, (size_t) snprintf(tmp, sizeof(tmp), "%.4e\t", v)); }
+  void f4(double v) { s.append(tmp, (size_t) snprintf(tmp, sizeof(tmp), "%.4f\t", v)); }
+  void u(unsigned v, char sep = '\t') { s.append(tmp, (size_t) snprintf(tmp, sizeof(tmp), "%u%c", v, sep)); }
+  void hu(unsigned short v) { s.append(tmp, (size_t) snprintf(tmp, sizeof(tmp), "%hu\t", v)); }
+  void lit(const char *t) { s.append(t); }
+  void ch(char c) { s.push_back(c); s.push_back('\t'); }
+};
+
+void format_indel(RowBuf &o, const gt16_indel &d) {
+  if (d.type == '*') { o.lit("*\t*\t*\t*\t"); return; }
+  o.s.append(o.tmp, (size_t) snprintf(o.tmp, sizeof(o.tmp), "%u%c\t", (unsigned) d.len, (char) d.type));
+  for (unsigned i = 0; i < d.len; ++i) o.s.push_back(kSym[(d.seq[i >> 2] >> ((i & 3) << 1)) & 3]);
+  o.s.push_back('\t');
+  o.u(d.hq); o.u(d.lq);
 }
 
+void format_row(std::string &out, const gt16_index *ix, const gt16_called_site &s, float lq, float rq) {
+  RowBuf o(out);
+  uint32_t chrPos = 0;
+  const char *chr = gt16_index_translate(ix, s.amb, &chrPos);
+  out.append(chr); out.push_back('\t');
+  o.u(chrPos);
+  o.ch(kSym[s.ref]);
+  if (s.is_indel) o.ch(kSym[s.ref]); else o.lit("*\t");
+  for (int g = 0; g < 16; ++g) o.e4(s.flh[g]);
+  out.append(kGenotypeString[s.genotype <= 16 ? s.genotype : 16]); out.push_back('\t');
+  o.e4(s.bestD); o.e4(s.secondD); o.e4(s.pD);
+  o.e4(0.0); o.lit("0\t");                                            // rfProb, rfMode (SNP_Caller.cpp:583-584)
+  format_indel(o, s.indel[0]);
+  format_indel(o, s.indel[1]);
+  o.u(s.W[0] + s.W[1] + s.W[2] + s.W[3]);
+  for (int b = 0; b < 4; ++b) o.hu((unsigned short) s.W[b]);
+  for (int b = 0; b < 4; ++b) { o.hu((unsigned short) s.F[b]); o.hu((unsigned short) s.R[b]); }
+  for (int g = 0; g < 16; ++g) o.e4(s.lh[g]);
+  if (s.is_indel) {
+    for (int k3 = 0; k3 < 3; ++k3) for (int b = 0; b < 4; ++b) o.e4(s.sb[k3][b]);
+    for (int k3 = 0; k3 < 3; ++k3) for (int b = 0; b < 4; ++b) o.e4(s.bqb[k3][b]);
+  } else {
+    for (int b = 0; b < 4; ++b) o.e4(s.sb[0][b]);
+    o.lit("*\t*\t*\t*\t*\t*\t*\t*\t");
+    for (int b = 0; b < 4; ++b) o.e4(s.bqb[0][b]);
+    o.lit("*\t*\t*\t*\t*\t*\t*\t*\t");
+  }
+  o.f4(s.rpb); o.f4(s.lgc); o.f4(s.rgc);
+  o.u(s.lg); o.u(s.rg);
+  o.f4(s.asc); o.f4(lq); o.f4(rq);
+  o.hu(s.polyrun);
+  o.u(s.total_hq); o.u(s.total_lq, '\n');
+}
+}  // namespace
+
+// Rows are formatted by worker threads into per-range strings and written in order: the only
+// row-to-row dependency, the surviving LQ/RQ values, is resolved by a sequential pre-pass.
 int gt16_write_txt(const char *path, const gt16_index *ix, const gt16_called_site *sites, uint64_t n, int append,
                    float *carry) {
   FILE *f = fopen(path, append ? "a" : "w");
   if (!f) return GT16_EIO;
-  std::vector<char> big(1 << 20);
-  setvbuf(f, big.data(), _IOFBF, big.size());
   if (!append) {
     fputs("Chr\tPos\tRef\tPreBase\t"
           "pAA\tpAC\tpAG\tpAT\tpCC\tpCG\tpCT\tpGG\tpGT\tpTT\tpAX\tpCX\tpGX\tpTX\tpXX\tpXY\t"
@@ -300,42 +388,37 @@ int gt16_write_txt(const char *path, const gt16_index *ix, const gt16_called_sit
           "totalHQ\ttotalLQ\n", f);
   }
   float lq = carry ? carry[0] : 0.0f, rq = carry ? carry[1] : 0.0f;
-  for (uint64_t k = 0; k < n; ++k) {
-    const gt16_called_site &s = sites[k];
-    uint32_t chrPos = 0;
-    const char *chr = gt16_index_translate(ix, s.amb, &chrPos);
-    fprintf(f, "%s\t%u\t%c\t", chr, chrPos, kSym[s.ref]);
-    if (s.is_indel) fprintf(f, "%c\t", kSym[s.ref]); else fputs("*\t", f);
-    for (int g = 0; g < 16; ++g) fprintf(f, "%.4e\t", s.flh[g]);
-    fprintf(f, "%s\t", kGenotypeString[s.genotype <= 16 ? s.genotype : 16]);
-    fprintf(f, "%.4e\t%.4e\t%.4e\t", s.bestD, s.secondD, s.pD);
-    fprintf(f, "%.4e\t%d\t", 0.0, 0);                               // rfProb, rfMode (SNP_Caller.cpp:583-584)
-    print_indel(f, s.indel[0]);
-    print_indel(f, s.indel[1]);
-    fprintf(f, "%u\t", s.W[0] + s.W[1] + s.W[2] + s.W[3]);
-    for (int b = 0; b < 4; ++b) fprintf(f, "%hu\t", (unsigned short) s.W[b]);
-    for (int b = 0; b < 4; ++b) fprintf(f, "%hu\t%hu\t", (unsigned short) s.F[b], (unsigned short) s.R[b]);
-    for (int g = 0; g < 16; ++g) fprintf(f, "%.4e\t", s.lh[g]);
-    if (s.is_indel) {
-      for (int k3 = 0; k3 < 3; ++k3) for (int b = 0; b < 4; ++b) fprintf(f, "%.4e\t", s.sb[k3][b]);
-      for (int k3 = 0; k3 < 3; ++k3) for (int b = 0; b < 4; ++b) fprintf(f, "%.4e\t", s.bqb[k3][b]);
-    } else {
-      for (int b = 0; b < 4; ++b) fprintf(f, "%.4e\t", s.sb[0][b]);
-      fputs("*\t*\t*\t*\t*\t*\t*\t*\t", f);
-      for (int b = 0; b < 4; ++b) fprintf(f, "%.4e\t", s.bqb[0][b]);
-      fputs("*\t*\t*\t*\t*\t*\t*\t*\t", f);
-    }
-    if (s.rq_assigned) { lq = s.lq; rq = s.rq; }                    // else: previous row's values survive
-    fprintf(f, "%.4f\t", s.rpb);
-    fprintf(f, "%.4f\t%.4f\t", s.lgc, s.rgc);
-    fprintf(f, "%u\t%u\t", (unsigned) s.lg, (unsigned) s.rg);
-    fprintf(f, "%.4f\t", s.asc);
-    fprintf(f, "%.4f\t%.4f\t", lq, rq);
-    fprintf(f, "%hu\t", s.polyrun);
-    fprintf(f, "%u\t%u\n", s.total_hq, s.total_lq);
+  const unsigned nt = n < 2048 ? 1u : io_threads();
+  const uint64_t per = (n + nt - 1) / (nt ? nt : 1);
+  // values in force at the start of each worker's range
+  std::vector<float> lq0(nt, 0.f), rq0(nt, 0.f);
+  for (unsigned t = 0; t < nt; ++t) {
+    lq0[t] = lq; rq0[t] = rq;
+    const uint64_t a = std::min<uint64_t>(n, t * per), b = std::min<uint64_t>(n, a + per);
+    for (uint64_t k = a; k < b; ++k) if (sites[k].rq_assigned) { lq = sites[k].lq; rq = sites[k].rq; }
   }
+  std::vector<std::string> parts(nt);
+  auto work = [&](unsigned t) {
+    const uint64_t a = std::min<uint64_t>(n, t * per), b = std::min<uint64_t>(n, a + per);
+    std::string &out = parts[t];
+    out.reserve((size_t) (b - a) * 720);
+    float l = lq0[t], r = rq0[t];
+    for (uint64_t k = a; k < b; ++k) {
+      if (sites[k].rq_assigned) { l = sites[k].lq; r = sites[k].rq; }   // else: previous row's values survive
+      format_row(out, ix, sites[k], l, r);
+    }
+  };
+  if (nt == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+    for (auto &x : th) x.join();
+  }
+  bool bad = false;
+  for (unsigned t = 0; t < nt; ++t)
+    if (!parts[t].empty() && fwrite(parts[t].data(), 1, parts[t].size(), f) != parts[t].size()) bad = true;
   if (carry) { carry[0] = lq; carry[1] = rq; }
-  int bad = ferror(f);
+  if (ferror(f)) bad = true;
   if (fclose(f) != 0 || bad) return GT16_EIO;
   return GT16_OK;
 }
