@@ -7,6 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -87,6 +89,8 @@ struct gt16_ctx {
   DevBuf sCounters, sInvalid, sOvf, sOvfBase, sPool, sRef;      // streamed (host-fed) snapshot
   std::vector<cudaEvent_t> evPool;
   std::shared_ptr<PinPool> pins = std::make_shared<PinPool>();
+  void *stagePin = nullptr;               // page-locked ring for callers whose counters live in pageable memory
+  cudaEvent_t stageEv[16] = {nullptr};    // slot k's last copy has left the ring
 };
 
 struct gt16_dev_snapshot {
@@ -219,6 +223,8 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->listA, &ctx->listB, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst,
                     &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
   for (auto e : ctx->evPool) cudaEventDestroy(e);
+  if (ctx->stagePin) cudaFreeHost(ctx->stagePin);
+  for (auto e : ctx->stageEv) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy); cudaStreamDestroy(ctx->d2h); cudaStreamDestroy(ctx->aux);
   delete ctx;
 }
@@ -396,7 +402,9 @@ int gt16_compute_bias(gt16_ctx *ctx, const void *w, const void *f, const void *r
 
 // ---- fused path -----------------------------------------------------------------------------
 // A context is driven by one host thread at a time; all scratch is owned by the context and only grows.
-static const uint32_t kCopyChunkSites = 1u << 22;     // 32 MiB of counters per cudaMemcpyAsync
+static const uint32_t kCopyChunkSites = 1u << 22;     // 32 MiB of counters per cudaMemcpyAsync (page-locked source)
+static const uint32_t kStageChunkSites = 1u << 20;    // 8 MiB per chunk when the source is pageable and goes through the ring
+static const int kStageThreads = 4, kStageSlots = 8;  // stager threads, ring slots (two per thread)
 // candidate records per kernel launch / D2H copy: a small first slice starts the device->host stream early,
 // later slices double up to kCandSliceMax so the kernels run at full occupancy
 static const uint32_t kCandSliceFirst = 4096, kCandSliceMax = 32768;
@@ -753,6 +761,14 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   const SnapView *V = nullptr;
   uint64_t copyLo = 0, copyHi = 0;
   size_t nChunks = 0, chunkEv0 = 0;
+  uint32_t chunkSites = kCopyChunkSites;
+  bool staged = false;
+  std::unique_ptr<std::atomic<int>[]> enqueued;
+  std::atomic<int> stageError{0};
+  std::vector<std::thread> stagers;
+  std::vector<cudaEvent_t> chunkEvents;
+  std::function<bool(uint64_t, uint64_t)> chunk_needed;                     // function scope: the stager threads use them
+  std::function<cudaError_t(size_t, const void *, bool)> enqueue_chunk;
   if (resident) {
     V = &resident->v;
   } else {
@@ -764,41 +780,103 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     V = &streamed.v;
     const uint32_t loPos = pl.ascending ? pl.pos_of(begin) : 0;
     const uint32_t hiPos = pl.ascending ? pl.pos_of(end - 1) : L - 1;
-    copyLo = loPos > 512 ? ((loPos - 512) / kCopyChunkSites) * (uint64_t) kCopyChunkSites : 0;
+    // page-locked source: cudaMemcpyAsync straight from the caller's buffer.  Pageable source (what a caller gets
+    // from malloc/fread; pinning half a gigabyte costs more than copying it): stager threads move 8 MiB chunks
+    // through a small page-locked ring.
+    cudaPointerAttributes pa;
+    staged = !(cudaPointerGetAttributes(&pa, hostView->counters) == cudaSuccess && pa.type == cudaMemoryTypeHost);
+    (void) cudaGetLastError();
+    chunkSites = staged ? kStageChunkSites : kCopyChunkSites;
+    copyLo = loPos > 512 ? ((loPos - 512) / chunkSites) * (uint64_t) chunkSites : 0;
     copyHi = std::min<uint64_t>((uint64_t) hiPos + 1024, L);
-    nChunks = (size_t) ((copyHi - copyLo + kCopyChunkSites - 1) / kCopyChunkSites);
+    nChunks = (size_t) ((copyHi - copyLo + chunkSites - 1) / chunkSites);
     chunkEv0 = evNext;
     evNext += nChunks;
-    for (size_t c = 0; c < nChunks; ++c) {
-      uint64_t a = copyLo + c * (uint64_t) kCopyChunkSites, b = std::min<uint64_t>(a + kCopyChunkSites, copyHi);
-      bool needed = true;
-      if (pl.ascending && pl.start.size() > 1) {         // sparse targets: skip chunks no region touches
-        needed = false;
-        size_t lo = 0, hi = pl.start.size();
-        while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if ((uint64_t) pl.start[mid] <= a + 0) lo = mid; else hi = mid; }
-        for (size_t r = lo; r < pl.start.size(); ++r) {
-          uint64_t rs = pl.start[r], re = rs + (pl.first[r + 1] - pl.first[r]);
-          if (rs > b + 512) break;
-          if (re + 512 > a && rs < b + 512) { needed = true; break; }
-        }
+    chunkEvents.resize(nChunks);      // own copy: stager threads must not look into evPool while it grows
+    for (size_t c = 0; c < nChunks; ++c) { rc = get_event(ctx, chunkEv0 + c, &chunkEvents[c]); if (rc) return rc; }
+    chunk_needed = [&](uint64_t a, uint64_t b) -> bool {
+      if (!(pl.ascending && pl.start.size() > 1)) return true;
+      size_t lo = 0, hi = pl.start.size();                 // sparse targets: skip chunks no region touches
+      while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if ((uint64_t) pl.start[mid] <= a + 0) lo = mid; else hi = mid; }
+      for (size_t r = lo; r < pl.start.size(); ++r) {
+        uint64_t rs = pl.start[r], re = rs + (pl.first[r + 1] - pl.first[r]);
+        if (rs > b + 512) break;
+        if (re + 512 > a && rs < b + 512) return true;
       }
-      if (needed)
-        CUF(cudaMemcpyAsync((char *) streamed.counters + a * 8, hostView->counters + a, (b - a) * 8, cudaMemcpyHostToDevice, ctx->copy));
-      else
-        CUF(cudaMemsetAsync((char *) streamed.counters + a * 8, 0, (b - a) * 8, ctx->copy));
-      if (c + 1 == nChunks && copyHi == L) { rc = finish_counters(ctx, &streamed, ctx->copy); if (rc) return rc; }
-      cudaEvent_t ce;
-      rc = get_event(ctx, chunkEv0 + c, &ce);
-      if (rc) return rc;
-      CUF(cudaEventRecord(ce, ctx->copy));
+      return false;
+    };
+    // enqueue chunk c on the copy stream (from `src`, the caller's buffer or a ring slot) and record its event
+    enqueue_chunk = [&](size_t c, const void *src, bool needed) -> cudaError_t {
+      const uint64_t a = copyLo + c * (uint64_t) chunkSites, b = std::min<uint64_t>(a + chunkSites, copyHi);
+      cudaError_t e = needed ? cudaMemcpyAsync((char *) streamed.counters + a * 8, src, (b - a) * 8, cudaMemcpyHostToDevice, ctx->copy)
+                             : cudaMemsetAsync((char *) streamed.counters + a * 8, 0, (b - a) * 8, ctx->copy);
+      if (e == cudaSuccess && c + 1 == nChunks && copyHi == L)
+        e = cudaMemcpyAsync((char *) streamed.counters + (size_t) L * 8, (char *) streamed.counters + (size_t) (L - 1) * 8, 8,
+                            cudaMemcpyDeviceToDevice, ctx->copy);          // counters[L] = counters[L-1]
+      if (e == cudaSuccess) e = cudaEventRecord(chunkEvents[c], ctx->copy);
+      return e;
+    };
+    if (!staged) {
+      for (size_t c = 0; c < nChunks; ++c) {
+        const uint64_t a = copyLo + c * (uint64_t) chunkSites, b = std::min<uint64_t>(a + chunkSites, copyHi);
+        CUF(enqueue_chunk(c, hostView->counters + a, chunk_needed(a, b)));
+      }
+    } else {
+      if (!ctx->stagePin) {
+        CUF(cudaHostAlloc(&ctx->stagePin, (size_t) kStageSlots * kStageChunkSites * 8, cudaHostAllocDefault));
+        for (int k = 0; k < kStageSlots; ++k) CUF(cudaEventCreateWithFlags(&ctx->stageEv[k], cudaEventDisableTiming));
+      }
+      enqueued.reset(new std::atomic<int>[nChunks]);
+      for (size_t c = 0; c < nChunks; ++c) enqueued[c].store(0);
+      const int dev = ctx->device;
+      for (int t = 0; t < kStageThreads; ++t)
+        stagers.emplace_back([&, t, dev]() {
+          cudaSetDevice(dev);
+          int use = 0;                                       // this thread alternates between its two ring slots
+          for (size_t c = (size_t) t; c < nChunks; c += kStageThreads, use ^= 1) {
+            const int slot = t * 2 + use;
+            const uint64_t a = copyLo + c * (uint64_t) chunkSites, b = std::min<uint64_t>(a + chunkSites, copyHi);
+            const bool needed = chunk_needed(a, b);
+            char *ring = (char *) ctx->stagePin + (size_t) slot * kStageChunkSites * 8;
+            cudaError_t e = cudaSuccess;
+            if (needed) {
+              if (c >= (size_t) 2 * kStageThreads) e = cudaEventSynchronize(ctx->stageEv[slot]);   // the slot's previous copy has left
+              if (e == cudaSuccess) memcpy(ring, hostView->counters + a, (size_t) (b - a) * 8);
+            }
+            if (e == cudaSuccess) e = enqueue_chunk(c, ring, needed);
+            if (e == cudaSuccess && needed) e = cudaEventRecord(ctx->stageEv[slot], ctx->copy);
+            if (e != cudaSuccess) stageError.store((int) e);
+            enqueued[c].store(1, std::memory_order_release);
+          }
+        });
     }
   }
+  // a stream must not be told to wait for an event that has not been recorded yet (that wait would be a no-op):
+  // with stager threads the host first waits until chunk c has been enqueued
+  auto host_wait_enqueued = [&](size_t c) {
+    if (!staged) return;
+    while (!enqueued[c].load(std::memory_order_acquire)) std::this_thread::yield();
+  };
+  struct JoinStagers {
+    std::vector<std::thread> &v;
+    ~JoinStagers() { for (auto &t : v) if (t.joinable()) t.join(); }
+  } joinStagers{stagers};
   // event of the chunk that holds position `need - 1` (host-fed ranges only)
-  auto chunk_event = [&](uint64_t need) -> cudaEvent_t {
-    if (resident) return nullptr;
-    if (!pl.ascending) return ctx->evPool[chunkEv0 + nChunks - 1];
-    need = std::min<uint64_t>(std::max<uint64_t>(need, copyLo + 1), copyHi);
-    return ctx->evPool[chunkEv0 + std::min((size_t) ((need - 1 - copyLo) / kCopyChunkSites), nChunks - 1)];
+  // make the compute stream wait until every chunk up to the one holding position `need - 1` has arrived.
+  // Chunks are enqueued out of order by the stager threads, so each chunk's own event is waited for (once).
+  size_t chunksWaited = 0;
+  auto wait_chunks = [&](uint64_t need) -> int {
+    if (resident) return GT16_OK;
+    size_t c = nChunks - 1;
+    if (pl.ascending) {
+      need = std::min<uint64_t>(std::max<uint64_t>(need, copyLo + 1), copyHi);
+      c = std::min((size_t) ((need - 1 - copyLo) / chunkSites), nChunks - 1);
+    }
+    for (; chunksWaited <= c; ++chunksWaited) {
+      host_wait_enqueued(chunksWaited);
+      CUF(cudaStreamWaitEvent(ctx->compute, chunkEvents[chunksWaited], 0));
+    }
+    return GT16_OK;
   };
 
   uint32_t seg = 0;
@@ -809,13 +887,14 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     CUF(cudaEventRecord(es0, ctx->compute));
     for (uint64_t c = a; c < b; c += kBatch) {           // classification of a batch waits for the chunk with its last position + 1
       const uint64_t d = std::min<uint64_t>(c + kBatch, b);
-      if (!resident) CUF(cudaStreamWaitEvent(ctx->compute, chunk_event(pl.ascending ? (uint64_t) pl.pos_of(d - 1) + 2 : copyHi), 0));
+      if ((rc = wait_chunks(pl.ascending ? (uint64_t) pl.pos_of(d - 1) + 2 : copyHi))) return rc;
       if (resident) { stream_range(ctx, *V, pl, a, b, useTables, D, P, mask + (a - begin) / 32); break; }
       stream_range(ctx, *V, pl, c, d, useTables, D, P, mask + (c - begin) / 32);
     }
     CUF(cudaEventRecord(es1, ctx->compute));
-    cudaEvent_t halo = resident ? nullptr : chunk_event(pl.ascending ? (uint64_t) pl.pos_of(b - 1) + 600 : copyHi);
-    rc = finish_segment(ctx, *V, pl, begin, a, b, useTables, D, evNext, seg, calls.get(), &st, resultHint, es0, es1, halo, timing, segCopied);
+    // windows, neighbours' Fisher tests and the indel look-ahead reach up to ~360 positions past the segment
+    if ((rc = wait_chunks(pl.ascending ? (uint64_t) pl.pos_of(b - 1) + 600 : copyHi))) return rc;
+    rc = finish_segment(ctx, *V, pl, begin, a, b, useTables, D, evNext, seg, calls.get(), &st, resultHint, es0, es1, nullptr, timing, segCopied);
     if (rc != GT16_OK) return rc;
   }
   // drain: results on the host, error word
@@ -823,7 +902,11 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   if ((rc = get_event(ctx, evNext++, &evD2H))) return rc;
   CUF(cudaEventRecord(evD2H, ctx->d2h));
   CUF(cudaStreamWaitEvent(ctx->compute, evD2H, 0));
-  if (!resident) CUF(cudaStreamWaitEvent(ctx->compute, ctx->evPool[chunkEv0 + nChunks - 1], 0));
+  if ((rc = wait_chunks(copyHi))) return rc;
+  if (staged) {
+    for (auto &t : stagers) t.join();
+    if (stageError.load()) { ctx->err = std::string("staged upload failed: ") + cudaGetErrorString((cudaError_t) stageError.load()); return GT16_ECUDA; }
+  }
   CUF(cudaMemcpyAsync(ctx->hPinned + 1, ctx->errWord, 4, cudaMemcpyDeviceToHost, ctx->compute));
   CUF(cudaEventRecord(evEnd, ctx->compute));
   CUF(cudaStreamSynchronize(ctx->compute));

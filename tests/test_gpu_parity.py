@@ -17,10 +17,12 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", list(T.CONFIGS))
-@pytest.mark.parametrize("mode", ["host_stream", "resident"])
+@pytest.mark.parametrize("mode", ["host_stream", "host_pageable", "resident"])
 def test_fused_path_matches_reference(gpu_caller, tmp_path, name, mode):
+    """host_stream: page-locked host buffers copied chunk by chunk; host_pageable: ordinary malloc'd buffers staged
+    through the library's page-locked ring by its stager threads; resident: snapshot uploaded once, then called"""
     idx, out, region = T.regenerate(name, tmp_path)
-    inp = T.LoadedInput(idx, out + ".snapshot", region)
+    inp = T.LoadedInput(idx, out + ".snapshot", region, pinned=0 if mode == "host_pageable" else 1)
     try:
         st = T.call_to_txt(gpu_caller, inp, out + ".txt", resident=(mode == "resident"))
     finally:
@@ -100,7 +102,7 @@ def test_full_size_callset_digest(gpu_caller, tmp_path, name, shards):
     whose floating-point columns print differently is bounded."""
     import hashlib
     idx, out, region = T.regenerate(name, tmp_path)
-    inp = T.LoadedInput(idx, out + ".snapshot", region)
+    inp = T.LoadedInput(idx, out + ".snapshot", region, pinned=0 if name == "stress_full" else 1)   # one of them through the staging ring
     try:
         st = T.call_to_txt(gpu_caller, inp, out + ".txt", shards=shards)
     finally:
