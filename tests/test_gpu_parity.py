@@ -130,3 +130,47 @@ def test_reference_harness_with_gt16_operator_shim(tmp_path, name):
     assert r.returncode == 0, r.stderr[-2000:]
     assert "Called Entries : %d" % T.manifest()[name]["rows"] in r.stdout
     T.compare_txt(open(out + ".txt", "rb").read(), T.golden_txt(name))
+
+
+def test_error_paths(tmp_path):
+    """failures are reported through status codes + gt16_last_error, never by computing something else"""
+    import ctypes
+    import numpy as np
+    L = T.capi()
+    idx, out, region = T.regenerate("wgs_small", tmp_path)
+    inp = T.LoadedInput(idx, out + ".snapshot", None)
+    ctx = ctypes.c_void_p()
+    assert L.gt16_ctx_create(0, ctypes.byref(ctx)) == 0
+    try:
+        calls = ctypes.c_void_p(); st = T.Stats()
+        # no tables yet
+        assert L.gt16_call_sites_host(ctx, ctypes.byref(inp.view), None, 0, 0, inp.total_sites, ctypes.byref(calls), ctypes.byref(st)) == -6
+        assert b"gt16_configure" in L.gt16_last_error(ctx)
+        assert L.gt16_configure(ctx, 0.01, 0.005, 1) == 0
+        # site_begin must be batch aligned
+        assert L.gt16_call_sites_host(ctx, ctypes.byref(inp.view), None, 0, 5, inp.total_sites, ctypes.byref(calls), ctypes.byref(st)) == -1
+        # region list that does not fit the index (VariantCaller.cpp:623-627)
+        bad = np.array([0, inp.view.text_length + 10], dtype=np.uint32)
+        assert L.gt16_call_sites_host(ctx, ctypes.byref(inp.view), bad.ctypes.data, 1, 0, 10, ctypes.byref(calls), ctypes.byref(st)) == -1
+        assert b"incompatible with the index" in L.gt16_last_error(ctx)
+        # a counter that points at an overflow record which does not exist -> GT16_EDATA, not a wild read
+        n = inp.view.text_length
+        counters = np.ctypeslib.as_array(ctypes.cast(inp.view.counters, ctypes.POINTER(ctypes.c_uint64)), (n,))
+        saved = int(counters[1000])
+        counters[1000] = 0xC000 | (0xC000 << 16) | (0x7FFFFFF0 << 32)
+        try:
+            rc = L.gt16_call_sites_host(ctx, ctypes.byref(inp.view), None, 0, 0, inp.total_sites, ctypes.byref(calls), ctypes.byref(st))
+            assert rc == -5 and b"overflow record" in L.gt16_last_error(ctx)
+        finally:
+            counters[1000] = saved
+        # and the context is still usable afterwards
+        assert L.gt16_call_sites_host(ctx, ctypes.byref(inp.view), None, 0, 0, inp.total_sites, ctypes.byref(calls), ctypes.byref(st)) == 0
+        assert L.gt16_calls_count(calls) == T.manifest()["wgs_small"]["rows"]
+        L.gt16_calls_free(calls)
+        # empty range
+        assert L.gt16_call_sites_host(ctx, ctypes.byref(inp.view), None, 0, 0, 0, ctypes.byref(calls), ctypes.byref(st)) == 0
+        assert L.gt16_calls_count(calls) == 0
+        L.gt16_calls_free(calls)
+    finally:
+        L.gt16_ctx_destroy(ctx)
+        inp.close()
