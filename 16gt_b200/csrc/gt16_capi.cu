@@ -83,6 +83,7 @@ struct gt16_ctx {
   double balance = 0.01, unbalance = 0.005;
   float prefillMs = 0.f, decisionMs = 0.f;
   uint32_t launches = 0;
+  uint32_t shortcutAlt = 0;               // stream_shortcut_bound() of the current decision bitmaps
   int numSMs = 148;
   // persistent scratch of the fused path
   DevBuf mask, counts, listA, listB, recs, recs2, planStart, planFirst;
@@ -306,6 +307,14 @@ int gt16_configure(gt16_ctx *ctx, double balance_sub_error, double unbalance_sub
   CU(cudaGetLastError());
   CU(cudaEventElapsedTime(&ctx->decisionMs, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  {
+    std::vector<uint32_t> h1(kS1Words), hp(kS2Words), hq(kS2Words);
+    CU(cudaMemcpy(h1.data(), ctx->s1, kS1Words * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hp.data(), ctx->s2p, kS2Words * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hq.data(), ctx->s2q, kS2Words * 4, cudaMemcpyDeviceToHost));
+    ctx->shortcutAlt = stream_shortcut_bound(h1.data(), hp.data(), hq.data());
+    if (getenv("GT16_NO_SHORTCUT")) ctx->shortcutAlt = 0;
+  }
   ctx->haveDecisions = true;
   return GT16_OK;
 }
@@ -609,7 +618,7 @@ void stream_range(gt16_ctx *ctx, const SnapView &V, const RegionPlan &pl, uint64
                   const DecisionTables &D, const EvalParams &P, uint32_t *mask) {
   if (tma_eligible(ctx, pl, a, useTables)) {
     uint32_t pBeg = pl.start[0] + (uint32_t) (a - pl.first[0]);
-    launch_stream_tma(V, pBeg, pBeg + (uint32_t) (b - a), D, mask, ctx->numSMs, ctx->compute);
+    launch_stream_tma(V, pBeg, pBeg + (uint32_t) (b - a), D, ctx->shortcutAlt, mask, ctx->numSMs, ctx->compute);
   } else {
     launch_stream(V, pl.map, a, (uint32_t) (b - a), useTables, D, P, mask, ctx->errWord, ctx->compute);
   }

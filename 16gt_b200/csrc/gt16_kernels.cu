@@ -166,10 +166,16 @@ __device__ __forceinline__ bool compact_needs_exact(const uint32_t *__restrict__
   return (s2[idx >> 5] >> (idx & 31)) & 1u;
 }
 
+// kShortcut (chosen at launch when the decision bitmaps allow it, see StreamShortcut): the bitmap (Wr) is all
+// zero -- a position where only the reference allele was seen is never a candidate -- and every row
+// (Wr < 1024, alt <= altBound >> 16) of the two-allele bitmaps is zero.  Then "reference allele in slot 1, plus
+// at most one more allele of weight <= bound in slot 2" is decided with two mask tests and no table read; that
+// is ~99 % of all positions of a 30x snapshot (a sequencing error adds one read of weight <= 4).
+template <bool kShortcut>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__ packedRef,
              const uint32_t *__restrict__ invalid, uint32_t pBeg, uint32_t pEnd, DecisionTables D,
-             uint32_t *__restrict__ mask) {
+             uint32_t altBound, uint32_t *__restrict__ mask) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
   StreamSmem &S = *reinterpret_cast<StreamSmem *>(smemRaw);
   const uint32_t nTiles = (pEnd - pBeg + kStreamTile - 1) / kStreamTile;
@@ -237,16 +243,26 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
       const uint32_t x = c[r].x, y = c[r].y, n = nlo[r];
       const uint32_t refx = rw[r] >> sh;
       const bool isRef1 = (((x >> 14) ^ refx) & 3u) == 0;
-      const bool oneSlot = (y - 1u) < 0xFFFFu;                 // slot 1 live, slot 2 dead
       const bool dead = y == 0;
       const bool special = ((x & 0xC000C000u) == 0xC000C000u) |
                            (((n & 0xC000C000u) == 0xC000C000u) & ((n & 0x20002000u) != 0));
       bool valid = (bw[r] & laneBit) == 0;
       if (partial) valid &= site < lim;
-      const bool simple1 = oneSlot & isRef1;
-      const bool bit = S.s1[x & 0x3FFFu] != 0;
-      const bool flag = valid & (special | (simple1 & bit) | (dead & deadBit));
-      const bool cplx = valid & !special & !simple1 & !dead;
+      bool flag, cplx;
+      if (kShortcut) {
+        const bool live1 = (y & 0xFFFFu) != 0;
+        const bool oneAllele = y < 0x10000u;                   // slot 2 dead
+        const bool tinyAlt = ((x & 0x3FFF0000u) <= altBound) & ((x & 0x3C00u) == 0);   // slot-2 weight <= bound, slot-1 weight < 1024
+        const bool settled = isRef1 & live1 & (oneAllele | tinyAlt);                   // certainly hom-ref
+        flag = valid & special;
+        cplx = valid & !special & !settled & !dead;
+      } else {
+        const bool oneSlot = (y - 1u) < 0xFFFFu;               // slot 1 live, slot 2 dead
+        const bool simple1 = oneSlot & isRef1;
+        const bool bit = S.s1[x & 0x3FFFu] != 0;
+        flag = valid & (special | (simple1 & bit) | (dead & deadBit));
+        cplx = valid & !special & !simple1 & !dead;
+      }
       const uint32_t word = __ballot_sync(0xffffffffu, flag);
       const uint32_t cw = __ballot_sync(0xffffffffu, cplx);
       if (lane == 0 && (!partial || site < lim)) mw[r] = word; // lane 0: site == first site of the row
@@ -286,15 +302,34 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
 
 // function attributes are per device: called once per context, with its device current
 cudaError_t configure_kernels() {
-  return cudaFuncSetAttribute(k_stream_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmem));
+  cudaError_t e = cudaFuncSetAttribute(k_stream_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_stream_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmem));
 }
 
-void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t *mask,
-                       int numSMs, cudaStream_t s) {
+// what the decision bitmaps (host copies) allow the streaming kernel to skip: returns the largest alt weight A
+// such that the (Wr) bitmap is all zero and rows alt = 1..A of both two-allele bitmaps are all zero (0 = none)
+uint32_t stream_shortcut_bound(const uint32_t *s1, const uint32_t *s2p, const uint32_t *s2q) {
+  for (size_t k = 0; k < kS1Words; ++k) if (s1[k]) return 0;
+  uint32_t a = 0;
+  for (uint32_t alt = 0; alt < (uint32_t) kS2A; ++alt) {       // row alt = 0 is the (Wr, 0) key again
+    bool zero = true;
+    for (uint32_t w = 0; w < (uint32_t) kS2R / 32 && zero; ++w) zero = !s2p[alt * (kS2R / 32) + w] && !s2q[alt * (kS2R / 32) + w];
+    if (!zero) break;
+    a = alt;
+  }
+  return a;
+}
+
+void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t shortcutAlt,
+                       uint32_t *mask, int numSMs, cudaStream_t s) {
   if (pEnd <= pBeg) return;
   uint32_t nTiles = (pEnd - pBeg + kStreamTile - 1) / kStreamTile;
   unsigned grid = nTiles < (uint32_t) numSMs ? nTiles : (unsigned) numSMs;
-  k_stream_tma<<<grid, kStreamThreads, sizeof(StreamSmem), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, mask);
+  if (shortcutAlt)
+    k_stream_tma<true><<<grid, kStreamThreads, sizeof(StreamSmem), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, shortcutAlt << 16, mask);
+  else
+    k_stream_tma<false><<<grid, kStreamThreads, sizeof(StreamSmem), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, 0, mask);
 }
 
 template <bool kUseTables>

@@ -42,8 +42,10 @@ void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint3
                    cudaStream_t s);
 // same contract for a dense single-region range of positions [pBeg,pEnd), pBeg % 128 == 0, arrays padded
 // by kStreamPadSites: persistent CTAs, TMA bulk copies into a shared-memory ring
-void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t *mask,
-                       int numSMs, cudaStream_t s);
+// shortcutAlt: stream_shortcut_bound() of the bitmaps in D (0 = take the table-driven path for every site)
+void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t shortcutAlt,
+                       uint32_t *mask, int numSMs, cudaStream_t s);
+uint32_t stream_shortcut_bound(const uint32_t *s1, const uint32_t *s2p, const uint32_t *s2q);
 // exact predicate for the listed (flagged) sites: clears bit list[j] of siteMask unless the site is a candidate
 void launch_eval_list(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
                       bool useTables, const DecisionTables &D, const EvalParams &P, uint32_t *siteMask,
