@@ -39,7 +39,18 @@ def main():
         try:
             argv, idx, out, region = synth_command(synth, name, wd)
             subprocess.run(argv, check=True, stderr=subprocess.DEVNULL)
-            cmd = [ref, idx, out] + ([region] if region else []) + ["-c", "/tmp/gt16_ref_lc.bin"]
+            exe = ref
+            ini = CONFIGS_ALL[name].get("ini")
+            cache = "/tmp/gt16_ref_lc.bin"
+            if ini:      # the reference reads <argv0>.ini: run it through a symlink with its own ini beside it
+                exe = os.path.join(wd, "ref_caller")
+                os.symlink(ref, exe)
+                text = open(ref + ".ini").read()
+                for k, v in ini.items():
+                    text = "\n".join(("%s=%g" % (k, v)) if l.split("=")[0].strip() == k else l for l in text.split("\n"))
+                open(exe + ".ini", "w").write(text)
+                cache = "/tmp/gt16_ref_lc_%s.bin" % name
+            cmd = [exe, idx, out] + ([region] if region else []) + ["-c", cache]
             r = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, text=True)
             called = [l for l in r.stdout.splitlines() if l.startswith("Called Entries")]
             txt = open(out + ".txt", "rb").read()
@@ -48,7 +59,7 @@ def main():
                     f.write(gzip.compress(txt, 9, mtime=0))
             files = {os.path.basename(p): sha(p) for p in
                      [out + ".snapshot", idx + ".pac", idx + ".ann", idx + ".tra"] + ([region] if region else [])}
-            manifest[name] = dict(inputs=files, rows=txt.count(b"\n") - 1, called=called[0] if called else "",
+            manifest[name] = dict(inputs=files, ini=CONFIGS_ALL[name].get("ini"), rows=txt.count(b"\n") - 1, called=called[0] if called else "",
                                   txt_sha256=hashlib.sha256(txt).hexdigest(), callset_sha256=T.callset_digest(txt)[0])
             print(name, manifest[name]["rows"], "rows")
         finally:

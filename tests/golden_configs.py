@@ -24,6 +24,13 @@ CONFIGS = {
                "--multi-pattern-frac", "0.5", "--long-indel-frac", "0.1", "--hotspot-rate", "2e-4",
                "--hotspot-depth", "1500", "--invalid-rate", "1e-3", "--ovf-regions", "7", "--gaps", "2:5000",
                "--seed", "13"], exome=False),
+    # same snapshot as stress_small, called with a non-default ini (ten distinct error tables, other decision
+    # bitmaps): pins the oracle and the GPU path against the reference away from the shipped error rates
+    "stress_small_ini2": dict(
+        synth=["--genome-len", "400000", "--n-contigs", "2", "--depth", "60", "--indel-rate", "2e-3",
+               "--multi-pattern-frac", "0.5", "--long-indel-frac", "0.1", "--hotspot-rate", "2e-4",
+               "--hotspot-depth", "1500", "--invalid-rate", "1e-3", "--ovf-regions", "7", "--gaps", "2:5000",
+               "--seed", "13"], exome=False, ini=dict(BalanceSubError=0.02, UnbalanceSubError=0.003)),
     "two_batch": dict(
         synth=["--genome-len", "8600000", "--n-contigs", "2", "--snp-rate", "4e-5", "--indel-rate", "1e-5",
                "--seed", "17"], exome=False),

@@ -21,7 +21,7 @@ REF_CALLER = os.path.join(REF_DIR, "ref_caller")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libgt16_oracle.so")
 EMU_LIB = os.path.join(ROOT, "tests", "host_emu", "libgt16_emu.so")
 
-from golden_configs import CONFIGS, synth_command  # noqa: E402
+from golden_configs import CONFIGS, CONFIGS_ALL, synth_command  # noqa: E402
 import importlib, sys
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -42,6 +42,12 @@ def sha256(path):
 
 def manifest():
     return json.load(open(os.path.join(GOLDEN, "MANIFEST.json")))
+
+
+def config_ini(name):
+    """(BalanceSubError, UnbalanceSubError) the config is called with"""
+    ini = CONFIGS_ALL[name].get("ini") or {}
+    return float(ini.get("BalanceSubError", 0.01)), float(ini.get("UnbalanceSubError", 0.005))
 
 
 def golden_txt(name):

@@ -23,10 +23,14 @@ def test_fused_path_matches_reference(gpu_caller, tmp_path, name, mode):
     through the library's page-locked ring by its stager threads; resident: snapshot uploaded once, then called"""
     idx, out, region = T.regenerate(name, tmp_path)
     inp = T.LoadedInput(idx, out + ".snapshot", region, pinned=0 if mode == "host_pageable" else 1)
+    bal, unbal = T.config_ini(name)
+    caller = gpu_caller if (bal, unbal) == (0.01, 0.005) else T.Caller(0, balance=bal, unbalance=unbal)
     try:
-        st = T.call_to_txt(gpu_caller, inp, out + ".txt", resident=(mode == "resident"))
+        st = T.call_to_txt(caller, inp, out + ".txt", resident=(mode == "resident"))
     finally:
         inp.close()
+        if caller is not gpu_caller:
+            caller.close()
     got = open(out + ".txt", "rb").read()
     want = T.golden_txt(name)
     nonident = T.compare_txt(got, want)
@@ -174,3 +178,36 @@ def test_error_paths(tmp_path):
     finally:
         L.gt16_ctx_destroy(ctx)
         inp.close()
+
+
+@pytest.mark.parametrize("name", ["wgs_small", "stress_small"])
+def test_table_driven_stream_variant(tmp_path, name, monkeypatch):
+    """the streaming kernel without the bitmap-derived shortcut (what a non-default ini may get): same output"""
+    monkeypatch.setenv("GT16_NO_SHORTCUT", "1")
+    idx, out, region = T.regenerate(name, tmp_path)
+    with T.Caller(0) as c:
+        inp = T.LoadedInput(idx, out + ".snapshot", region)
+        T.call_to_txt(c, inp, out + ".txt", resident=True)
+        inp.close()
+    T.compare_txt(open(out + ".txt", "rb").read(), T.golden_txt(name))
+
+
+@pytest.mark.parametrize("balance,unbalance", [(0.02, 0.01), (0.004, 0.001)])
+def test_non_default_ini_against_oracle(tmp_path, balance, unbalance):
+    """BalanceSubError / UnbalanceSubError other than the shipped ones: ten distinct tables, other decision bitmaps,
+    another (or no) shortcut bound.  The checker is the C oracle (pinned on the reference at the default ini; its
+    table and likelihood code is parametric in the two rates exactly like the reference's)."""
+    import ctypes
+    O = ctypes.CDLL(T.ORACLE_LIB)
+    O.oracle_run.argtypes = [ctypes.c_char_p] * 3 + [ctypes.c_double, ctypes.c_double, ctypes.c_char_p,
+                                                     ctypes.POINTER(ctypes.c_ulonglong)]
+    idx, out, region = T.regenerate("stress_small", tmp_path)
+    n = ctypes.c_ulonglong()
+    assert O.oracle_run(idx.encode(), (out + ".snapshot").encode(), b"", balance, unbalance, (out + ".oracle.txt").encode(),
+                        ctypes.byref(n)) == 0
+    with T.Caller(0, balance=balance, unbalance=unbalance) as c:
+        inp = T.LoadedInput(idx, out + ".snapshot", None)
+        st = T.call_to_txt(c, inp, out + ".txt")
+        inp.close()
+    assert sum(s.called for s in st) == n.value
+    T.compare_txt(open(out + ".txt", "rb").read(), open(out + ".oracle.txt", "rb").read())

@@ -79,7 +79,8 @@ def test_expf_reimplementation_is_glibc_expf(E):
 @pytest.mark.parametrize("name", list(T.CONFIGS))
 def test_whole_path_matches_reference_txt(E, tmp_path, name):
     idx, out, region = T.regenerate(name, tmp_path)
-    rc = E.emu_run(idx.encode(), (out + ".snapshot").encode(), (region or "").encode(), None, 0.01, 0.005,
+    bal, unbal = T.config_ini(name)
+    rc = E.emu_run(idx.encode(), (out + ".snapshot").encode(), (region or "").encode(), None, bal, unbal,
                    (out + ".txt").encode())
     assert rc == 0
     assert open(out + ".txt", "rb").read() == T.golden_txt(name)

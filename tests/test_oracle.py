@@ -97,7 +97,8 @@ def test_whole_path_matches_the_reference_txt(O, tmp_path, name):
     """snapshot in, .txt out: byte-identical to what oracle/_ref/ref_caller wrote for the same input"""
     idx, out, region = T.regenerate(name, tmp_path)
     n = ctypes.c_ulonglong()
-    rc = O.oracle_run(idx.encode(), (out + ".snapshot").encode(), (region or "").encode(), 0.01, 0.005,
+    bal, unbal = T.config_ini(name)
+    rc = O.oracle_run(idx.encode(), (out + ".snapshot").encode(), (region or "").encode(), bal, unbal,
                       (out + ".txt").encode(), ctypes.byref(n))
     assert rc == 0 and n.value == T.manifest()[name]["rows"]
     assert open(out + ".txt", "rb").read() == T.golden_txt(name)
