@@ -100,6 +100,11 @@ struct gt16_dev_snapshot {
   bool borrowed = false;      // buffers belong to the context's streaming arena
 };
 
+struct gt16_dev_calls {          // records left in the context's record buffer
+  const gt16_called_site *recs = nullptr;
+  uint64_t n = 0;
+};
+
 struct gt16_calls {
   std::shared_ptr<PinPool> pins;
   gt16_called_site *sites = nullptr;
@@ -651,7 +656,7 @@ struct SegTimes { float stream = 0, scan = 0, eval = 0, cand = 0; };
 int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t begin, uint64_t a, uint64_t b,
                    bool usedTables, const DecisionTables &D, size_t &evNext, uint32_t seg, gt16_calls *calls,
                    gt16_stats *st, uint64_t resultHint, cudaEvent_t evStream0, cudaEvent_t evStream1, cudaEvent_t haloReady,
-                   std::vector<cudaEvent_t> &timing, std::vector<cudaEvent_t> &segCopied) {
+                   std::vector<cudaEvent_t> &timing, std::vector<cudaEvent_t> &segCopied, gt16_dev_calls *devOut) {
   EvalParams P = eval_params(ctx);
   uint32_t *mask = (uint32_t *) ctx->mask.p + (a - begin) / 32;
   const uint32_t n = (uint32_t) (b - a), off = (uint32_t) (a - begin);
@@ -677,8 +682,7 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
   // may still be in flight while the next one is being written
   DevBuf &rb = (seg & 1) ? ctx->recs2 : ctx->recs;
   CUF(rb.ensure((size_t) (nB ? nB : 1) * sizeof(gt16_called_site)));
-  rc = reserve_results(ctx, calls, nB, resultHint);
-  if (rc) return rc;
+  if (!devOut) { rc = reserve_results(ctx, calls, nB, resultHint); if (rc) return rc; }
   if (haloReady) CUF(cudaStreamWaitEvent(ctx->compute, haloReady, 0));   // windows reach up to 355 positions past b
   if (seg >= 2) CUF(cudaStreamWaitEvent(ctx->compute, segCopied[seg - 2], 0));   // this record buffer's previous contents are on the host
   CUF(cudaEventRecord(ev[2], ctx->compute));
@@ -696,8 +700,10 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
     CUF(cudaStreamWaitEvent(ctx->aux, se, 0));
     launch_bias(V, pl.map, begin, finalList + o, cnt, P, recs + o, ctx->aux);
     CUF(cudaEventRecord(be, ctx->aux));
-    CUF(cudaStreamWaitEvent(ctx->d2h, be, 0));
-    CUF(cudaMemcpyAsync(calls->sites + calls->n + o, recs + o, (size_t) cnt * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->d2h));
+    if (!devOut) {
+      CUF(cudaStreamWaitEvent(ctx->d2h, be, 0));
+      CUF(cudaMemcpyAsync(calls->sites + calls->n + o, recs + o, (size_t) cnt * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->d2h));
+    }
   }
   {                                                          // the segment's timing ends when its last tests are done
     cudaEvent_t auxDone;
@@ -713,7 +719,7 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
     CUF(cudaEventRecord(done, ctx->d2h));
     segCopied.push_back(done);
   }
-  calls->n += nB;
+  if (devOut) { devOut->recs = recs; devOut->n = nB; } else calls->n += nB;
   st->flagged += nA;
   st->called += nB;
   timing.push_back(evStream0); timing.push_back(evStream1);
@@ -725,9 +731,10 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
 
 static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const gt16_dev_snapshot *resident,
                        const gt16_region *regions, uint32_t nRegions, uint64_t begin, uint64_t end,
-                       gt16_calls **out, gt16_stats *stats) {
-  if (!ctx || !out) return GT16_EINVAL;
+                       gt16_calls **out, gt16_stats *stats, gt16_dev_calls **devOutHandle = nullptr) {
+  if (!ctx || (!out && !devOutHandle)) return GT16_EINVAL;
   if (!ctx->havePrefill) return fail(ctx, GT16_ESTATE, "gt16_configure / gt16_prefill_likelihood_cache must run first");
+  std::unique_ptr<gt16_dev_calls> devOut(devOutHandle ? new gt16_dev_calls() : nullptr);
   CU(cudaSetDevice(ctx->device));
   const uint32_t L = resident ? resident->v.L : hostView->text_length;
   RegionPlan pl;
@@ -748,7 +755,11 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   gt16_stats st;
   memset(&st, 0, sizeof(st));
   st.sites = n;
-  if (n == 0) { *out = calls.release(); if (stats) *stats = st; return GT16_OK; }
+  if (n == 0) {
+    if (devOutHandle) *devOutHandle = devOut.release(); else *out = calls.release();
+    if (stats) *stats = st;
+    return GT16_OK;
+  }
 
   size_t evNext = 0;
   cudaEvent_t evBegin, evEnd;
@@ -903,7 +914,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     CUF(cudaEventRecord(es1, ctx->compute));
     // windows, neighbours' Fisher tests and the indel look-ahead reach up to ~360 positions past the segment
     if ((rc = wait_chunks(pl.ascending ? (uint64_t) pl.pos_of(b - 1) + 600 : copyHi))) return rc;
-    rc = finish_segment(ctx, *V, pl, begin, a, b, useTables, D, evNext, seg, calls.get(), &st, resultHint, es0, es1, nullptr, timing, segCopied);
+    rc = finish_segment(ctx, *V, pl, begin, a, b, useTables, D, evNext, seg, calls.get(), &st, resultHint, es0, es1, nullptr, timing, segCopied, devOut.get());
     if (rc != GT16_OK) return rc;
   }
   // drain: results on the host, error word
@@ -935,7 +946,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   st.ms_total_device = ms_between(evBegin, evEnd);
   st.ms_d2h = st.ms_total_device - lastCand;            // tail after the last candidate slice was written
   st.kernel_launches = ctx->launches - launches0;
-  *out = calls.release();
+  if (devOutHandle) *devOutHandle = devOut.release(); else *out = calls.release();
   if (stats) *stats = st;
   return GT16_OK;
 }
@@ -946,6 +957,30 @@ int gt16_call_sites(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_reg
                     uint64_t site_begin, uint64_t site_end, gt16_calls **out, gt16_stats *stats) {
   if (!snap) return GT16_EINVAL;
   return call_common(ctx, nullptr, snap, regions, n_regions, site_begin, site_end, out, stats);
+}
+
+int gt16_call_sites_device(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
+                           uint64_t site_begin, uint64_t site_end, gt16_dev_calls **out, gt16_stats *stats) {
+  if (!snap || !out) return GT16_EINVAL;
+  return call_common(ctx, nullptr, snap, regions, n_regions, site_begin, site_end, nullptr, stats, out);
+}
+uint64_t gt16_dev_calls_count(const gt16_dev_calls *c) { return c ? c->n : 0; }
+const void *gt16_dev_calls_device_ptr(const gt16_dev_calls *c) { return c && c->n ? c->recs : nullptr; }
+void gt16_dev_calls_free(gt16_dev_calls *c) { delete c; }
+int gt16_dev_calls_fetch(gt16_ctx *ctx, const gt16_dev_calls *c, gt16_calls **out) {
+  if (!ctx || !c || !out) return GT16_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  std::unique_ptr<gt16_calls> calls(new gt16_calls());
+  calls->pins = ctx->pins;
+  if (c->n) {
+    calls->sites = (gt16_called_site *) ctx->pins->take((size_t) c->n * sizeof(gt16_called_site), &calls->cap);
+    if (!calls->sites) return fail(ctx, GT16_ECUDA, "cudaHostAlloc of the result buffer failed");
+    CU(cudaMemcpyAsync(calls->sites, c->recs, (size_t) c->n * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->d2h));
+    CU(cudaStreamSynchronize(ctx->d2h));
+    calls->n = c->n;
+  }
+  *out = calls.release();
+  return GT16_OK;
 }
 
 int gt16_call_sites_host(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt16_region *regions,

@@ -161,6 +161,25 @@ def reference_arm(args):
     return 0
 
 
+def bind_to_gpu_numa_node(device):
+    """Run this rank (and allocate its page-locked buffers) on the CPUs next to its GPU: with one process per GPU on
+    a two-socket box, host<->device copies from the far socket cross the inter-socket link and collapse when all
+    ranks copy at once.  Uses NVML's CPU affinity for the device; silently does nothing if that is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def main():
     # exactly ONE line on stdout: libraries (NCCL's version banner, ...) that print to fd 1 are sent to stderr
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -187,6 +206,7 @@ def main():
         sys.stderr.write("bench.py: no CUDA device -- the hot path has no CPU implementation\n")
         return 2
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -211,6 +231,15 @@ def main():
         caller.check(L.gt16_snapshot_upload(caller.ctx, ctypes.byref(inp.view), ctypes.byref(dev)))
 
         def step_resident():
+            # inputs resident in HBM, records left in HBM (gt16_call_sites_device): the device-side pipeline
+            calls, st = ctypes.c_void_p(), capi.Stats()
+            caller.check(L.gt16_call_sites_device(caller.ctx, dev, None, 0, 0, sites, ctypes.byref(calls), ctypes.byref(st)))
+            n = L.gt16_dev_calls_count(calls)
+            L.gt16_dev_calls_free(calls)
+            return st, n
+
+        def step_resident_host_results():
+            # same, but the records are also copied to page-locked host memory inside the step (gt16_call_sites)
             calls, st = ctypes.c_void_p(), capi.Stats()
             caller.check(L.gt16_call_sites(caller.ctx, dev, None, 0, 0, sites, ctypes.byref(calls), ctypes.byref(st)))
             n = L.gt16_calls_count(calls)
@@ -241,6 +270,7 @@ def main():
             return dt, stats, clocks
 
         dt, stats, clocks = timed(step_resident, args.warmup, args.steps, rank == 0)
+        dt_hr, stats_hr, _ = timed(step_resident_host_results, 1, max(2, min(args.steps, 5)), False)
         dt_e2e, stats_e2e, _ = timed(step_host, 1, max(2, min(args.steps, 5)), False)
         n_e2e = len(stats_e2e)
 
@@ -279,6 +309,10 @@ def main():
                        "setup_ms": {"table_prefill": pre_ms.value, "decision_bitmaps": dec_ms.value}},
             "e2e": {"value": world * sites * n_e2e / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1000.0 * dt_e2e / n_e2e},
+            "value_with_host_results": {"value": world * sites * len(stats_hr) / dt_hr, "unit": UNIT,
+                                        "ms_per_step": 1000.0 * dt_hr / len(stats_hr), "d2h_bytes_per_step": d2h,
+                                        "note": "value = inputs AND called-site records resident in HBM (gt16_call_sites_device); "
+                                                "this line adds the copy of the records to page-locked host memory"},
             "gpu_launches": launches,
             "device_ms_per_step": ms_dev, "device_ms_breakdown": parts,
             "roofline": {"bound": "hbm", "kernel": "k_stream (decode + 16-genotype classification of every site)",

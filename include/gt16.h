@@ -159,6 +159,17 @@ void gt16_snapshot_release(gt16_ctx *ctx, gt16_dev_snapshot *snap);
 int gt16_call_sites(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
                     uint64_t site_begin, uint64_t site_end, gt16_calls **out, gt16_stats *stats);
 
+/* Same call with the result left in HBM (inputs resident, outputs resident): for callers that consume the records
+ * on the device or fetch them later.  The handle refers to storage owned by the context and is valid until the
+ * next call on that context; gt16_dev_calls_fetch() copies the records to the host. */
+typedef struct gt16_dev_calls gt16_dev_calls;
+int gt16_call_sites_device(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
+                           uint64_t site_begin, uint64_t site_end, gt16_dev_calls **out, gt16_stats *stats);
+uint64_t gt16_dev_calls_count(const gt16_dev_calls *calls);
+const void *gt16_dev_calls_device_ptr(const gt16_dev_calls *calls);   /* gt16_called_site[count] in device memory */
+int gt16_dev_calls_fetch(gt16_ctx *ctx, const gt16_dev_calls *calls, gt16_calls **out);
+void gt16_dev_calls_free(gt16_dev_calls *calls);
+
 /* Same, from HOST buffers: counter blocks are streamed into HBM on the copy stream while the
  * previous block is being evaluated; includes the device->host copy of the calls. */
 int gt16_call_sites_host(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt16_region *regions,

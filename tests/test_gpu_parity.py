@@ -211,3 +211,31 @@ def test_non_default_ini_against_oracle(tmp_path, balance, unbalance):
         inp.close()
     assert sum(s.called for s in st) == n.value
     T.compare_txt(open(out + ".txt", "rb").read(), open(out + ".oracle.txt", "rb").read())
+
+
+def test_device_resident_results(gpu_caller, tmp_path):
+    """gt16_call_sites_device leaves the records in HBM; fetching them gives exactly the records gt16_call_sites returns"""
+    import ctypes
+    import numpy as np
+    L = gpu_caller.L
+    idx, out, region = T.regenerate("stress_small", tmp_path)
+    inp = T.LoadedInput(idx, out + ".snapshot", None)
+    dev = ctypes.c_void_p()
+    gpu_caller.check(L.gt16_snapshot_upload(gpu_caller.ctx, ctypes.byref(inp.view), ctypes.byref(dev)))
+    try:
+        a = ctypes.c_void_p(); st = T.Stats()
+        gpu_caller.check(L.gt16_call_sites(gpu_caller.ctx, dev, None, 0, 0, inp.total_sites, ctypes.byref(a), ctypes.byref(st)))
+        ra = T.capi_mod.calls_array(L, a)
+        L.gt16_calls_free(a)
+        d = ctypes.c_void_p()
+        gpu_caller.check(L.gt16_call_sites_device(gpu_caller.ctx, dev, None, 0, 0, inp.total_sites, ctypes.byref(d), ctypes.byref(st)))
+        assert L.gt16_dev_calls_count(d) == len(ra) == T.manifest()["stress_small"]["rows"]
+        assert L.gt16_dev_calls_device_ptr(d)
+        b = ctypes.c_void_p()
+        gpu_caller.check(L.gt16_dev_calls_fetch(gpu_caller.ctx, d, ctypes.byref(b)))
+        rb = T.capi_mod.calls_array(L, b)
+        L.gt16_calls_free(b); L.gt16_dev_calls_free(d)
+        assert ra.tobytes() == rb.tobytes()
+    finally:
+        L.gt16_snapshot_release(gpu_caller.ctx, dev)
+        inp.close()
