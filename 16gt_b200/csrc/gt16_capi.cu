@@ -19,6 +19,7 @@
 using namespace gt16;
 
 static std::string g_createError;
+static const uint32_t kBiasCacheEntries = 1u << 20;     // 8 MB, stays in L2
 
 namespace {
 
@@ -84,6 +85,7 @@ struct gt16_ctx {
   float prefillMs = 0.f, decisionMs = 0.f;
   uint32_t launches = 0;
   uint32_t shortcutAlt = 0;               // stream_shortcut_bound() of the current decision bitmaps
+  uint2 *biasCache = nullptr;             // memoised Fisher tests (k_bias), kBiasCacheEntries entries
   int numSMs = 148;
   // persistent scratch of the fused path
   DevBuf mask, counts, listA, listB, recs, recs2, planStart, planFirst;
@@ -195,6 +197,8 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   ctx->dTotal = ctx->errWord + 1;
   if ((e = cudaHostAlloc(&ctx->hPinned, 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
   if ((e = cudaMemset(ctx->errWord, 0, 2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMalloc(&ctx->biasCache, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemset(ctx->biasCache, 0xFF, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMemset", e);
   // defaults of selectPossibleSNPs (VariantCaller.cpp:506-513)
   const unsigned g2i[16] = {0, 1, 2, 3, 9, 10, 11, 18, 19, 27, 4, 12, 20, 28, 36, 37};
   double prior[256];
@@ -225,6 +229,7 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   cudaFree(ctx->ycsq); cudaFree(ctx->prior); cudaFree(ctx->g2i); cudaFree(ctx->lnfact);
   cudaFree(ctx->s1); cudaFree(ctx->s2p); cudaFree(ctx->s2q); cudaFree(ctx->g4);
   cudaFree(ctx->errWord);
+  cudaFree(ctx->biasCache);
   cudaFreeHost(ctx->hPinned);
   for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->listA, &ctx->listB, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst,
                     &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
@@ -698,7 +703,7 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
     if ((rc = get_event(ctx, evNext++, &se)) || (rc = get_event(ctx, evNext++, &be))) return rc;
     CUF(cudaEventRecord(se, ctx->compute));
     CUF(cudaStreamWaitEvent(ctx->aux, se, 0));
-    launch_bias(V, pl.map, begin, finalList + o, cnt, P, recs + o, ctx->aux);
+    launch_bias(V, pl.map, begin, finalList + o, cnt, P, ctx->biasCache, kBiasCacheEntries - 1, recs + o, ctx->aux);
     CUF(cudaEventRecord(be, ctx->aux));
     if (!devOut) {
       CUF(cudaStreamWaitEvent(ctx->d2h, be, 0));

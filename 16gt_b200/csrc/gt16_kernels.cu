@@ -579,7 +579,7 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
-__global__ void __launch_bounds__(kCandThreads) k_candidates(SnapView V, DevSiteMap M, uint64_t base,
+__global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevSiteMap M, uint64_t base,
                                                              const uint32_t *__restrict__ list, uint32_t n,
                                                              EvalParams P, gt16_called_site *__restrict__ out,
                                                              uint32_t *errWord) {
@@ -742,7 +742,7 @@ struct BiasTask { uint32_t W, F, R, dst; };      // dst = record * 12 + k * 4 + 
 struct FisherWalk {                               // state of one fisher2tailC evaluation
   int n1_, n_1, n, x, lo, hi, n11;
   float pox, poa, poa_e, two;
-  uint32_t dst;
+  uint32_t dst, key;                              // key: cache key of the running test (0xFFFFFFFF = not cacheable)
   int phase;                                      // 0 idle, 1 left walk, 2 right walk
   bool stopAtZero;
 };
@@ -786,8 +786,20 @@ __device__ __forceinline__ void walk_step(FisherWalk &w) {
   }
 }
 
+// A test is a pure function of its three counts, and a genome repeats the same (F, R) and (W, F+R) pairs
+// endlessly, so finished tests are memoised in a direct-mapped cache in global memory (L2-resident, owned by the
+// context, kept across calls): {key, result} in one aligned 8-byte word.  A hit returns the very value a walk
+// would produce; a miss runs the walk and stores it.  Keys that do not fit 32 bits (W >= 32768 or F+R >= 65536)
+// are simply not cached.
+__device__ __forceinline__ uint32_t bias_key(bool bqb, uint32_t W, uint32_t F, uint32_t R) {
+  if (bqb) { const uint32_t S = F + R; return (W < 32768u && S < 65536u && !(W == 32767u && S == 65535u)) ? (0x80000000u | (W << 16) | S) : 0xFFFFFFFFu; }
+  return (F < 32768u && R < 65536u) ? ((F << 16) | R) : 0xFFFFFFFFu;
+}
+__device__ __forceinline__ uint32_t bias_slot(uint32_t key, uint32_t mask) { return ((key * 0x9E3779B1u) ^ (key >> 15)) & mask; }
+
 __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M, uint64_t base,
                                                        const uint32_t *__restrict__ list, uint32_t n, LnFact G,
+                                                       uint2 *__restrict__ cache, uint32_t cacheMask,
                                                        gt16_called_site *__restrict__ out) {
   __shared__ float lnS[kLnSmem];
   __shared__ BiasTask queue[kBiasThreads / 32][kBiasQueue];
@@ -809,6 +821,10 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
     const uint32_t k = (d % 12) >> 2, b = d & 3;
     const float v = fminf(1.0f, w.two);
     if (w.dst >> 31) o.bqb[k][b] = v; else o.sb[k][b] = v;
+    if (w.key != 0xFFFFFFFFu) {                      // memoise (8-byte store: key and value land together)
+      *reinterpret_cast<volatile unsigned long long *>(cache + bias_slot(w.key, cacheMask)) =
+          (unsigned long long) w.key | ((unsigned long long) __float_as_uint(v) << 32);
+    }
   };
   auto refill = [&]() {                            // finished lanes store; idle lanes take queued tests
     if (w.phase == 3) { store_result(); w.phase = 0; }
@@ -818,6 +834,7 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
       const uint32_t rank = __popc(idle & ltMask);
       if (w.phase == 0 && rank < avail) {
         const BiasTask t = q[(qhead + rank) % kBiasQueue];
+        w.key = bias_key(t.dst >> 31, t.W, t.F, t.R);
         if (t.dst >> 31) { const int S = (int) ((t.F + t.R) * 4); walk_begin(L, w, (int) t.W, S, S, S, t.dst); }      // getBaseQualityBias
         else { const int S = (int) (t.F + t.R); walk_begin(L, w, (int) t.F, (int) t.R, (int) (S * 0.5), (int) (S * 0.5), t.dst); }  // getStrandBiasC
       }
@@ -866,8 +883,21 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
       if (!pending) { out[j].sb[k][b] = sbv; out[j].bqb[k][b] = bqv; }
     }
     BiasTask tb = t; tb.dst |= 0x80000000u;
-    push(pending, t);                               // strand test
-    push(pending, tb);                              // base-quality test
+    bool needS = pending, needB = pending;
+    if (pending) {                                  // memoised?
+      const uint32_t kS = bias_key(false, t.W, t.F, t.R), kB = bias_key(true, t.W, t.F, t.R);
+      const uint32_t j = slot / 12, k = (slot % 12) >> 2, b = slot & 3;
+      if (kS != 0xFFFFFFFFu) {
+        const unsigned long long e = *reinterpret_cast<const volatile unsigned long long *>(cache + bias_slot(kS, cacheMask));
+        if ((uint32_t) e == kS) { out[j].sb[k][b] = __uint_as_float((uint32_t) (e >> 32)); needS = false; }
+      }
+      if (kB != 0xFFFFFFFFu) {
+        const unsigned long long e = *reinterpret_cast<const volatile unsigned long long *>(cache + bias_slot(kB, cacheMask));
+        if ((uint32_t) e == kB) { out[j].bqb[k][b] = __uint_as_float((uint32_t) (e >> 32)); needB = false; }
+      }
+    }
+    push(needS, t);                                 // strand test
+    push(needB, tb);                                // base-quality test
     // keep room for the next chunk's (up to 64) tests
     while (qtail - qhead > (uint32_t) (kBiasQueue - 64)) {
       refill();
@@ -883,7 +913,7 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
   }
 }
 void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
-                 const EvalParams &P, gt16_called_site *out, cudaStream_t s) {
+                 const EvalParams &P, uint2 *cache, uint32_t cacheMask, gt16_called_site *out, cudaStream_t s) {
   if (!n) return;
   const uint32_t chunks = (n * 12u + 31) / 32, perBlock = kBiasThreads / 32;
   // the walks are long dependent chains: what matters is how many run at once, so spread the chunks
@@ -891,7 +921,7 @@ void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const ui
   unsigned grid = (chunks + perBlock - 1) / perBlock;
   if (grid > 148 * 4) grid = 148 * 4;
   if (grid < 1) grid = 1;
-  k_bias<<<grid, kBiasThreads, 0, s>>>(V, M, base, list, n, P.lnfact, out);
+  k_bias<<<grid, kBiasThreads, 0, s>>>(V, M, base, list, n, P.lnfact, cache, cacheMask, out);
 }
 
 // ------------------------------------------------------------------------------ operator seam

@@ -64,8 +64,9 @@ void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, co
                        const EvalParams &P, gt16_called_site *out, uint32_t *errWord, cudaStream_t s);
 
 // strand-bias / base-quality-bias Fisher tests of the records written by launch_candidates (same list)
+// cache: (cacheMask + 1) 8-byte {key, result} entries, all bytes 0xFF when empty (see k_bias)
 void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
-                 const EvalParams &P, gt16_called_site *out, cudaStream_t s);
+                 const EvalParams &P, uint2 *cache, uint32_t cacheMask, gt16_called_site *out, cudaStream_t s);
 
 // operator seam kernels
 void launch_op_likelihood(const EvalParams &P, const uint8_t *w, size_t wStride, const uint8_t *ref,
