@@ -237,6 +237,18 @@ struct Posterior {
 };
 GT16_HD int hom_ref_genotype(int ref) { return ref == 0 ? 0 : ref == 1 ? 4 : ref == 2 ? 7 : 9; }  // SNP_Caller.cpp:400
 
+// best / second-best scan over the 16 posteriors with the reference's tie rules (:383-504)
+GT16_HD void argmax_posteriors(Posterior &o) {
+  int best; double f0, f1;
+  if (o.flh[0] >= o.flh[1]) { best = 0; f0 = o.flh[0]; f1 = o.flh[1]; }
+  else { best = 1; f0 = o.flh[1]; f1 = o.flh[0]; }
+  for (int g = 2; g < 16; ++g) {
+    if (o.flh[g] > f0) { f1 = f0; f0 = o.flh[g]; best = g; }
+    else if (o.flh[g] > f1) { f1 = o.flh[g]; }
+  }
+  o.bestD = f0; o.secondD = f1; o.genotype = best;
+}
+
 GT16_HDN void select_genotype(int ref, const double *lh, const double *prior256, const uint32_t *g2i,
                               Posterior &o) {
   double pD = lh[0];
@@ -249,14 +261,7 @@ GT16_HDN void select_genotype(int ref, const double *lh, const double *prior256,
     return;
   }
   for (int g = 0; g < 16; ++g) o.flh[g] = lh[g] / pD * prior256[(ref << 6) | g2i[g]];
-  int best; double f0, f1;
-  if (o.flh[0] >= o.flh[1]) { best = 0; f0 = o.flh[0]; f1 = o.flh[1]; }
-  else { best = 1; f0 = o.flh[1]; f1 = o.flh[0]; }
-  for (int g = 2; g < 16; ++g) {
-    if (o.flh[g] > f0) { f1 = f0; f0 = o.flh[g]; best = g; }
-    else if (o.flh[g] > f1) { f1 = o.flh[g]; }
-  }
-  o.bestD = f0; o.secondD = f1; o.genotype = best;
+  argmax_posteriors(o);
 }
 
 // prior table (createSnpPriorArray, SNPFunctions.cpp:13-70); index ref<<6 | a1<<3 | a2

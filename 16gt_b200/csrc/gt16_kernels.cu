@@ -568,6 +568,7 @@ void launch_mask_scatter(const uint32_t *mask, uint32_t nItems, const uint32_t *
 constexpr int kCandThreads = 128;
 struct CandWarpSmem {
   double lh[16];
+  double flh[16];
   uint32_t sc[2][kWindow + 4];
   uint32_t w[2][kWindow + 4];
   uint8_t fl[2][kWindow + 4];      // bit0 valid, bit1 gc
@@ -610,8 +611,26 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
     double lh[16];
 #pragma unroll
     for (int g = 0; g < 16; ++g) lh[g] = sm.lh[g];
+    // posterior (selectGenotype, FisherExactTest.cpp:317-509): the sum is sequential in every lane, the sixteen
+    // divisions -- by far the most expensive part in FP64 -- are one per lane, the best / second scan reads them back
     Posterior po;
-    select_genotype(ref, lh, P.prior, P.g2i, po);
+    {
+      double pD = lh[0];
+#pragma unroll
+      for (int g = 1; g < 16; ++g) pD = pD + lh[g];
+      po.pD = pD;
+      if (pD == 0.0) {
+        po.genotype = hom_ref_genotype(ref);
+        for (int g = 0; g < 16; ++g) po.flh[g] = 0;
+        po.bestD = 0; po.secondD = 0;
+      } else {
+        if (lane < 16) sm.flh[lane] = lh[lane] / pD * P.prior[(ref << 6) | P.g2i[lane]];
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 16; ++g) po.flh[g] = sm.flh[g];
+        argmax_posteriors(po);
+      }
+    }
     const uint8_t isValid = (uint8_t) (1 + ii.isValidPlus);
     uint8_t isIndel = 0, nextBp = 0;
     if (po.genotype > 9) {                                              // SNP_Caller.cpp:228-239
