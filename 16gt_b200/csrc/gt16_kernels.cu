@@ -574,11 +574,7 @@ struct CandWarpSmem {
   uint8_t fl[2][kWindow + 4];      // bit0 valid, bit1 gc
 };
 
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }   // one REDUX.SUM
 
 __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevSiteMap M, uint64_t base,
                                                              const uint32_t *__restrict__ list, uint32_t n,
