@@ -254,24 +254,28 @@ def main():
             L.gt16_calls_free(calls)
             return st, n
 
-        def timed(fn, warmup, steps, sample_clocks):
+        def timed(fn, warmup, steps):
             for _ in range(warmup):
                 fn()
-            sampler = ClockSampler(local) if sample_clocks else None
             barrier()
-            if sampler:
-                sampler.start()
             t0 = time.perf_counter()
             stats = [fn() for _ in range(steps)]
             barrier()
             dt = time.perf_counter() - t0
-            clocks = sampler.stop() if sampler else None
             dt = sharding.max_over_ranks(dt, dist if world > 1 else None, "cuda")
-            return dt, stats, clocks
+            return dt, stats
 
-        dt, stats, clocks = timed(step_resident, args.warmup, args.steps, rank == 0)
-        dt_hr, stats_hr, _ = timed(step_resident_host_results, 1, max(2, min(args.steps, 5)), False)
-        dt_e2e, stats_e2e, _ = timed(step_host, 1, max(2, min(args.steps, 5)), False)
+        # clocks / throttle reasons are sampled over the whole measurement phase (warm-ups and the three timed loops
+        # are all under load; one timed loop alone lasts only milliseconds, less than nvidia-smi's sampling period)
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+            for _ in range(40):            # keep the GPU busy until the sampler has certainly started
+                step_resident()
+        dt, stats = timed(step_resident, args.warmup, args.steps)
+        dt_hr, stats_hr = timed(step_resident_host_results, 1, max(2, min(args.steps, 5)))
+        dt_e2e, stats_e2e = timed(step_host, 1, max(2, min(args.steps, 5)))
+        clocks = sampler.stop() if sampler else None
         n_e2e = len(stats_e2e)
 
         launches = sum(s.kernel_launches for s, _ in stats)
