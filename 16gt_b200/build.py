@@ -72,6 +72,12 @@ def build(force=False, verbose=True):
               "-L", os.path.join(PKG, "lib"), "-lgt16", "-Wl,-rpath,$ORIGIN/../lib",
               "-Wl,-rpath-link,/usr/local/cuda/lib64", "-lpthread"])
         shutil.copyfile(os.path.join(PKG, "host", "snapshotSnpcaller.ini"), cli + ".ini")
+    rib_src = os.path.join(PKG, "host", "RegionIndexBuilder.cpp")
+    rib = os.path.join(PKG, "bin", "RegionIndexBuilder")
+    if os.path.exists(rib_src) and (force or not _newer(rib, [rib_src, lib] + hdrs)):
+        _run([HOST_CXX, "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), rib_src, "-o", rib,
+              "-L", os.path.join(PKG, "lib"), "-lgt16", "-Wl,-rpath,$ORIGIN/../lib",
+              "-Wl,-rpath-link,/usr/local/cuda/lib64", "-lpthread"])
     # synthetic data generator
     synth_src = os.path.join(ROOT, "tools", "gt16_synth.cpp")
     synth = os.path.join(ROOT, "tools", "gt16_synth")

@@ -293,6 +293,26 @@ const char *gt16_index_translate(const gt16_index *ix, uint32_t amb, uint32_t *c
   return c < ix->names.size() ? ix->names[c].c_str() : "?";
 }
 
+int gt16_index_locate(const gt16_index *ix, const char *chrName, uint32_t chrPos, uint32_t *amb) {
+  if (!ix || !chrName || !amb) return -1;
+  // getChrIDFromName: exact name, else the name without a leading "chr" (indexFunction.cpp:42-66; its third
+  // attempt compares the unprefixed name again and so never matches anything new)
+  size_t id = ix->names.size();
+  for (size_t i = 0; i < ix->names.size(); ++i) if (ix->names[i] == chrName) { id = i; break; }
+  if (id == ix->names.size() && strncmp(chrName, "chr", 3) == 0)
+    for (size_t i = 0; i < ix->names.size(); ++i) if (ix->names[i] == chrName + 3) { id = i; break; }
+  if (id == ix->names.size()) return -1;
+  // getAmbPos: the concatenated position whose translation is (id + 1, chrPos)
+  for (size_t k = 0; k < ix->translate.size(); ++k) {
+    const gt16_index::Tr &t = ix->translate[k];
+    if ((size_t) t.chrID != id + 1) continue;
+    const uint32_t a = chrPos + t.correction;
+    const uint64_t next = k + 1 < ix->translate.size() ? ix->translate[k + 1].startPos : (uint64_t) ix->length;
+    if (a >= t.startPos && (uint64_t) a < next && a < ix->length) { *amb = a; return 0; }
+  }
+  return -1;
+}
+
 void gt16_index_free(gt16_index *ix) { delete ix; }
 
 // ---- .txt emitter (interpreter.cpp:5-156) ---------------------------------------------

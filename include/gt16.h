@@ -194,6 +194,10 @@ uint32_t gt16_index_length(const gt16_index *ix);
 const uint32_t *gt16_index_packed(const gt16_index *ix, uint32_t *n_words);
 /* getChrAndPos (HSP.h:273-275): concatenated position -> (sequence name, 1-based position) */
 const char *gt16_index_translate(const gt16_index *ix, uint32_t amb, uint32_t *chr_pos);
+/* getChrIDFromName + getAmbPos (indexFunction.cpp:6-66): sequence name (with the reference's "chr" prefix
+ * leniency) and 1-based position -> concatenated position; returns 0 and *amb, or -1 when there is no such
+ * position (unknown sequence, beyond its end, inside a removed stretch) */
+int gt16_index_locate(const gt16_index *ix, const char *chr_name, uint32_t chr_pos, uint32_t *amb);
 void gt16_index_free(gt16_index *ix);
 
 /* printHeader + printPossibleSNP (interpreter.cpp:8-31,107-156): byte-identical layout */

@@ -78,6 +78,45 @@ def test_index_and_snapshot_readers(tmp_path):
     assert b"Error opening" in err.value
 
 
+def test_region_index_builder_matches_reference(tmp_path):
+    """RegionIndexBuilder (buildRegionList.cpp): byte-identical region.bin for the seeded BED and GFF lists of
+    tests/golden/regions (made by the unmodified reference tool, tests/golden/make_region_golden.py); plus the
+    coordinate lookup it rests on (getChrIDFromName / getAmbPos, indexFunction.cpp:6-66)."""
+    idx, out, region = T.regenerate("stress_small", tmp_path)
+    rib = os.path.join(T.PKG, "bin", "RegionIndexBuilder")
+    for fmt in ("bed", "gff"):
+        src = os.path.join(T.GOLDEN, "regions", "targets." + fmt)
+        got = str(tmp_path / ("region." + fmt + ".bin"))
+        r = subprocess.run([rib, idx, src, got, "-" + fmt], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        want = open(src + ".region.bin", "rb").read()
+        assert open(got, "rb").read() == want
+        n = int(np.frombuffer(want[:4], dtype=np.uint32)[0])
+        assert "Removed Overlapped entries : %u remained" % n in r.stdout
+        reg = np.frombuffer(want[4:], dtype=np.uint32).reshape(n, 2)
+        assert np.all(reg[1:, 0] >= reg[:-1, 0])
+    r = subprocess.run([rib, idx, src, got], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Usage:" in r.stderr
+    r = subprocess.run([rib, idx, src, got, "-vcf"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Invalid input format" in r.stdout
+    L = T.capi()
+    err = ctypes.create_string_buffer(256)
+    ix = ctypes.c_void_p()
+    assert L.gt16_index_read(idx.encode(), ctypes.byref(ix), err, 256) == 0
+    try:
+        amb, pos = ctypes.c_uint32(), ctypes.c_uint32()
+        assert L.gt16_index_locate(ix, b"chr2", 1, ctypes.byref(amb)) == 0 and amb.value == 222222
+        assert L.gt16_index_locate(ix, b"chrchr2", 5, ctypes.byref(amb)) == 0 and amb.value == 222226   # one "chr" is dropped
+        assert L.gt16_index_locate(ix, b"2", 5, ctypes.byref(amb)) == -1           # ... but never added (:54-63)
+        assert L.gt16_index_locate(ix, b"chrX", 5, ctypes.byref(amb)) == -1
+        assert L.gt16_index_locate(ix, b"chr1", 222223, ctypes.byref(amb)) == -1       # beyond the sequence
+        for a in (0, 1, 222221, 222222, 399999):                                      # locate inverts translate
+            name = L.gt16_index_translate(ix, a, ctypes.byref(pos))
+            assert L.gt16_index_locate(ix, name, pos.value, ctypes.byref(amb)) == 0 and amb.value == a
+    finally:
+        L.gt16_index_free(ix)
+
+
 def test_cli_usage_errors():
     r = subprocess.run([T.CLI], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "Usage:" in r.stderr and "-e <Exome Region Index>" in r.stderr
