@@ -49,6 +49,10 @@ FULL_CONFIGS = {
     # config 4 flavour: 20,000 targets of ~300 bp at 150x on a 256 Mb genome, sparse (mode 2) snapshot, -e region.bin
     "exome_mid": dict(synth=["--genome-len", "256000000", "--n-contigs", "8", "--exome", "20000:300", "--depth", "150",
                              "--seed", "4"], exome=True),
+    # config 4 at FULL size: 200,000 targets of ~300 bp at 150x on a 3.1 Gb genome of 24 contigs (positions beyond
+    # 2^31), sparse (mode 2) snapshot, -e region.bin
+    "exome_full": dict(synth=["--genome-len", "3100000000", "--n-contigs", "24", "--exome", "200000:300", "--depth", "150",
+                              "--seed", "6"], exome=True),
 }
 CONFIGS_ALL = dict(CONFIGS, **FULL_CONFIGS)
 

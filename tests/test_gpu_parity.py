@@ -98,10 +98,11 @@ def test_dropin_binary_errors(tmp_path):
     assert r.returncode == 1
 
 
-@pytest.mark.parametrize("name,shards", [("chr20_full", 3), ("stress_full", 2), ("exome_mid", 1)])
+@pytest.mark.parametrize("name,shards", [("chr20_full", 3), ("stress_full", 2), ("exome_mid", 1), ("exome_full", 2)])
 def test_full_size_callset_digest(gpu_caller, tmp_path, name, shards):
     """Full-size configs (chr20_full is what bench.py times; stress_full is the config-5 flavour with 189,080
-    rows; exome_mid the config-4 flavour with a sparse snapshot and 20,000 regions): the call-set columns of
+    rows; exome_mid the config-4 flavour with a sparse snapshot and 20,000 regions; exome_full is config 4 at full
+    size -- 200,000 targets on a 3.1 Gb genome, positions beyond 2^31): the call-set columns of
     every row hash to the digest of the reference's own .txt for the same snapshot, and the number of rows
     whose floating-point columns print differently is bounded."""
     import hashlib
