@@ -142,13 +142,15 @@ struct LhTables {
 #define GT16_TABLE_READ(T, k, w_total, w_target) ((T).t[k][(w_total) * kFisherN + (w_target)])
 #endif
 
+// chi-square fallback of a table read (likelihood_cache.cpp:57-72): deep sites only, kept out of line
+GT16_HDN double table_fallback(const LhTables &T, int w_target, int err, int w_total) {
+  double dist = chi2_uniform_distance(w_target, w_total, err, w_total);
+  int di = (int) (dist * 10 + 0.5);
+  if (di >= kYcsqN) di = kYcsqN - 1;
+  return T.ycsq[di];
+}
 GT16_HD double table_lookup(const LhTables &T, int k, int w_target, int err, int w_total) {
-  if (w_target >= kFisherN || w_total >= kFisherN) {            // likelihood_cache.cpp:70-72
-    double dist = chi2_uniform_distance(w_target, w_total, err, w_total);
-    int di = (int) (dist * 10 + 0.5);
-    if (di >= kYcsqN) di = kYcsqN - 1;
-    return T.ycsq[di];
-  }
+  if (w_target >= kFisherN || w_total >= kFisherN) return table_fallback(T, w_target, err, w_total);   // :70-72
   return GT16_TABLE_READ(T, k, w_total, w_target);
 }
 
@@ -163,27 +165,25 @@ GT16_HD double scale_back(double ret) {  // checkOverflowAndReturn, FisherExactT
 
 GT16_HD int nonneg(int v) { return v < 0 ? 0 : v; }  // centre element of GenerateIntegerArrayFlanking5
 
-// hom(x): tables (ka, ke); p_err = error rate of the class   (:135-171)
-GT16_HD double lh_hom(const LhTables &T, const uint32_t *W, int x, int wt, double p_err, int ka, int ke) {
-  int error0 = (int) (wt * (1.0f - p_err) + 0.5f);
-  int error1 = (int) (wt * p_err + 0.5f);
-  double a = table_lookup(T, ka, (int) W[x], error0, wt);
-  double e = table_lookup(T, ke, nonneg((int) (wt - W[x])), error1, wt);
-  double ret = a * kOverflowHandler * e;
-  return scale_back(ret);
-}
-// het(x,y): tables (k1 for x, k2 for y, ke)                   (:173-247)
-GT16_HD double lh_het(const LhTables &T, const uint32_t *W, int x, int y, int wt, double p_err,
-                      int k1, int k2, int ke) {
-  double p_half = p_err * 0.5f;
-  int error0 = (int) (wt * (0.5f - p_half) + 0.5f);
-  int error1 = (int) (wt * p_half + 0.5f);
-  int wh = (int) (wt * 0.5f + 0.5f);                                  // float arithmetic (:179)
-  double a1 = table_lookup(T, k1, (int) W[x], error0, wh);
-  double a2 = table_lookup(T, k2, (int) W[y], error0, wh);
-  double e = table_lookup(T, ke, nonneg((int) (wt - W[x] - W[y])), error1, wt);
-  double ret = sqrt(a1) * sqrt(a2) * kOverflowHandler * e;            // pow(.,0.5f) (:192)
-  return scale_back(ret);
+// One genotype class of FisherExactTest.cpp:135-247 in a single code path (the five reference functions differ
+// only in their tables, their error rate and hom/het):
+//   hom(x)  : T[ka][wt][W[x]] * OH * T[ke][wt][max(0, wt - W[x])]                                        (:135-171)
+//   het(x,y): sqrt(T[k1][wh][W[x]]) * sqrt(T[k2][wh][W[y]]) * OH * T[ke][wt][max(0, wt - W[x] - W[y])]    (:173-247)
+// with wh = (int)(wt * 0.5f + 0.5f) in float arithmetic (:179).  The expected counts error0/error1 (used by the
+// chi-square fallback only) are computed in double from the class error rate: p_err for hom, p_err * 0.5f for het.
+struct LhClass { int x, y; bool het; double p_err; int k1, k2, ke; };
+
+GT16_HD double lh_class(const LhTables &T, const uint32_t *W, int wt, const LhClass &c) {
+  const double q = c.het ? c.p_err * 0.5f : c.p_err;
+  const double full = c.het ? 0.5f : 1.0f;
+  const int error0 = (int) (wt * (full - q) + 0.5f);
+  const int error1 = (int) (wt * q + 0.5f);
+  const int wx = (int) W[c.x], wy = c.het ? (int) W[c.y] : 0;
+  const int wa = c.het ? (int) (wt * 0.5f + 0.5f) : wt;
+  double first = table_lookup(T, c.k1, wx, error0, wa);
+  if (c.het) first = sqrt(first) * sqrt(table_lookup(T, c.k2, wy, error0, wa));        // pow(.,0.5f) (:192)
+  const double e = table_lookup(T, c.ke, nonneg(wt - wx - wy), error1, wt);
+  return scale_back(first * kOverflowHandler * e);
 }
 
 // ref-weight penalty when indel evidence is present (:251-260) and W_total (:262-266)
@@ -201,24 +201,29 @@ GT16_HD int penalised_weights(const uint32_t *Win, int ref, uint32_t *W) {
   return wt;
 }
 
-// likelihood of genotype g (0..9 = AA,AC,AG,AT,CC,CG,CT,GG,GT,TT; 10..13 = AX,CX,GX,TX; 14 = XX;
-// 15 = XY) from the penalised weights (:268-284)
-GT16_HDN double genotype_lh_one(const LhTables &T, const uint32_t *W, int wt, int g) {
+// class of genotype g (0..9 = AA,AC,AG,AT,CC,CG,CT,GG,GT,TT; 10..13 = AX,CX,GX,TX; 14 = XX; 15 = XY)  (:268-284)
+GT16_HD LhClass genotype_class(const LhTables &T, int g) {
   const double ps = T.p_err_s, pi = T.p_err_i;
-  double v;
+  LhClass c;
   if (g < 10) {
     int i = 0, rem = g;                       // (i, j) of the g-th pair in the i <= j enumeration
     while (rem >= 4 - i) { rem -= 4 - i; ++i; }
-    int j = i + rem;
-    v = (i == j) ? lh_hom(T, W, i, wt, 3 * ps + 2 * pi, 0, 1) : lh_het(T, W, i, j, wt, 2 * ps + 2 * pi, 4, 4, 5);
+    c.x = i; c.y = i + rem; c.het = rem != 0;
+    c.p_err = c.het ? 2 * ps + 2 * pi : 3 * ps + 2 * pi;
+    c.k1 = c.het ? 4 : 0; c.k2 = 4; c.ke = c.het ? 5 : 1;
   } else if (g < 14) {
-    v = lh_het(T, W, g - 10, 4, wt, 3 * ps + pi, 6, 8, 7);
+    c.x = g - 10; c.y = 4; c.het = true; c.p_err = 3 * ps + pi; c.k1 = 6; c.k2 = 8; c.ke = 7;
   } else if (g == 14) {
-    v = lh_hom(T, W, 4, wt, 4 * ps + pi, 2, 3);
+    c.x = 4; c.y = 4; c.het = false; c.p_err = 4 * ps + pi; c.k1 = 2; c.k2 = 2; c.ke = 3;
   } else {
-    v = lh_het(T, W, 5, 4, wt, 4 * ps, 8, 8, 9);
+    c.x = 5; c.y = 4; c.het = true; c.p_err = 4 * ps; c.k1 = 8; c.k2 = 8; c.ke = 9;
   }
-  return fmin(1.0, v);
+  return c;
+}
+
+// likelihood of genotype g from the penalised weights
+GT16_HDN double genotype_lh_one(const LhTables &T, const uint32_t *W, int wt, int g) {
+  return fmin(1.0, lh_class(T, W, wt, genotype_class(T, g)));
 }
 
 // W[6] = A,C,G,T,deepest indel,second indel weighted counts; ref in 0..3; lh[16] out (:249-289)

@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_list(SnapView V, DevSiteM
                                                             DecisionTables D, EvalParams P, uint32_t *__restrict__ siteMask,
                                                             uint32_t *errWord) {
   __shared__ double lhS[kEvalThreads / 32][2][16];
+  __shared__ uint32_t wpS[kEvalThreads / 32][2][6];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, g = lane & 15;
   const uint32_t warpsTotal = gridDim.x * (kEvalThreads / 32);
   for (uint32_t j0 = (blockIdx.x * (kEvalThreads / 32) + warp) * 32u; j0 < n; j0 += warpsTotal * 32u) {
@@ -448,9 +449,24 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_list(SnapView V, DevSiteM
       for (int k = 0; k < 6; ++k) Ws[k] = __shfl_sync(0xffffffffu, W[k], src);
       const int refS = __shfl_sync(0xffffffffu, ref, src);
       const uint32_t vpS = __shfl_sync(0xffffffffu, validPlus, src);
-      uint32_t Wp[6];
-      const int wt = penalised_weights(Ws, refS, Wp);
-      lhS[warp][half][g] = genotype_lh_one(P.lh, Wp, wt, (int) g);
+      // penalised weights (penalised_weights(), FisherExactTest.cpp:251-266) into shared memory: the likelihood
+      // classes index them by allele
+      if (g < 6) {
+        uint32_t v = g == 0 ? Ws[0] : g == 1 ? Ws[1] : g == 2 ? Ws[2] : g == 3 ? Ws[3] : g == 4 ? Ws[4] : Ws[5];
+        const uint32_t indelCount = Ws[4] + Ws[5];
+        if ((int) g == refS && indelCount) {
+          double tmp = (double) indelCount * (1.375f) + 0.5f;
+          tmp = v - tmp;
+          if (tmp <= 0) tmp = 0;
+          v = (uint32_t) tmp;
+        }
+        wpS[warp][half][g] = v;
+      }
+      __syncwarp();
+      int wt = 0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) wt += (int) wpS[warp][half][k];
+      lhS[warp][half][g] = genotype_lh_one(P.lh, wpS[warp][half], wt, (int) g);
       __syncwarp();
       int res = 0;                                    // bit0 candidate, bit1 genotype error
       if (g == 0) {
@@ -569,10 +585,72 @@ constexpr int kCandThreads = 128;
 struct CandWarpSmem {
   double lh[16];
   double flh[16];
+  uint32_t W[6], F[6], R[6], Wp[6];   // counts of the site (A,C,G,T,deepest indel,second indel), penalised weights
   uint32_t sc[2][kWindow + 4];
   uint32_t w[2][kWindow + 4];
   uint8_t fl[2][kWindow + 4];      // bit0 valid, bit1 gc
 };
+
+// what the window sums need of one position (SNP_Caller.cpp:276-367): strand count, weighted depth, flags
+struct WinLite { uint32_t sc, w, fl; };                      // fl: bit0 valid, bit1 C-or-G seen, bit2 G seen
+
+// decode_bases() reduced to those sums (same conditions: a slot is live iff its strand counts are not both zero,
+// an overflow record's base is counted iff F|R != 0; a record index out of range leaves a valid, empty entry).
+// Overflow records are 32-byte aligned in device memory (alloc_snapshot), read with two vector loads.
+__device__ __forceinline__ WinLite win_decode(const SnapView &V, uint32_t p, uint64_t c) {
+  WinLite e; e.sc = 0; e.w = 0; e.fl = 1;
+  const uint32_t lo = (uint32_t) c, hi = (uint32_t) (c >> 32);
+  if (!is_overflow_type(c)) {
+    const bool l1 = (hi & 0xFFFFu) != 0, l2 = (hi >> 16) != 0;
+    const uint32_t b1 = (lo >> 14) & 3u, b2 = lo >> 30;
+    if (l1) { e.sc += (hi & 0xFFu) + ((hi >> 8) & 0xFFu); e.w += lo & 0x3FFFu; }
+    if (l2) { e.sc += ((hi >> 16) & 0xFFu) + (hi >> 24); e.w += (lo >> 16) & 0x3FFFu; }
+    const bool gc = (l1 && (b1 == 1 || b1 == 2)) || (l2 && (b2 == 1 || b2 == 2));
+    const bool g = (l1 && b1 == 2) || (l2 && b2 == 2);
+    e.fl |= (gc ? 2u : 0u) | (g ? 4u : 0u);
+  } else {
+    const uint8_t *r = ovf_record(V, ovf_region(V, p), hi);
+    if (r) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4 *>(r));           // W[4], F[4] (u16 each)
+      const uint2 b = __ldg(reinterpret_cast<const uint2 *>(r + 16));      // R[4]
+      const uint32_t F[4] = {a.z & 0xFFFFu, a.z >> 16, a.w & 0xFFFFu, a.w >> 16};
+      const uint32_t R[4] = {b.x & 0xFFFFu, b.x >> 16, b.y & 0xFFFFu, b.y >> 16};
+      const uint32_t W[4] = {a.x & 0xFFFFu, a.x >> 16, a.y & 0xFFFFu, a.y >> 16};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (F[i] | R[i]) { e.sc += F[i] + R[i]; e.w += W[i]; if (i == 1 || i == 2) e.fl |= 2u; if (i == 2) e.fl |= 4u; }
+    }
+  }
+  return e;
+}
+
+__device__ __forceinline__ uint32_t region_of(const SiteMap &M, uint64_t i) {      // last region with regFirst <= i
+  uint32_t lo = 0, hi = M.nRegions;
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (M.regFirst[mid] <= i) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// genome position of entry k of the batch's mwInfo array (the cases of window_entry()); false = the reference never
+// fills the entry or it lies beyond the genome (zeros either way).  reg: a region index not above the entry's own
+// (multi-region maps), advanced in place -- a lane's entries are visited in increasing k.
+__device__ __forceinline__ bool win_pos(const SnapView &V, const SiteMap &M, const BatchGeom &B, uint64_t k, uint32_t &reg,
+                                        uint32_t &p) {
+  if (k < (uint64_t) kWindow) {                                   // left margin, VariantCaller.cpp:713-729
+    if (!(B.amb0 > (uint32_t) kWindow)) return false;
+    p = B.amb0 - kWindow + (uint32_t) k;
+  } else if (k < (uint64_t) kWindow + B.n) {
+    const uint64_t i = B.first + (k - kWindow);
+    if (M.nRegions > 1) while (reg + 1 < M.nRegions && M.regFirst[reg + 1] <= i) ++reg;
+    p = M.regStart[reg] + (uint32_t) (i - M.regFirst[reg]);
+  } else {                                                        // right margin, :731-747
+    const uint64_t j = k - kWindow - B.n;
+    if (j >= (uint64_t) kWindow - 1) return false;                // only 99 entries are ever filled
+    const uint64_t pp = (uint64_t) B.ambLast + 1 + j;
+    if (pp >= V.L) return false;
+    p = (uint32_t) pp;
+  }
+  return p < V.L;
+}
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }   // one REDUX.SUM
 
@@ -589,47 +667,82 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
     const uint32_t p = site_pos(M, i);
     gt16_called_site &o = out[j];
     uint32_t err = 0;
-    // -- decode (uniform across the warp: broadcast loads)
-    BaseCounts bc;
-    decode_bases(V, p, bc);
+    // -- counts of the site: base `lane` on lanes 0..3 (decode_bases, one base per lane), the two deepest indel
+    //    patterns on lanes 4 and 5; everything the warp shares lives in shared memory, not in per-lane arrays
+    const int ref = (int) ref_base(V, p);
     IndelInfo ii; PatRef d0, d1;
     decode_indel_refs(V, p, ii, d0, d1);
-    if (bc.bad || ii.bad) err |= kErrBadSnapshot;
-    const int ref = (int) ref_base(V, p);
-    const uint32_t W[6] = {bc.W[0], bc.W[1], bc.W[2], bc.W[3], ii.W4, ii.W5};
-    // -- 16 genotype likelihoods, one per lane
+    if (ii.bad) err |= kErrBadSnapshot;
     {
-      uint32_t Wp[6];
-      const int wt = penalised_weights(W, ref, Wp);
-      if (lane < 16) sm.lh[lane] = genotype_lh_one(P.lh, Wp, wt, (int) lane);
+      uint32_t w = 0, f = 0, r = 0;
+      bool bad = false;
+      if (lane < 4 && !is_invalid(V, p)) {
+        const uint64_t c = V.counters[p];
+        const uint32_t lo = (uint32_t) c, hi = (uint32_t) (c >> 32);
+        if (!is_overflow_type(c)) {
+          if ((hi & 0xFFFFu) && ((lo >> 14) & 3u) == lane) { w = lo & 0x3FFFu; f = hi & 0xFFu; r = (hi >> 8) & 0xFFu; }
+          if ((hi >> 16) && (lo >> 30) == lane) { w = (lo >> 16) & 0x3FFFu; f = (hi >> 16) & 0xFFu; r = hi >> 24; }   // second slot wins
+        } else {
+          const uint8_t *rec = ovf_record(V, ovf_region(V, p), hi);
+          if (!rec) bad = true;
+          else {
+            f = rd16(rec + 8 + 2 * lane); r = rd16(rec + 16 + 2 * lane);
+            if (f | r) w = rd16(rec + 2 * lane);
+          }
+        }
+      }
+      if (lane == 4) { w = ii.W4; f = ii.F4; r = ii.R4; }
+      if (lane == 5) { w = ii.W5; f = ii.F5; r = ii.R5; }
+      if (__any_sync(0xffffffffu, bad)) err |= kErrBadSnapshot;
+      if (lane < 6) {
+        sm.W[lane] = w; sm.F[lane] = f; sm.R[lane] = r;
+        const uint32_t indelCount = ii.W4 + ii.W5;                         // penalised_weights(), FisherExactTest.cpp:251-260
+        if ((int) lane == ref && indelCount) {
+          double tmp = (double) indelCount * (1.375f) + 0.5f;
+          tmp = w - tmp;
+          if (tmp <= 0) tmp = 0;
+          w = (uint32_t) tmp;
+        }
+        sm.Wp[lane] = w;
+      }
     }
     __syncwarp();
-    double lh[16];
+    // -- 16 genotype likelihoods, one per lane
+    {
+      int wt = 0;
 #pragma unroll
-    for (int g = 0; g < 16; ++g) lh[g] = sm.lh[g];
+      for (int k = 0; k < 6; ++k) wt += (int) sm.Wp[k];
+      if (lane < 16) sm.lh[lane] = genotype_lh_one(P.lh, sm.Wp, wt, (int) lane);
+    }
+    __syncwarp();
     // posterior (selectGenotype, FisherExactTest.cpp:317-509): the sum is sequential in every lane, the sixteen
     // divisions -- by far the most expensive part in FP64 -- are one per lane, the best / second scan reads them back
-    Posterior po;
-    {
-      double pD = lh[0];
+    double pD = sm.lh[0], bestD = 0, secondD = 0;
+    int genotype;
 #pragma unroll
-      for (int g = 1; g < 16; ++g) pD = pD + lh[g];
-      po.pD = pD;
-      if (pD == 0.0) {
-        po.genotype = hom_ref_genotype(ref);
-        for (int g = 0; g < 16; ++g) po.flh[g] = 0;
-        po.bestD = 0; po.secondD = 0;
-      } else {
-        if (lane < 16) sm.flh[lane] = lh[lane] / pD * P.prior[(ref << 6) | P.g2i[lane]];
-        __syncwarp();
+    for (int g = 1; g < 16; ++g) pD = pD + sm.lh[g];
+    if (pD == 0.0) {
+      genotype = hom_ref_genotype(ref);
+      if (lane < 16) sm.flh[lane] = 0;
+      __syncwarp();
+    } else {
+      if (lane < 16) sm.flh[lane] = sm.lh[lane] / pD * P.prior[(ref << 6) | P.g2i[lane]];
+      __syncwarp();
+      // argmax_posteriors(): first index wins ties, `>=` only between 0 and 1 (:383-504)
+      double f0 = sm.flh[0], f1 = sm.flh[1];
+      genotype = 0;
+      if (!(f0 >= f1)) { genotype = 1; const double t = f0; f0 = f1; f1 = t; }
 #pragma unroll
-        for (int g = 0; g < 16; ++g) po.flh[g] = sm.flh[g];
-        argmax_posteriors(po);
+      for (int g = 2; g < 16; ++g) {
+        const double v = sm.flh[g];
+        if (v > f0) { f1 = f0; f0 = v; genotype = g; }
+        else if (v > f1) f1 = v;
       }
+      bestD = f0; secondD = f1;
     }
     const uint8_t isValid = (uint8_t) (1 + ii.isValidPlus);
     uint8_t isIndel = 0, nextBp = 0;
-    if (po.genotype > 9) {                                              // SNP_Caller.cpp:228-239
+    if (genotype > 9) {                                                 // SNP_Caller.cpp:228-239
       if (isValid >= 2) { isIndel = isValid; if (d0.type == 'D') nextBp = d0.len; }
       else err |= kErrGenotype;
     }
@@ -642,14 +755,37 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
     const uint32_t idx = (uint32_t) (i - B.first);
 
     // -- windows (reference's un-offset mwInfo indexing)                                 :276-367
+    // Four entries per lane and side.  The positions are resolved first, then all the lane's loads of a side are
+    // issued together (invalid words + counters: eight independent gathers in flight instead of one), then decoded
+    // by win_decode -- only what the window sums need of a position.
     const bool haveLeft = idx >= (uint32_t) kWindow;
-    for (uint32_t t = lane; t <= (uint32_t) kWindow; t += 32) {
+    const bool multi = M.m.nRegions > 1;
 #pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        if (side == 0 && !haveLeft) continue;
-        const uint64_t k0 = side == 0 ? (uint64_t) idx - kWindow : (uint64_t) idx + nextBp;
-        WinEntry e = window_entry(V, M.m, B, k0 + t);
-        sm.sc[side][t] = e.sc; sm.w[side][t] = e.w; sm.fl[side][t] = (uint8_t) (e.valid | (e.gc << 1));
+    for (int side = 0; side < 2; ++side) {
+      if (side == 0 && !haveLeft) continue;
+      const uint64_t k0 = side == 0 ? (uint64_t) idx - kWindow : (uint64_t) idx + nextBp;
+      uint32_t reg = 0;                                       // region of the first in-batch entry (exome): a lower bound
+      if (multi) reg = region_of(M.m, B.first + (k0 >= (uint64_t) kWindow ? k0 - kWindow : 0));
+      uint32_t pp[4]; bool ex[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const uint32_t t = lane + 32u * it;
+        pp[it] = 0;
+        ex[it] = t <= (uint32_t) kWindow && win_pos(V, M.m, B, k0 + t, reg, pp[it]);
+      }
+      uint32_t iw[4]; uint64_t cc[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        iw[it] = (ex[it] && V.invalid) ? __ldg(V.invalid + (pp[it] >> 5)) : 0u;
+        cc[it] = ex[it] ? __ldg(reinterpret_cast<const unsigned long long *>(V.counters) + pp[it]) : 0ull;
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const uint32_t t = lane + 32u * it;
+        if (t > (uint32_t) kWindow) continue;
+        WinLite e; e.sc = e.w = e.fl = 0;
+        if (ex[it] && !((iw[it] >> (31 - (pp[it] & 31))) & 1u)) e = win_decode(V, pp[it], cc[it]);
+        sm.sc[side][t] = e.sc; sm.w[side][t] = e.w; sm.fl[side][t] = (uint8_t) e.fl;
       }
     }
     __syncwarp();
@@ -669,21 +805,20 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
       strandSum[side] = warp_sum(a0); depthSum[side] = warp_sum(a1); gcSum[side] = warp_sum(a2) & 0xFF;
       validSum[side] = warp_sum(a3) & 0xFF; deltaSum[side] = warp_sum(a4);
     }
-    __syncwarp();
-    // G counts of the three sites before / after                                        :355-367
+    // G counts of the three sites before / after (:355-367): mwInfo entries idx-3..idx-1 and idx+nextBp..+2, i.e.
+    // entries 97..99 of the left window and 0..2 of the right one (valid bit 0, G bit 2)
     bool gbit = false;
-    if (lane < 3) { if (idx >= 3) { WinEntry e = window_entry(V, M.m, B, (uint64_t) idx - 3 + lane); gbit = e.valid && e.g; } }
-    else if (lane < 6) { WinEntry e = window_entry(V, M.m, B, (uint64_t) idx + nextBp + (lane - 3)); gbit = e.valid && e.g; }
+    if (lane < 3) {
+      if (haveLeft) gbit = (sm.fl[0][kWindow - 3 + lane] & 5u) == 5u;
+      else if (idx >= 3) { WinEntry e = window_entry(V, M.m, B, (uint64_t) idx - 3 + lane); gbit = e.valid && e.g; }
+    } else if (lane < 6) gbit = (sm.fl[1][lane - 3] & 5u) == 5u;
     const uint32_t gb = __ballot_sync(0xffffffffu, gbit);
+    __syncwarp();
     const uint32_t run = polyrun(V, p);
 
     // -- record
-    if (lane < 16) { o.lh[lane] = lh[lane]; o.flh[lane] = po.flh[lane]; }
-    if (lane < 6) {
-      o.W[lane] = lane < 4 ? bc.W[lane] : (lane == 4 ? ii.W4 : ii.W5);
-      o.F[lane] = lane < 4 ? bc.F[lane] : (lane == 4 ? ii.F4 : ii.F5);
-      o.R[lane] = lane < 4 ? bc.R[lane] : (lane == 4 ? ii.R4 : ii.R5);
-    }
+    if (lane < 16) { o.lh[lane] = sm.lh[lane]; o.flh[lane] = sm.flh[lane]; }
+    if (lane < 6) { o.W[lane] = sm.W[lane]; o.F[lane] = sm.F[lane]; o.R[lane] = sm.R[lane]; }
     for (int k = 0; k < 2; ++k) {                                       // indel pattern bytes, two per lane
       gt16_indel &d = o.indel[k];
       const PatRef &pr = k ? d1 : d0;
@@ -700,8 +835,8 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
       if (lane == 0) { d.type = have ? pr.type : (uint8_t) '*'; d.len = have ? pr.len : 0; d.hq = have ? pr.hq : 0; d.lq = have ? pr.lq : 0; }
     }
     if (lane == 0) {
-      o.amb = p; o.ref = (uint8_t) ref; o.genotype = (uint8_t) po.genotype; o.is_indel = isIndel;
-      o.pD = po.pD; o.bestD = po.bestD; o.secondD = po.secondD;
+      o.amb = p; o.ref = (uint8_t) ref; o.genotype = (uint8_t) genotype; o.is_indel = isIndel;
+      o.pD = pD; o.bestD = bestD; o.secondD = secondD;
       float avgSC[2] = {0.f, 0.f}, avgD[2] = {0.f, 0.f};
       if (deltaSum[0] | deltaSum[1]) o.rpb = (deltaSum[0] - deltaSum[1] + 0.0f) / (deltaSum[0] + deltaSum[1]);
       else o.rpb = 0.0f;

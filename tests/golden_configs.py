@@ -54,6 +54,13 @@ FULL_CONFIGS = {
     "exome_full": dict(synth=["--genome-len", "3100000000", "--n-contigs", "24", "--exome", "200000:300", "--depth", "150",
                               "--seed", "6"], exome=True),
 }
+# configs[2] at FULL size: 3.1 Gb, 24 contigs, 30x, dense snapshot (24.8 GB of counters, 370 batches), coverage gaps.
+# Needs ~30 GB of RAM and disk to regenerate: run by tools/full_genome_check.py / GT16_RUN_HUGE=1, not by default.
+HUGE_CONFIGS = {
+    "wgs_full": dict(synth=["--genome-len", "3100000000", "--n-contigs", "24", "--gaps", "8:100000", "--seed", "3"],
+                     exome=False),
+}
+FULL_CONFIGS.update(HUGE_CONFIGS)
 CONFIGS_ALL = dict(CONFIGS, **FULL_CONFIGS)
 
 
