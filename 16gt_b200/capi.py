@@ -114,6 +114,7 @@ def capi():
         "gt16_index_packed": (vp, [vp, P(u32)]),
         "gt16_index_translate": (cp, [vp, u32, P(u32)]),
         "gt16_index_locate": (i32, [vp, cp, u32, P(u32)]),
+        "gt16_index_pin": (i32, [vp]),
         "gt16_index_free": (None, [vp]),
         "gt16_write_txt": (i32, [cp, vp, vp, u64, i32, vp]),
     }
@@ -165,6 +166,8 @@ class LoadedInput:
             raise RuntimeError(err.value.decode())
         if L.gt16_snapshot_read(snapshot_path.encode(), pinned, ctypes.byref(self.hs), err, 512) != 0:
             raise RuntimeError(err.value.decode())
+        if pinned:
+            L.gt16_index_pin(self.ix)        # best effort: without a device the reference stays pageable
         self.view = View()
         L.gt16_snapshot_view_of(self.hs, ctypes.byref(self.view))
         n = ctypes.c_uint32()

@@ -904,9 +904,18 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     return GT16_OK;
   };
 
+  // segment boundaries; a host-fed range ends with a segment of its own for the last batch: everything after the
+  // streaming pass of that segment is exposed (the bus is idle by then), so it should be short
+  std::vector<uint64_t> cuts;
+  for (uint64_t a = begin; a < end; a += segSites) cuts.push_back(a);
+  if (!resident) {
+    const uint64_t lastBatch = begin + ((uint64_t) (n - 1) / kBatch) * kBatch;
+    if (lastBatch > cuts.back()) cuts.push_back(lastBatch);
+  }
+  cuts.push_back(end);
   uint32_t seg = 0;
-  for (uint64_t a = begin; a < end; a += segSites, ++seg) {
-    const uint64_t b = std::min<uint64_t>(a + segSites, end);
+  for (size_t ci = 0; ci + 1 < cuts.size(); ++ci, ++seg) {
+    const uint64_t a = cuts[ci], b = cuts[ci + 1];
     cudaEvent_t es0, es1;
     if ((rc = get_event(ctx, evNext++, &es0)) || (rc = get_event(ctx, evNext++, &es1))) return rc;
     CUF(cudaEventRecord(es0, ctx->compute));

@@ -101,6 +101,7 @@ struct gt16_index {
   std::vector<std::string> names;          // annotation[i].text
   struct Tr { uint32_t startPos; uint16_t chrID; uint32_t correction; };
   std::vector<Tr> translate;               // HSP.translate
+  bool pinned = false;                     // packed[] is page-locked (gt16_index_pin)
 };
 
 extern "C" {
@@ -283,6 +284,19 @@ const uint32_t *gt16_index_packed(const gt16_index *ix, uint32_t *nWords) {
   return ix->packed.data();
 }
 
+// Page-lock the packed reference where it lies, so that host-fed calls copy it with a plain asynchronous DMA
+// (from pageable memory the driver stages it synchronously on the calling thread, ahead of the counter chunks).
+int gt16_index_pin(gt16_index *ix) {
+  if (!ix) return GT16_EINVAL;
+  if (ix->pinned || ix->packed.empty()) return GT16_OK;
+  if (cudaHostRegister(ix->packed.data(), ix->packed.size() * 4, cudaHostRegisterDefault) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return GT16_ECUDA;
+  }
+  ix->pinned = true;
+  return GT16_OK;
+}
+
 // getChrAndPos: last translate entry starting at or before amb; position = amb - correction
 const char *gt16_index_translate(const gt16_index *ix, uint32_t amb, uint32_t *chrPos) {
   size_t lo = 0, hi = ix->translate.size();
@@ -313,7 +327,10 @@ int gt16_index_locate(const gt16_index *ix, const char *chrName, uint32_t chrPos
   return -1;
 }
 
-void gt16_index_free(gt16_index *ix) { delete ix; }
+void gt16_index_free(gt16_index *ix) {
+  if (ix && ix->pinned) cudaHostUnregister(ix->packed.data());
+  delete ix;
+}
 
 // ---- .txt emitter (interpreter.cpp:5-156) ---------------------------------------------
 static const char kGenotypeString[][4] = {"AA", "AC", "AG", "AT", "CC", "CG", "CT", "GG", "GT", "TT",

@@ -139,20 +139,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 //                    into the mask words the warp wrote earlier.
 // Requires pBeg % 128 == 0 (16-byte alignment of all three sources) and arrays padded by one tile.
 struct StreamQueueEntry { uint32_t x, y, bit, ref; };
-struct StreamSmem {
-  uint64_t counters[kStreamStages][kStreamTile + 2];
-  uint32_t ref[kStreamStages][kStreamTile / 16];
-  uint32_t bm[kStreamStages][kStreamTile / 32];
-  uint8_t s1[kS1Bits];                                   // byte per weight: 1 = needs exact evaluation
+// The ring is as deep as shared memory allows: what bounds the kernel once the per-site work is small is the number
+// of bytes in flight per SM (a stage is requested again only after all 32 warps have left it, and HBM latency under
+// load is ~3 us), so the shortcut variant -- which never reads the (Wr) byte table -- spends those 16 KB on a fifth stage.
+template <bool kShortcut>
+struct StreamSmemT {
+  static constexpr int kStages = kShortcut ? kStreamStages + 1 : kStreamStages;
+  uint64_t counters[kStages][kStreamTile + 2];
+  uint32_t ref[kStages][kStreamTile / 16];
+  uint32_t bm[kStages][kStreamTile / 32];
+  uint8_t s1[kShortcut ? 16 : kS1Bits];                  // byte per weight: 1 = needs exact evaluation (all zero when kShortcut)
   uint32_t s2[2 * kS2Words];                             // bitmaps (Wr, Wp) and (Wr, Wq)
   StreamQueueEntry queue[kStreamThreads / 32][64];
-  uint64_t full[kStreamStages];                          // TMA bytes have landed
-  uint32_t released[kStreamStages];                      // warps that are done reading the stage
+  uint64_t full[kStages];                                // TMA bytes have landed
+  uint32_t released[kStages];                            // warps that are done reading the stage
 };
 static_assert(sizeof(uint64_t) * (kStreamTile + 2) % 16 == 0, "bulk copy sizes must be multiples of 16 bytes");
-static_assert(sizeof(StreamSmem) <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(StreamSmemT<false>) <= 227 * 1024 && sizeof(StreamSmemT<true>) <= 227 * 1024, "shared memory budget");
 
 // general role-indexed test of one compact (non-overflow) counter; same verdict as lookup_needs_exact
+template <bool kShortcut>
 __device__ __forceinline__ bool compact_needs_exact(const uint32_t *__restrict__ s2, const uint8_t *__restrict__ s1,
                                                     uint32_t x, uint32_t y, uint32_t ref) {
   uint32_t v1 = (y & 0xFFFFu) ? (x & 0x3FFFu) : 0u, v2 = (y >> 16) ? ((x >> 16) & 0x3FFFu) : 0u;
@@ -160,7 +166,7 @@ __device__ __forceinline__ bool compact_needs_exact(const uint32_t *__restrict__
   if (r1 == r2 && (y >> 16)) v1 = 0;                       // the second slot overwrites the first
   const uint32_t wr = (r1 == 0 ? v1 : 0u) | (r2 == 0 ? v2 : 0u);
   const uint32_t a1 = r1 ? v1 : 0u, a2 = r2 ? v2 : 0u, alt = a1 | a2, ar = a1 ? r1 : r2;
-  if (alt == 0) return s1[wr] != 0;
+  if (alt == 0) return kShortcut ? false : s1[wr] != 0;      // kShortcut: the (Wr) bitmap is all zero
   if ((a1 && a2) || wr >= (uint32_t) kS2R || alt >= (uint32_t) kS2A) return true;
   const uint32_t idx = (ar == 2 ? 0u : (uint32_t) (kS2R * kS2A)) + alt * kS2R + wr;
   return (s2[idx >> 5] >> (idx & 31)) & 1u;
@@ -177,7 +183,9 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
              const uint32_t *__restrict__ invalid, uint32_t pBeg, uint32_t pEnd, DecisionTables D,
              uint32_t altBound, uint32_t *__restrict__ mask) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
-  StreamSmem &S = *reinterpret_cast<StreamSmem *>(smemRaw);
+  using Smem = StreamSmemT<kShortcut>;
+  constexpr int kStages = Smem::kStages;
+  Smem &S = *reinterpret_cast<Smem *>(smemRaw);
   const uint32_t nTiles = (pEnd - pBeg + kStreamTile - 1) / kStreamTile;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t kBytesC = sizeof(uint64_t) * (kStreamTile + 2), kBytesR = kStreamTile / 4, kBytesB = kStreamTile / 8;
@@ -192,20 +200,21 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
   };
 
   if (tid == 0) {
-    for (int s = 0; s < kStreamStages; ++s) { mbar_init(&S.full[s], 1); S.released[s] = 0; }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&S.full[s], 1); S.released[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (uint32_t k = tid; k < (uint32_t) kS1Bits / 4; k += kStreamThreads) {     // expand the s1 bitmap to bytes
-    const uint32_t bits = (__ldg(D.s1 + (k >> 3)) >> ((k & 7) << 2)) & 0xFu;
-    reinterpret_cast<uint32_t *>(S.s1)[k] = (bits & 1u) | ((bits & 2u) << 7) | ((bits & 4u) << 14) | ((bits & 8u) << 21);
-  }
+  if (!kShortcut)
+    for (uint32_t k = tid; k < (uint32_t) kS1Bits / 4; k += kStreamThreads) {     // expand the s1 bitmap to bytes
+      const uint32_t bits = (__ldg(D.s1 + (k >> 3)) >> ((k & 7) << 2)) & 0xFu;
+      reinterpret_cast<uint32_t *>(S.s1)[k] = (bits & 1u) | ((bits & 2u) << 7) | ((bits & 4u) << 14) | ((bits & 8u) << 21);
+    }
   for (uint32_t k = tid; k < 2 * kS2Words; k += kStreamThreads)
     S.s2[k] = k < kS2Words ? __ldg(D.s2p + k) : __ldg(D.s2q + (k - kS2Words));
   if (!invalid)
-    for (uint32_t k = tid; k < kStreamStages * (kStreamTile / 32); k += kStreamThreads) (&S.bm[0][0])[k] = 0;
+    for (uint32_t k = tid; k < kStages * (kStreamTile / 32); k += kStreamThreads) (&S.bm[0][0])[k] = 0;
   __syncthreads();
   if (tid == 0)
-    for (uint32_t s = 0; s < (uint32_t) kStreamStages; ++s) {
+    for (uint32_t s = 0; s < (uint32_t) kStages; ++s) {
       uint32_t t = blockIdx.x + s * gridDim.x;
       if (t < nTiles) issue(s, t);
     }
@@ -216,7 +225,7 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
   auto drain = [&](uint32_t count) {                        // lanes < count run one parked site each
     if (lane < count) {
       const StreamQueueEntry e = q[(qhead + lane) & 63u];
-      if (compact_needs_exact(S.s2, S.s1, e.x, e.y, e.ref)) atomicOr(mask + (e.bit >> 5), 1u << (e.bit & 31));
+      if (compact_needs_exact<kShortcut>(S.s2, S.s1, e.x, e.y, e.ref)) atomicOr(mask + (e.bit >> 5), 1u << (e.bit & 31));
     }
     qhead += count;
   };
@@ -224,11 +233,10 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
   const uint32_t sh = 30u - ((lane & 15u) << 1), laneBit = 0x80000000u >> lane, ltMask = (1u << lane) - 1u;
   const uint32_t site0 = warp * (32 * kRows) + lane;        // this lane's site in row 0 of a tile
   const uint32_t refIdx0 = site0 >> 4, bmIdx0 = warp * kRows;
-  const bool deadBit = S.s1[0] != 0;                        // verdict for a position without coverage
+  const bool deadBit = kShortcut ? false : S.s1[0] != 0;    // verdict for a position without coverage
 
-  uint32_t k = 0;
-  for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++k) {
-    const uint32_t stage = k % kStreamStages, parity = (k / kStreamStages) & 1;
+  uint32_t stage = 0, parity = 0;
+  for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
     mbar_wait(&S.full[stage], parity);
     const uint2 *sc = reinterpret_cast<const uint2 *>(S.counters[stage]) + site0;
     const uint32_t *sr = S.ref[stage] + refIdx0, *sb = S.bm[stage] + bmIdx0;
@@ -291,10 +299,11 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
       if (atomicAdd(&S.released[stage], 1u) == kStreamThreads / 32 - 1) {
         S.released[stage] = 0;
         __threadfence_block();
-        const uint32_t nt = tile + kStreamStages * gridDim.x;
+        const uint32_t nt = tile + kStages * gridDim.x;
         if (nt < nTiles) issue(stage, nt);
       }
     }
+    if (++stage == (uint32_t) kStages) { stage = 0; parity ^= 1u; }
   }
   __syncwarp();
   drain(qtail - qhead);
@@ -302,9 +311,9 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
 
 // function attributes are per device: called once per context, with its device current
 cudaError_t configure_kernels() {
-  cudaError_t e = cudaFuncSetAttribute(k_stream_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmem));
+  cudaError_t e = cudaFuncSetAttribute(k_stream_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmemT<false>));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_stream_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmem));
+  return cudaFuncSetAttribute(k_stream_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmemT<true>));
 }
 
 // what the decision bitmaps (host copies) allow the streaming kernel to skip: returns the largest alt weight A
@@ -327,9 +336,9 @@ void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const De
   uint32_t nTiles = (pEnd - pBeg + kStreamTile - 1) / kStreamTile;
   unsigned grid = nTiles < (uint32_t) numSMs ? nTiles : (unsigned) numSMs;
   if (shortcutAlt)
-    k_stream_tma<true><<<grid, kStreamThreads, sizeof(StreamSmem), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, shortcutAlt << 16, mask);
+    k_stream_tma<true><<<grid, kStreamThreads, sizeof(StreamSmemT<true>), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, shortcutAlt << 16, mask);
   else
-    k_stream_tma<false><<<grid, kStreamThreads, sizeof(StreamSmem), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, 0, mask);
+    k_stream_tma<false><<<grid, kStreamThreads, sizeof(StreamSmemT<false>), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, 0, mask);
 }
 
 template <bool kUseTables>

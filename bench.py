@@ -180,6 +180,26 @@ def bind_to_gpu_numa_node(device):
         return None
 
 
+def measure_host_link(torch, nbytes):
+    """What the host link of this box delivers: one pinned->device and one device->pinned copy of nbytes, CUDA
+    events, best of 5.  Reported beside e2e (which moves 545 MB in and 46 MB out per step) as its floor."""
+    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    best = {"h2d": 1e9, "d2h": 1e9}
+    for _ in range(6):
+        for kind in ("h2d", "d2h"):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            if kind == "h2d":
+                dev.copy_(host, non_blocking=True)
+            else:
+                host.copy_(dev, non_blocking=True)
+            b.record()
+            b.synchronize()
+            best[kind] = min(best[kind], a.elapsed_time(b))
+    return {"h2d_gbs": nbytes / best["h2d"] / 1e6, "d2h_gbs": nbytes / best["d2h"] / 1e6, "bytes": nbytes}
+
+
 def main():
     # exactly ONE line on stdout: libraries (NCCL's version banner, ...) that print to fd 1 are sent to stderr
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -274,9 +294,10 @@ def main():
                 step_resident()
         dt, stats = timed(step_resident, args.warmup, args.steps)
         dt_hr, stats_hr = timed(step_resident_host_results, 1, max(2, min(args.steps, 5)))
-        dt_e2e, stats_e2e = timed(step_host, 1, max(2, min(args.steps, 5)))
+        dt_e2e, stats_e2e = timed(step_host, 2, max(2, args.steps))
         clocks = sampler.stop() if sampler else None
         n_e2e = len(stats_e2e)
+        link = measure_host_link(torch, min(sites * 8, 1 << 29))
 
         launches = sum(s.kernel_launches for s, _ in stats)
         called = stats[0][1]
@@ -312,7 +333,10 @@ def main():
                        "parallelism": "region-sharded x%d, no collective on the data path" % world,
                        "setup_ms": {"table_prefill": pre_ms.value, "decision_bitmaps": dec_ms.value}},
             "e2e": {"value": world * sites * n_e2e / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1000.0 * dt_e2e / n_e2e},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1000.0 * dt_e2e / n_e2e,
+                    "host_link": dict(link, h2d_floor_ms=h2d / (link["h2d_gbs"] * 1e6),
+                                      note="plain cudaMemcpyAsync from page-locked memory on this box, best of 5: the "
+                                           "time the step's input bytes need on the bus whatever the kernels do")},
             "value_with_host_results": {"value": world * sites * len(stats_hr) / dt_hr, "unit": UNIT,
                                         "ms_per_step": 1000.0 * dt_hr / len(stats_hr), "d2h_bytes_per_step": d2h,
                                         "note": "value = inputs AND called-site records resident in HBM (gt16_call_sites_device); "

@@ -192,6 +192,9 @@ typedef struct gt16_index gt16_index;
 int gt16_index_read(const char *prefix, gt16_index **out, char *err, size_t err_len);
 uint32_t gt16_index_length(const gt16_index *ix);
 const uint32_t *gt16_index_packed(const gt16_index *ix, uint32_t *n_words);
+/* Page-lock the packed reference in place (optional; worthwhile when the index serves many gt16_call_sites_host
+ * calls: the copy to HBM then is an asynchronous DMA).  GT16_ECUDA when there is no device. */
+int gt16_index_pin(gt16_index *ix);
 /* getChrAndPos (HSP.h:273-275): concatenated position -> (sequence name, 1-based position) */
 const char *gt16_index_translate(const gt16_index *ix, uint32_t amb, uint32_t *chr_pos);
 /* getChrIDFromName + getAmbPos (indexFunction.cpp:6-66): sequence name (with the reference's "chr" prefix
