@@ -639,28 +639,6 @@ __device__ __forceinline__ uint32_t region_of(const SiteMap &M, uint64_t i) {   
   return lo;
 }
 
-// genome position of entry k of the batch's mwInfo array (the cases of window_entry()); false = the reference never
-// fills the entry or it lies beyond the genome (zeros either way).  reg: a region index not above the entry's own
-// (multi-region maps), advanced in place -- a lane's entries are visited in increasing k.
-__device__ __forceinline__ bool win_pos(const SnapView &V, const SiteMap &M, const BatchGeom &B, uint64_t k, uint32_t &reg,
-                                        uint32_t &p) {
-  if (k < (uint64_t) kWindow) {                                   // left margin, VariantCaller.cpp:713-729
-    if (!(B.amb0 > (uint32_t) kWindow)) return false;
-    p = B.amb0 - kWindow + (uint32_t) k;
-  } else if (k < (uint64_t) kWindow + B.n) {
-    const uint64_t i = B.first + (k - kWindow);
-    if (M.nRegions > 1) while (reg + 1 < M.nRegions && M.regFirst[reg + 1] <= i) ++reg;
-    p = M.regStart[reg] + (uint32_t) (i - M.regFirst[reg]);
-  } else {                                                        // right margin, :731-747
-    const uint64_t j = k - kWindow - B.n;
-    if (j >= (uint64_t) kWindow - 1) return false;                // only 99 entries are ever filled
-    const uint64_t pp = (uint64_t) B.ambLast + 1 + j;
-    if (pp >= V.L) return false;
-    p = (uint32_t) pp;
-  }
-  return p < V.L;
-}
-
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }   // one REDUX.SUM
 
 __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevSiteMap M, uint64_t base,
@@ -737,16 +715,27 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
     } else {
       if (lane < 16) sm.flh[lane] = sm.lh[lane] / pD * P.prior[(ref << 6) | P.g2i[lane]];
       __syncwarp();
-      // argmax_posteriors(): first index wins ties, `>=` only between 0 and 1 (:383-504)
-      double f0 = sm.flh[0], f1 = sm.flh[1];
-      genotype = 0;
-      if (!(f0 >= f1)) { genotype = 1; const double t = f0; f0 = f1; f1 = t; }
+      // argmax_posteriors() (:383-504) across the lanes: the winner is the LOWEST index holding the maximum (the
+      // reference replaces its best only on a strict `>`, and prefers 0 to 1 on a tie), the runner-up is the largest
+      // value among the other fifteen.  Posteriors are >= 0; lanes 16..31 carry -1.
+      double v = lane < 16 ? sm.flh[lane] : -1.0;
+      double f0 = v;
+      genotype = (int) lane;
 #pragma unroll
-      for (int g = 2; g < 16; ++g) {
-        const double v = sm.flh[g];
-        if (v > f0) { f1 = f0; f0 = v; genotype = g; }
-        else if (v > f1) f1 = v;
+      for (int o = 8; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, f0, o);
+        const int gw = __shfl_xor_sync(0xffffffffu, genotype, o);
+        if (w > f0 || (w == f0 && gw < genotype)) { f0 = w; genotype = gw; }
       }
+      f0 = __shfl_sync(0xffffffffu, f0, 0);
+      genotype = __shfl_sync(0xffffffffu, genotype, 0);
+      double f1 = (int) lane == genotype ? -1.0 : v;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, f1, o);
+        if (w > f1) f1 = w;
+      }
+      f1 = __shfl_sync(0xffffffffu, f1, 0);
       bestD = f0; secondD = f1;
     }
     const uint8_t isValid = (uint8_t) (1 + ii.isValidPlus);
@@ -769,18 +758,35 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
     // by win_decode -- only what the window sums need of a position.
     const bool haveLeft = idx >= (uint32_t) kWindow;
     const bool multi = M.m.nRegions > 1;
+    // entry k of the batch's mwInfo array (k < n + 200; the cases of window_entry()): the left margin [0, 100) holds
+    // the positions before the batch's first site -- filled only when amb0 > 100 (VariantCaller.cpp:713-729) --, then
+    // the n sites of the batch, then 99 positions after its last site as far as the genome goes (:731-747).  In a
+    // single-region call all three are one run of consecutive positions.
+    const uint32_t kLo = B.amb0 > (uint32_t) kWindow ? 0u : (uint32_t) kWindow;
+    const uint32_t past = V.L - 1u - B.ambLast;
+    const uint32_t kHi = (uint32_t) kWindow + B.n + (past < (uint32_t) kWindow - 1u ? past : (uint32_t) kWindow - 1u);
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
       if (side == 0 && !haveLeft) continue;
-      const uint64_t k0 = side == 0 ? (uint64_t) idx - kWindow : (uint64_t) idx + nextBp;
+      const uint32_t k0 = side == 0 ? idx - (uint32_t) kWindow : idx + nextBp;
       uint32_t reg = 0;                                       // region of the first in-batch entry (exome): a lower bound
-      if (multi) reg = region_of(M.m, B.first + (k0 >= (uint64_t) kWindow ? k0 - kWindow : 0));
+      if (multi) reg = region_of(M.m, B.first + (k0 >= (uint32_t) kWindow ? k0 - kWindow : 0u));
       uint32_t pp[4]; bool ex[4];
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const uint32_t t = lane + 32u * it;
-        pp[it] = 0;
-        ex[it] = t <= (uint32_t) kWindow && win_pos(V, M.m, B, k0 + t, reg, pp[it]);
+        const uint32_t t = lane + 32u * it, k = k0 + t;
+        ex[it] = t <= (uint32_t) kWindow && k >= kLo && k < kHi;
+        pp[it] = B.amb0 - (uint32_t) kWindow + k;
+        if (multi && ex[it] && k >= (uint32_t) kWindow) {
+          if (k < (uint32_t) kWindow + B.n) {
+            const uint64_t q = B.first + (k - (uint32_t) kWindow);
+            while (reg + 1 < M.m.nRegions && M.m.regFirst[reg + 1] <= q) ++reg;
+            pp[it] = M.m.regStart[reg] + (uint32_t) (q - M.m.regFirst[reg]);
+          } else {
+            pp[it] = B.ambLast + 1u + (k - (uint32_t) kWindow - B.n);
+          }
+        }
+        ex[it] = ex[it] && pp[it] < V.L;
       }
       uint32_t iw[4]; uint64_t cc[4];
 #pragma unroll

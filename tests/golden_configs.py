@@ -59,6 +59,12 @@ FULL_CONFIGS = {
 HUGE_CONFIGS = {
     "wgs_full": dict(synth=["--genome-len", "3100000000", "--n-contigs", "24", "--gaps", "8:100000", "--seed", "3"],
                      exome=False),
+    # configs[4] at FULL size: 3.1 Gb at 60x, indels 1/500 with pooled multi-pattern lists, depth hotspots (overflow
+    # promotion, chi-square fallback), invalid bits, coverage gaps
+    "stress_huge": dict(synth=["--genome-len", "3100000000", "--n-contigs", "24", "--depth", "60", "--indel-rate", "2e-3",
+                               "--multi-pattern-frac", "0.4", "--long-indel-frac", "0.05", "--hotspot-rate", "2e-5",
+                               "--hotspot-depth", "1500", "--invalid-rate", "1e-4", "--gaps", "12:100000",
+                               "--seed", "9"], exome=False),
 }
 FULL_CONFIGS.update(HUGE_CONFIGS)
 CONFIGS_ALL = dict(CONFIGS, **FULL_CONFIGS)
