@@ -115,6 +115,7 @@ def capi():
         "gt16_index_translate": (cp, [vp, u32, P(u32)]),
         "gt16_index_locate": (i32, [vp, cp, u32, P(u32)]),
         "gt16_index_pin": (i32, [vp]),
+        "gt16_format_number": (i32, [ctypes.c_double, i32, cp]),
         "gt16_index_free": (None, [vp]),
         "gt16_write_txt": (i32, [cp, vp, vp, u64, i32, vp]),
     }

@@ -491,21 +491,47 @@ static int alloc_snapshot(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_de
   return GT16_OK;
 }
 
-// everything except the counters (small: 0.375 B/site + overflow records + pool), plus the padding
+// everything except the counters (0.375 B/site + overflow records + pool), plus the padding.  [loPos, hiPos] is the
+// range of positions the call evaluates: only what those positions can reach is copied --
+//   packed reference: +-70,000 positions (a homopolymer run is followed until its count saturates at 65,535,
+//                     VariantCaller.cpp:659-685; deleted bases and windows reach < 1,000 positions),
+//   invalid bitmap  : +-1,024 positions (windows, neighbour tests, look-ahead),
+//   overflow arrays : the regions (findRegionByPosition) of positions within +-1,024,
+// so that a shard of a sharded genome moves its own part of the side arrays over the host link, not all of them.
+static const uint32_t kRefReach = 70000, kSideReach = 1024;
+static uint32_t host_ovf_region(const gt16_snapshot_view *view, uint32_t p) {
+  const uint32_t n = view->n_overflow_regions, len = view->text_length / n;
+  if (len == 0) return n - 1;
+  const uint32_t r = p / len;
+  return r < n - 1 ? r : n - 1;
+}
 static int upload_aux(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot *ds,
-                      const std::vector<uint32_t> &ovfBase, cudaStream_t s) {
+                      const std::vector<uint32_t> &ovfBase, cudaStream_t s, uint32_t loPos, uint32_t hiPos) {
   const uint32_t L = view->text_length;
-  for (uint32_t r = 0; r < view->n_overflow_regions; ++r)
-    if (view->overflow_size[r])
-      CUF(cudaMemcpyAsync((char *) ds->ovf + (size_t) ovfBase[r] * 32, view->overflow[r], (size_t) view->overflow_size[r] * 32,
-                          cudaMemcpyHostToDevice, s));
+  if (hiPos >= L) hiPos = L - 1;
+  if (loPos > hiPos) loPos = hiPos;
+  const uint32_t sLo = loPos > kSideReach ? loPos - kSideReach : 0, sHi = (uint32_t) std::min<uint64_t>((uint64_t) hiPos + kSideReach, L - 1);
+  if (view->n_overflow_regions) {
+    const uint32_t rLo = host_ovf_region(view, sLo), rHi = host_ovf_region(view, sHi);
+    for (uint32_t r = rLo; r <= rHi; ++r)
+      if (view->overflow_size[r])
+        CUF(cudaMemcpyAsync((char *) ds->ovf + (size_t) ovfBase[r] * 32, view->overflow[r], (size_t) view->overflow_size[r] * 32,
+                            cudaMemcpyHostToDevice, s));
+  }
   CUF(cudaMemcpyAsync(ds->ovfBase, ovfBase.data(), ovfBase.size() * 4, cudaMemcpyHostToDevice, s));
   if (view->pool_bytes) CUF(cudaMemcpyAsync(ds->pool, view->pool, view->pool_bytes, cudaMemcpyHostToDevice, s));
-  CUF(cudaMemcpyAsync(ds->ref, view->packed_ref, (size_t) view->packed_ref_words * 4, cudaMemcpyHostToDevice, s));
-  CUF(cudaMemsetAsync((char *) ds->ref + (size_t) view->packed_ref_words * 4, 0, (kStreamPadSites / 16 + 4) * 4, s));
+  {
+    const size_t wLo = (loPos > kRefReach ? loPos - kRefReach : 0) >> 4;
+    const size_t wHi = std::min<size_t>(view->packed_ref_words, (((size_t) hiPos + kRefReach) >> 4) + 1);
+    if (wHi > wLo)
+      CUF(cudaMemcpyAsync((uint32_t *) ds->ref + wLo, view->packed_ref + wLo, (wHi - wLo) * 4, cudaMemcpyHostToDevice, s));
+    CUF(cudaMemsetAsync((char *) ds->ref + (size_t) view->packed_ref_words * 4, 0, (kStreamPadSites / 16 + 4) * 4, s));
+  }
   if (view->invalid_bitmap) {
     const size_t w = ((size_t) L + 31) >> 5;
-    CUF(cudaMemcpyAsync(ds->invalid, view->invalid_bitmap, w * 4, cudaMemcpyHostToDevice, s));
+    const size_t wLo = sLo >> 5, wHi = std::min<size_t>(w, ((size_t) sHi >> 5) + 1);
+    if (wHi > wLo)
+      CUF(cudaMemcpyAsync((uint32_t *) ds->invalid + wLo, view->invalid_bitmap + wLo, (wHi - wLo) * 4, cudaMemcpyHostToDevice, s));
     CUF(cudaMemsetAsync((char *) ds->invalid + w * 4, 0, (kStreamPadSites / 32 + 4) * 4, s));
   }
   CUF(cudaMemsetAsync((char *) ds->counters + (size_t) L * 8, 0, kStreamPadSites * 8, s));
@@ -545,7 +571,7 @@ extern "C" int gt16_snapshot_upload(gt16_ctx *ctx, const gt16_snapshot_view *vie
   gt16_dev_snapshot *ds = new gt16_dev_snapshot();
   std::vector<uint32_t> ovfBase;
   rc = alloc_snapshot(ctx, view, ds, ovfBase, false);
-  if (rc == GT16_OK) rc = upload_aux(ctx, view, ds, ovfBase, ctx->copy);
+  if (rc == GT16_OK) rc = upload_aux(ctx, view, ds, ovfBase, ctx->copy, 0, view->text_length - 1);
   if (rc == GT16_OK) {
     const uint32_t L = view->text_length;
     for (uint64_t a = 0; a < L && rc == GT16_OK; a += kCopyChunkSites) {
@@ -800,11 +826,11 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     // counters stream in on the copy stream in genome order (32 MiB chunks, all queued up front)
     std::vector<uint32_t> ovfBase;
     rc = alloc_snapshot(ctx, hostView, &streamed, ovfBase, true);
-    if (rc == GT16_OK) rc = upload_aux(ctx, hostView, &streamed, ovfBase, ctx->copy);
-    if (rc != GT16_OK) return rc;
-    V = &streamed.v;
     const uint32_t loPos = pl.ascending ? pl.pos_of(begin) : 0;
     const uint32_t hiPos = pl.ascending ? pl.pos_of(end - 1) : L - 1;
+    if (rc == GT16_OK) rc = upload_aux(ctx, hostView, &streamed, ovfBase, ctx->copy, loPos, hiPos);
+    if (rc != GT16_OK) return rc;
+    V = &streamed.v;
     // page-locked source: cudaMemcpyAsync straight from the caller's buffer.  Pageable source (what a caller gets
     // from malloc/fread; pinning half a gigabyte costs more than copying it): stager threads move 8 MiB chunks
     // through a small page-locked ring.

@@ -6,7 +6,12 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <math.h>
+#include <float.h>
+#include <cmath>
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
 #include <string>
@@ -25,11 +30,13 @@ void set_err(char *err, size_t n, const char *fmt, ...) {
   va_end(ap);
 }
 
-// big host buffer, page-locked on request
+// big host buffer: page-locked on request, or a read-only private mapping of a byte range of a file
 struct HostBuf {
   void *p = nullptr;
   size_t bytes = 0;
   bool pinned = false;
+  void *mapBase = nullptr;                 // mmap()ed range that holds p (map_file)
+  size_t mapBytes = 0;
   bool alloc(size_t n, bool pin) {
     bytes = n ? n : 1;
     if (pin && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) { pinned = true; return true; }
@@ -38,10 +45,31 @@ struct HostBuf {
     p = malloc(bytes);
     return p != nullptr;
   }
+  // p = the n bytes at offset `off` of the file, straight from the page cache: no copy into anonymous memory.
+  // (The library only ever copies out of the counter array; a page-locked ring stands between it and the DMA.)
+  bool map_file(const char *path, uint64_t off, size_t n) {
+    const long page = sysconf(_SC_PAGESIZE);
+    const uint64_t lo = off & ~(uint64_t) (page - 1);
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || (uint64_t) st.st_size < off + n) { close(fd); return false; }
+    void *m = mmap(nullptr, (size_t) (off - lo) + n, PROT_READ, MAP_PRIVATE, fd, (off_t) lo);
+    close(fd);
+    if (m == MAP_FAILED) return false;
+    madvise(m, (size_t) (off - lo) + n, MADV_SEQUENTIAL);
+    mapBase = m; mapBytes = (size_t) (off - lo) + n;
+    p = (char *) m + (off - lo);
+    bytes = n;
+    pinned = false;
+    return true;
+  }
   void release() {
     if (!p) return;
-    if (pinned) cudaFreeHost(p); else free(p);
-    p = nullptr;
+    if (mapBase) munmap(mapBase, mapBytes);
+    else if (pinned) cudaFreeHost(p);
+    else free(p);
+    p = nullptr; mapBase = nullptr;
   }
 };
 
@@ -125,8 +153,13 @@ int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, c
     memcpy(&hs->textLength, head + 1, 4);
     const uint32_t L = hs->textLength;
     if (!L) { set_err(err, errLen, "%s: empty snapshot", path); rc = GT16_EDATA; break; }
-    if (!hs->counters.alloc((size_t) L * 8 + 16, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
-    if (mode & 1) {
+    // Dense counters of a pageable snapshot are mapped, not read: the only consumer copies them chunk by chunk into
+    // page-locked memory on their way to the GPU, so a private copy would just be one more pass over 8 bytes per
+    // site of host memory (the slowest resource of the drop-in binary on a 3.1 Gb genome).
+    const bool mapped = (mode & 1) && !pinned && !getenv("GT16_NO_MMAP") && hs->counters.map_file(path, start[1] + 5, (size_t) L * 8);
+    if (!mapped && !hs->counters.alloc((size_t) L * 8 + 16, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
+    if (mapped) {
+    } else if (mode & 1) {
       if (!pread_parallel(path, start[1] + 5, hs->counters.p, (size_t) L * 8)) { set_err(err, errLen, "%s: truncated counters", path); rc = GT16_EIO; break; }
       memset((char *) hs->counters.p + (size_t) L * 8, 0, 16);
     } else if (mode & 2) {
@@ -340,14 +373,78 @@ static const char kSym[] = {'A', 'C', 'G', 'T', 'X', 'Y', 'N'};
 // one row of the .txt (printPossibleSNP, interpreter.cpp:107-156) appended to `out`; lq / rq are the values the
 // reference would print for this row (its ReadQuality variable survives rows that do not assign it)
 namespace {
+// ---- number formatting -------------------------------------------------------------------------------------
+// A row holds ~60 "%.4e" fields; through snprintf they cost more than everything else the drop-in does on the
+// host after the GPU is done.  fmt_e4 / fmt_f4 produce the very bytes glibc's printf produces (exact decimal value
+// of the double, round-half-even): the scaled value is computed in 80-bit arithmetic (relative error < 2^-60), and
+// whenever it lies within 1e-7 of a rounding boundary -- where that error could matter, exact ties included --
+// the field is handed to snprintf.  tests/test_capi_cpu.py compares both on millions of values.
+struct Pow10 {
+  long double p[701];                                         // 10^(k-350), correctly rounded
+  Pow10() { char b[16]; for (int k = 0; k <= 700; ++k) { snprintf(b, sizeof(b), "1e%d", k - 350); p[k] = strtold(b, nullptr); } }
+  long double operator()(int k) const { return p[k + 350]; }
+};
+const Pow10 kPow10;
+
+inline char *put_u32(char *o, uint32_t v) {
+  char t[10]; int n = 0;
+  do { t[n++] = (char) ('0' + v % 10); v /= 10; } while (v);
+  while (n) *o++ = t[--n];
+  return o;
+}
+
+// "%.4e" of v followed by a tab; returns the end of the output
+inline char *fmt_e4(char *o, double v) {
+  if (v == 0.0 && !std::signbit(v)) { memcpy(o, "0.0000e+00\t", 11); return o + 11; }
+  if (v == 1.0) { memcpy(o, "1.0000e+00\t", 11); return o + 11; }
+  const double a = fabs(v);
+  if (!(a > 0.0) || !(a <= DBL_MAX)) return o + snprintf(o, 40, "%.4e\t", v);      // -0, inf, nan
+  int e2;
+  frexp(a, &e2);
+  int e = (int) floor((e2 - 1) * 0.30102999566398120);          // floor(log10 a) or one less
+  long double sc = (long double) a * kPow10(4 - e);
+  if (sc >= 100000.0L) { ++e; sc = (long double) a * kPow10(4 - e); }
+  if (sc < 10000.0L || sc >= 100000.0L) return o + snprintf(o, 40, "%.4e\t", v);
+  const long double fl = floorl(sc), fr = sc - fl;
+  if (fr > 0.4999999L && fr < 0.5000001L) return o + snprintf(o, 40, "%.4e\t", v);
+  uint32_t d = (uint32_t) fl + (fr > 0.5L ? 1u : 0u);
+  if (d >= 100000u) { d = 10000u; ++e; }                         // 9.99996 -> 1.0000e+01
+  if (std::signbit(v)) *o++ = '-';
+  o[0] = (char) ('0' + d / 10000u); o[1] = '.';
+  o[2] = (char) ('0' + d / 1000u % 10u); o[3] = (char) ('0' + d / 100u % 10u);
+  o[4] = (char) ('0' + d / 10u % 10u); o[5] = (char) ('0' + d % 10u);
+  o[6] = 'e'; o[7] = e < 0 ? '-' : '+';
+  const uint32_t ae = (uint32_t) (e < 0 ? -e : e);
+  o += 8;
+  if (ae < 10) { *o++ = '0'; *o++ = (char) ('0' + ae); } else o = put_u32(o, ae);
+  *o++ = '\t';
+  return o;
+}
+
+// "%.4f" of v (a float widened to double) followed by a tab
+inline char *fmt_f4(char *o, double v) {
+  const double a = fabs(v);
+  if (!(a < 4.0e5)) return o + snprintf(o, 64, "%.4f\t", v);     // large, inf, nan
+  const long double sc = (long double) a * 10000.0L;
+  const long double fl = floorl(sc), fr = sc - fl;
+  if (fr > 0.4999999L && fr < 0.5000001L) return o + snprintf(o, 64, "%.4f\t", v);
+  const uint64_t d = (uint64_t) fl + (fr > 0.5L ? 1u : 0u);
+  if (std::signbit(v)) *o++ = '-';
+  o = put_u32(o, (uint32_t) (d / 10000u));
+  const uint32_t f = (uint32_t) (d % 10000u);
+  o[0] = '.'; o[1] = (char) ('0' + f / 1000u); o[2] = (char) ('0' + f / 100u % 10u);
+  o[3] = (char) ('0' + f / 10u % 10u); o[4] = (char) ('0' + f % 10u); o[5] = '\t';
+  return o + 6;
+}
+
 struct RowBuf {
   std::string &s;
   char tmp[96];
   explicit RowBuf(std::string &str) : s(str) {}
-  void e4(double v) { s.append(tmp, (size_t) snprintf(tmp, sizeof(tmp), "%.4e\t", v)); }
-  void f4(double v) { s.append(tmp, (size_t) snprintf(tmp, sizeof(tmp), "%.4f\t", v)); }
-  void u(unsigned v, char sep = '\t') { s.append(tmp, (size_t) snprintf(tmp, sizeof(tmp), "%u%c", v, sep)); }
-  void hu(unsigned short v) { s.append(tmp, (size_t) snprintf(tmp, sizeof(tmp), "%hu\t", v)); }
+  void e4(double v) { s.append(tmp, (size_t) (fmt_e4(tmp, v) - tmp)); }
+  void f4(double v) { s.append(tmp, (size_t) (fmt_f4(tmp, v) - tmp)); }
+  void u(unsigned v, char sep = '\t') { char *e = put_u32(tmp, v); *e++ = sep; s.append(tmp, (size_t) (e - tmp)); }
+  void hu(unsigned short v) { u(v); }
   void lit(const char *t) { s.append(t); }
   void ch(char c) { s.push_back(c); s.push_back('\t'); }
 };
@@ -458,6 +555,13 @@ int gt16_write_txt(const char *path, const gt16_index *ix, const gt16_called_sit
   if (ferror(f)) bad = true;
   if (fclose(f) != 0 || bad) return GT16_EIO;
   return GT16_OK;
+}
+
+// test hook: the two fast formatters (tests compare them with printf on millions of values)
+int gt16_format_number(double v, int kind, char *out) {
+  char *e = kind == 0 ? fmt_e4(out, v) : fmt_f4(out, v);
+  e[-1] = 0;                                   // drop the tab
+  return (int) (e - 1 - out);
 }
 
 }  // extern "C"

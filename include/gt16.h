@@ -202,6 +202,9 @@ const char *gt16_index_translate(const gt16_index *ix, uint32_t amb, uint32_t *c
  * position (unknown sequence, beyond its end, inside a removed stretch) */
 int gt16_index_locate(const gt16_index *ix, const char *chr_name, uint32_t chr_pos, uint32_t *amb);
 void gt16_index_free(gt16_index *ix);
+/* Test hook: the emitter's own "%.4e" (kind 0) / "%.4f" (kind 1) formatting of v into out (>= 64 bytes); returns the
+ * length.  Must equal printf's output byte for byte. */
+int gt16_format_number(double v, int kind, char *out);
 
 /* printHeader + printPossibleSNP (interpreter.cpp:8-31,107-156): byte-identical layout */
 int gt16_write_txt(const char *path, const gt16_index *ix, const gt16_called_site *sites, uint64_t n, int append,

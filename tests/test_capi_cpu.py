@@ -117,6 +117,47 @@ def test_region_index_builder_matches_reference(tmp_path):
         L.gt16_index_free(ix)
 
 
+def test_fast_number_formatting_equals_printf():
+    """The .txt emitter formats "%.4e" / "%.4f" fields itself (80-bit scaling, snprintf whenever the value lies close
+    to a rounding boundary): every byte must be what libc's printf writes -- random bit patterns over all exponents,
+    subnormals, values next to d.dddd5 boundaries and next to powers of ten, exact ties of the fixed format."""
+    import math, random, struct
+    L = T.capi()
+    libc = ctypes.CDLL("libc.so.6")
+    libc.snprintf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_double]
+    got, want = ctypes.create_string_buffer(128), ctypes.create_string_buffer(128)
+    rnd = random.Random(11)
+
+    def check(v, kind):
+        n = L.gt16_format_number(v, kind, got)
+        m = libc.snprintf(want, 128, b"%.4e" if kind == 0 else b"%.4f", v)
+        assert got.raw[:n] == want.raw[:m], (v, kind, got.raw[:n], want.raw[:m])
+
+    for _ in range(60000):
+        v = struct.unpack("<d", struct.pack("<Q", rnd.getrandbits(64)))[0]
+        if math.isfinite(v):
+            check(v, 0)
+        check(10 ** rnd.uniform(-320, 0.5), 0)
+        k = rnd.randint(-300, 10)
+        v = (rnd.randint(10000, 99999) + 0.5) * 10.0 ** (k - 4)
+        for w in (v, math.nextafter(v, 0), math.nextafter(v, math.inf)):
+            check(w, 0)
+        f = struct.unpack("<f", struct.pack("<f", rnd.uniform(-3, 3) * 10 ** rnd.uniform(-6, 5)))[0]
+        check(f, 1)
+    for k in range(-320, 300):
+        for m in (9.99995, 9.999949999, 9.99995000001, 1.0, 0.99999999999, 1.00005):
+            check(m * 10.0 ** k, 0)
+    for v in (0.0, -0.0, 0.5, 0.00005, 0.125, 1.00005, 2.5e-5, -2.5e-5, 1e-9, -1e-9, 399999.99996, 4e5, 1e10, 0.99995,
+              5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, float("inf"), float("nan")):
+        check(v, 0)
+        if not abs(v) > 3.5e38:                                                # "%.4f" fields are floats
+            check(v, 1)
+    check(3.4028234663852886e38, 1)
+    for i in range(1, 40000):
+        check(i / 32768.0, 1)                                                  # exact ties
+        check(struct.unpack("<f", struct.pack("<f", i * 0.00005))[0], 1)
+
+
 def test_cli_usage_errors():
     r = subprocess.run([T.CLI], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "Usage:" in r.stderr and "-e <Exome Region Index>" in r.stderr
