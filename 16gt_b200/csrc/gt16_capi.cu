@@ -93,7 +93,7 @@ struct gt16_ctx {
   std::vector<cudaEvent_t> evPool;
   std::shared_ptr<PinPool> pins = std::make_shared<PinPool>();
   void *stagePin = nullptr;               // page-locked ring for callers whose counters live in pageable memory
-  cudaEvent_t stageEv[16] = {nullptr};    // slot k's last copy has left the ring
+  cudaEvent_t stageEv[32] = {nullptr};    // slot k's last copy has left the ring
 };
 
 struct gt16_dev_snapshot {
@@ -423,7 +423,12 @@ int gt16_compute_bias(gt16_ctx *ctx, const void *w, const void *f, const void *r
 // A context is driven by one host thread at a time; all scratch is owned by the context and only grows.
 static const uint32_t kCopyChunkSites = 1u << 22;     // 32 MiB of counters per cudaMemcpyAsync (page-locked source)
 static const uint32_t kStageChunkSites = 1u << 20;    // 8 MiB per chunk when the source is pageable and goes through the ring
-static const int kStageThreads = 4, kStageSlots = 8;  // stager threads, ring slots (two per thread)
+static const int kStageThreadsMax = 16, kStageSlots = 2 * kStageThreadsMax;  // stager threads, ring slots (two per thread)
+static int stage_threads() {                              // GT16_STAGE_THREADS, default 4
+  int n = 4;
+  if (const char *e = getenv("GT16_STAGE_THREADS")) { int v = atoi(e); if (v >= 1 && v <= kStageThreadsMax) n = v; }
+  return n;
+}
 // candidate records per kernel launch / D2H copy: a small first slice starts the device->host stream early,
 // later slices double up to kCandSliceMax so the kernels run at full occupancy
 static const uint32_t kCandSliceFirst = 4096, kCandSliceMax = 32768;
@@ -874,14 +879,15 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
       }
     } else {
       if (!ctx->stagePin) {
-        CUF(cudaHostAlloc(&ctx->stagePin, (size_t) kStageSlots * kStageChunkSites * 8, cudaHostAllocDefault));
+        CUF(cudaHostAlloc(&ctx->stagePin, (size_t) 2 * stage_threads() * kStageChunkSites * 8, cudaHostAllocDefault));
         for (int k = 0; k < kStageSlots; ++k) CUF(cudaEventCreateWithFlags(&ctx->stageEv[k], cudaEventDisableTiming));
       }
       enqueued.reset(new std::atomic<int>[nChunks]);
       for (size_t c = 0; c < nChunks; ++c) enqueued[c].store(0);
       const int dev = ctx->device;
+      const int kStageThreads = stage_threads();
       for (int t = 0; t < kStageThreads; ++t)
-        stagers.emplace_back([&, t, dev]() {
+        stagers.emplace_back([&, t, dev, kStageThreads]() {
           cudaSetDevice(dev);
           int use = 0;                                       // this thread alternates between its two ring slots
           for (size_t c = (size_t) t; c < nChunks; c += kStageThreads, use ^= 1) {

@@ -90,6 +90,21 @@ def test_dropin_binary_multi_shard(tmp_path):
     T.compare_txt(open(out + ".txt", "rb").read(), T.golden_txt("two_batch"))
 
 
+def test_dropin_binary_pieces(tmp_path):
+    """a shard is called in pieces whose rows are appended while the next piece computes (GT16_PIECE_BATCHES=1: every
+    batch its own call, with its own shard-local upload of the side arrays); the read-instead-of-map path of the
+    snapshot reader (GT16_NO_MMAP) gives the same bytes"""
+    idx, out, region = T.regenerate("two_batch", tmp_path)
+    want = T.golden_txt("two_batch")
+    for extra in (dict(GT16_PIECE_BATCHES="1"), dict(GT16_PIECE_BATCHES="1", GT16_NO_MMAP="1", GT16_STAGE_THREADS="7")):
+        r = subprocess.run([T.CLI, "-i", idx, "-o", out, "-v"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                           timeout=600, env=dict(os.environ, **extra))
+        assert r.returncode == 0, r.stderr
+        assert "2 pieces" in r.stdout
+        T.compare_txt(open(out + ".txt", "rb").read(), want)
+        os.remove(out + ".txt")
+
+
 def test_dropin_binary_errors(tmp_path):
     r = subprocess.run([T.CLI], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "Usage:" in r.stderr

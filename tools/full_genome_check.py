@@ -36,6 +36,12 @@ def main():
     print("synth: %.1f s, snapshot %.1f GB" % (time.time() - t0, os.path.getsize(out + ".snapshot") / 1e9), flush=True)
     for p in (idx + ".pac", idx + ".ann", idx + ".tra"):
         assert T.sha256(p) == m["inputs"][os.path.basename(p)], "regenerated input differs from the golden input: " + p
+    for setting in [a for a in sys.argv[2:] if "=" in a]:         # optional sweeps: NAME=v1,v2 (timed only)
+        key, vals = setting.split("=", 1)
+        for v in vals.split(","):
+            t0 = time.time()
+            subprocess.run([T.CLI, "-i", idx, "-o", out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=dict(os.environ, **{key: v}))
+            print("sweep %s=%s: %.2f s wall" % (key, v, time.time() - t0), flush=True)
     t0 = time.time()
     r = subprocess.run([T.CLI, "-i", idx, "-o", out, "-v"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     wall = time.time() - t0
