@@ -78,7 +78,7 @@ struct gt16_ctx {
   uint32_t *g2i = nullptr;
   float *lnfact = nullptr;
   uint32_t *s1 = nullptr, *s2p = nullptr, *s2q = nullptr, *g4 = nullptr;
-  uint32_t *errWord = nullptr, *dTotal = nullptr;
+  uint32_t *errWord = nullptr, *dTotal = nullptr, *dFlagged = nullptr;   // one allocation: error bits, compaction total, sites evaluated exactly
   uint32_t *hPinned = nullptr;          // [0] total, [1] error word
   bool havePrefill = false, haveDecisions = false, useDecisions = true;
   double balance = 0.01, unbalance = 0.005;
@@ -88,7 +88,7 @@ struct gt16_ctx {
   uint2 *biasCache = nullptr;             // memoised Fisher tests (k_bias), kBiasCacheEntries entries
   int numSMs = 148;
   // persistent scratch of the fused path
-  DevBuf mask, counts, listA, listB, recs, recs2, planStart, planFirst;
+  DevBuf mask, counts, listB, recs, recs2, planStart, planFirst;
   DevBuf sCounters, sInvalid, sOvf, sOvfBase, sPool, sRef;      // streamed (host-fed) snapshot
   std::vector<cudaEvent_t> evPool;
   std::shared_ptr<PinPool> pins = std::make_shared<PinPool>();
@@ -193,10 +193,11 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   if ((e = cudaMalloc(&ctx->g2i, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->ycsq, kYcsqN * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->lnfact, (size_t) kLnFactTab * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMalloc(&ctx->errWord, 2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->errWord, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   ctx->dTotal = ctx->errWord + 1;
+  ctx->dFlagged = ctx->errWord + 2;
   if ((e = cudaHostAlloc(&ctx->hPinned, 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
-  if ((e = cudaMemset(ctx->errWord, 0, 2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMemset(ctx->errWord, 0, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = cudaMalloc(&ctx->biasCache, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(ctx->biasCache, 0xFF, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMemset", e);
   // defaults of selectPossibleSNPs (VariantCaller.cpp:506-513)
@@ -231,7 +232,7 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   cudaFree(ctx->errWord);
   cudaFree(ctx->biasCache);
   cudaFreeHost(ctx->hPinned);
-  for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->listA, &ctx->listB, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst,
+  for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->listB, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst,
                     &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
   for (auto e : ctx->evPool) cudaEventDestroy(e);
   if (ctx->stagePin) cudaFreeHost(ctx->stagePin);
@@ -698,22 +699,19 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
   const uint32_t n = (uint32_t) (b - a), off = (uint32_t) (a - begin);
   cudaEvent_t ev[4];
   for (int k = 0; k < 4; ++k) { int rc = get_event(ctx, evNext++, &ev[k]); if (rc) return rc; }
-  uint32_t nA = 0, nB = 0;
-  int rc = compact(ctx, mask, n, off, ctx->listA, &nA);
-  if (rc) return rc;
+  // exact evaluation of the flagged sites straight from the mask (clears the bits of non-candidates), then ONE ordered
+  // compaction: what is left are the called sites, in order
+  uint32_t nB = 0;
+  int rc;
   CUF(cudaEventRecord(ev[0], ctx->compute));
-  const uint32_t *finalList = (const uint32_t *) ctx->listA.p;
-  nB = nA;
   if (usedTables) {
-    launch_eval_list(V, pl.map, begin, (const uint32_t *) ctx->listA.p, nA, true, D, P, (uint32_t *) ctx->mask.p, ctx->errWord, ctx->compute);
+    launch_eval_mask(V, pl.map, begin, off, n, true, D, P, (uint32_t *) ctx->mask.p, ctx->errWord, ctx->dFlagged, ctx->compute);
     ctx->launches++;
-    CUF(cudaEventRecord(ev[1], ctx->compute));
-    rc = compact(ctx, mask, n, off, ctx->listB, &nB);
-    if (rc) return rc;
-    finalList = (const uint32_t *) ctx->listB.p;
-  } else {
-    CUF(cudaEventRecord(ev[1], ctx->compute));
   }
+  CUF(cudaEventRecord(ev[1], ctx->compute));
+  rc = compact(ctx, mask, n, off, ctx->listB, &nB);
+  if (rc) return rc;
+  const uint32_t *finalList = (const uint32_t *) ctx->listB.p;
   // candidate records of this segment: device buffers alternate between segments so that a segment's copies
   // may still be in flight while the next one is being written
   DevBuf &rb = (seg & 1) ? ctx->recs2 : ctx->recs;
@@ -756,7 +754,6 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
     segCopied.push_back(done);
   }
   if (devOut) { devOut->recs = recs; devOut->n = nB; } else calls->n += nB;
-  st->flagged += nA;
   st->called += nB;
   timing.push_back(evStream0); timing.push_back(evStream1);
   for (int k = 0; k < 4; ++k) timing.push_back(ev[k]);
@@ -811,6 +808,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   uint32_t *mask = (uint32_t *) ctx->mask.p;
   const uint64_t resultHint = std::max<uint64_t>(4096, (uint64_t) n / 512);
   std::vector<cudaEvent_t> timing, segCopied;
+  CUF(cudaMemsetAsync(ctx->dFlagged, 0, 4, ctx->compute));
   CUF(cudaEventRecord(evBegin, ctx->compute));
 
   gt16_dev_snapshot streamed;
@@ -973,11 +971,12 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     for (auto &t : stagers) t.join();
     if (stageError.load()) { ctx->err = std::string("staged upload failed: ") + cudaGetErrorString((cudaError_t) stageError.load()); return GT16_ECUDA; }
   }
-  CUF(cudaMemcpyAsync(ctx->hPinned + 1, ctx->errWord, 4, cudaMemcpyDeviceToHost, ctx->compute));
+  CUF(cudaMemcpyAsync(ctx->hPinned + 1, ctx->errWord, 12, cudaMemcpyDeviceToHost, ctx->compute));   // error bits, (total), sites evaluated
   CUF(cudaEventRecord(evEnd, ctx->compute));
   CUF(cudaStreamSynchronize(ctx->compute));
   CUF(cudaGetLastError());
   const uint32_t errw = ctx->hPinned[1];
+  st.flagged = useTables ? ctx->hPinned[3] : st.called;
   if (errw) CUF(cudaMemset(ctx->errWord, 0, 4));
   if (errw & kErrBadSnapshot) return fail(ctx, GT16_EDATA, "snapshot refers to an overflow record or pool range that does not exist");
   if (errw & kErrGenotype) return fail(ctx, GT16_EGENOTYPE, "Error in selecting Genotype");

@@ -406,22 +406,23 @@ void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint3
 // A site that is NOT a candidate has its bit cleared in the site mask, so that one more ordered
 // compaction of the mask yields the candidate list.
 constexpr int kEvalThreads = 128;
-__global__ void __launch_bounds__(kEvalThreads) k_eval_list(SnapView V, DevSiteMap M, uint64_t base,
-                                                            const uint32_t *__restrict__ list, uint32_t n, bool useTables,
-                                                            DecisionTables D, EvalParams P, uint32_t *__restrict__ siteMask,
-                                                            uint32_t *errWord) {
-  __shared__ double lhS[kEvalThreads / 32][2][16];
-  __shared__ uint32_t wpS[kEvalThreads / 32][2][6];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, g = lane & 15;
-  const uint32_t warpsTotal = gridDim.x * (kEvalThreads / 32);
-  for (uint32_t j0 = (blockIdx.x * (kEvalThreads / 32) + warp) * 32u; j0 < n; j0 += warpsTotal * 32u) {
-    const uint32_t j = j0 + lane;
-    uint32_t e = 0, i = 0;
+constexpr int kEvalQueue = 64;                       // per-warp ring of flagged site indices
+
+// Exact evaluation of up to 32 flagged sites, one per lane (site index i relative to `base`, lanes with !active idle).
+// Lane phase: decode + the general bitmap test; warp phase: the sites that still need the full evaluator are taken
+// two at a time, each half-warp computing the 16 genotype likelihoods of one site (one genotype per lane).  A site
+// that is NOT a candidate has its bit cleared in the site mask.
+__device__ __forceinline__ void eval_group(const SnapView &V, const DevSiteMap &M, uint64_t base, uint32_t i, bool active,
+                                           bool useTables, const DecisionTables &D, const EvalParams &P,
+                                           uint32_t *__restrict__ siteMask, uint32_t *errWord,
+                                           double (*lhS)[16], uint32_t (*wpS)[6]) {
+  const uint32_t lane = threadIdx.x & 31, half = lane >> 4, g = lane & 15;
+  {
+    uint32_t e = 0;
     bool cand = false, full = false;
     uint32_t W[6] = {0, 0, 0, 0, 0, 0};
     int ref = 0; uint32_t validPlus = 0;
-    if (j < n) {
-      i = list[j];
+    if (active) {
       const uint32_t p = site_pos(M, base + i);
       BaseCounts bc;
       decode_bases(V, p, bc);
@@ -469,20 +470,30 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_list(SnapView V, DevSiteM
           if (tmp <= 0) tmp = 0;
           v = (uint32_t) tmp;
         }
-        wpS[warp][half][g] = v;
+        wpS[half][g] = v;
       }
       __syncwarp();
       int wt = 0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) wt += (int) wpS[warp][half][k];
-      lhS[warp][half][g] = genotype_lh_one(P.lh, wpS[warp][half], wt, (int) g);
+      for (int k = 0; k < 6; ++k) wt += (int) wpS[half][k];
+      lhS[half][g] = genotype_lh_one(P.lh, wpS[half], wt, (int) g);
       __syncwarp();
-      int res = 0;                                    // bit0 candidate, bit1 genotype error
-      if (g == 0) {
-        Posterior po;
-        select_genotype(refS, lhS[warp][half], P.prior, P.g2i, po);
-        res = (po.genotype != hom_ref_genotype(refS) ? 1 : 0) | ((po.genotype > 9 && vpS == 0) ? 2 : 0);   // SNP_Caller.cpp:235-239
+      // selectGenotype (FisherExactTest.cpp:317-509) across the half-warp: the sum in the reference's order in every
+      // lane, ONE posterior division per lane, the winner (lowest index holding the maximum) by shuffles.  pD == 0
+      // makes the reference call hom-ref (:351-361): that lane alone gets a non-zero score.
+      double pD = lhS[half][0];
+#pragma unroll
+      for (int k = 1; k < 16; ++k) pD = pD + lhS[half][k];
+      const int homRef = hom_ref_genotype(refS);
+      double f0 = pD == 0.0 ? ((int) g == homRef ? 1.0 : 0.0) : lhS[half][g] / pD * P.prior[(refS << 6) | P.g2i[g]];
+      int genotype = (int) g;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, f0, o);
+        const int gw = __shfl_xor_sync(0xffffffffu, genotype, o);
+        if (w > f0 || (w == f0 && gw < genotype)) { f0 = w; genotype = gw; }
       }
+      const int res = (genotype != homRef ? 1 : 0) | ((genotype > 9 && vpS == 0) ? 2 : 0);   // bit0 candidate, bit1 genotype error (SNP_Caller.cpp:235-239)
       const int res0 = __shfl_sync(0xffffffffu, res, 0), res1 = __shfl_sync(0xffffffffu, res, 16);
       if ((int) lane == src0) { cand = res0 & 1; if (res0 & 2) e |= kErrGenotype; }
       if ((int) lane == src1 && src1 != src0) { cand = res1 & 1; if (res1 & 2) e |= kErrGenotype; }
@@ -490,16 +501,64 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_list(SnapView V, DevSiteM
       __syncwarp();
     }
     if (e) atomicOr(errWord, e);
-    if (j < n && !cand) atomicAnd(siteMask + (i >> 5), ~(1u << (i & 31)));
+    if (active && !cand) atomicAnd(siteMask + (i >> 5), ~(1u << (i & 31)));
   }
 }
-void launch_eval_list(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
+
+// Exact evaluation of every site flagged in mask words [wordBegin, wordBegin + nWords) of the call's site mask (bit k of
+// word w = site 32 w + k relative to `base`).  No compaction pass and no host round trip in front of it: a warp walks
+// chunks of 32 mask words, parks the set bits in a shared-memory ring and evaluates them 32 at a time (flag density is
+// ~0.4 %, so one chunk of 1,024 sites yields ~4 sites).  *flagged += number of sites evaluated.
+__global__ void __launch_bounds__(kEvalThreads, 6) k_eval_mask(SnapView V, DevSiteMap M, uint64_t base, uint32_t wordBegin,
+                                                            uint32_t nWords, bool useTables, DecisionTables D, EvalParams P,
+                                                            uint32_t *__restrict__ siteMask, uint32_t *errWord,
+                                                            uint32_t *flagged) {
+  __shared__ double lhS[kEvalThreads / 32][2][16];
+  __shared__ uint32_t wpS[kEvalThreads / 32][2][6];
+  __shared__ uint32_t ringS[kEvalThreads / 32][kEvalQueue];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *ring = ringS[warp];
+  const uint32_t warpsTotal = gridDim.x * (kEvalThreads / 32), nChunks = (nWords + 31) / 32;
+  uint32_t head = 0, tail = 0, seen = 0;
+  for (uint32_t c = blockIdx.x * (kEvalThreads / 32) + warp; c < nChunks; c += warpsTotal) {
+    const uint32_t wi = c * 32 + lane;
+    // plain load: the words are cleared by atomics of this very launch (other warps' sites never share a word with ours
+    // before it has been read: a word is read by exactly one lane, and only bits it has queued are cleared)
+    uint32_t bits = wi < nWords ? siteMask[wordBegin + wi] : 0u;
+    seen += __popc(bits);
+    uint32_t any = __ballot_sync(0xffffffffu, bits != 0);
+    while (any) {                                       // one bit per lane and round
+      const bool have = bits != 0;
+      if (have) {
+        const uint32_t b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        ring[(tail + __popc(any & ((1u << lane) - 1u))) & (kEvalQueue - 1)] = (wordBegin + wi) * 32 + b;
+      }
+      tail += __popc(any);
+      __syncwarp();
+      if (tail - head >= 32u) {
+        eval_group(V, M, base, ring[(head + lane) & (kEvalQueue - 1)], true, useTables, D, P, siteMask, errWord, lhS[warp], wpS[warp]);
+        head += 32;
+        __syncwarp();
+      }
+      any = __ballot_sync(0xffffffffu, bits != 0);
+    }
+  }
+  if (tail != head) {
+    const bool active = lane < tail - head;
+    eval_group(V, M, base, active ? ring[(head + lane) & (kEvalQueue - 1)] : 0u, active, useTables, D, P, siteMask, errWord, lhS[warp], wpS[warp]);
+  }
+  seen = __reduce_add_sync(0xffffffffu, seen);
+  if (lane == 0 && seen) atomicAdd(flagged, seen);
+}
+void launch_eval_mask(const SnapView &V, const DevSiteMap &M, uint64_t base, uint32_t firstSite, uint32_t nSites,
                       bool useTables, const DecisionTables &D, const EvalParams &P, uint32_t *siteMask,
-                      uint32_t *errWord, cudaStream_t s) {
-  if (!n) return;
-  unsigned grid = (n + kEvalThreads - 1) / kEvalThreads;
-  if (grid > 148 * 16) grid = 148 * 16;
-  k_eval_list<<<grid, kEvalThreads, 0, s>>>(V, M, base, list, n, useTables, D, P, siteMask, errWord);
+                      uint32_t *errWord, uint32_t *flagged, cudaStream_t s) {
+  if (!nSites) return;
+  const uint32_t nWords = (nSites + 31) / 32, nChunks = (nWords + 31) / 32;
+  unsigned grid = (nChunks + (kEvalThreads / 32) - 1) / (kEvalThreads / 32);
+  if (grid > 148 * 6) grid = 148 * 6;                     // one resident wave (launch bounds: 6 blocks of 128 threads per SM)
+  k_eval_mask<<<grid, kEvalThreads, 0, s>>>(V, M, base, firstSite / 32, nWords, useTables, D, P, siteMask, errWord, flagged);
 }
 
 // ------------------------------------------------------------------------------ ordered compaction

@@ -46,10 +46,11 @@ void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint3
 void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t shortcutAlt,
                        uint32_t *mask, int numSMs, cudaStream_t s);
 uint32_t stream_shortcut_bound(const uint32_t *s1, const uint32_t *s2p, const uint32_t *s2q);
-// exact predicate for the listed (flagged) sites: clears bit list[j] of siteMask unless the site is a candidate
-void launch_eval_list(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
+// exact predicate for every site flagged in bits [firstSite, firstSite + nSites) of siteMask (firstSite % 32 == 0; bit i =
+// site base + i): clears the bit unless the site is a candidate; *flagged += number of sites evaluated
+void launch_eval_mask(const SnapView &V, const DevSiteMap &M, uint64_t base, uint32_t firstSite, uint32_t nSites,
                       bool useTables, const DecisionTables &D, const EvalParams &P, uint32_t *siteMask,
-                      uint32_t *errWord, cudaStream_t s);
+                      uint32_t *errWord, uint32_t *flagged, cudaStream_t s);
 
 // ordered compaction of a bit mask over nItems items
 constexpr int kScanBlock = 256;                       // mask words per block
