@@ -2,10 +2,13 @@
 """Full-size parity check of BASELINE.json configs[2] (3.1 Gb genome, 24 contigs, 30x, dense snapshot: 24.8 GB of counters,
 370 batches, positions beyond 2^31).  Regenerates the snapshot with tools/gt16_synth (a pure function of its arguments),
 runs the drop-in binary 16gt_b200/bin/snapshotSnpcaller on it with every visible GPU, and compares the .txt with the digest
-of the UNMODIFIED reference's .txt for the same snapshot (tests/golden/MANIFEST.json: wgs_full, made in the build
+of the UNMODIFIED reference's .txt for the same snapshot (tests/golden/MANIFEST.json: wgs_full / stress_huge, made in the build
 container by tests/golden/make_golden.py wgs_full -- 25 min of reference CPU time on 8 cores).
 
-    python tools/full_genome_check.py [workdir]        (needs ~30 GB of RAM and of disk)
+    python tools/full_genome_check.py [workdir] [--config wgs_full|stress_huge] [ENV=v1,v2 ...]   (needs ~40 GB of disk, 70 GB of RAM)
+stress_huge is configs[4] at full size (3.1 Gb at 60x, indels 1/500 with pooled multi-pattern lists, depth hotspots, invalid
+bits, gaps; reference: 9,235,032 rows in 38 min).  ENV=v1,v2 runs the binary once per value of an environment knob first
+(timing only).
 """
 import hashlib, json, os, shutil, subprocess, sys, time
 
@@ -14,11 +17,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import gt16_testlib as T  # noqa: E402
 from golden_configs import synth_command  # noqa: E402
 
-NAME = "wgs_full"
-
-
 def main():
-    wd = sys.argv[1] if len(sys.argv) > 1 else "/tmp/gt16_full"
+    args = sys.argv[1:]
+    NAME = "wgs_full"                    # or --config stress_huge (configs[4] at full size: 60x, 9,235,032 rows)
+    if "--config" in args:
+        k = args.index("--config")
+        NAME = args[k + 1]
+        del args[k:k + 2]
+    wd = args[0] if args and "=" not in args[0] else "/tmp/gt16_full"
     os.makedirs(wd, exist_ok=True)
     free_disk = shutil.disk_usage(wd).free / 2**30
     avail_ram = 0
@@ -36,7 +42,7 @@ def main():
     print("synth: %.1f s, snapshot %.1f GB" % (time.time() - t0, os.path.getsize(out + ".snapshot") / 1e9), flush=True)
     for p in (idx + ".pac", idx + ".ann", idx + ".tra"):
         assert T.sha256(p) == m["inputs"][os.path.basename(p)], "regenerated input differs from the golden input: " + p
-    for setting in [a for a in sys.argv[2:] if "=" in a]:         # optional sweeps: NAME=v1,v2 (timed only)
+    for setting in [a for a in args if "=" in a]:         # optional sweeps: NAME=v1,v2 (timed only)
         key, vals = setting.split("=", 1)
         for v in vals.split(","):
             t0 = time.time()
