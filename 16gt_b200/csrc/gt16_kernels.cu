@@ -3,10 +3,11 @@
 //   k_build_table / k_build_ycsq   error tables (replaces the ~70 s CPU prefill,
 //                                  likelihood_cache.cpp:5-54)
 //   k_build_decisions              exact memoised decision bitmaps, built by the same evaluator
-//   k_stream                       HBM-bound pass over the counters: decode + classify + ballot
-//   k_mask_count/scan/scatter      ordered compaction (ballot / prefix sums)
-//   k_eval_list                    exact 16-genotype evaluation of the flagged sites
-//   k_candidates                   full record (likelihoods, posterior, SB/BQB Fisher, windows)
+//   k_stream_tma / k_stream        HBM-bound pass over the counters: decode + classify + ballot -> flag bitmap
+//   k_eval_mask                    exact 16-genotype evaluation of the flagged sites, straight from the bitmap
+//   k_mask_count/scan/scatter      ordered compaction of what is left (ballot / prefix sums)
+//   k_candidates                   full record (likelihoods, posterior, windows, indel patterns)
+//   k_bias                         SB/BQB Fisher tests of the records
 //   k_op_*                         the reference's operator seam on HBM-resident AoS buffers
 //
 // No tensor cores: the path is byte/integer decode plus table lookups (HBM roofline).
