@@ -104,7 +104,8 @@ class ClockSampler:
 
 
 def run_reference_once(idx, out, threads, lc_cache):
-    """one pass of the reference's own CPU path; returns (select_seconds, prefill_seconds, called)"""
+    """one pass of the reference's own CPU path; returns (select_seconds, prefill_seconds, called); the operator-only
+    time the reference itself reports with -v is left in run_reference_once.operators"""
     cmd = [REF_CALLER, idx, out, "-v", "-t", str(threads)]
     if lc_cache:
         cmd += ["-c", lc_cache]
@@ -112,6 +113,8 @@ def run_reference_once(idx, out, threads, lc_cache):
     sel = float(re.search(r"REF_SELECT_SECONDS\s+([0-9.]+)", r.stdout).group(1))
     pre = float(re.search(r"REF_PREFILL_SECONDS\s+([0-9.]+)", r.stdout).group(1))
     called = int(re.search(r"Called Entries : (\d+)", r.stdout).group(1))
+    m = re.search(r"Total Likelihood and Bias computing time :\s+([0-9.]+)", r.stdout)
+    run_reference_once.operators = float(m.group(1)) if m else None
     return sel, pre, called
 
 
@@ -366,8 +369,11 @@ def main():
                     "value": SAMPLE_SITES / sel, "unit": UNIT, "cores": th, "kind": "reference",
                     "sample": "oracle/_ref/ref_caller (unmodified reference objects) on the first %d sites of the same "
                               "synthetic 30x workload: selectPossibleSNPs %.2f s (serial decode loop + OpenMP operators "
-                              "on %d threads + consumer thread), %d called; one-off table prefill %.1f s not included"
-                              % (SAMPLE_SITES, sel, th, ccalled, pre)}
+                              "on %d threads + consumer thread), %d called; of that, the operators alone (the reference's "
+                              "own 'Total Likelihood and Bias computing time'): %s s; one-off table prefill %.1f s not included"
+                              % (SAMPLE_SITES, sel, th, ccalled,
+                                 "%.2f" % run_reference_once.operators if run_reference_once.operators is not None else "n/a", pre),
+                    "select_seconds": sel, "operator_seconds": run_reference_once.operators, "prefill_seconds": pre}
             finally:
                 shutil.rmtree(swd, ignore_errors=True)
         elif rank == 0 and world == 1:
