@@ -231,7 +231,9 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
     qhead += count;
   };
   constexpr int kRows = kStreamTile / kStreamThreads;       // 32-site rows per warp and tile
-  const uint32_t sh = 30u - ((lane & 15u) << 1), laneBit = 0x80000000u >> lane, ltMask = (1u << lane) - 1u;
+  // the lane's reference base sits in bits (31 - 2l, 30 - 2l) of its packed word, l = lane % 16: rotated to bits 15:14 it
+  // lines up with the base of counter slot 1
+  const uint32_t rsh = (48u - ((lane & 15u) << 1)) & 31u, ltMask = (1u << lane) - 1u;
   const uint32_t site0 = warp * (32 * kRows) + lane;        // this lane's site in row 0 of a tile
   const uint32_t refIdx0 = site0 >> 4, bmIdx0 = warp * kRows;
   const bool deadBit = kShortcut ? false : S.s1[0] != 0;    // verdict for a position without coverage
@@ -247,37 +249,46 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
 #pragma unroll
     for (int r = 0; r < kRows; ++r) { c[r] = sc[32 * r]; nlo[r] = sc[32 * r + 1].x; rw[r] = sr[2 * r]; bw[r] = sb[r]; }
     uint32_t *mw = mask + ((pT - pBeg) >> 5) + warp * kRows;
-    auto row = [&](int r, bool partial) {                      // partial: the range ends inside this tile
+    // masked: some position of this warp's rows is invalid, or (partial) the range ends inside this tile -- decided
+    // once per tile visit, so that the common rows carry no validity test at all
+    auto row = [&](int r, bool partial, bool masked) {
       const uint32_t site = site0 + 32 * r;
       const uint32_t x = c[r].x, y = c[r].y, n = nlo[r];
-      const uint32_t refx = rw[r] >> sh;
-      const bool isRef1 = (((x >> 14) ^ refx) & 3u) == 0;
+      const uint32_t rot = __funnelshift_r(rw[r], rw[r], rsh);
+      const bool isRef1 = ((x ^ rot) & 0xC000u) == 0;
       const bool dead = y == 0;
-      const bool special = ((x & 0xC000C000u) == 0xC000C000u) |
-                           (((n & 0xC000C000u) == 0xC000C000u) & ((n & 0x20002000u) != 0));
-      bool valid = (bw[r] & laneBit) == 0;
-      if (partial) valid &= site < lim;
+      // special: an overflow-type counter, or a successor that is overflow-type AND carries indel records.  The successor
+      // test is ONE compare: with m = n & 0xE000E000, m >= 0xC000E000 holds for the three true patterns (C000E000,
+      // E000C000, E000E000) and otherwise only for a compact successor whose slot 2 holds base T with weight >= 8192 --
+      // such a site is flagged needlessly and settled by the exact evaluator.
+      const bool special = ((x & 0xC000C000u) == 0xC000C000u) | ((n & 0xE000E000u) >= 0xC000E000u);
       bool flag, cplx;
       if (kShortcut) {
         const bool live1 = (y & 0xFFFFu) != 0;
         const bool oneAllele = y < 0x10000u;                   // slot 2 dead
         const bool tinyAlt = ((x & 0x3FFF0000u) <= altBound) & ((x & 0x3C00u) == 0);   // slot-2 weight <= bound, slot-1 weight < 1024
         const bool settled = isRef1 & live1 & (oneAllele | tinyAlt);                   // certainly hom-ref
-        flag = valid & special;
-        cplx = valid & !special & !settled & !dead;
+        flag = special;
+        cplx = !special & !settled & !dead;
       } else {
         const bool oneSlot = (y - 1u) < 0xFFFFu;               // slot 1 live, slot 2 dead
         const bool simple1 = oneSlot & isRef1;
         const bool bit = S.s1[x & 0x3FFFu] != 0;
-        flag = valid & (special | (simple1 & bit) | (dead & deadBit));
-        cplx = valid & !special & !simple1 & !dead;
+        flag = special | (simple1 & bit) | (dead & deadBit);
+        cplx = !special & !simple1 & !dead;
+      }
+      if (masked) {                                            // invalid positions / positions beyond the range in this tile visit
+        bool valid = (bw[r] & (0x80000000u >> lane)) == 0;     // bitmap word of the row, MSB first
+        if (partial) valid &= site < lim;
+        flag &= valid; cplx &= valid;
       }
       const uint32_t word = __ballot_sync(0xffffffffu, flag);
       const uint32_t cw = __ballot_sync(0xffffffffu, cplx);
-      if (lane == 0 && (!partial || site < lim)) mw[r] = word; // lane 0: site == first site of the row
+      if (partial) { if (lane == 0 && site < lim) mw[r] = word; }
+      else mw[r] = word;                                       // every lane, same address, same value: one transaction
       if (cw) {
-        if (cplx) {
-          StreamQueueEntry e; e.x = x; e.y = y; e.bit = pT - pBeg + site; e.ref = refx & 3u;
+        if ((cw >> lane) & 1u) {
+          StreamQueueEntry e; e.x = x; e.y = y; e.bit = pT - pBeg + site; e.ref = (rot >> 14) & 3u;
           q[(qtail + __popc(cw & ltMask)) & 63u] = e;
         }
         qtail += __popc(cw);
@@ -286,11 +297,19 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
       }
     };
     if (lim == (uint32_t) kStreamTile) {                       // all tiles but the last: no per-site range test
+      uint32_t anyInvalid = 0;
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) row(r, false);
+      for (int r = 0; r < kRows; ++r) anyInvalid |= bw[r];
+      if (anyInvalid == 0) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) row(r, false, false);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) row(r, false, true);
+      }
     } else {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) row(r, true);
+      for (int r = 0; r < kRows; ++r) row(r, true, true);
     }
     __syncwarp();
     // This warp no longer reads the stage.  The LAST warp to say so refills it (no producer warp, nobody waits
