@@ -10,7 +10,7 @@ import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-LIB = os.path.join(PKG, "lib", "libgt16.so")
+LIB = os.environ.get("GT16_LIB") or os.path.join(PKG, "lib", "libgt16.so")   # GT16_LIB: kernel-variant builds (tools/probes)
 CLI = os.path.join(PKG, "bin", "snapshotSnpcaller")
 BATCH_SITES = 8388608   # VariantCaller.cpp:526-528
 

@@ -25,7 +25,10 @@ struct DecisionTables {
 // TMA-staged streaming kernel geometry
 constexpr int kStreamTile = 4096;      // positions per tile (32 KB of counters)
 constexpr int kStreamStages = 4;       // mbarrier ring depth
-constexpr int kStreamThreads = 1024;
+#ifndef GT16_STREAM_THREADS
+#define GT16_STREAM_THREADS 1024
+#endif
+constexpr int kStreamThreads = GT16_STREAM_THREADS;
 // bytes by which every streamed array must be over-allocated so that full tiles can be copied
 constexpr size_t kStreamPadSites = kStreamTile + 64;
 
