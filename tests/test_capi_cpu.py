@@ -110,6 +110,8 @@ def test_region_index_builder_matches_reference(tmp_path):
         assert L.gt16_index_locate(ix, b"2", 5, ctypes.byref(amb)) == -1           # ... but never added (:54-63)
         assert L.gt16_index_locate(ix, b"chrX", 5, ctypes.byref(amb)) == -1
         assert L.gt16_index_locate(ix, b"chr1", 222223, ctypes.byref(amb)) == -1       # beyond the sequence
+        if not have_gpu():                                                            # page-locking needs a device: reported, not faked
+            assert L.gt16_index_pin(ix) == -3                                         # GT16_ECUDA
         for a in (0, 1, 222221, 222222, 399999):                                      # locate inverts translate
             name = L.gt16_index_translate(ix, a, ctypes.byref(pos))
             assert L.gt16_index_locate(ix, name, pos.value, ctypes.byref(amb)) == 0 and amb.value == a
