@@ -99,6 +99,8 @@ def capi():
         "gt16_call_sites": (i32, [vp, vp, vp, u32, u64, u64, P(vp), P(Stats)]),
         "gt16_call_sites_host": (i32, [vp, P(View), vp, u32, u64, u64, P(vp), P(Stats)]),
         "gt16_call_sites_device": (i32, [vp, vp, vp, u32, u64, u64, P(vp), P(Stats)]),
+        "gt16_call_sites_device_nowait": (i32, [vp, vp, vp, u32, u64, u64, P(vp), P(Stats)]),
+        "gt16_dev_calls_wait": (i32, [vp, vp, P(Stats)]),
         "gt16_dev_calls_count": (u64, [vp]),
         "gt16_dev_calls_device_ptr": (vp, [vp]),
         "gt16_dev_calls_fetch": (i32, [vp, vp, P(vp)]),

@@ -79,7 +79,8 @@ struct gt16_ctx {
   float *lnfact = nullptr;
   uint32_t *s1 = nullptr, *s2p = nullptr, *s2q = nullptr, *g4 = nullptr;
   uint32_t *errWord = nullptr, *dTotal = nullptr, *dFlagged = nullptr;   // one allocation: error bits, compaction total, sites evaluated exactly
-  uint32_t *hPinned = nullptr;          // [0] total, [1] error word
+  uint32_t *hPinnedRing = nullptr;      // kCallRing slots of 4 words
+  uint32_t *hPinned = nullptr;          // the current call's slot: [0] compaction total, [1] error word, [2] (total), [3] sites evaluated exactly
   bool havePrefill = false, haveDecisions = false, useDecisions = true;
   double balance = 0.01, unbalance = 0.005;
   float prefillMs = 0.f, decisionMs = 0.f;
@@ -92,7 +93,11 @@ struct gt16_ctx {
   std::vector<uint32_t> lastPlanStart;   // host copy of what planStart / planFirst hold (make_plan)
   std::vector<uint64_t> lastPlanFirst;
   DevBuf sCounters, sInvalid, sOvf, sOvfBase, sPool, sRef;      // streamed (host-fed) snapshot
-  std::vector<cudaEvent_t> evPool;
+  // events and the small pinned read-back slot of a call come from ring entry evCur: a call that returns before its tail
+  // has run (gt16_call_sites_device_nowait) keeps its entry until kCallRing further calls have been made
+  static const int kCallRing = 128;
+  std::vector<cudaEvent_t> evPool[kCallRing];
+  int evCur = 0;
   std::shared_ptr<PinPool> pins = std::make_shared<PinPool>();
   void *stagePin = nullptr;               // page-locked ring for callers whose counters live in pageable memory
   cudaEvent_t stageEv[32] = {nullptr};    // slot k's last copy has left the ring
@@ -107,6 +112,12 @@ struct gt16_dev_snapshot {
 struct gt16_dev_calls {          // records left in the context's record buffer
   const gt16_called_site *recs = nullptr;
   uint64_t n = 0;
+  // completion of a call that returned before its tail had run (gt16_dev_calls_wait)
+  bool pending = false, useTables = false;
+  cudaEvent_t evBegin = nullptr, evEnd = nullptr;
+  std::vector<cudaEvent_t> timing;
+  const uint32_t *slot = nullptr;         // the call's pinned read-back slot
+  gt16_stats st;
 };
 
 struct gt16_calls {
@@ -198,7 +209,8 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   if ((e = cudaMalloc(&ctx->errWord, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   ctx->dTotal = ctx->errWord + 1;
   ctx->dFlagged = ctx->errWord + 2;
-  if ((e = cudaHostAlloc(&ctx->hPinned, 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  if ((e = cudaHostAlloc(&ctx->hPinnedRing, gt16_ctx::kCallRing * 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  ctx->hPinned = ctx->hPinnedRing;
   if ((e = cudaMemset(ctx->errWord, 0, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = cudaMalloc(&ctx->biasCache, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(ctx->biasCache, 0xFF, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMemset", e);
@@ -233,10 +245,10 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   cudaFree(ctx->s1); cudaFree(ctx->s2p); cudaFree(ctx->s2q); cudaFree(ctx->g4);
   cudaFree(ctx->errWord);
   cudaFree(ctx->biasCache);
-  cudaFreeHost(ctx->hPinned);
+  cudaFreeHost(ctx->hPinnedRing);
   for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->listB, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst,
                     &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
-  for (auto e : ctx->evPool) cudaEventDestroy(e);
+  for (auto &pool : ctx->evPool) for (auto e : pool) cudaEventDestroy(e);
   if (ctx->stagePin) cudaFreeHost(ctx->stagePin);
   for (auto e : ctx->stageEv) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy); cudaStreamDestroy(ctx->d2h); cudaStreamDestroy(ctx->aux);
@@ -450,12 +462,13 @@ static const uint32_t kSegBatchesDefault = 2;         // batches per segment of 
   } while (0)
 
 static int get_event(gt16_ctx *ctx, size_t k, cudaEvent_t *out) {
-  while (ctx->evPool.size() <= k) {
+  std::vector<cudaEvent_t> &pool = ctx->evPool[ctx->evCur];
+  while (pool.size() <= k) {
     cudaEvent_t e;
     CUF(cudaEventCreate(&e));
-    ctx->evPool.push_back(e);
+    pool.push_back(e);
   }
-  *out = ctx->evPool[k];
+  *out = pool[k];
   return GT16_OK;
 }
 
@@ -770,10 +783,40 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
 
 }  // namespace
 
+static void fill_timings(gt16_stats &st, cudaEvent_t evBegin, cudaEvent_t evEnd, const std::vector<cudaEvent_t> &timing) {
+  float lastCand = 0.f;
+  for (size_t k = 0; k + 6 <= timing.size(); k += 6) {
+    st.ms_stream += ms_between(timing[k], timing[k + 1]);
+    st.ms_scan += ms_between(timing[k + 1], timing[k + 2]) + ms_between(timing[k + 3], timing[k + 4]);
+    st.ms_eval += ms_between(timing[k + 2], timing[k + 3]);
+    st.ms_candidates += ms_between(timing[k + 4], timing[k + 5]);
+    lastCand = ms_between(evBegin, timing[k + 5]);
+  }
+  st.ms_total_device = ms_between(evBegin, evEnd);
+  st.ms_d2h = st.ms_total_device - lastCand;            // tail after the last candidate slice was written
+}
+
+// completion of a device-resident call: wait for its tail, look at the error word, fill in flagged and the timings
+static int finish_dev_call(gt16_ctx *ctx, gt16_dev_calls *c) {
+  if (!c->pending) return GT16_OK;
+  CUF(cudaEventSynchronize(c->evEnd));
+  CUF(cudaGetLastError());
+  c->pending = false;
+  const uint32_t errw = c->slot[1];
+  c->st.flagged = c->useTables ? c->slot[3] : c->st.called;
+  if (errw) CUF(cudaMemset(ctx->errWord, 0, 4));
+  if (errw & kErrBadSnapshot) return fail(ctx, GT16_EDATA, "snapshot refers to an overflow record or pool range that does not exist");
+  if (errw & kErrGenotype) return fail(ctx, GT16_EGENOTYPE, "Error in selecting Genotype");
+  fill_timings(c->st, c->evBegin, c->evEnd, c->timing);
+  return GT16_OK;
+}
+
 static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const gt16_dev_snapshot *resident,
                        const gt16_region *regions, uint32_t nRegions, uint64_t begin, uint64_t end,
-                       gt16_calls **out, gt16_stats *stats, gt16_dev_calls **devOutHandle = nullptr) {
+                       gt16_calls **out, gt16_stats *stats, gt16_dev_calls **devOutHandle = nullptr, bool nowait = false) {
   if (!ctx || (!out && !devOutHandle)) return GT16_EINVAL;
+  ctx->evCur = (ctx->evCur + 1) % gt16_ctx::kCallRing;
+  ctx->hPinned = ctx->hPinnedRing + 4 * ctx->evCur;
   if (!ctx->havePrefill) return fail(ctx, GT16_ESTATE, "gt16_configure / gt16_prefill_likelihood_cache must run first");
   std::unique_ptr<gt16_dev_calls> devOut(devOutHandle ? new gt16_dev_calls() : nullptr);
   CU(cudaSetDevice(ctx->device));
@@ -981,6 +1024,19 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   }
   CUF(cudaMemcpyAsync(ctx->hPinned + 1, ctx->errWord, 12, cudaMemcpyDeviceToHost, ctx->compute));   // error bits, (total), sites evaluated
   CUF(cudaEventRecord(evEnd, ctx->compute));
+  st.kernel_launches = ctx->launches - launches0;
+  if (devOutHandle) {
+    // the rest -- waiting for the tail, the error word, the timings -- is gt16_dev_calls_wait's
+    devOut->pending = true; devOut->useTables = useTables;
+    devOut->evBegin = evBegin; devOut->evEnd = evEnd; devOut->timing = timing; devOut->slot = ctx->hPinned; devOut->st = st;
+    if (!nowait) {
+      rc = finish_dev_call(ctx, devOut.get());
+      if (rc != GT16_OK) return rc;
+    }
+    if (stats) *stats = devOut->st;
+    *devOutHandle = devOut.release();
+    return GT16_OK;
+  }
   CUF(cudaStreamSynchronize(ctx->compute));
   CUF(cudaGetLastError());
   const uint32_t errw = ctx->hPinned[1];
@@ -988,18 +1044,8 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   if (errw) CUF(cudaMemset(ctx->errWord, 0, 4));
   if (errw & kErrBadSnapshot) return fail(ctx, GT16_EDATA, "snapshot refers to an overflow record or pool range that does not exist");
   if (errw & kErrGenotype) return fail(ctx, GT16_EGENOTYPE, "Error in selecting Genotype");
-  float lastCand = 0.f;
-  for (size_t k = 0; k + 6 <= timing.size(); k += 6) {
-    st.ms_stream += ms_between(timing[k], timing[k + 1]);
-    st.ms_scan += ms_between(timing[k + 1], timing[k + 2]) + ms_between(timing[k + 3], timing[k + 4]);
-    st.ms_eval += ms_between(timing[k + 2], timing[k + 3]);
-    st.ms_candidates += ms_between(timing[k + 4], timing[k + 5]);
-    lastCand = ms_between(evBegin, timing[k + 5]);
-  }
-  st.ms_total_device = ms_between(evBegin, evEnd);
-  st.ms_d2h = st.ms_total_device - lastCand;            // tail after the last candidate slice was written
-  st.kernel_launches = ctx->launches - launches0;
-  if (devOutHandle) *devOutHandle = devOut.release(); else *out = calls.release();
+  fill_timings(st, evBegin, evEnd, timing);
+  *out = calls.release();
   if (stats) *stats = st;
   return GT16_OK;
 }
@@ -1017,12 +1063,25 @@ int gt16_call_sites_device(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const g
   if (!snap || !out) return GT16_EINVAL;
   return call_common(ctx, nullptr, snap, regions, n_regions, site_begin, site_end, nullptr, stats, out);
 }
+int gt16_call_sites_device_nowait(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
+                                  uint64_t site_begin, uint64_t site_end, gt16_dev_calls **out, gt16_stats *stats) {
+  if (!snap || !out) return GT16_EINVAL;
+  return call_common(ctx, nullptr, snap, regions, n_regions, site_begin, site_end, nullptr, stats, out, true);
+}
+int gt16_dev_calls_wait(gt16_ctx *ctx, gt16_dev_calls *c, gt16_stats *stats) {
+  if (!ctx || !c) return GT16_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  int rc = finish_dev_call(ctx, c);
+  if (stats) *stats = c->st;
+  return rc;
+}
 uint64_t gt16_dev_calls_count(const gt16_dev_calls *c) { return c ? c->n : 0; }
 const void *gt16_dev_calls_device_ptr(const gt16_dev_calls *c) { return c && c->n ? c->recs : nullptr; }
 void gt16_dev_calls_free(gt16_dev_calls *c) { delete c; }
 int gt16_dev_calls_fetch(gt16_ctx *ctx, const gt16_dev_calls *c, gt16_calls **out) {
   if (!ctx || !c || !out) return GT16_EINVAL;
   CU(cudaSetDevice(ctx->device));
+  if (c->pending) { int rc = finish_dev_call(ctx, const_cast<gt16_dev_calls *>(c)); if (rc != GT16_OK) return rc; }
   std::unique_ptr<gt16_calls> calls(new gt16_calls());
   calls->pins = ctx->pins;
   if (c->n) {

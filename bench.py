@@ -253,13 +253,29 @@ def main():
         dev = ctypes.c_void_p()
         caller.check(L.gt16_snapshot_upload(caller.ctx, ctypes.byref(inp.view), ctypes.byref(dev)))
 
+        pending = []
+
         def step_resident():
-            # inputs resident in HBM, records left in HBM (gt16_call_sites_device): the device-side pipeline
+            # inputs resident in HBM, records left in HBM: the device-side pipeline.  gt16_call_sites_device_nowait returns
+            # when the number of called sites is known and the records + Fisher tests are enqueued, so the host prepares
+            # step k+1 while the GPU finishes step k; every step is completed (gt16_dev_calls_wait: error word, CUDA-event
+            # timings) after the timed region's closing synchronize
             calls, st = ctypes.c_void_p(), capi.Stats()
-            caller.check(L.gt16_call_sites_device(caller.ctx, dev, None, 0, 0, sites, ctypes.byref(calls), ctypes.byref(st)))
-            n = L.gt16_dev_calls_count(calls)
-            L.gt16_dev_calls_free(calls)
-            return st, n
+            caller.check(L.gt16_call_sites_device_nowait(caller.ctx, dev, None, 0, 0, sites, ctypes.byref(calls), ctypes.byref(st)))
+            pending.append(calls)
+            return st, L.gt16_dev_calls_count(calls)
+
+        def complete_resident(stats):
+            """wait for the steps enqueued by step_resident (after the timed region) and return their final stats"""
+            done = []
+            for (st0, n), calls in zip(stats, pending[-len(stats):]):
+                st = capi.Stats()
+                caller.check(L.gt16_dev_calls_wait(caller.ctx, calls, ctypes.byref(st)))
+                done.append((st, n))
+            for calls in pending:
+                L.gt16_dev_calls_free(calls)
+            del pending[:]
+            return done
 
         def step_resident_host_results():
             # same, but the records are also copied to page-locked host memory inside the step (gt16_call_sites)
@@ -295,7 +311,13 @@ def main():
             sampler.start()
             for _ in range(40):            # keep the GPU busy until the sampler has certainly started
                 step_resident()
+            complete_resident([(None, 0)] * 40)
+        if args.steps + args.warmup > 120:
+            sys.stderr.write("bench.py: at most 120 steps + warm-ups are kept in flight per run\n")
+            return 2
+        del pending[:]
         dt, stats = timed(step_resident, args.warmup, args.steps)
+        stats = complete_resident(stats)
         dt_hr, stats_hr = timed(step_resident_host_results, 1, max(2, min(args.steps, 5)))
         dt_e2e, stats_e2e = timed(step_host, 2, max(2, args.steps))
         clocks = sampler.stop() if sampler else None

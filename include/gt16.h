@@ -165,6 +165,15 @@ int gt16_call_sites(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_reg
 typedef struct gt16_dev_calls gt16_dev_calls;
 int gt16_call_sites_device(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
                            uint64_t site_begin, uint64_t site_end, gt16_dev_calls **out, gt16_stats *stats);
+/* The same call, returning as soon as the number of called sites is known and the rest of the work (records, Fisher
+ * tests) has been enqueued: the host prepares the next call while the GPU finishes this one (work of successive calls on
+ * one context is stream-ordered, and the records of a call stay valid until the next call on the context, as with
+ * gt16_call_sites_device).  stats: sites, called and kernel_launches are final; flagged and the ms_* fields, like any
+ * error found on the device, arrive with gt16_dev_calls_wait (also implied by gt16_dev_calls_fetch), which may be called
+ * until 128 further calls have been made on the context. */
+int gt16_call_sites_device_nowait(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
+                                  uint64_t site_begin, uint64_t site_end, gt16_dev_calls **out, gt16_stats *stats);
+int gt16_dev_calls_wait(gt16_ctx *ctx, gt16_dev_calls *calls, gt16_stats *stats);
 uint64_t gt16_dev_calls_count(const gt16_dev_calls *calls);
 const void *gt16_dev_calls_device_ptr(const gt16_dev_calls *calls);   /* gt16_called_site[count] in device memory */
 int gt16_dev_calls_fetch(gt16_ctx *ctx, const gt16_dev_calls *calls, gt16_calls **out);

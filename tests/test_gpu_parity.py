@@ -252,6 +252,31 @@ def test_device_resident_results(gpu_caller, tmp_path):
         rb = T.capi_mod.calls_array(L, b)
         L.gt16_calls_free(b); L.gt16_dev_calls_free(d)
         assert ra.tobytes() == rb.tobytes()
+        assert st.flagged > 0 and st.ms_total_device > 0
+        # the call that returns before its tail has run: three in a row without waiting (stream-ordered on the context),
+        # then completed out of order; the last one's records are the ones in the context's buffer
+        hs, sts = [], []
+        for _ in range(3):
+            h, s0 = ctypes.c_void_p(), T.Stats()
+            gpu_caller.check(L.gt16_call_sites_device_nowait(gpu_caller.ctx, dev, None, 0, 0, inp.total_sites, ctypes.byref(h), ctypes.byref(s0)))
+            assert L.gt16_dev_calls_count(h) == len(ra) and s0.called == len(ra) and s0.sites == inp.total_sites
+            hs.append(h); sts.append(s0)
+        for h in (hs[2], hs[0], hs[1]):
+            s1 = T.Stats()
+            gpu_caller.check(L.gt16_dev_calls_wait(gpu_caller.ctx, h, ctypes.byref(s1)))
+            assert s1.flagged == st.flagged and s1.called == len(ra) and s1.ms_stream > 0 and s1.ms_total_device > 0
+            gpu_caller.check(L.gt16_dev_calls_wait(gpu_caller.ctx, h, ctypes.byref(s1)))      # idempotent
+        c = ctypes.c_void_p()
+        gpu_caller.check(L.gt16_dev_calls_fetch(gpu_caller.ctx, hs[2], ctypes.byref(c)))
+        assert T.capi_mod.calls_array(L, c).tobytes() == ra.tobytes()
+        L.gt16_calls_free(c)
+        h, s0 = ctypes.c_void_p(), T.Stats()                                          # fetch completes a pending call by itself
+        gpu_caller.check(L.gt16_call_sites_device_nowait(gpu_caller.ctx, dev, None, 0, 0, inp.total_sites, ctypes.byref(h), ctypes.byref(s0)))
+        gpu_caller.check(L.gt16_dev_calls_fetch(gpu_caller.ctx, h, ctypes.byref(c)))
+        assert T.capi_mod.calls_array(L, c).tobytes() == ra.tobytes()
+        L.gt16_calls_free(c)
+        for x in hs + [h]:
+            L.gt16_dev_calls_free(x)
     finally:
         L.gt16_snapshot_release(gpu_caller.ctx, dev)
         inp.close()
