@@ -959,7 +959,10 @@ void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, co
                        const EvalParams &P, gt16_called_site *out, uint32_t *errWord, cudaStream_t s) {
   if (!n) return;
   unsigned grid = (n + (kCandThreads / 32) - 1) / (kCandThreads / 32);
-  if (grid > 148 * 32) grid = 148 * 32;
+#ifndef GT16_CAND_GRID
+#define GT16_CAND_GRID 32
+#endif
+  if (grid > 148 * GT16_CAND_GRID) grid = 148 * GT16_CAND_GRID;
   k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, list, n, P, out, errWord);
 }
 

@@ -1,7 +1,7 @@
 #!/bin/bash
-# sweep_variants.sh NAME ...: ms of the streaming kernel (and of the device step) for each tools/probes/variants/libgt16_NAME.so
+# sweep_variants.sh NAME ...: device-step breakdown for each tools/probes/variants/libgt16_NAME.so
 cd "$(dirname "$0")/../.."
 for v in "$@"; do
   GT16_LIB=$PWD/tools/probes/variants/libgt16_$v.so python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.readline()); print('$v', 'stream %.4f ms' % d['device_ms_breakdown']['ms_stream'], 'step %.4f ms' % d['ms_per_step'], 'frac %.3f' % d['roofline']['frac'])"
+import json,sys; d=json.loads(sys.stdin.readline()); b=d['device_ms_breakdown']; print('$v', 'stream %.4f eval %.4f cand %.4f' % (b['ms_stream'], b['ms_eval'], b['ms_candidates']), 'step %.4f ms' % d['ms_per_step'], 'frac %.3f' % d['roofline']['frac'])"
 done
