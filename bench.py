@@ -364,7 +364,7 @@ def main():
                                            "time the step's input bytes need on the bus whatever the kernels do")},
             "value_with_host_results": {"value": world * sites * len(stats_hr) / dt_hr, "unit": UNIT,
                                         "ms_per_step": 1000.0 * dt_hr / len(stats_hr), "d2h_bytes_per_step": d2h,
-                                        "note": "value = inputs AND called-site records resident in HBM (gt16_call_sites_device); "
+                                        "note": "value = inputs AND called-site records resident in HBM (gt16_call_sites_device_nowait); "
                                                 "this line adds the copy of the records to page-locked host memory"},
             "gpu_launches": launches,
             "device_ms_per_step": ms_dev, "device_ms_breakdown": parts,
