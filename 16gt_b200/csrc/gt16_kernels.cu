@@ -674,9 +674,8 @@ struct CandWarpSmem {
   double lh[16];
   double flh[16];
   uint32_t W[6], F[6], R[6], Wp[6];   // counts of the site (A,C,G,T,deepest indel,second indel), penalised weights
-  uint32_t sc[2][kWindow + 4];
-  uint32_t w[2][kWindow + 4];
-  uint8_t fl[2][kWindow + 4];      // bit0 valid, bit1 gc
+  uint32_t sc[2][kWindow + 4];        // window entries: strand count (< 2^20) | valid << 31
+  uint32_t w[2][kWindow + 4];         //                 weighted depth (< 2^18) | flags << 24 (bit0 valid, bit1 C-or-G, bit2 G)
 };
 
 // what the window sums need of one position (SNP_Caller.cpp:276-367): strand count, weighted depth, flags
@@ -689,13 +688,15 @@ __device__ __forceinline__ WinLite win_decode(const SnapView &V, uint32_t p, uin
   WinLite e; e.sc = 0; e.w = 0; e.fl = 1;
   const uint32_t lo = (uint32_t) c, hi = (uint32_t) (c >> 32);
   if (!is_overflow_type(c)) {
-    const bool l1 = (hi & 0xFFFFu) != 0, l2 = (hi >> 16) != 0;
-    const uint32_t b1 = (lo >> 14) & 3u, b2 = lo >> 30;
-    if (l1) { e.sc += (hi & 0xFFu) + ((hi >> 8) & 0xFFu); e.w += lo & 0x3FFFu; }
-    if (l2) { e.sc += ((hi >> 16) & 0xFFu) + (hi >> 24); e.w += (lo >> 16) & 0x3FFFu; }
-    const bool gc = (l1 && (b1 == 1 || b1 == 2)) || (l2 && (b2 == 1 || b2 == 2));
-    const bool g = (l1 && b1 == 2) || (l2 && b2 == 2);
-    e.fl |= (gc ? 2u : 0u) | (g ? 4u : 0u);
+    // branch-free: a dead slot has both strand counts zero, so the four count bytes can be summed as they are; its
+    // weight and base fields are masked out (they need not be zero).  base in {C, G} <=> bit0 ^ bit1, base == G <=> 10b.
+    const uint32_t live = ((hi & 0xFFFFu) ? 0xFFFFu : 0u) | ((hi >> 16) ? 0xFFFF0000u : 0u);
+    const uint32_t f = lo & live;
+    e.sc = __dp4a(hi, 0x01010101u, 0u);
+    e.w = (f & 0x3FFFu) + ((f >> 16) & 0x3FFFu);
+    const uint32_t cg = (f ^ (f >> 1)) & 0x40004000u;            // bit 14 / bit 30: slot holds C or G
+    const uint32_t gg = (f & ~(f << 1)) & 0x80008000u;           // bit 15 / bit 31: slot holds G (bit1 set, bit0 clear)
+    e.fl = 1u | (cg ? 2u : 0u) | (gg ? 4u : 0u);
   } else {
     const uint8_t *r = ovf_record(V, ovf_region(V, p), hi);
     if (r) {
@@ -879,7 +880,7 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
         if (t > (uint32_t) kWindow) continue;
         WinLite e; e.sc = e.w = e.fl = 0;
         if (ex[it] && !((iw[it] >> (31 - (pp[it] & 31))) & 1u)) e = win_decode(V, pp[it], cc[it]);
-        sm.sc[side][t] = e.sc; sm.w[side][t] = e.w; sm.fl[side][t] = (uint8_t) e.fl;
+        sm.sc[side][t] = e.sc | (e.fl << 31); sm.w[side][t] = e.w | (e.fl << 24);
       }
     }
     __syncwarp();
@@ -889,11 +890,11 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
       if (side == 0 && !haveLeft) continue;
       int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
       for (uint32_t t = lane; t < (uint32_t) kWindow; t += 32) {
-        const uint32_t f = sm.fl[side][t];
-        if (f & 1) {
-          const uint32_t sc = sm.sc[side][t], sn = sm.sc[side][t + 1];
-          a0 += (int) sc; a1 += (int) sm.w[side][t]; a2 += (int) ((f >> 1) & 1); a3 += 1;
-          if (sm.fl[side][t + 1] & 1) a4 += (int) (sc > sn ? sc - sn : sn - sc);
+        const uint32_t sv = sm.sc[side][t];
+        if (sv >> 31) {
+          const uint32_t sc = sv & 0x7FFFFFFFu, nv = sm.sc[side][t + 1], sn = nv & 0x7FFFFFFFu, wf = sm.w[side][t];
+          a0 += (int) sc; a1 += (int) (wf & 0xFFFFFFu); a2 += (int) ((wf >> 25) & 1); a3 += 1;
+          if (nv >> 31) a4 += (int) (sc > sn ? sc - sn : sn - sc);
         }
       }
       strandSum[side] = warp_sum(a0); depthSum[side] = warp_sum(a1); gcSum[side] = warp_sum(a2) & 0xFF;
@@ -903,9 +904,9 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
     // entries 97..99 of the left window and 0..2 of the right one (valid bit 0, G bit 2)
     bool gbit = false;
     if (lane < 3) {
-      if (haveLeft) gbit = (sm.fl[0][kWindow - 3 + lane] & 5u) == 5u;
+      if (haveLeft) gbit = ((sm.w[0][kWindow - 3 + lane] >> 24) & 5u) == 5u;
       else if (idx >= 3) { WinEntry e = window_entry(V, M.m, B, (uint64_t) idx - 3 + lane); gbit = e.valid && e.g; }
-    } else if (lane < 6) gbit = (sm.fl[1][lane - 3] & 5u) == 5u;
+    } else if (lane < 6) gbit = ((sm.w[1][lane - 3] >> 24) & 5u) == 5u;
     const uint32_t gb = __ballot_sync(0xffffffffu, gbit);
     __syncwarp();
     const uint32_t run = polyrun(V, p);
