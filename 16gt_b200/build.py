@@ -78,6 +78,10 @@ def build(force=False, verbose=True):
         _run([HOST_CXX, "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), rib_src, "-o", rib,
               "-L", os.path.join(PKG, "lib"), "-lgt16", "-Wl,-rpath,$ORIGIN/../lib",
               "-Wl,-rpath-link,/usr/local/cuda/lib64", "-lpthread"])
+    t2v_src = os.path.join(PKG, "host", "txt2vcf.cpp")
+    t2v = os.path.join(PKG, "bin", "txt2vcf")
+    if os.path.exists(t2v_src) and (force or not _newer(t2v, [t2v_src])):
+        _run([HOST_CXX, "-O2", "-std=c++17", "-Wall", t2v_src, "-o", t2v, "-lpthread"])
     # synthetic data generator
     synth_src = os.path.join(ROOT, "tools", "gt16_synth.cpp")
     synth = os.path.join(ROOT, "tools", "gt16_synth")
