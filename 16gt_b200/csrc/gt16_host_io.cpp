@@ -291,18 +291,31 @@ int gt16_index_read(const char *prefix, gt16_index **out, char *err, size_t errL
     fclose(f);
     if (!ok || ix->translate.empty()) { set_err(err, errLen, "%s.tra: truncated", prefix); rc = GT16_EDATA; break; }
     // .pac: 4 bases / byte, first base in bits 7..6; trailing byte = length % 4
-    f = fopen((pre + ".pac").c_str(), "rb");
-    if (!f) { set_err(err, errLen, "Cannot open %s.pac", prefix); rc = GT16_EIO; break; }
+    // read straight into the word array (parallel pread), then swap each word's bytes in place: base 0 of a word
+    // ends up in bits 31..30
     size_t nBytes = ((size_t) len + 3) / 4;
-    std::vector<uint8_t> bytes(nBytes + 8, 0);
-    size_t got = fread(bytes.data(), 1, nBytes, f);
-    fclose(f);
-    if (got != nBytes) { set_err(err, errLen, "%s.pac: truncated", prefix); rc = GT16_EIO; break; }
     size_t nWords = ((size_t) len + 15) / 16 + 2;
     ix->packed.assign(nWords, 0);
-    for (size_t w = 0; w * 4 < nBytes; ++w)
-      ix->packed[w] = ((uint32_t) bytes[w * 4] << 24) | ((uint32_t) bytes[w * 4 + 1] << 16) |
-                      ((uint32_t) bytes[w * 4 + 2] << 8) | (uint32_t) bytes[w * 4 + 3];
+    {
+      struct stat st;
+      if (stat((pre + ".pac").c_str(), &st) != 0) { set_err(err, errLen, "Cannot open %s.pac", prefix); rc = GT16_EIO; break; }
+      if ((uint64_t) st.st_size < nBytes || !pread_parallel((pre + ".pac").c_str(), 0, ix->packed.data(), nBytes)) {
+        set_err(err, errLen, "%s.pac: truncated", prefix); rc = GT16_EIO; break;
+      }
+    }
+    {
+      const size_t nw = (nBytes + 3) / 4;
+      const unsigned nt = nw < (1u << 20) ? 1u : io_threads();
+      const size_t per = (nw + nt - 1) / nt;
+      uint32_t *w = ix->packed.data();
+      auto swap = [&](unsigned t) { for (size_t k = t * per, e = std::min(nw, k + per); k < e; ++k) w[k] = __builtin_bswap32(w[k]); };
+      if (nt == 1) swap(0);
+      else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(swap, t);
+        for (auto &x : th) x.join();
+      }
+    }
     // clear bits beyond the last base so reads past the end see 'A' like a zeroed trailer
     if (len % 16) ix->packed[len / 16] &= ~0u << (32 - 2 * (len % 16));
   } while (0);
