@@ -82,6 +82,10 @@ def build(force=False, verbose=True):
     t2v = os.path.join(PKG, "bin", "txt2vcf")
     if os.path.exists(t2v_src) and (force or not _newer(t2v, [t2v_src])):
         _run([HOST_CXX, "-O2", "-std=c++17", "-Wall", t2v_src, "-o", t2v, "-lpthread"])
+    flt_src = os.path.join(PKG, "host", "filterVCF.cpp")
+    flt = os.path.join(PKG, "bin", "filterVCF")
+    if os.path.exists(flt_src) and (force or not _newer(flt, [flt_src])):
+        _run([HOST_CXX, "-O2", "-std=c++17", "-Wall", flt_src, "-o", flt])
     # synthetic data generator
     synth_src = os.path.join(ROOT, "tools", "gt16_synth.cpp")
     synth = os.path.join(ROOT, "tools", "gt16_synth")

@@ -15,6 +15,8 @@ import gt16_testlib as T
 from golden_configs import synth_command
 
 BIN = os.path.join(T.PKG, "bin", "txt2vcf")
+FILTER = os.path.join(T.PKG, "bin", "filterVCF")
+REF_FILTER = "/root/reference/filterVCF.pl"
 REF_SCRIPT = "/root/reference/txt2vcf.pl"
 
 
@@ -70,3 +72,41 @@ def test_vcf_matches_reference_script_live(tmp_path):
     a = subprocess.run(["perl", REF_SCRIPT, wd + "/v.txt", "S", other], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     b = subprocess.run([BIN, wd + "/v.txt", "S", other], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert a.stdout == b.stdout and 40 < a.stdout.count(b"\n") < 5000
+
+
+def _golden_maker():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_vcf_golden", os.path.join(T.GOLDEN, "make_vcf_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("name", ["wgs_small", "stress_small"])
+def test_filtervcf_matches_reference_script(tmp_path, name):
+    """16gt_b200/bin/filterVCF against filterVCF.pl: same bytes for the golden VCF and a seeded stand-in for dbSNP, with
+    the default and with non-default thresholds, plain, gzip'ed and .list input"""
+    G = _golden_maker()
+    vcf_bytes = gzip.decompress(open(os.path.join(T.GOLDEN, name + ".vcf.gz"), "rb").read())
+    vcf, db = str(tmp_path / (name + ".vcf")), str(tmp_path / (name + ".db.vcf"))
+    open(vcf, "wb").write(vcf_bytes)
+    open(db, "w").write(G.fake_dbsnp(vcf_bytes.decode(), 5))
+    for tag, extra in (("filtered", []), ("filtered2", G.FILTER_ARGS)):
+        want = gzip.decompress(open(os.path.join(T.GOLDEN, "%s.%s.vcf.gz" % (name, tag)), "rb").read())
+        r = subprocess.run([FILTER, vcf, db] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == want
+        assert b"Mean DP: " in r.stderr and b"Second pass (add filter tags) ..." in r.stderr
+    assert b"\trs" in want and b"QUALlow" in want
+    with open(vcf, "rb") as f, gzip.open(vcf + ".gz", "wb") as g:
+        shutil.copyfileobj(f, g)
+    open(str(tmp_path / "in.list"), "w").write(vcf + ".gz\n")
+    r = subprocess.run([FILTER, str(tmp_path / "in.list"), db] + G.FILTER_ARGS, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0 and r.stdout == b""
+    assert open(str(tmp_path / (name + ".filtered.vcf")), "rb").read() == want
+    r = subprocess.run([FILTER], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0 and b"<16GT VCF Input> <dbSNP VCF Input> [Min QUAL, 10]" in r.stderr
+    if os.path.exists(REF_FILTER) and shutil.which("perl"):      # live, stderr protocol included
+        a = subprocess.run(["perl", REF_FILTER, vcf, db], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        b = subprocess.run([FILTER, vcf, db], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert a.stdout == b.stdout and a.stderr == b.stderr
