@@ -253,28 +253,36 @@ def main():
         dev = ctypes.c_void_p()
         caller.check(L.gt16_snapshot_upload(caller.ctx, ctypes.byref(inp.view), ctypes.byref(dev)))
 
-        pending = []
+        pending, completed = [], []          # calls in flight (handle, n); final stats of the completed ones, in call order
+
+        def retire(count):
+            """gt16_dev_calls_wait + free for the `count` oldest calls in flight (error word, CUDA-event timings)"""
+            for calls, n in pending[:count]:
+                st = capi.Stats()
+                caller.check(L.gt16_dev_calls_wait(caller.ctx, calls, ctypes.byref(st)))
+                L.gt16_dev_calls_free(calls)
+                completed.append((st, n))
+            del pending[:count]
 
         def step_resident():
             # inputs resident in HBM, records left in HBM: the device-side pipeline.  gt16_call_sites_device_nowait returns
             # when the number of called sites is known and the records + Fisher tests are enqueued, so the host prepares
-            # step k+1 while the GPU finishes step k; every step is completed (gt16_dev_calls_wait: error word, CUDA-event
-            # timings) after the timed region's closing synchronize
+            # step k+1 while the GPU finishes step k; a step is completed (gt16_dev_calls_wait) after the timed region's
+            # closing synchronize -- or, in a run of more than 96 steps, once it is 48 steps old and long finished (the
+            # library keeps the events of the last 128 calls)
+            if len(pending) >= 96:
+                retire(48)
             calls, st = ctypes.c_void_p(), capi.Stats()
             caller.check(L.gt16_call_sites_device_nowait(caller.ctx, dev, None, 0, 0, sites, ctypes.byref(calls), ctypes.byref(st)))
-            pending.append(calls)
-            return st, L.gt16_dev_calls_count(calls)
+            n = L.gt16_dev_calls_count(calls)
+            pending.append((calls, n))
+            return st, n
 
         def complete_resident(stats):
-            """wait for the steps enqueued by step_resident (after the timed region) and return their final stats"""
-            done = []
-            for (st0, n), calls in zip(stats, pending[-len(stats):]):
-                st = capi.Stats()
-                caller.check(L.gt16_dev_calls_wait(caller.ctx, calls, ctypes.byref(st)))
-                done.append((st, n))
-            for calls in pending:
-                L.gt16_dev_calls_free(calls)
-            del pending[:]
+            """complete every step still in flight (after the timed region) and return the final stats of the last len(stats)"""
+            retire(len(pending))
+            done = completed[-len(stats):] if stats else []
+            del completed[:]
             return done
 
         def step_resident_host_results():
@@ -312,10 +320,6 @@ def main():
             for _ in range(40):            # keep the GPU busy until the sampler has certainly started
                 step_resident()
             complete_resident([(None, 0)] * 40)
-        if args.steps + args.warmup > 120:
-            sys.stderr.write("bench.py: at most 120 steps + warm-ups are kept in flight per run\n")
-            return 2
-        del pending[:]
         dt, stats = timed(step_resident, args.warmup, args.steps)
         stats = complete_resident(stats)
         dt_hr, stats_hr = timed(step_resident_host_results, 1, max(2, min(args.steps, 5)))
