@@ -45,7 +45,7 @@ def main():
         subprocess.run(argv + ["--fasta", fa], check=True, stderr=subprocess.DEVNULL)
         txt = os.path.join(wd, name + ".txt")
         open(txt, "wb").write(T.golden_txt(name))
-        r = subprocess.run(["perl", "/root/reference/txt2vcf.pl", txt, SAMPLE, fa], check=True, stdout=subprocess.PIPE)
+        r = subprocess.run(["perl", "/root/reference/txt2vcf.pl", txt, SAMPLE, fa], check=True, stdout=subprocess.PIPE, cwd=wd)   # perl Inline caches its build in the cwd
         with open(os.path.join(HERE, name + ".vcf.gz"), "wb") as f:
             f.write(gzip.compress(r.stdout, 9, mtime=0))
         print(name, r.stdout.count(b"\n"), "lines")

@@ -61,7 +61,7 @@ def test_vcf_matches_reference_script_live(tmp_path):
     gts = [l.split("\t")[20] for l in open(wd + "/v.txt").read().split("\n")[1:] if l]
     for g in ("XX", "XY", "AX", "CX", "AC", "GG"):
         assert g in gts
-    a = subprocess.run(["perl", REF_SCRIPT, wd + "/v.txt", "S", wd + "/v.fa"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    a = subprocess.run(["perl", REF_SCRIPT, wd + "/v.txt", "S", wd + "/v.fa"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=wd)   # perl Inline caches its build in the cwd
     b = subprocess.run([BIN, wd + "/v.txt", "S", wd + "/v.fa"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert a.returncode == 0 and b.returncode == 0
     assert a.stdout.count(b"\n") > 10000
@@ -69,7 +69,7 @@ def test_vcf_matches_reference_script_live(tmp_path):
     # a FASTA that does not belong to the call set: the rows failing the reference check are dropped, the same ones
     _, other = _inputs("wgs_small", tmp_path)
     subprocess.run(["sed", "-i", "s/^>chrA/>chr1/", other], check=True)
-    a = subprocess.run(["perl", REF_SCRIPT, wd + "/v.txt", "S", other], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    a = subprocess.run(["perl", REF_SCRIPT, wd + "/v.txt", "S", other], stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=wd)
     b = subprocess.run([BIN, wd + "/v.txt", "S", other], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert a.stdout == b.stdout and 40 < a.stdout.count(b"\n") < 5000
 
