@@ -961,7 +961,7 @@ void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, co
   if (!n) return;
   unsigned grid = (n + (kCandThreads / 32) - 1) / (kCandThreads / 32);
 #ifndef GT16_CAND_GRID
-#define GT16_CAND_GRID 32
+#define GT16_CAND_GRID 32      // blocks per SM the grid is capped at (tools/probes/build_variant.sh sweeps it: 5..8 slower, 32 = 64 = uncapped)
 #endif
   if (grid > 148 * GT16_CAND_GRID) grid = 148 * GT16_CAND_GRID;
   k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, list, n, P, out, errWord);
