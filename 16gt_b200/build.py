@@ -91,6 +91,10 @@ def build(force=False, verbose=True):
     synth = os.path.join(ROOT, "tools", "gt16_synth")
     if force or not _newer(synth, [synth_src]):
         _run([HOST_CXX, "-O2", "-std=c++17", "-Wall", "-pthread", synth_src, "-o", synth])
+    rs_src = os.path.join(ROOT, "tools", "gt16_readsim.cpp")
+    rs = os.path.join(ROOT, "tools", "gt16_readsim")
+    if force or not _newer(rs, [rs_src]):
+        _run([HOST_CXX, "-O2", "-std=c++17", "-Wall", rs_src, "-o", rs])
     # test-only oracle (C restatement) and the reference objects
     mk = os.path.join(ROOT, "oracle", "Makefile")
     if os.path.exists(mk):

@@ -18,7 +18,7 @@
 
 using namespace gt16;
 
-static std::string g_createError;
+static thread_local std::string g_createError;      // per thread: the drop-in creates one context per shard thread
 static const uint32_t kBiasCacheEntries = 1u << 20;     // 8 MB, stays in L2
 
 namespace {
@@ -141,12 +141,12 @@ struct gt16_calls {
 
 static int fail(gt16_ctx *ctx, int code, const char *msg) { if (ctx) ctx->err = msg; return code; }
 
-static EvalParams eval_params(const gt16_ctx *ctx) {
+static EvalParams eval_params(const gt16_ctx *ctx, double balance, double unbalance) {
   EvalParams P;
   for (int k = 0; k < 10; ++k) P.lh.t[k] = ctx->tab[k];
   P.lh.ycsq = ctx->ycsq;
-  P.lh.p_err_s = ctx->balance / 4;        // FisherExactTest.cpp:298
-  P.lh.p_err_i = ctx->unbalance / 2;      // :299
+  P.lh.p_err_s = balance / 4;             // FisherExactTest.cpp:298
+  P.lh.p_err_i = unbalance / 2;           // :299
   P.prior = ctx->prior;
   P.g2i = ctx->g2i;
   P.lnfact.tab = ctx->lnfact;
@@ -154,6 +154,32 @@ static EvalParams eval_params(const gt16_ctx *ctx) {
   P.lnfact.far = nullptr;
   P.lnfact.farSize = 0;
   return P;
+}
+static EvalParams eval_params(const gt16_ctx *ctx) { return eval_params(ctx, ctx->balance, ctx->unbalance); }
+
+// scratch of the operator seam: freed on every return path
+namespace {
+struct DevScratch {
+  void *p = nullptr;
+  ~DevScratch() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <class T> T *as() const { return (T *) p; }
+};
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  cudaError_t create() { cudaError_t e = cudaEventCreate(&a); return e != cudaSuccess ? e : cudaEventCreate(&b); }
+};
+}  // namespace
+
+// defaults of selectPossibleSNPs (VariantCaller.cpp:506-513)
+static cudaError_t install_default_tables(gt16_ctx *ctx) {
+  const unsigned g2i[16] = {0, 1, 2, 3, 9, 10, 11, 18, 19, 27, 4, 12, 20, 28, 36, 37};
+  double prior[256];
+  make_prior(prior);
+  cudaError_t e = cudaMemcpy(ctx->g2i, g2i, sizeof(g2i), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(ctx->prior, prior, sizeof(prior), cudaMemcpyHostToDevice);
 }
 
 extern "C" {
@@ -193,7 +219,8 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   ctx->numSMs = prop.multiProcessorCount;
   auto bail = [&](const char *what, cudaError_t ce) {
     g_createError = std::string(what) + ": " + cudaGetErrorString(ce);
-    delete ctx;
+    (void) cudaGetLastError();
+    gt16_ctx_destroy(ctx);                 // streams, device and page-locked allocations made so far
     return GT16_ECUDA;
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
@@ -214,12 +241,7 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   if ((e = cudaMemset(ctx->errWord, 0, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = cudaMalloc(&ctx->biasCache, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(ctx->biasCache, 0xFF, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMemset", e);
-  // defaults of selectPossibleSNPs (VariantCaller.cpp:506-513)
-  const unsigned g2i[16] = {0, 1, 2, 3, 9, 10, 11, 18, 19, 27, 4, 12, 20, 28, 36, 37};
-  double prior[256];
-  make_prior(prior);
-  if ((e = cudaMemcpy(ctx->g2i, g2i, sizeof(g2i), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
-  if ((e = cudaMemcpy(ctx->prior, prior, sizeof(prior), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+  if ((e = install_default_tables(ctx)) != cudaSuccess) return bail("cudaMemcpy", e);
   // float log-factorial table: lnfactC(n) = lgammaf((float)(n+1)) from the host libm, i.e. the
   // very function the reference calls (SNPFunctions.cpp:82-84) -- a constant table, like the prior
   {
@@ -245,13 +267,14 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   cudaFree(ctx->s1); cudaFree(ctx->s2p); cudaFree(ctx->s2q); cudaFree(ctx->g4);
   cudaFree(ctx->errWord);
   cudaFree(ctx->biasCache);
-  cudaFreeHost(ctx->hPinnedRing);
+  if (ctx->hPinnedRing) cudaFreeHost(ctx->hPinnedRing);
   for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->listB, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst,
                     &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
   for (auto &pool : ctx->evPool) for (auto e : pool) cudaEventDestroy(e);
   if (ctx->stagePin) cudaFreeHost(ctx->stagePin);
   for (auto e : ctx->stageEv) if (e) cudaEventDestroy(e);
-  cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy); cudaStreamDestroy(ctx->d2h); cudaStreamDestroy(ctx->aux);
+  for (cudaStream_t st : {ctx->compute, ctx->copy, ctx->d2h, ctx->aux}) if (st) cudaStreamDestroy(st);
+  (void) cudaGetLastError();
   delete ctx;
 }
 
@@ -278,8 +301,9 @@ int gt16_prefill_likelihood_cache(gt16_ctx *ctx, float b_err, float ub_err, void
   for (int k = 0; k < ctx->nOwned; ++k) { cudaFree(ctx->tabOwned[k]); ctx->tabOwned[k] = nullptr; }
   ctx->nOwned = 0;
   ctx->havePrefill = false; ctx->haveDecisions = false;
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  EventPair ev;
+  CU(ev.create());
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   CU(cudaEventRecord(e0, ctx->compute));
   const size_t bytes = (size_t) kFisherN * kFisherN * sizeof(double);
   for (int k = 0; k < 10; ++k) {
@@ -299,7 +323,6 @@ int gt16_prefill_likelihood_cache(gt16_ctx *ctx, float b_err, float ub_err, void
   CU(cudaStreamSynchronize(ctx->compute));
   CU(cudaGetLastError());
   CU(cudaEventElapsedTime(&ctx->prefillMs, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   ctx->havePrefill = true;
   if (lc_host) {                                  // LikelihoodCache layout, likelihood_cache.h:13-31
     char *dst = (char *) lc_host;
@@ -314,6 +337,12 @@ int gt16_configure(gt16_ctx *ctx, double balance_sub_error, double unbalance_sub
   ctx->balance = balance_sub_error;
   ctx->unbalance = unbalance_sub_error;
   ctx->useDecisions = use_decision_tables != 0;
+  // start-up state of selectPossibleSNPs (VariantCaller.cpp:506-513): the default genotype2int and prior, whatever an
+  // earlier gt16_copy_* installed.  The decision bitmaps below are built from them, and key_needs_exact's labelling
+  // argument (one representative reference base) needs the role symmetry of the default prior; a caller that installs
+  // its own tables AFTER configure gets the exact-inline path (gt16_copy_* clear haveDecisions).
+  CU(cudaSetDevice(ctx->device));
+  CU(install_default_tables(ctx));
   // snapshotSnpcaller.cpp:230-231 passes the ini doubles through float parameters
   int rc = gt16_prefill_likelihood_cache(ctx, (float) balance_sub_error, (float) unbalance_sub_error, nullptr);
   if (rc != GT16_OK) return rc;
@@ -322,8 +351,9 @@ int gt16_configure(gt16_ctx *ctx, double balance_sub_error, double unbalance_sub
     CU(cudaMalloc(&ctx->s1, kS1Words * 4)); CU(cudaMalloc(&ctx->s2p, kS2Words * 4));
     CU(cudaMalloc(&ctx->s2q, kS2Words * 4)); CU(cudaMalloc(&ctx->g4, kG4Words * 4));
   }
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  EventPair ev;
+  CU(ev.create());
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   CU(cudaEventRecord(e0, ctx->compute));
   launch_build_decisions(eval_params(ctx), ctx->s1, ctx->s2p, ctx->s2q, ctx->g4, ctx->compute);
   ctx->launches++;
@@ -331,7 +361,6 @@ int gt16_configure(gt16_ctx *ctx, double balance_sub_error, double unbalance_sub
   CU(cudaStreamSynchronize(ctx->compute));
   CU(cudaGetLastError());
   CU(cudaEventElapsedTime(&ctx->decisionMs, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   {
     std::vector<uint32_t> h1(kS1Words), hp(kS2Words), hq(kS2Words);
     CU(cudaMemcpy(h1.data(), ctx->s1, kS1Words * 4, cudaMemcpyDeviceToHost));
@@ -358,7 +387,8 @@ int gt16_compute_genotype_likelihood(gt16_ctx *ctx, const void *w, size_t in_str
   if (!ctx->havePrefill) return fail(ctx, GT16_ESTATE, "likelihood cache not prefilled");
   if (!n) return GT16_OK;
   CU(cudaSetDevice(ctx->device));
-  ctx->balance = balance; ctx->unbalance = unbalance;
+  // the call's own error rates go straight into the kernel parameters: the context's (which the fused path and its
+  // decision bitmaps were configured with) are not touched
   // only W[0..5] and refChar are read by the operator: gather them on the host side of the copy
   std::vector<uint32_t> wbuf((size_t) n * 6);
   std::vector<uint8_t> rbuf(n);
@@ -366,16 +396,16 @@ int gt16_compute_genotype_likelihood(gt16_ctx *ctx, const void *w, size_t in_str
     memcpy(&wbuf[(size_t) i * 6], (const char *) w + (size_t) i * in_stride, 24);
     rbuf[i] = *((const uint8_t *) ref_char + (size_t) i * ref_stride);
   }
-  uint32_t *dW = nullptr; uint8_t *dR = nullptr; double *dL = nullptr;
-  CU(cudaMalloc(&dW, wbuf.size() * 4)); CU(cudaMalloc(&dR, n)); CU(cudaMalloc(&dL, (size_t) n * 128));
+  DevScratch sW, sR, sL;
+  CU(sW.alloc(wbuf.size() * 4)); CU(sR.alloc(n)); CU(sL.alloc((size_t) n * 128));
+  uint32_t *dW = sW.as<uint32_t>(); uint8_t *dR = sR.as<uint8_t>(); double *dL = sL.as<double>();
   CU(cudaMemcpyAsync(dW, wbuf.data(), wbuf.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
   CU(cudaMemcpyAsync(dR, rbuf.data(), n, cudaMemcpyHostToDevice, ctx->compute));
-  launch_op_likelihood(eval_params(ctx), (const uint8_t *) dW, 24, dR, 1, dL, n, ctx->compute);
+  launch_op_likelihood(eval_params(ctx, balance, unbalance), (const uint8_t *) dW, 24, dR, 1, dL, n, ctx->compute);
   ctx->launches++;
   CU(cudaMemcpyAsync(lh, dL, (size_t) n * 128, cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
   CU(cudaGetLastError());
-  cudaFree(dW); cudaFree(dR); cudaFree(dL);
   return GT16_OK;
 }
 
@@ -384,9 +414,10 @@ int gt16_compute_genotype(gt16_ctx *ctx, const unsigned char *ref_char, const do
   if (!ctx || !ref_char || !lh || !info || info_stride < 160) return GT16_EINVAL;
   if (!n) return GT16_OK;
   CU(cudaSetDevice(ctx->device));
-  uint8_t *dR = nullptr, *dI = nullptr; double *dL = nullptr;
   const size_t dStride = 160;   // pD, genotype(+pad), flh[16], bestD, secondD
-  CU(cudaMalloc(&dR, n)); CU(cudaMalloc(&dL, (size_t) n * 128)); CU(cudaMalloc(&dI, (size_t) n * dStride));
+  DevScratch sR, sL, sI;
+  CU(sR.alloc(n)); CU(sL.alloc((size_t) n * 128)); CU(sI.alloc((size_t) n * dStride));
+  uint8_t *dR = sR.as<uint8_t>(), *dI = sI.as<uint8_t>(); double *dL = sL.as<double>();
   CU(cudaMemcpyAsync(dR, ref_char, n, cudaMemcpyHostToDevice, ctx->compute));
   CU(cudaMemcpyAsync(dL, lh, (size_t) n * 128, cudaMemcpyHostToDevice, ctx->compute));
   CU(cudaMemsetAsync(dI, 0, (size_t) n * dStride, ctx->compute));
@@ -404,7 +435,6 @@ int gt16_compute_genotype(gt16_ctx *ctx, const unsigned char *ref_char, const do
     memcpy(d + 16, s + 16, 128);              // flh
     memcpy(d + 144, s + 144, 16);             // bestD, secondD (rfProb/rfMode untouched)
   }
-  cudaFree(dR); cudaFree(dL); cudaFree(dI);
   return GT16_OK;
 }
 
@@ -419,8 +449,9 @@ int gt16_compute_bias(gt16_ctx *ctx, const void *w, const void *f, const void *r
     memcpy(&buf[(size_t) i * 12 + 4], (const char *) f + (size_t) i * stride, 16);
     memcpy(&buf[(size_t) i * 12 + 8], (const char *) r + (size_t) i * stride, 16);
   }
-  uint8_t *d = nullptr; float *dS = nullptr, *dB = nullptr;
-  CU(cudaMalloc(&d, buf.size() * 4)); CU(cudaMalloc(&dS, (size_t) n * 16)); CU(cudaMalloc(&dB, (size_t) n * 16));
+  DevScratch sD, sS, sB;
+  CU(sD.alloc(buf.size() * 4)); CU(sS.alloc((size_t) n * 16)); CU(sB.alloc((size_t) n * 16));
+  uint8_t *d = sD.as<uint8_t>(); float *dS = sS.as<float>(), *dB = sB.as<float>();
   CU(cudaMemcpyAsync(d, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
   launch_op_bias(eval_params(ctx), d, d + 16, d + 32, 48, n, dS, dB, ctx->compute);
   ctx->launches++;
@@ -428,7 +459,6 @@ int gt16_compute_bias(gt16_ctx *ctx, const void *w, const void *f, const void *r
   CU(cudaMemcpyAsync(bqb, dB, (size_t) n * 16, cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
   CU(cudaGetLastError());
-  cudaFree(d); cudaFree(dS); cudaFree(dB);
   return GT16_OK;
 }
 
@@ -613,12 +643,22 @@ namespace {
 struct RegionPlan {
   std::vector<uint32_t> start;
   std::vector<uint64_t> first;      // nRegions + 1
+  std::vector<uint64_t> maxEnd;     // running maximum of the region ends (regions may overlap)
   bool ascending = true;
   DevSiteMap map;
   uint32_t pos_of(uint64_t i) const {
     size_t lo = 0, hi = start.size();
     while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (first[mid] <= i) lo = mid; else hi = mid; }
     return start[lo] + (uint32_t) (i - first[lo]);
+  }
+  uint64_t hi_pos(uint64_t i) const {              // highest position any site up to processed index i can have
+    const uint64_t p = pos_of(i);
+    return start.size() > 1 ? std::max<uint64_t>(p, max_end_upto(i) - 1) : p;
+  }
+  uint64_t max_end_upto(uint64_t i) const {        // highest region end among the regions up to the one holding site i
+    size_t lo = 0, hi = start.size();
+    while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (first[mid] <= i) lo = mid; else hi = mid; }
+    return maxEnd[lo];
   }
 };
 
@@ -633,9 +673,10 @@ int make_plan(gt16_ctx *ctx, uint32_t L, const gt16_region *regions, uint32_t nR
     if (!pl.start.empty() && regions[r].start < pl.start.back()) pl.ascending = false;
     pl.start.push_back(regions[r].start);
     pl.first.push_back(acc);
+    pl.maxEnd.push_back(std::max<uint64_t>(pl.maxEnd.empty() ? 0 : pl.maxEnd.back(), regions[r].end));
     acc += regions[r].end - regions[r].start;
   }
-  if (pl.start.empty()) { pl.start.push_back(0); pl.first.push_back(0); }
+  if (pl.start.empty()) { pl.start.push_back(0); pl.first.push_back(0); pl.maxEnd.push_back(0); }
   pl.first.push_back(acc);
   // the device copy of the plan survives between calls: the same region list (every call of a bench loop, every piece
   // of a shard) costs neither a copy nor a host round trip
@@ -826,6 +867,21 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   if (rc) return rc;
   if (end > pl.map.totalSites) end = pl.map.totalSites;
   if (begin > end) begin = end;
+  std::unique_ptr<gt16_calls> calls(new gt16_calls());
+  calls->pins = ctx->pins;
+  // an error return must not hand the page-locked result buffer back to the pool while copies into it are queued
+  struct DrainD2H {
+    gt16_ctx *c; bool armed = true;
+    ~DrainD2H() { if (armed) { cudaStreamSynchronize(c->d2h); (void) cudaGetLastError(); } }
+  } drainD2H{ctx};
+  gt16_stats st;
+  memset(&st, 0, sizeof(st));
+  if (begin == end) {                        // an empty shard (more ranks than batches) is not an error, aligned or not
+    drainD2H.armed = false;
+    if (devOutHandle) *devOutHandle = devOut.release(); else *out = calls.release();
+    if (stats) *stats = st;
+    return GT16_OK;
+  }
   if (begin % kBatch) return fail(ctx, GT16_EINVAL, "site_begin must be a multiple of GT16_BATCH_SITES");
   if (end - begin >= 0xFFFFFFFFull) return fail(ctx, GT16_EINVAL, "range too long");
   const uint32_t n = (uint32_t) (end - begin);
@@ -833,22 +889,12 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   const bool useTables = ctx->useDecisions && ctx->haveDecisions;
   DecisionTables D = {ctx->s1, ctx->s2p, ctx->s2q, ctx->g4};
   EvalParams P = eval_params(ctx);
-
-  std::unique_ptr<gt16_calls> calls(new gt16_calls());
-  calls->pins = ctx->pins;
-  gt16_stats st;
-  memset(&st, 0, sizeof(st));
   st.sites = n;
-  if (n == 0) {
-    if (devOutHandle) *devOutHandle = devOut.release(); else *out = calls.release();
-    if (stats) *stats = st;
-    return GT16_OK;
-  }
 
   size_t evNext = 0;
   cudaEvent_t evBegin, evEnd;
   if ((rc = get_event(ctx, evNext++, &evBegin)) || (rc = get_event(ctx, evNext++, &evEnd))) return rc;
-  CUF(ctx->mask.ensure(((size_t) (n + 31) / 32 + 64) * 4));
+  CUF(ctx->mask.ensure((((size_t) n + 31) / 32 + 64) * 4));
   // A resident range is one segment (one streaming launch, D2H overlapped by slicing).  A host-fed range is
   // cut into segments of kSegBatches batches so that everything after the streaming pass -- including the
   // records' trip back -- runs while later counter chunks are still on the bus.
@@ -880,8 +926,13 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     // counters stream in on the copy stream in genome order (32 MiB chunks, all queued up front)
     std::vector<uint32_t> ovfBase;
     rc = alloc_snapshot(ctx, hostView, &streamed, ovfBase, true);
+    // positions the call can touch: its own sites, and -- when the range does not end on a batch boundary -- the
+    // sites after `end` that the windows / neighbour tests of its last sites walk in processed order (up to
+    // ~360 sites, which in a multi-region list may lie in later regions); overlapping regions: the highest end so far
+    const uint64_t reachEnd = std::min<uint64_t>(pl.map.totalSites, end + 512);
     const uint32_t loPos = pl.ascending ? pl.pos_of(begin) : 0;
-    const uint32_t hiPos = pl.ascending ? pl.pos_of(end - 1) : L - 1;
+    uint32_t hiPos = L - 1;
+    if (pl.ascending) hiPos = (uint32_t) std::min<uint64_t>(L - 1, pl.hi_pos(reachEnd - 1));
     if (rc == GT16_OK) rc = upload_aux(ctx, hostView, &streamed, ovfBase, ctx->copy, loPos, hiPos);
     if (rc != GT16_OK) return rc;
     V = &streamed.v;
@@ -903,6 +954,9 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
       if (!(pl.ascending && pl.start.size() > 1)) return true;
       size_t lo = 0, hi = pl.start.size();                 // sparse targets: skip chunks no region touches
       while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if ((uint64_t) pl.start[mid] <= a + 0) lo = mid; else hi = mid; }
+      // regions may nest or overlap (starts ascend, ends need not: the reference's merge can emit such lists,
+      // buildRegionList.cpp:199-216): an earlier region reaches into [a, b) iff the running maximum of the ends does
+      if (lo > 0 && pl.maxEnd[lo - 1] + 512 > a) return true;
       for (size_t r = lo; r < pl.start.size(); ++r) {
         uint64_t rs = pl.start[r], re = rs + (pl.first[r + 1] - pl.first[r]);
         if (rs > b + 512) break;
@@ -1002,13 +1056,13 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     CUF(cudaEventRecord(es0, ctx->compute));
     for (uint64_t c = a; c < b; c += kBatch) {           // classification of a batch waits for the chunk with its last position + 1
       const uint64_t d = std::min<uint64_t>(c + kBatch, b);
-      if ((rc = wait_chunks(pl.ascending ? (uint64_t) pl.pos_of(d - 1) + 2 : copyHi))) return rc;
+      if ((rc = wait_chunks(pl.ascending ? pl.hi_pos(d - 1) + 2 : copyHi))) return rc;
       if (resident) { stream_range(ctx, *V, pl, a, b, useTables, D, P, mask + (a - begin) / 32); break; }
       stream_range(ctx, *V, pl, c, d, useTables, D, P, mask + (c - begin) / 32);
     }
     CUF(cudaEventRecord(es1, ctx->compute));
     // windows, neighbours' Fisher tests and the indel look-ahead reach up to ~360 positions past the segment
-    if ((rc = wait_chunks(pl.ascending ? (uint64_t) pl.pos_of(b - 1) + 600 : copyHi))) return rc;
+    if ((rc = wait_chunks(pl.ascending ? pl.hi_pos(std::min<uint64_t>(pl.map.totalSites, b + 512) - 1) + 600 : copyHi))) return rc;
     rc = finish_segment(ctx, *V, pl, begin, a, b, useTables, D, evNext, seg, calls.get(), &st, resultHint, es0, es1, nullptr, timing, segCopied, devOut.get());
     if (rc != GT16_OK) return rc;
   }
@@ -1034,6 +1088,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
       if (rc != GT16_OK) return rc;
     }
     if (stats) *stats = devOut->st;
+    drainD2H.armed = false;
     *devOutHandle = devOut.release();
     return GT16_OK;
   }
@@ -1045,6 +1100,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   if (errw & kErrBadSnapshot) return fail(ctx, GT16_EDATA, "snapshot refers to an overflow record or pool range that does not exist");
   if (errw & kErrGenotype) return fail(ctx, GT16_EGENOTYPE, "Error in selecting Genotype");
   fill_timings(st, evBegin, evEnd, timing);
+  drainD2H.armed = false;
   *out = calls.release();
   if (stats) *stats = st;
   return GT16_OK;

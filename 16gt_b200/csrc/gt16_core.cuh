@@ -535,6 +535,9 @@ GT16_HDN void decode_indel_refs(const SnapView &V, uint32_t p, IndelInfo &o, Pat
       if ((uint64_t) ptr + size > V.poolBytes) { o.bad = 1; return; }
       const uint8_t *info = V.pool + ptr;
       while (i < size) {
+        // an entry is 1 + ceil(len/4) + 4 bytes; one that runs past the list is a corrupt snapshot (the reference
+        // would read whatever follows in the pool)
+        if (i + 1 + ((uint32_t) info[i] + 3) / 4 + 4 > size) { o.bad = 1; return; }
         cur.type = 'I'; cur.len = info[i++]; cur.seq = info + i; cur.delPos = 0;
         i += ((uint32_t) cur.len + 3) / 4;
         cur.hq = (uint16_t) rd16(info + i); cur.lq = (uint16_t) rd16(info + i + 2); i += 4;
@@ -554,6 +557,7 @@ GT16_HDN void decode_indel_refs(const SnapView &V, uint32_t p, IndelInfo &o, Pat
       if ((uint64_t) ptr + size > V.poolBytes) { o.bad = 1; return; }
       const uint8_t *info = V.pool + ptr;
       while (i < size) {
+        if (i + 5 > size) { o.bad = 1; return; }
         cur.type = 'D'; cur.len = info[i]; cur.hq = (uint16_t) rd16(info + i + 1); cur.lq = (uint16_t) rd16(info + i + 3);
         i += 5; cur.seq = nullptr; cur.delPos = q;
         o.hqTotal += cur.hq; o.lqTotal += cur.lq;

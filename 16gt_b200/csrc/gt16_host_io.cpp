@@ -187,16 +187,21 @@ int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, c
     {
       std::vector<std::vector<uint8_t> > tmp(hs->nRegions);
       size_t total = 0;
-      bool ok = true;
+      bool ok = true, bad = false;
       for (uint32_t r = 0; r < hs->nRegions && ok; ++r) {
         uint32_t sz, lim;
         if (fread(&sz, 4, 1, f) != 1 || fread(&lim, 4, 1, f) != 1) { ok = false; break; }
+        // the writer stores `size` records behind every (size, limit) pair (SnapshotHandler.cpp:214-219) and size <= limit
+        // always holds there; anything else is not a snapshot the reference could have written (its reader would skip the
+        // records of a limit-0 region and mis-parse the rest, :313)
+        if (sz > lim) { bad = true; break; }
         hs->ovfSize.push_back(sz);
         if (lim == 0) continue;                       // SnapshotHandler.cpp:313
         tmp[r].resize((size_t) sz * 32);
         if (sz && fread(tmp[r].data(), 32, sz, f) != sz) { ok = false; break; }
         total += (size_t) sz * 32;
       }
+      if (bad) { set_err(err, errLen, "%s: overflow region with more records than its limit", path); rc = GT16_EDATA; break; }
       if (!ok) { set_err(err, errLen, "%s: truncated overflow arrays", path); rc = GT16_EIO; break; }
       if (!hs->ovfAll.alloc(total + 32, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
       size_t off = 0;

@@ -11,8 +11,10 @@
 // usage: ref_caller <indexPrefix> <outPrefix> [region.bin] [-v] [-t threads] [-c tables.bin]
 // reads  <outPrefix>.snapshot, writes <outPrefix>.txt
 // -c: keep the reference's own prefilled LikelihoodCache in a file between runs (the prefill
-//     takes ~70-90 s and is identical for identical ini error rates); used only when
-//     generating golden fixtures, never when the reference is being timed.
+//     takes ~26-90 s and is identical for identical ini error rates).  Used when generating
+//     golden fixtures and by bench.py's reference arm: the prefill is outside the timed quantity
+//     (REF_SELECT_SECONDS = selectPossibleSNPs alone) on both arms, so reusing the reference's own
+//     table bytes between its steps changes nothing that is measured.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>

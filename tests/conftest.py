@@ -32,3 +32,8 @@ def gpu_caller():
     c = T.Caller(0)
     yield c
     c.close()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    import producer_fixture
+    producer_fixture.cleanup()

@@ -67,6 +67,21 @@ HUGE_CONFIGS = {
                                "--seed", "9"], exome=False),
 }
 FULL_CONFIGS.update(HUGE_CONFIGS)
+
+# Snapshots written by the reference's OWN producer (tests/golden/make_producer_golden.py): tools/gt16_readsim makes a
+# FASTA and aligned reads (SAM), oracle/_ref/ref_mkindex and oracle/_ref/ref_bam2snapshot -- the unmodified reference
+# tools -- turn them into index files and a snapshot.
+#   prod_5mb       BASELINE.json configs[0]: 5 Mb, three contigs, 30x diploid, planted SNPs (1/1000, het:hom 2:1) and
+#                  indels (1/8000, 1-12 bp plus 13-30 bp ones that need pooled patterns, compound hets), soft clips,
+#                  duplicates, three 1500x hotspots (overflow promotion, chi-square fallback) and one 20000x hotspot
+#                  (u16 counters saturate: invalid bits)
+#   prod_two_batch more than 8,388,608 sites (two batches: per-batch window reset, batch-aligned sharding) at 12x
+PRODUCER_CONFIGS = {
+    "prod_5mb": dict(readsim=["--contigs", "chrA:3000000,chrB:1500000,chrC:500000", "--hotspots", "3:300:1500,1:120:20000",
+                              "--seed", "1"]),
+    "prod_two_batch": dict(readsim=["--contigs", "chrA:5000000,chrB:3700000", "--depth", "12", "--snp-rate", "1e-4",
+                                    "--indel-rate", "2e-5", "--hotspots", "1:200:1200", "--seed", "2"]),
+}
 CONFIGS_ALL = dict(CONFIGS, **FULL_CONFIGS)
 
 

@@ -115,3 +115,108 @@ def compare_txt(got: bytes, want: bytes, rel=1e-6):
     return nonident
 
 
+
+
+# ---- snapshots written by the reference's OWN producer ------------------------------------------
+# tools/gt16_readsim (FASTA + SAM, a pure function of its arguments) -> oracle/_ref/ref_mkindex (the reference's
+# packer) -> oracle/_ref/ref_bam2snapshot (the unmodified bam2snapshot: SNP.cpp promotion rules, the
+# writeSnpInfoSnapshot container with its page-aligned subfiles, the full 1 GiB pool and the soft-clip subfile).
+READSIM = os.path.join(ROOT, "tools", "gt16_readsim")
+REF_MKINDEX = os.path.join(REF_DIR, "ref_mkindex")
+REF_BAM2SNAPSHOT = os.path.join(REF_DIR, "ref_bam2snapshot")
+
+from golden_configs import PRODUCER_CONFIGS  # noqa: E402
+
+
+def parse_snapshot_container(path):
+    """Independent (numpy) reading of the container writeSnpInfoSnapshot produces (SnapshotHandler.cpp:83-236): returns
+    a dict of its meaningful content.  The file itself is not byte-reproducible (the pool is written at its full
+    capacity and only its first curPtr bytes are initialised), so identity of two snapshots is the identity of this
+    content."""
+    with open(path, "rb") as f:
+        hdr = f.read(4 + 5 * 16 + 1)
+        page = int(np.frombuffer(hdr, "<i4", 1, 0)[0])
+        tab = np.frombuffer(hdr, "<u8", 10, 4).reshape(5, 2)
+        f.seek(int(tab[0, 0]))
+        cur = int(np.frombuffer(f.read(4), "<u4")[0]); cap = int(np.frombuffer(f.read(8), "<u8")[0])
+        pool = f.read(cur)
+        f.seek(int(tab[1, 0]))
+        mode = f.read(1)[0]
+        L = int(np.frombuffer(f.read(4), "<u4")[0])
+        if mode & 1:
+            counters = np.fromfile(f, "<u8", L)
+        else:
+            rec = np.fromfile(f, np.dtype([("pos", "<u4"), ("c", "<u8")]), int(tab[1, 1]) // 12)
+            counters = np.zeros(L, "<u8"); counters[rec["pos"]] = rec["c"]
+        f.seek(int(tab[2, 0]))
+        nreg = int(np.frombuffer(f.read(4), "<u4")[0])
+        ovf = []
+        for _ in range(nreg):
+            sz, lim = (int(x) for x in np.frombuffer(f.read(8), "<u4"))
+            ovf.append(f.read(sz * 32) if lim else b"")
+        bitmap = None
+        if int(tab[3, 1]):
+            f.seek(int(tab[3, 0]))
+            bitmap = np.fromfile(f, "<u4", (L + 31) >> 5)
+    return dict(page=page, subfiles=tab, pool=pool, pool_capacity=cap, mode=mode, L=L, counters=counters, ovf=ovf,
+                bitmap=bitmap, amplicon=hdr[-1])
+
+
+def snapshot_content_digest(path):
+    """sha256 of what a snapshot MEANS.  bam2snapshot resolves its overflow buffers with one thread per region, and
+    those threads allocate pattern lists from the shared pool in whatever order they get there: pool offsets (and so
+    the pointer bytes of the overflow records) differ from run to run, the lists themselves do not.  The digest
+    therefore replaces every pool pointer by the bytes it points to."""
+    c = parse_snapshot_container(path)
+    L, nreg = c["L"], len(c["ovf"])
+    cnt = c["counters"]
+    lo = (cnt & 0xFFFFFFFF).astype(np.uint32)
+    recs = [np.frombuffer(o, np.uint8).reshape(-1, 32).copy() for o in c["ovf"]]
+    lists = []
+    pos = np.nonzero(((lo & (lo >> 16)) & 0xC000) == 0xC000)[0]
+    seg = max(1, L // nreg)
+    for p in pos[((lo[pos] & 0x3000) == 0x3000) | (((lo[pos] >> 16) & 0x3000) == 0x3000)]:
+        r = min(int(p) // seg, nreg - 1) if L // nreg else nreg - 1      # findRegionByPosition (coreStruct.h:141-154)
+        rec = recs[r][int(cnt[p] >> 32)]
+        for w, off in ((int(lo[p]) & 0xFFFF, 24), (int(lo[p]) >> 16, 28)):
+            if (w & 0x3000) == 0x3000:
+                ptr = int(rec[off:off + 4].view("<u4")[0])
+                lists.append(np.array([p, off, w & 0xFFF], "<u8").tobytes() + c["pool"][ptr:ptr + (w & 0xFFF)])
+                rec[off:off + 4] = 0
+    h = hashlib.sha256()
+    h.update(np.array([L, c["mode"], nreg, len(c["pool"])], "<u8").tobytes())
+    h.update(cnt.tobytes())
+    for o in recs:
+        h.update(np.array([len(o)], "<u8").tobytes()); h.update(o.tobytes())
+    if c["bitmap"] is not None:
+        h.update(c["bitmap"].tobytes())
+    for x in lists:
+        h.update(x)
+    return h.hexdigest()
+
+
+def producer_pipeline(name, workdir):
+    """reads -> index -> snapshot with the reference's own tools; returns (index_prefix, out_prefix)"""
+    cfg = PRODUCER_CONFIGS[name]
+    wd = str(workdir)
+    pre = os.path.join(wd, name)
+    subprocess.run([READSIM, "--out", pre] + cfg["readsim"], check=True, stderr=subprocess.DEVNULL)
+    idx = pre + ".index"
+    subprocess.run([REF_MKINDEX, pre + ".fa", idx], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    os.makedirs(os.path.join(wd, "out"), exist_ok=True)
+    out = os.path.join(wd, "out", name)
+    subprocess.run([REF_BAM2SNAPSHOT, "-i", idx, "-s", pre + ".sam", "-o", out], check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    os.remove(pre + ".sam")
+    return idx, out
+
+
+def regenerate_producer(name, workdir, check=True):
+    """producer_pipeline + proof that the inputs are the ones the committed golden was made from"""
+    idx, out = producer_pipeline(name, workdir)
+    if check:
+        want = manifest()[name]["inputs"]
+        for p in (idx + ".pac", idx + ".ann", idx + ".tra"):
+            assert sha256(p) == want[os.path.basename(p)], "regenerated input differs from golden input: " + p
+        assert snapshot_content_digest(out + ".snapshot") == want["snapshot_content"], "producer-written snapshot differs"
+    return idx, out
