@@ -78,9 +78,14 @@ struct gt16_ctx {
   uint32_t *g2i = nullptr;
   float *lnfact = nullptr;
   uint32_t *s1 = nullptr, *s2p = nullptr, *s2q = nullptr, *g4 = nullptr;
-  uint32_t *errWord = nullptr, *dTotal = nullptr, *dFlagged = nullptr;   // one allocation: error bits, compaction total, sites evaluated exactly
+  uint32_t *errWord = nullptr, *dTotal = nullptr, *dFlagged = nullptr;   // one allocation: error bits, compaction total, sites evaluated exactly, ...
+  uint32_t *dCounts = nullptr;          // ... and kMaxSegs per-segment candidate counters (written by k_eval_mask, read by the kernels behind it)
+  static const int kMaxSegs = 512;
   uint32_t *hPinnedRing = nullptr;      // kCallRing slots of 4 words
-  uint32_t *hPinned = nullptr;          // the current call's slot: [0] compaction total, [1] error word, [2] (total), [3] sites evaluated exactly
+  uint32_t *hPinned = nullptr;          // the current call's slot: [0] records of a device-resident call, [1] error word, [2] (scan total), [3] sites evaluated exactly
+  uint32_t *hCounts = nullptr;          // page-locked copy of dCounts (host-result calls)
+  uint32_t recCap = 0;                  // records the candidate buffers (part, rankOf, list, recs, recs2) hold per segment
+  uint32_t recCapWanted = 0;            // set when a call found more candidates than recCap: the retry allocates this many
   bool havePrefill = false, haveDecisions = false, useDecisions = true;
   double balance = 0.01, unbalance = 0.005;
   float prefillMs = 0.f, decisionMs = 0.f;
@@ -89,7 +94,7 @@ struct gt16_ctx {
   uint2 *biasCache = nullptr;             // memoised Fisher tests (k_bias), kBiasCacheEntries entries
   int numSMs = 148;
   // persistent scratch of the fused path
-  DevBuf mask, counts, listB, recs, recs2, planStart, planFirst;
+  DevBuf mask, counts, part, rankOf, list, recs, recs2, planStart, planFirst;
   std::vector<uint32_t> lastPlanStart;   // host copy of what planStart / planFirst hold (make_plan)
   std::vector<uint64_t> lastPlanFirst;
   DevBuf sCounters, sInvalid, sOvf, sOvfBase, sPool, sRef;      // streamed (host-fed) snapshot
@@ -111,7 +116,13 @@ struct gt16_dev_snapshot {
 
 struct gt16_dev_calls {          // records left in the context's record buffer
   const gt16_called_site *recs = nullptr;
-  uint64_t n = 0;
+  uint64_t n = 0;                 // known once the call has completed (gt16_dev_calls_wait)
+  gt16_ctx *ctx = nullptr;
+  // what the call was, in case it has to be repeated with larger record buffers
+  const gt16_dev_snapshot *snap = nullptr;
+  std::vector<gt16_region> regions;
+  uint64_t begin = 0, end = 0;
+  uint32_t cap = 0;
   // completion of a call that returned before its tail had run (gt16_dev_calls_wait)
   bool pending = false, useTables = false;
   cudaEvent_t evBegin = nullptr, evEnd = nullptr;
@@ -233,12 +244,14 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   if ((e = cudaMalloc(&ctx->g2i, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->ycsq, kYcsqN * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->lnfact, (size_t) kLnFactTab * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMalloc(&ctx->errWord, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->errWord, (4 + gt16_ctx::kMaxSegs) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   ctx->dTotal = ctx->errWord + 1;
   ctx->dFlagged = ctx->errWord + 2;
+  ctx->dCounts = ctx->errWord + 4;
+  if ((e = cudaHostAlloc(&ctx->hCounts, gt16_ctx::kMaxSegs * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
   if ((e = cudaHostAlloc(&ctx->hPinnedRing, gt16_ctx::kCallRing * 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
   ctx->hPinned = ctx->hPinnedRing;
-  if ((e = cudaMemset(ctx->errWord, 0, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMemset(ctx->errWord, 0, (4 + gt16_ctx::kMaxSegs) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = cudaMalloc(&ctx->biasCache, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(ctx->biasCache, 0xFF, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = install_default_tables(ctx)) != cudaSuccess) return bail("cudaMemcpy", e);
@@ -268,7 +281,8 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   cudaFree(ctx->errWord);
   cudaFree(ctx->biasCache);
   if (ctx->hPinnedRing) cudaFreeHost(ctx->hPinnedRing);
-  for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->listB, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst,
+  if (ctx->hCounts) cudaFreeHost(ctx->hCounts);
+  for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->part, &ctx->rankOf, &ctx->list, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst,
                     &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
   for (auto &pool : ctx->evPool) for (auto e : pool) cudaEventDestroy(e);
   if (ctx->stagePin) cudaFreeHost(ctx->stagePin);
@@ -474,9 +488,12 @@ static int stage_threads() {                              // GT16_STAGE_THREADS,
   if (const char *e = getenv("GT16_STAGE_THREADS")) { int v = atoi(e); if (v >= 1 && v <= kStageThreadsMax) n = v; }
   return n;
 }
-// candidate records per kernel launch / D2H copy: a small first slice starts the device->host stream early,
-// later slices double up to kCandSliceMax so the kernels run at full occupancy
-static const uint32_t kCandSliceFirst = 4096, kCandSliceMax = 32768;
+// Record buffers are sized by a bound, not by the count (which only the device knows until the call completes): one
+// candidate per 128 sites plus a floor -- about seven times the called fraction of a 30x genome, 2.5 times that of the
+// 60x stress configs.  A call that finds more raises kErrRecordOverflow, and is repeated once with buffers of the size
+// it asked for (the buffers only grow, so this happens at most once per context and workload).
+static uint32_t record_bound(uint64_t segSites) { return (uint32_t) std::min<uint64_t>(segSites / 128 + 16384, 0x7FFFFFFFull / 12); }
+static const int kRetryLargerBuffers = 1;             // internal return code of call_common
 static const uint32_t kSegBatchesDefault = 2;         // batches per segment of a host-fed range (GT16_SEG_BATCHES overrides)
 
 #define CUF(call)                                                                                  \
@@ -696,21 +713,6 @@ int make_plan(gt16_ctx *ctx, uint32_t L, const gt16_region *regions, uint32_t nR
   return GT16_OK;
 }
 
-// ordered compaction of mask bits [0, nItems) -> list of (bit index + offset), grown on demand; returns the count
-int compact(gt16_ctx *ctx, const uint32_t *mask, uint32_t nItems, uint32_t offset, DevBuf &list, uint32_t *count) {
-  uint32_t *counts = (uint32_t *) ctx->counts.p;
-  launch_mask_count(mask, nItems, counts, ctx->compute);
-  launch_scan_counts(counts, scan_blocks(nItems), ctx->dTotal, ctx->compute);
-  ctx->launches += 2;
-  CUF(cudaMemcpyAsync(ctx->hPinned, ctx->dTotal, 4, cudaMemcpyDeviceToHost, ctx->compute));
-  CUF(cudaStreamSynchronize(ctx->compute));
-  *count = ctx->hPinned[0];
-  CUF(list.ensure((size_t) (*count ? *count : 1) * 4));
-  launch_mask_scatter(mask, nItems, counts, nullptr, offset, (uint32_t *) list.p, ctx->compute);
-  ctx->launches++;
-  return GT16_OK;
-}
-
 float ms_between(cudaEvent_t a, cudaEvent_t b) { float m = 0.f; cudaEventElapsedTime(&m, a, b); return m; }
 
 // can [pos(begin), pos(end)) go through the TMA-staged kernel?
@@ -747,76 +749,47 @@ int reserve_results(gt16_ctx *ctx, gt16_calls *calls, uint64_t need, uint64_t hi
   return GT16_OK;
 }
 
-struct SegTimes { float stream = 0, scan = 0, eval = 0, cand = 0; };
-
-// One segment [a, b) of the processed range after its streaming pass: compaction, exact evaluation (clears
-// bits), compaction, then candidate records slice by slice (k_candidates + k_bias) while the previous slice
-// travels to the host on the d2h stream.  `mask` is the flag bitmap of the whole call (bit 0 = site `begin`).
+// One segment [a, b) of the processed range after its streaming pass, all of it enqueued without a host round trip:
+//   k_eval_mask   exact evaluation of the flagged sites straight from the mask; clears the bits of non-candidates and
+//                 leaves likelihoods / posteriors of the candidates in part[] (device-side counter dCounts[seg])
+//   count + scan  block counts of what is left in the mask
+//   k_rank        place of every candidate in the ordered output
+//   k_candidates (compute stream) || k_bias (aux stream): records and their Fisher tests, both persistent grids that
+//                 read the count on the device and write disjoint fields of recs[rank]
+// `mask` is the flag bitmap of the whole call (bit 0 = site `begin`).
 int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t begin, uint64_t a, uint64_t b,
-                   bool usedTables, const DecisionTables &D, size_t &evNext, uint32_t seg, gt16_calls *calls,
-                   gt16_stats *st, uint64_t resultHint, cudaEvent_t evStream0, cudaEvent_t evStream1, cudaEvent_t haloReady,
-                   std::vector<cudaEvent_t> &timing, std::vector<cudaEvent_t> &segCopied, gt16_dev_calls *devOut) {
+                   bool usedTables, const DecisionTables &D, size_t &evNext, uint32_t seg, cudaEvent_t evStream0,
+                   cudaEvent_t evStream1, std::vector<cudaEvent_t> &timing, const std::vector<cudaEvent_t> &segCopied) {
   EvalParams P = eval_params(ctx);
-  uint32_t *mask = (uint32_t *) ctx->mask.p + (a - begin) / 32;
-  const uint32_t n = (uint32_t) (b - a), off = (uint32_t) (a - begin);
-  cudaEvent_t ev[4];
-  for (int k = 0; k < 4; ++k) { int rc = get_event(ctx, evNext++, &ev[k]); if (rc) return rc; }
-  // exact evaluation of the flagged sites straight from the mask (clears the bits of non-candidates), then ONE ordered
-  // compaction: what is left are the called sites, in order
-  uint32_t nB = 0;
+  const uint32_t n = (uint32_t) (b - a), off = (uint32_t) (a - begin), cap = ctx->recCap;
+  uint32_t *maskAll = (uint32_t *) ctx->mask.p, *counts = (uint32_t *) ctx->counts.p;
+  uint32_t *dCount = ctx->dCounts + seg;
+  EvalOut *part = (EvalOut *) ctx->part.p;
+  uint32_t *rankOf = (uint32_t *) ctx->rankOf.p, *list = (uint32_t *) ctx->list.p;
+  cudaEvent_t ev[4], auxDone;
   int rc;
+  for (int k = 0; k < 4; ++k) if ((rc = get_event(ctx, evNext++, &ev[k]))) return rc;
+  if ((rc = get_event(ctx, evNext++, &auxDone))) return rc;
   CUF(cudaEventRecord(ev[0], ctx->compute));
-  if (usedTables) {
-    launch_eval_mask(V, pl.map, begin, off, n, true, D, P, (uint32_t *) ctx->mask.p, ctx->errWord, ctx->dFlagged, ctx->compute);
-    ctx->launches++;
-  }
+  launch_eval_mask(V, pl.map, begin, off, n, usedTables, D, P, maskAll, ctx->errWord, ctx->dFlagged, part, dCount, cap, ctx->compute);
   CUF(cudaEventRecord(ev[1], ctx->compute));
-  rc = compact(ctx, mask, n, off, ctx->listB, &nB);
-  if (rc) return rc;
-  const uint32_t *finalList = (const uint32_t *) ctx->listB.p;
-  // candidate records of this segment: device buffers alternate between segments so that a segment's copies
-  // may still be in flight while the next one is being written
-  DevBuf &rb = (seg & 1) ? ctx->recs2 : ctx->recs;
-  CUF(rb.ensure((size_t) (nB ? nB : 1) * sizeof(gt16_called_site)));
-  if (!devOut) { rc = reserve_results(ctx, calls, nB, resultHint); if (rc) return rc; }
-  if (haloReady) CUF(cudaStreamWaitEvent(ctx->compute, haloReady, 0));   // windows reach up to 355 positions past b
-  if (seg >= 2) CUF(cudaStreamWaitEvent(ctx->compute, segCopied[seg - 2], 0));   // this record buffer's previous contents are on the host
+  launch_mask_count(maskAll + off / 32, n, counts, ctx->compute);
+  launch_scan_counts(counts, scan_blocks(n), ctx->dTotal, ctx->compute);
+  launch_rank(maskAll, off, counts, part, dCount, cap, rankOf, list, ctx->compute);
   CUF(cudaEventRecord(ev[2], ctx->compute));
-  gt16_called_site *recs = (gt16_called_site *) rb.p;
-  uint32_t sliceLen = kCandSliceFirst;
-  for (uint32_t o = 0, cnt = 0; o < nB; o += cnt, sliceLen = std::min(sliceLen * 2, kCandSliceMax)) {
-    cnt = std::min<uint32_t>(sliceLen, nB - o);
-    // records of slice k on the compute stream, their Fisher tests on the aux stream (both kernels are
-    // latency-bound at low occupancy, so slice k's tests run beside slice k+1's records), then the copy home
-    launch_candidates(V, pl.map, begin, finalList + o, cnt, P, recs + o, ctx->errWord, ctx->compute);
-    ctx->launches += 2;
-    cudaEvent_t se, be;
-    if ((rc = get_event(ctx, evNext++, &se)) || (rc = get_event(ctx, evNext++, &be))) return rc;
-    CUF(cudaEventRecord(se, ctx->compute));
-    CUF(cudaStreamWaitEvent(ctx->aux, se, 0));
-    launch_bias(V, pl.map, begin, finalList + o, cnt, P, ctx->biasCache, kBiasCacheEntries - 1, recs + o, ctx->aux);
-    CUF(cudaEventRecord(be, ctx->aux));
-    if (!devOut) {
-      CUF(cudaStreamWaitEvent(ctx->d2h, be, 0));
-      CUF(cudaMemcpyAsync(calls->sites + calls->n + o, recs + o, (size_t) cnt * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->d2h));
-    }
+  // record buffers alternate between segments: a segment's copy home may still be in flight while the next one is written
+  gt16_called_site *recs = (gt16_called_site *) ((seg & 1) ? ctx->recs2.p : ctx->recs.p);
+  if (seg >= 2) {                                             // this buffer's previous contents are on the host
+    CUF(cudaStreamWaitEvent(ctx->compute, segCopied[seg - 2], 0));
+    CUF(cudaStreamWaitEvent(ctx->aux, segCopied[seg - 2], 0));
   }
-  {                                                          // the segment's timing ends when its last tests are done
-    cudaEvent_t auxDone;
-    if ((rc = get_event(ctx, evNext++, &auxDone))) return rc;
-    CUF(cudaEventRecord(auxDone, ctx->aux));
-    CUF(cudaStreamWaitEvent(ctx->compute, auxDone, 0));
-  }
+  CUF(cudaStreamWaitEvent(ctx->aux, ev[2], 0));
+  launch_candidates(V, pl.map, begin, part, rankOf, dCount, cap, recs, ctx->errWord, ctx->numSMs, ctx->compute);
+  launch_bias(V, pl.map, begin, part, rankOf, dCount, cap, P, ctx->biasCache, kBiasCacheEntries - 1, recs, ctx->numSMs, ctx->aux);
+  ctx->launches += 6;
+  CUF(cudaEventRecord(auxDone, ctx->aux));
+  CUF(cudaStreamWaitEvent(ctx->compute, auxDone, 0));         // part / rankOf / list are reused by the next segment
   CUF(cudaEventRecord(ev[3], ctx->compute));
-  {
-    cudaEvent_t done;
-    rc = get_event(ctx, evNext++, &done);
-    if (rc) return rc;
-    CUF(cudaEventRecord(done, ctx->d2h));
-    segCopied.push_back(done);
-  }
-  if (devOut) { devOut->recs = recs; devOut->n = nB; } else calls->n += nB;
-  st->called += nB;
   timing.push_back(evStream0); timing.push_back(evStream1);
   for (int k = 0; k < 4; ++k) timing.push_back(ev[k]);
   return GT16_OK;
@@ -837,24 +810,50 @@ static void fill_timings(gt16_stats &st, cudaEvent_t evBegin, cudaEvent_t evEnd,
   st.ms_d2h = st.ms_total_device - lastCand;            // tail after the last candidate slice was written
 }
 
-// completion of a device-resident call: wait for its tail, look at the error word, fill in flagged and the timings
+static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const gt16_dev_snapshot *resident,
+                       const gt16_region *regions, uint32_t nRegions, uint64_t begin, uint64_t end,
+                       gt16_calls **out, gt16_stats *stats, gt16_dev_calls **devOutHandle = nullptr, bool nowait = false);
+
+static int report_device_errors(gt16_ctx *ctx, uint32_t errw) {
+  if (errw) CUF(cudaMemset(ctx->errWord, 0, 4));
+  if (errw & kErrBadSnapshot) return fail(ctx, GT16_EDATA, "snapshot refers to an overflow record or pool range that does not exist");
+  if (errw & kErrGenotype) return fail(ctx, GT16_EGENOTYPE, "Error in selecting Genotype");
+  return GT16_OK;
+}
+
+// completion of a device-resident call: wait for its tail, read the record count and the error word, fill in flagged and
+// the timings.  A call that found more candidates than the record buffers hold is repeated here, blocking, with larger ones.
 static int finish_dev_call(gt16_ctx *ctx, gt16_dev_calls *c) {
   if (!c->pending) return GT16_OK;
   CUF(cudaEventSynchronize(c->evEnd));
   CUF(cudaGetLastError());
   c->pending = false;
-  const uint32_t errw = c->slot[1];
-  c->st.flagged = c->useTables ? c->slot[3] : c->st.called;
-  if (errw) CUF(cudaMemset(ctx->errWord, 0, 4));
-  if (errw & kErrBadSnapshot) return fail(ctx, GT16_EDATA, "snapshot refers to an overflow record or pool range that does not exist");
-  if (errw & kErrGenotype) return fail(ctx, GT16_EGENOTYPE, "Error in selecting Genotype");
+  const uint32_t found = c->slot[0], errw = c->slot[1];
+  if (found > c->cap) {
+    CUF(cudaDeviceSynchronize());                                 // later calls on the context may be in flight
+    CUF(cudaMemset(ctx->errWord, 0, 4));
+    ctx->recCapWanted = found + found / 8 + 1024;
+    gt16_dev_calls *again = nullptr;
+    gt16_stats st2;
+    int rc = call_common(ctx, nullptr, c->snap, c->regions.empty() ? nullptr : c->regions.data(), (uint32_t) c->regions.size(),
+                         c->begin, c->end, nullptr, &st2, &again, false);
+    if (rc != GT16_OK) return rc;
+    c->recs = again->recs; c->n = again->n; c->cap = again->cap; c->st = again->st;
+    delete again;
+    return GT16_OK;
+  }
+  c->n = found;
+  c->st.called = found;
+  c->st.flagged = c->slot[3];
+  int rc = report_device_errors(ctx, errw);
+  if (rc != GT16_OK) return rc;
   fill_timings(c->st, c->evBegin, c->evEnd, c->timing);
   return GT16_OK;
 }
 
 static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const gt16_dev_snapshot *resident,
                        const gt16_region *regions, uint32_t nRegions, uint64_t begin, uint64_t end,
-                       gt16_calls **out, gt16_stats *stats, gt16_dev_calls **devOutHandle = nullptr, bool nowait = false) {
+                       gt16_calls **out, gt16_stats *stats, gt16_dev_calls **devOutHandle, bool nowait) {
   if (!ctx || (!out && !devOutHandle)) return GT16_EINVAL;
   ctx->evCur = (ctx->evCur + 1) % gt16_ctx::kCallRing;
   ctx->hPinned = ctx->hPinnedRing + 4 * ctx->evCur;
@@ -895,17 +894,31 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   cudaEvent_t evBegin, evEnd;
   if ((rc = get_event(ctx, evNext++, &evBegin)) || (rc = get_event(ctx, evNext++, &evEnd))) return rc;
   CUF(ctx->mask.ensure((((size_t) n + 31) / 32 + 64) * 4));
-  // A resident range is one segment (one streaming launch, D2H overlapped by slicing).  A host-fed range is
-  // cut into segments of kSegBatches batches so that everything after the streaming pass -- including the
-  // records' trip back -- runs while later counter chunks are still on the bus.
+  // A call whose records stay in HBM is one segment: one streaming launch and six more kernels, nothing else.  A call
+  // that returns its records to the host is cut into segments of kSegBatches batches, so that a segment's records
+  // travel home while the next one computes -- and, when the counters come from the host too, everything after a
+  // segment's streaming pass runs while later counter chunks are still on the bus.
   uint32_t segBatches = kSegBatchesDefault;
   if (const char *e = getenv("GT16_SEG_BATCHES")) { int v = atoi(e); if (v >= 1 && v <= 64) segBatches = (uint32_t) v; }
-  const uint64_t segSites = resident ? (uint64_t) n : (uint64_t) segBatches * kBatch;
-  CUF(ctx->counts.ensure(((size_t) scan_blocks((uint32_t) std::min<uint64_t>(segSites, n)) + 1) * 4));
+  const uint64_t segSites = devOutHandle ? (uint64_t) n : (uint64_t) segBatches * kBatch;
+  const uint64_t segLongest = std::min<uint64_t>(segSites, n);
+  CUF(ctx->counts.ensure(((size_t) scan_blocks((uint32_t) segLongest) + 1) * 4));
+  {
+    const uint32_t capWant = std::max(std::max(ctx->recCap, ctx->recCapWanted), record_bound(segLongest));
+    ctx->recCap = capWant;
+    CUF(ctx->part.ensure((size_t) capWant * sizeof(EvalOut)));
+    CUF(ctx->rankOf.ensure((size_t) capWant * 4));
+    CUF(ctx->list.ensure((size_t) capWant * 4));
+    CUF(ctx->recs.ensure((size_t) capWant * sizeof(gt16_called_site)));
+    if (!devOutHandle && n > kBatch) CUF(ctx->recs2.ensure((size_t) capWant * sizeof(gt16_called_site)));   // more than one segment
+  }
   uint32_t *mask = (uint32_t *) ctx->mask.p;
   const uint64_t resultHint = std::max<uint64_t>(4096, (uint64_t) n / 512);
-  std::vector<cudaEvent_t> timing, segCopied;
+  std::vector<cudaEvent_t> timing, segCopied, segDone;
+  const uint32_t nSegsBound = (uint32_t) ((n + segSites - 1) / segSites) + 1;
+  if (nSegsBound > (uint32_t) gt16_ctx::kMaxSegs) return fail(ctx, GT16_EINVAL, "range too long for GT16_SEG_BATCHES");
   CUF(cudaMemsetAsync(ctx->dFlagged, 0, 4, ctx->compute));
+  CUF(cudaMemsetAsync(ctx->dCounts, 0, nSegsBound * 4, ctx->compute));
   CUF(cudaEventRecord(evBegin, ctx->compute));
 
   gt16_dev_snapshot streamed;
@@ -1048,6 +1061,30 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     if (lastBatch > cuts.back()) cuts.push_back(lastBatch);
   }
   cuts.push_back(end);
+  // records of segment `sg` -> the caller's page-locked buffer, once the segment has finished on the device: the one
+  // place where the host learns a count, and it gets there after the NEXT segment has been enqueued
+  bool overflow = false;
+  auto collect = [&](uint32_t sg) -> int {
+    CUF(cudaEventSynchronize(segDone[sg]));
+    const uint32_t cnt = ctx->hCounts[sg];
+    cudaEvent_t done;
+    int rc2 = get_event(ctx, evNext++, &done);
+    if (rc2) return rc2;
+    if (cnt > ctx->recCap) {
+      overflow = true;
+      ctx->recCapWanted = std::max(ctx->recCapWanted, cnt + cnt / 8 + 1024);
+    } else if (cnt && !overflow) {
+      if ((rc2 = reserve_results(ctx, calls.get(), cnt, resultHint))) return rc2;
+      const gt16_called_site *recs = (const gt16_called_site *) ((sg & 1) ? ctx->recs2.p : ctx->recs.p);
+      CUF(cudaStreamWaitEvent(ctx->d2h, segDone[sg], 0));
+      CUF(cudaMemcpyAsync(calls->sites + calls->n, recs, (size_t) cnt * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->d2h));
+      calls->n += cnt;
+      st.called += cnt;
+    }
+    CUF(cudaEventRecord(done, ctx->d2h));
+    segCopied.push_back(done);
+    return GT16_OK;
+  };
   uint32_t seg = 0;
   for (size_t ci = 0; ci + 1 < cuts.size(); ++ci, ++seg) {
     const uint64_t a = cuts[ci], b = cuts[ci + 1];
@@ -1063,9 +1100,18 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     CUF(cudaEventRecord(es1, ctx->compute));
     // windows, neighbours' Fisher tests and the indel look-ahead reach up to ~360 positions past the segment
     if ((rc = wait_chunks(pl.ascending ? pl.hi_pos(std::min<uint64_t>(pl.map.totalSites, b + 512) - 1) + 600 : copyHi))) return rc;
-    rc = finish_segment(ctx, *V, pl, begin, a, b, useTables, D, evNext, seg, calls.get(), &st, resultHint, es0, es1, nullptr, timing, segCopied, devOut.get());
+    rc = finish_segment(ctx, *V, pl, begin, a, b, useTables, D, evNext, seg, es0, es1, timing, segCopied);
     if (rc != GT16_OK) return rc;
+    if (!devOutHandle) {
+      cudaEvent_t sd;
+      if ((rc = get_event(ctx, evNext++, &sd))) return rc;
+      CUF(cudaMemcpyAsync(ctx->hCounts + seg, ctx->dCounts + seg, 4, cudaMemcpyDeviceToHost, ctx->compute));
+      CUF(cudaEventRecord(sd, ctx->compute));
+      segDone.push_back(sd);
+      if (seg >= 1 && (rc = collect(seg - 1))) return rc;
+    }
   }
+  if (!devOutHandle && (rc = collect(seg - 1))) return rc;
   // drain: results on the host, error word
   cudaEvent_t evD2H;
   if ((rc = get_event(ctx, evNext++, &evD2H))) return rc;
@@ -1076,12 +1122,16 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     for (auto &t : stagers) t.join();
     if (stageError.load()) { ctx->err = std::string("staged upload failed: ") + cudaGetErrorString((cudaError_t) stageError.load()); return GT16_ECUDA; }
   }
+  if (devOutHandle) CUF(cudaMemcpyAsync(ctx->hPinned, ctx->dCounts, 4, cudaMemcpyDeviceToHost, ctx->compute));   // records of the (single) segment
   CUF(cudaMemcpyAsync(ctx->hPinned + 1, ctx->errWord, 12, cudaMemcpyDeviceToHost, ctx->compute));   // error bits, (total), sites evaluated
   CUF(cudaEventRecord(evEnd, ctx->compute));
   st.kernel_launches = ctx->launches - launches0;
   if (devOutHandle) {
-    // the rest -- waiting for the tail, the error word, the timings -- is gt16_dev_calls_wait's
-    devOut->pending = true; devOut->useTables = useTables;
+    // the rest -- waiting for the tail, the record count, the error word, the timings -- is gt16_dev_calls_wait's
+    devOut->pending = true; devOut->useTables = useTables; devOut->ctx = ctx;
+    devOut->recs = (const gt16_called_site *) ctx->recs.p; devOut->cap = ctx->recCap;
+    devOut->snap = resident; devOut->begin = begin; devOut->end = end;
+    if (regions && nRegions) devOut->regions.assign(regions, regions + nRegions);
     devOut->evBegin = evBegin; devOut->evEnd = evEnd; devOut->timing = timing; devOut->slot = ctx->hPinned; devOut->st = st;
     if (!nowait) {
       rc = finish_dev_call(ctx, devOut.get());
@@ -1095,10 +1145,13 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   CUF(cudaStreamSynchronize(ctx->compute));
   CUF(cudaGetLastError());
   const uint32_t errw = ctx->hPinned[1];
-  st.flagged = useTables ? ctx->hPinned[3] : st.called;
-  if (errw) CUF(cudaMemset(ctx->errWord, 0, 4));
-  if (errw & kErrBadSnapshot) return fail(ctx, GT16_EDATA, "snapshot refers to an overflow record or pool range that does not exist");
-  if (errw & kErrGenotype) return fail(ctx, GT16_EGENOTYPE, "Error in selecting Genotype");
+  st.flagged = ctx->hPinned[3];
+  if (overflow) {                                   // more candidates than the record buffers hold: again, with larger ones
+    CUF(cudaDeviceSynchronize());
+    CUF(cudaMemset(ctx->errWord, 0, 4));
+    return kRetryLargerBuffers;
+  }
+  if ((rc = report_device_errors(ctx, errw))) return rc;
   fill_timings(st, evBegin, evEnd, timing);
   drainD2H.armed = false;
   *out = calls.release();
@@ -1106,18 +1159,29 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   return GT16_OK;
 }
 
+// host-result calls: repeated once when the first attempt found more candidates than the record buffers hold
+static int call_with_retry(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const gt16_dev_snapshot *resident,
+                           const gt16_region *regions, uint32_t nRegions, uint64_t begin, uint64_t end,
+                           gt16_calls **out, gt16_stats *stats) {
+  int rc = kRetryLargerBuffers;
+  for (int attempt = 0; attempt < 3 && rc == kRetryLargerBuffers; ++attempt)
+    rc = call_common(ctx, hostView, resident, regions, nRegions, begin, end, out, stats, nullptr, false);
+  if (rc == kRetryLargerBuffers) return fail(ctx, GT16_ECUDA, "record buffers could not be sized");
+  return rc;
+}
+
 extern "C" {
 
 int gt16_call_sites(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
                     uint64_t site_begin, uint64_t site_end, gt16_calls **out, gt16_stats *stats) {
   if (!snap) return GT16_EINVAL;
-  return call_common(ctx, nullptr, snap, regions, n_regions, site_begin, site_end, out, stats);
+  return call_with_retry(ctx, nullptr, snap, regions, n_regions, site_begin, site_end, out, stats);
 }
 
 int gt16_call_sites_device(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
                            uint64_t site_begin, uint64_t site_end, gt16_dev_calls **out, gt16_stats *stats) {
   if (!snap || !out) return GT16_EINVAL;
-  return call_common(ctx, nullptr, snap, regions, n_regions, site_begin, site_end, nullptr, stats, out);
+  return call_common(ctx, nullptr, snap, regions, n_regions, site_begin, site_end, nullptr, stats, out, false);
 }
 int gt16_call_sites_device_nowait(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
                                   uint64_t site_begin, uint64_t site_end, gt16_dev_calls **out, gt16_stats *stats) {
@@ -1131,8 +1195,12 @@ int gt16_dev_calls_wait(gt16_ctx *ctx, gt16_dev_calls *c, gt16_stats *stats) {
   if (stats) *stats = c->st;
   return rc;
 }
-uint64_t gt16_dev_calls_count(const gt16_dev_calls *c) { return c ? c->n : 0; }
-const void *gt16_dev_calls_device_ptr(const gt16_dev_calls *c) { return c && c->n ? c->recs : nullptr; }
+// the count (and with it the extent of the record array) is known when the call has completed: both complete it if need be
+static void complete_quietly(const gt16_dev_calls *c) {
+  if (c && c->pending && c->ctx) { cudaSetDevice(c->ctx->device); (void) finish_dev_call(c->ctx, const_cast<gt16_dev_calls *>(c)); }
+}
+uint64_t gt16_dev_calls_count(const gt16_dev_calls *c) { complete_quietly(c); return c ? c->n : 0; }
+const void *gt16_dev_calls_device_ptr(const gt16_dev_calls *c) { complete_quietly(c); return c && c->n ? c->recs : nullptr; }
 void gt16_dev_calls_free(gt16_dev_calls *c) { delete c; }
 int gt16_dev_calls_fetch(gt16_ctx *ctx, const gt16_dev_calls *c, gt16_calls **out) {
   if (!ctx || !c || !out) return GT16_EINVAL;
@@ -1157,7 +1225,7 @@ int gt16_call_sites_host(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt
   if (!ctx) return GT16_EINVAL;
   int rc = check_view(ctx, view);
   if (rc) return rc;
-  return call_common(ctx, view, nullptr, regions, n_regions, site_begin, site_end, out, stats);
+  return call_with_retry(ctx, view, nullptr, regions, n_regions, site_begin, site_end, out, stats);
 }
 
 uint64_t gt16_calls_count(const gt16_calls *c) { return c ? c->n : 0; }

@@ -644,7 +644,7 @@ GT16_HDN WinEntry window_entry(const SnapView &V, const SiteMap &M, const BatchG
 }
 
 // error bits raised by the per-site routines
-enum : uint32_t { kErrBadSnapshot = 1u, kErrGenotype = 2u };
+enum : uint32_t { kErrBadSnapshot = 1u, kErrGenotype = 2u, kErrRecordOverflow = 4u };
 
 struct EvalParams {
   LhTables lh;

@@ -435,13 +435,14 @@ constexpr int kEvalQueue = 64;                       // per-warp ring of flagged
 __device__ __forceinline__ void eval_group(const SnapView &V, const DevSiteMap &M, uint64_t base, uint32_t i, bool active,
                                            bool useTables, const DecisionTables &D, const EvalParams &P,
                                            uint32_t *__restrict__ siteMask, uint32_t *errWord,
-                                           double (*lhS)[16], uint32_t (*wpS)[6]) {
+                                           double (*lhS)[16], uint32_t (*wpS)[6],
+                                           EvalOut *__restrict__ part, uint32_t *count, uint32_t cap) {
   const uint32_t lane = threadIdx.x & 31, half = lane >> 4, g = lane & 15;
   {
     uint32_t e = 0;
     bool cand = false, full = false;
     uint32_t W[6] = {0, 0, 0, 0, 0, 0};
-    int ref = 0; uint32_t validPlus = 0;
+    int ref = 0; uint32_t validPlus = 0, delLen = 0;
     if (active) {
       const uint32_t p = site_pos(M, base + i);
       BaseCounts bc;
@@ -455,6 +456,7 @@ __device__ __forceinline__ void eval_group(const SnapView &V, const DevSiteMap &
           ref = (int) ref_base(V, p);
           W[0] = bc.W[0]; W[1] = bc.W[1]; W[2] = bc.W[2]; W[3] = bc.W[3]; W[4] = ii.W4; W[5] = ii.W5;
           validPlus = ii.isValidPlus;
+          delLen = d0.type == 'D' ? d0.len : 0u;
           full = true;
           if (useTables && (ii.W4 | ii.W5) == 0) {
             const uint32_t wr = ref == 0 ? W[0] : ref == 1 ? W[1] : ref == 2 ? W[2] : W[3];
@@ -479,6 +481,7 @@ __device__ __forceinline__ void eval_group(const SnapView &V, const DevSiteMap &
       for (int k = 0; k < 6; ++k) Ws[k] = __shfl_sync(0xffffffffu, W[k], src);
       const int refS = __shfl_sync(0xffffffffu, ref, src);
       const uint32_t vpS = __shfl_sync(0xffffffffu, validPlus, src);
+      const uint32_t siteS = __shfl_sync(0xffffffffu, i, src), delS = __shfl_sync(0xffffffffu, delLen, src);
       // penalised weights (penalised_weights(), FisherExactTest.cpp:251-266) into shared memory: the likelihood
       // classes index them by allele
       if (g < 6) {
@@ -506,6 +509,7 @@ __device__ __forceinline__ void eval_group(const SnapView &V, const DevSiteMap &
       for (int k = 1; k < 16; ++k) pD = pD + lhS[half][k];
       const int homRef = hom_ref_genotype(refS);
       double f0 = pD == 0.0 ? ((int) g == homRef ? 1.0 : 0.0) : lhS[half][g] / pD * P.prior[(refS << 6) | P.g2i[g]];
+      const double fMine = f0;
       int genotype = (int) g;
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) {
@@ -514,6 +518,36 @@ __device__ __forceinline__ void eval_group(const SnapView &V, const DevSiteMap &
         if (w > f0 || (w == f0 && gw < genotype)) { f0 = w; genotype = gw; }
       }
       const int res = (genotype != homRef ? 1 : 0) | ((genotype > 9 && vpS == 0) ? 2 : 0);   // bit0 candidate, bit1 genotype error (SNP_Caller.cpp:235-239)
+      // A candidate (pD != 0 then: pD == 0 is hom-ref by definition) leaves what has just been computed to the record
+      // and Fisher-test kernels: likelihoods, posteriors, best / second (the runner-up is the largest of the other
+      // fifteen, argmax_posteriors()), genotype, indel kind and the deletion length the neighbour tests skip.
+      const bool emit = (res & 1) && (half == 0 || src1 != src0);
+      if (__any_sync(0xffffffffu, emit)) {
+        double f1 = (int) g == genotype ? -1.0 : fMine;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          const double w = __shfl_xor_sync(0xffffffffu, f1, o);
+          if (w > f1) f1 = w;
+        }
+        uint32_t slot = 0;
+        if (emit && g == 0) slot = atomicAdd(count, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, half << 4);
+        if (emit) {
+          if (slot < cap) {
+            EvalOut &eo = part[slot];
+            eo.lh[g] = lhS[half][g];
+            eo.flh[g] = fMine;
+            if (g == 0) {
+              const bool indel = genotype > 9 && vpS != 0;
+              eo.pD = pD; eo.bestD = f0; eo.secondD = f1; eo.site = siteS;
+              eo.genotype = (uint8_t) genotype; eo.isIndel = indel ? (uint8_t) (1 + vpS) : (uint8_t) 0;
+              eo.nextBp = indel ? (uint8_t) delS : (uint8_t) 0; eo.pad = 0;
+            }
+          } else if (g == 0) {
+            e |= kErrRecordOverflow;
+          }
+        }
+      }
       const int res0 = __shfl_sync(0xffffffffu, res, 0), res1 = __shfl_sync(0xffffffffu, res, 16);
       if ((int) lane == src0) { cand = res0 & 1; if (res0 & 2) e |= kErrGenotype; }
       if ((int) lane == src1 && src1 != src0) { cand = res1 & 1; if (res1 & 2) e |= kErrGenotype; }
@@ -532,7 +566,8 @@ __device__ __forceinline__ void eval_group(const SnapView &V, const DevSiteMap &
 __global__ void __launch_bounds__(kEvalThreads, 6) k_eval_mask(SnapView V, DevSiteMap M, uint64_t base, uint32_t wordBegin,
                                                             uint32_t nWords, bool useTables, DecisionTables D, EvalParams P,
                                                             uint32_t *__restrict__ siteMask, uint32_t *errWord,
-                                                            uint32_t *flagged) {
+                                                            uint32_t *flagged, EvalOut *__restrict__ part, uint32_t *count,
+                                                            uint32_t cap) {
   __shared__ double lhS[kEvalThreads / 32][2][16];
   __shared__ uint32_t wpS[kEvalThreads / 32][2][6];
   __shared__ uint32_t ringS[kEvalThreads / 32][kEvalQueue];
@@ -557,7 +592,7 @@ __global__ void __launch_bounds__(kEvalThreads, 6) k_eval_mask(SnapView V, DevSi
       tail += __popc(any);
       __syncwarp();
       if (tail - head >= 32u) {
-        eval_group(V, M, base, ring[(head + lane) & (kEvalQueue - 1)], true, useTables, D, P, siteMask, errWord, lhS[warp], wpS[warp]);
+        eval_group(V, M, base, ring[(head + lane) & (kEvalQueue - 1)], true, useTables, D, P, siteMask, errWord, lhS[warp], wpS[warp], part, count, cap);
         head += 32;
         __syncwarp();
       }
@@ -566,19 +601,19 @@ __global__ void __launch_bounds__(kEvalThreads, 6) k_eval_mask(SnapView V, DevSi
   }
   if (tail != head) {
     const bool active = lane < tail - head;
-    eval_group(V, M, base, active ? ring[(head + lane) & (kEvalQueue - 1)] : 0u, active, useTables, D, P, siteMask, errWord, lhS[warp], wpS[warp]);
+    eval_group(V, M, base, active ? ring[(head + lane) & (kEvalQueue - 1)] : 0u, active, useTables, D, P, siteMask, errWord, lhS[warp], wpS[warp], part, count, cap);
   }
   seen = __reduce_add_sync(0xffffffffu, seen);
   if (lane == 0 && seen) atomicAdd(flagged, seen);
 }
 void launch_eval_mask(const SnapView &V, const DevSiteMap &M, uint64_t base, uint32_t firstSite, uint32_t nSites,
                       bool useTables, const DecisionTables &D, const EvalParams &P, uint32_t *siteMask,
-                      uint32_t *errWord, uint32_t *flagged, cudaStream_t s) {
+                      uint32_t *errWord, uint32_t *flagged, EvalOut *part, uint32_t *count, uint32_t cap, cudaStream_t s) {
   if (!nSites) return;
   const uint32_t nWords = (nSites + 31) / 32, nChunks = (nWords + 31) / 32;
   unsigned grid = (nChunks + (kEvalThreads / 32) - 1) / (kEvalThreads / 32);
   if (grid > 148 * 6) grid = 148 * 6;                     // one resident wave (launch bounds: 6 blocks of 128 threads per SM)
-  k_eval_mask<<<grid, kEvalThreads, 0, s>>>(V, M, base, firstSite / 32, nWords, useTables, D, P, siteMask, errWord, flagged);
+  k_eval_mask<<<grid, kEvalThreads, 0, s>>>(V, M, base, firstSite / 32, nWords, useTables, D, P, siteMask, errWord, flagged, part, count, cap);
 }
 
 // ------------------------------------------------------------------------------ ordered compaction
@@ -634,32 +669,32 @@ void launch_scan_counts(uint32_t *blockCounts, uint32_t nBlocks, uint32_t *total
   k_scan_counts<<<1, 1024, 0, s>>>(blockCounts, nBlocks, total);
 }
 
-__global__ void __launch_bounds__(kScanBlock) k_mask_scatter(const uint32_t *__restrict__ mask, uint32_t nWords,
-                                                            const uint32_t *__restrict__ blockOffsets,
-                                                            const uint32_t *__restrict__ values, uint32_t offset,
-                                                            uint32_t *__restrict__ out) {
-  __shared__ uint32_t warpTot[kScanBlock / 32];
-  uint32_t w = blockIdx.x * kScanBlock + threadIdx.x;
-  uint32_t bits = w < nWords ? mask[w] : 0;
-  uint32_t c = __popc(bits), x = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-  if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = x;
-  __syncthreads();
-  uint32_t pre = 0;
-  for (uint32_t k = 0; k < (threadIdx.x >> 5); ++k) pre += warpTot[k];
-  uint32_t dst = blockOffsets[blockIdx.x] + pre + x - c;
-  while (bits) {
-    uint32_t b = __ffs(bits) - 1;
-    bits &= bits - 1;
-    uint32_t item = w * 32 + b;
-    out[dst++] = values ? values[item] : item + offset;
+// Place of every candidate in the ordered output: rank = number of set mask bits before its site, from the scanned block
+// counts plus the (at most kScanBlock) words of its own block.  One warp per candidate; the count is read on the device.
+__global__ void __launch_bounds__(256) k_rank(const uint32_t *__restrict__ mask, uint32_t firstWord,
+                                              const uint32_t *__restrict__ blockOffsets, const EvalOut *__restrict__ part,
+                                              const uint32_t *__restrict__ count, uint32_t cap,
+                                              uint32_t *__restrict__ rankOf, uint32_t *__restrict__ list) {
+  const uint32_t n = *count < cap ? *count : cap;
+  const uint32_t lane = threadIdx.x & 31, warpsTotal = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += warpsTotal) {
+    const uint32_t site = part[j].site;
+    const uint32_t w = (site >> 5) - firstWord, w0 = (w / kScanBlock) * kScanBlock;
+    uint32_t c = 0;
+    for (uint32_t k = w0 + lane; k < w; k += 32) c += __popc(mask[firstWord + k]);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) {
+      const uint32_t r = blockOffsets[w / kScanBlock] + c + __popc(mask[firstWord + w] & ((1u << (site & 31)) - 1u));
+      rankOf[j] = r;
+      list[r] = site;
+    }
   }
 }
-void launch_mask_scatter(const uint32_t *mask, uint32_t nItems, const uint32_t *blockOffsets,
-                         const uint32_t *values, uint32_t offset, uint32_t *out, cudaStream_t s) {
-  uint32_t nb = scan_blocks(nItems);
-  if (nb) k_mask_scatter<<<nb, kScanBlock, 0, s>>>(mask, (nItems + 31) / 32, blockOffsets, values, offset, out);
+void launch_rank(const uint32_t *siteMask, uint32_t firstSite, const uint32_t *blockOffsets, const EvalOut *part,
+                 const uint32_t *count, uint32_t cap, uint32_t *rankOf, uint32_t *list, cudaStream_t s) {
+  unsigned grid = (cap + 7) / 8;
+  if (grid > 148 * 8) grid = 148 * 8;
+  k_rank<<<grid, 256, 0, s>>>(siteMask, firstSite / 32, blockOffsets, part, count, cap, rankOf, list);
 }
 
 // ------------------------------------------------------------------------------ candidates
@@ -671,9 +706,6 @@ void launch_mask_scatter(const uint32_t *mask, uint32_t nItems, const uint32_t *
 // uses, so the bits are the same.
 constexpr int kCandThreads = 128;
 struct CandWarpSmem {
-  double lh[16];
-  double flh[16];
-  uint32_t W[6], F[6], R[6], Wp[6];   // counts of the site (A,C,G,T,deepest indel,second indel), penalised weights
   uint32_t sc[2][kWindow + 4];        // window entries: strand count (< 2^20) | valid << 31
   uint32_t w[2][kWindow + 4];         //                 weighted depth (< 2^18) | flags << 24 (bit0 valid, bit1 C-or-G, bit2 G)
 };
@@ -722,20 +754,27 @@ __device__ __forceinline__ uint32_t region_of(const SiteMap &M, uint64_t i) {   
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }   // one REDUX.SUM
 
 __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevSiteMap M, uint64_t base,
-                                                             const uint32_t *__restrict__ list, uint32_t n,
-                                                             EvalParams P, gt16_called_site *__restrict__ out,
-                                                             uint32_t *errWord) {
+                                                             const EvalOut *__restrict__ part,
+                                                             const uint32_t *__restrict__ rankOf,
+                                                             const uint32_t *__restrict__ count, uint32_t cap,
+                                                             gt16_called_site *__restrict__ out, uint32_t *errWord) {
   __shared__ CandWarpSmem smAll[kCandThreads / 32];
   CandWarpSmem &sm = smAll[threadIdx.x >> 5];
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warpsTotal = gridDim.x * (kCandThreads / 32);
+  const uint32_t n = *count < cap ? *count : cap;
   for (uint32_t j = blockIdx.x * (kCandThreads / 32) + (threadIdx.x >> 5); j < n; j += warpsTotal) {
-    const uint64_t i = base + list[j];
+    const EvalOut &eo = part[j];
+    const uint64_t i = base + eo.site;
     const uint32_t p = site_pos(M, i);
-    gt16_called_site &o = out[j];
+    gt16_called_site &o = out[rankOf[j]];
     uint32_t err = 0;
+    // -- the likelihoods, posteriors and the call itself come from the exact evaluator (k_eval_mask), which computed them
+    //    to decide that this site is a candidate
+    if (lane < 16) { o.lh[lane] = eo.lh[lane]; o.flh[lane] = eo.flh[lane]; }
+    const int genotype = eo.genotype;
     // -- counts of the site: base `lane` on lanes 0..3 (decode_bases, one base per lane), the two deepest indel
-    //    patterns on lanes 4 and 5; everything the warp shares lives in shared memory, not in per-lane arrays
+    //    patterns on lanes 4 and 5
     const int ref = (int) ref_base(V, p);
     IndelInfo ii; PatRef d0, d1;
     decode_indel_refs(V, p, ii, d0, d1);
@@ -761,69 +800,10 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
       if (lane == 4) { w = ii.W4; f = ii.F4; r = ii.R4; }
       if (lane == 5) { w = ii.W5; f = ii.F5; r = ii.R5; }
       if (__any_sync(0xffffffffu, bad)) err |= kErrBadSnapshot;
-      if (lane < 6) {
-        sm.W[lane] = w; sm.F[lane] = f; sm.R[lane] = r;
-        const uint32_t indelCount = ii.W4 + ii.W5;                         // penalised_weights(), FisherExactTest.cpp:251-260
-        if ((int) lane == ref && indelCount) {
-          double tmp = (double) indelCount * (1.375f) + 0.5f;
-          tmp = w - tmp;
-          if (tmp <= 0) tmp = 0;
-          w = (uint32_t) tmp;
-        }
-        sm.Wp[lane] = w;
-      }
+      if (lane < 6) { o.W[lane] = w; o.F[lane] = f; o.R[lane] = r; }
     }
-    __syncwarp();
-    // -- 16 genotype likelihoods, one per lane
-    {
-      int wt = 0;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) wt += (int) sm.Wp[k];
-      if (lane < 16) sm.lh[lane] = genotype_lh_one(P.lh, sm.Wp, wt, (int) lane);
-    }
-    __syncwarp();
-    // posterior (selectGenotype, FisherExactTest.cpp:317-509): the sum is sequential in every lane, the sixteen
-    // divisions -- by far the most expensive part in FP64 -- are one per lane, the best / second scan reads them back
-    double pD = sm.lh[0], bestD = 0, secondD = 0;
-    int genotype;
-#pragma unroll
-    for (int g = 1; g < 16; ++g) pD = pD + sm.lh[g];
-    if (pD == 0.0) {
-      genotype = hom_ref_genotype(ref);
-      if (lane < 16) sm.flh[lane] = 0;
-      __syncwarp();
-    } else {
-      if (lane < 16) sm.flh[lane] = sm.lh[lane] / pD * P.prior[(ref << 6) | P.g2i[lane]];
-      __syncwarp();
-      // argmax_posteriors() (:383-504) across the lanes: the winner is the LOWEST index holding the maximum (the
-      // reference replaces its best only on a strict `>`, and prefers 0 to 1 on a tie), the runner-up is the largest
-      // value among the other fifteen.  Posteriors are >= 0; lanes 16..31 carry -1.
-      double v = lane < 16 ? sm.flh[lane] : -1.0;
-      double f0 = v;
-      genotype = (int) lane;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        const double w = __shfl_xor_sync(0xffffffffu, f0, o);
-        const int gw = __shfl_xor_sync(0xffffffffu, genotype, o);
-        if (w > f0 || (w == f0 && gw < genotype)) { f0 = w; genotype = gw; }
-      }
-      f0 = __shfl_sync(0xffffffffu, f0, 0);
-      genotype = __shfl_sync(0xffffffffu, genotype, 0);
-      double f1 = (int) lane == genotype ? -1.0 : v;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        const double w = __shfl_xor_sync(0xffffffffu, f1, o);
-        if (w > f1) f1 = w;
-      }
-      f1 = __shfl_sync(0xffffffffu, f1, 0);
-      bestD = f0; secondD = f1;
-    }
-    const uint8_t isValid = (uint8_t) (1 + ii.isValidPlus);
-    uint8_t isIndel = 0, nextBp = 0;
-    if (genotype > 9) {                                                 // SNP_Caller.cpp:228-239
-      if (isValid >= 2) { isIndel = isValid; if (d0.type == 'D') nextBp = d0.len; }
-      else err |= kErrGenotype;
-    }
+    const uint8_t isIndel = eo.isIndel, nextBp = eo.nextBp;             // SNP_Caller.cpp:228-239 (decided by the evaluator)
+    if (genotype > 9 && !isIndel) err |= kErrGenotype;
     BatchGeom B;
     B.first = (i / kBatch) * (uint64_t) kBatch;
     const uint64_t left = M.totalSites - B.first;
@@ -912,8 +892,6 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
     const uint32_t run = polyrun(V, p);
 
     // -- record
-    if (lane < 16) { o.lh[lane] = sm.lh[lane]; o.flh[lane] = sm.flh[lane]; }
-    if (lane < 6) { o.W[lane] = sm.W[lane]; o.F[lane] = sm.F[lane]; o.R[lane] = sm.R[lane]; }
     for (int k = 0; k < 2; ++k) {                                       // indel pattern bytes, two per lane
       gt16_indel &d = o.indel[k];
       const PatRef &pr = k ? d1 : d0;
@@ -931,7 +909,7 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
     }
     if (lane == 0) {
       o.amb = p; o.ref = (uint8_t) ref; o.genotype = (uint8_t) genotype; o.is_indel = isIndel;
-      o.pD = pD; o.bestD = bestD; o.secondD = secondD;
+      o.pD = eo.pD; o.bestD = eo.bestD; o.secondD = eo.secondD;
       float avgSC[2] = {0.f, 0.f}, avgD[2] = {0.f, 0.f};
       if (deltaSum[0] | deltaSum[1]) o.rpb = (deltaSum[0] - deltaSum[1] + 0.0f) / (deltaSum[0] + deltaSum[1]);
       else o.rpb = 0.0f;
@@ -956,15 +934,15 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
     __syncwarp();
   }
 }
-void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
-                       const EvalParams &P, gt16_called_site *out, uint32_t *errWord, cudaStream_t s) {
-  if (!n) return;
-  unsigned grid = (n + (kCandThreads / 32) - 1) / (kCandThreads / 32);
-#ifndef GT16_CAND_GRID
-#define GT16_CAND_GRID 32      // blocks per SM the grid is capped at (tools/probes/build_variant.sh sweeps it: 5..8 slower, 32 = 64 = uncapped)
-#endif
-  if (grid > 148 * GT16_CAND_GRID) grid = 148 * GT16_CAND_GRID;
-  k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, list, n, P, out, errWord);
+void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
+                       const uint32_t *count, uint32_t cap, gt16_called_site *out, uint32_t *errWord, int numSMs,
+                       cudaStream_t s) {
+  // persistent grid: the number of records is only known on the device; 8 blocks of 4 warps per SM (launch bounds), and a
+  // small call (cap is a bound on its records) does not need more warps than records
+  unsigned grid = (cap + (kCandThreads / 32) - 1) / (kCandThreads / 32);
+  const unsigned full = (unsigned) numSMs * 8u;
+  if (grid > full) grid = full;
+  k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, part, rankOf, count, cap, out, errWord);
 }
 
 // ------------------------------------------------------------------------------ Fisher tests of the candidates
@@ -1046,9 +1024,13 @@ __device__ __forceinline__ uint32_t bias_key(bool bqb, uint32_t W, uint32_t F, u
 __device__ __forceinline__ uint32_t bias_slot(uint32_t key, uint32_t mask) { return ((key * 0x9E3779B1u) ^ (key >> 15)) & mask; }
 
 __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M, uint64_t base,
-                                                       const uint32_t *__restrict__ list, uint32_t n, LnFact G,
+                                                       const EvalOut *__restrict__ part,
+                                                       const uint32_t *__restrict__ rankOf,
+                                                       const uint32_t *__restrict__ count, uint32_t cap, LnFact G,
                                                        uint2 *__restrict__ cache, uint32_t cacheMask,
                                                        gt16_called_site *__restrict__ out) {
+  const uint32_t n = *count < cap ? *count : cap;
+  if (blockIdx.x * (kBiasThreads / 32) * 32u >= n * 12u) return;     // persistent grid sized for the bound, not the count
   __shared__ float lnS[kLnSmem];
   __shared__ BiasTask queue[kBiasThreads / 32][kBiasQueue];
   const uint32_t nS = G.size < (uint32_t) kLnSmem ? G.size : (uint32_t) kLnSmem;
@@ -1102,13 +1084,16 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
   for (uint32_t chunk = blockIdx.x * (kBiasThreads / 32) + warp; chunk * 32u < nSlots; chunk += warpsTotal) {
     const uint32_t slot = chunk * 32u + lane;
     bool pending = false;
-    BiasTask t; t.W = t.F = t.R = 0; t.dst = slot;
+    BiasTask t; t.W = t.F = t.R = 0; t.dst = 0;
+    uint32_t rec = 0;                                 // the record this slot belongs to (ordered output)
     if (slot < nSlots) {
       const uint32_t j = slot / 12, k = (slot % 12) >> 2, b = slot & 3;
-      const gt16_called_site &o = out[j];
-      const uint32_t isIndel = o.is_indel;
-      const uint32_t nextBp = (isIndel && o.indel[0].type == 'D') ? o.indel[0].len : 0;
-      const uint64_t i = base + list[j];
+      const EvalOut &eo = part[j];
+      rec = rankOf[j];
+      t.dst = rec * 12u + (slot % 12);
+      const uint32_t isIndel = eo.isIndel;
+      const uint32_t nextBp = eo.nextBp;
+      const uint64_t i = base + eo.site;
       const uint64_t bFirst = (i / kBatch) * (uint64_t) kBatch;
       const uint64_t left = M.totalSites - bFirst;
       const uint32_t bn = left < kBatch ? (uint32_t) left : kBatch, idx = (uint32_t) (i - bFirst);
@@ -1128,20 +1113,20 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
         pending = (t.W | t.F | t.R) != 0;
         sbv = sbEmpty; bqv = bqbEmpty;
       }
-      if (!pending) { out[j].sb[k][b] = sbv; out[j].bqb[k][b] = bqv; }
+      if (!pending) { out[rec].sb[k][b] = sbv; out[rec].bqb[k][b] = bqv; }
     }
     BiasTask tb = t; tb.dst |= 0x80000000u;
     bool needS = pending, needB = pending;
     if (pending) {                                  // memoised?
       const uint32_t kS = bias_key(false, t.W, t.F, t.R), kB = bias_key(true, t.W, t.F, t.R);
-      const uint32_t j = slot / 12, k = (slot % 12) >> 2, b = slot & 3;
+      const uint32_t k = (slot % 12) >> 2, b = slot & 3;
       if (kS != 0xFFFFFFFFu) {
         const unsigned long long e = *reinterpret_cast<const volatile unsigned long long *>(cache + bias_slot(kS, cacheMask));
-        if ((uint32_t) e == kS) { out[j].sb[k][b] = __uint_as_float((uint32_t) (e >> 32)); needS = false; }
+        if ((uint32_t) e == kS) { out[rec].sb[k][b] = __uint_as_float((uint32_t) (e >> 32)); needS = false; }
       }
       if (kB != 0xFFFFFFFFu) {
         const unsigned long long e = *reinterpret_cast<const volatile unsigned long long *>(cache + bias_slot(kB, cacheMask));
-        if ((uint32_t) e == kB) { out[j].bqb[k][b] = __uint_as_float((uint32_t) (e >> 32)); needB = false; }
+        if ((uint32_t) e == kB) { out[rec].bqb[k][b] = __uint_as_float((uint32_t) (e >> 32)); needB = false; }
       }
     }
     push(needS, t);                                 // strand test
@@ -1160,16 +1145,16 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
     for (int it = 0; it < kBiasStepsPerRefill; ++it) walk_step(w);
   }
 }
-void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
-                 const EvalParams &P, uint2 *cache, uint32_t cacheMask, gt16_called_site *out, cudaStream_t s) {
-  if (!n) return;
-  const uint32_t chunks = (n * 12u + 31) / 32, perBlock = kBiasThreads / 32;
-  // the walks are long dependent chains: what matters is how many run at once, so spread the chunks
-  // over as many resident warps as the device holds (4 blocks of 8 warps per SM)
+void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
+                 const uint32_t *count, uint32_t cap, const EvalParams &P, uint2 *cache, uint32_t cacheMask,
+                 gt16_called_site *out, int numSMs, cudaStream_t s) {
+  // the walks are long dependent chains: what matters is how many run at once, so spread the chunks over as many
+  // resident warps as the device holds (4 blocks of 8 warps per SM); blocks beyond the device-side count leave at once
+  const uint32_t chunks = (uint32_t) (((uint64_t) cap * 12u + 31) / 32), perBlock = kBiasThreads / 32;
   unsigned grid = (chunks + perBlock - 1) / perBlock;
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid > (unsigned) numSMs * 4u) grid = (unsigned) numSMs * 4u;
   if (grid < 1) grid = 1;
-  k_bias<<<grid, kBiasThreads, 0, s>>>(V, M, base, list, n, P.lnfact, cache, cacheMask, out);
+  k_bias<<<grid, kBiasThreads, 0, s>>>(V, M, base, part, rankOf, count, cap, P.lnfact, cache, cacheMask, out);
 }
 
 // ------------------------------------------------------------------------------ operator seam

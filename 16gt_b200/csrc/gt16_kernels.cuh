@@ -49,11 +49,32 @@ void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint3
 void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t shortcutAlt,
                        uint32_t *mask, int numSMs, cudaStream_t s);
 uint32_t stream_shortcut_bound(const uint32_t *s1, const uint32_t *s2p, const uint32_t *s2q);
+// What the exact evaluator knows about a site it declares a candidate (one per called site, in the order the warps get
+// there): the 16 likelihoods and posteriors it has just computed -- so that the record kernel does not evaluate them a
+// second time -- and what the Fisher-test kernel needs to find the site's neighbours.
+struct EvalOut {
+  double lh[16];      // GenotypeLikelihood
+  double flh[16];     // SnpCallingInfo.flh
+  double pD, bestD, secondD;
+  uint32_t site;      // processed index relative to the call's first site
+  uint8_t genotype;
+  uint8_t isIndel;    // 0, 2 or 3 (SNP_Caller.cpp:228-234)
+  uint8_t nextBp;     // length of the deepest pattern when it is a deletion (:254-265)
+  uint8_t pad;
+};
+static_assert(sizeof(EvalOut) == 288, "EvalOut layout");
+
 // exact predicate for every site flagged in bits [firstSite, firstSite + nSites) of siteMask (firstSite % 32 == 0; bit i =
-// site base + i): clears the bit unless the site is a candidate; *flagged += number of sites evaluated
+// site base + i): clears the bit unless the site is a candidate; *flagged += number of sites evaluated.  Every candidate
+// takes the next free entry of part[] (*count is the number taken; entries beyond `cap` are counted, not written, and
+// kErrRecordOverflow is raised).
 void launch_eval_mask(const SnapView &V, const DevSiteMap &M, uint64_t base, uint32_t firstSite, uint32_t nSites,
                       bool useTables, const DecisionTables &D, const EvalParams &P, uint32_t *siteMask,
-                      uint32_t *errWord, uint32_t *flagged, cudaStream_t s);
+                      uint32_t *errWord, uint32_t *flagged, EvalOut *part, uint32_t *count, uint32_t cap, cudaStream_t s);
+// rankOf[j] = number of set mask bits before part[j].site among sites [firstSite, ...) (its place in the ordered output),
+// list[rank] = part[j].site; blockOffsets = scanned block counts of the same mask range
+void launch_rank(const uint32_t *siteMask, uint32_t firstSite, const uint32_t *blockOffsets, const EvalOut *part,
+                 const uint32_t *count, uint32_t cap, uint32_t *rankOf, uint32_t *list, cudaStream_t s);
 
 // ordered compaction of a bit mask over nItems items
 constexpr int kScanBlock = 256;                       // mask words per block
@@ -64,13 +85,17 @@ void launch_scan_counts(uint32_t *blockCounts, uint32_t nBlocks, uint32_t *total
 void launch_mask_scatter(const uint32_t *mask, uint32_t nItems, const uint32_t *blockOffsets,
                          const uint32_t *values, uint32_t offset, uint32_t *out, cudaStream_t s);
 
-void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
-                       const EvalParams &P, gt16_called_site *out, uint32_t *errWord, cudaStream_t s);
+// full records of the candidates in part[0, min(*count, cap)): out[rankOf[j]] (persistent grid, the count is read on the device)
+void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
+                       const uint32_t *count, uint32_t cap, gt16_called_site *out, uint32_t *errWord, int numSMs,
+                       cudaStream_t s);
 
-// strand-bias / base-quality-bias Fisher tests of the records written by launch_candidates (same list)
+// strand-bias / base-quality-bias Fisher tests of the same candidates, written into out[rankOf[j]].sb / .bqb; may run
+// beside launch_candidates (the two kernels write disjoint fields)
 // cache: (cacheMask + 1) 8-byte {key, result} entries, all bytes 0xFF when empty (see k_bias)
-void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const uint32_t *list, uint32_t n,
-                 const EvalParams &P, uint2 *cache, uint32_t cacheMask, gt16_called_site *out, cudaStream_t s);
+void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
+                 const uint32_t *count, uint32_t cap, const EvalParams &P, uint2 *cache, uint32_t cacheMask,
+                 gt16_called_site *out, int numSMs, cudaStream_t s);
 
 // operator seam kernels
 void launch_op_likelihood(const EvalParams &P, const uint8_t *w, size_t wStride, const uint8_t *ref,

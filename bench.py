@@ -256,12 +256,12 @@ def main():
         pending, completed = [], []          # calls in flight (handle, n); final stats of the completed ones, in call order
 
         def retire(count):
-            """gt16_dev_calls_wait + free for the `count` oldest calls in flight (error word, CUDA-event timings)"""
-            for calls, n in pending[:count]:
+            """gt16_dev_calls_wait + free for the `count` oldest calls in flight (record count, error word, CUDA-event timings)"""
+            for calls in pending[:count]:
                 st = capi.Stats()
                 caller.check(L.gt16_dev_calls_wait(caller.ctx, calls, ctypes.byref(st)))
                 L.gt16_dev_calls_free(calls)
-                completed.append((st, n))
+                completed.append((st, st.called))
             del pending[:count]
 
         def step_resident():
@@ -274,9 +274,8 @@ def main():
                 retire(48)
             calls, st = ctypes.c_void_p(), capi.Stats()
             caller.check(L.gt16_call_sites_device_nowait(caller.ctx, dev, None, 0, 0, sites, ctypes.byref(calls), ctypes.byref(st)))
-            n = L.gt16_dev_calls_count(calls)
-            pending.append((calls, n))
-            return st, n
+            pending.append(calls)
+            return st, None
 
         def complete_resident(stats):
             """complete every step still in flight (after the timed region) and return the final stats of the last len(stats)"""

@@ -165,17 +165,20 @@ int gt16_call_sites(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_reg
 typedef struct gt16_dev_calls gt16_dev_calls;
 int gt16_call_sites_device(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
                            uint64_t site_begin, uint64_t site_end, gt16_dev_calls **out, gt16_stats *stats);
-/* The same call, returning as soon as the number of called sites is known and the rest of the work (records, Fisher
- * tests) has been enqueued: the host prepares the next call while the GPU finishes this one (work of successive calls on
- * one context is stream-ordered, and the records of a call stay valid until the next call on the context, as with
- * gt16_call_sites_device).  stats: sites, called and kernel_launches are final; flagged and the ms_* fields, like any
- * error found on the device, arrive with gt16_dev_calls_wait (also implied by gt16_dev_calls_fetch), which may be called
- * until 128 further calls have been made on the context. */
+/* The same call, returning as soon as the work has been ENQUEUED: the whole call -- streaming pass, exact evaluation,
+ * ordered placement, records, Fisher tests -- is stream-ordered on the context without one host round trip (record
+ * counts live on the device; the kernels behind the evaluator read them there), so the host prepares the next call
+ * while the GPU runs this one.  The records of a call stay valid until the next call on the context, as with
+ * gt16_call_sites_device.  stats at return: sites and kernel_launches; called, flagged, the ms_* fields and any error
+ * found on the device arrive with gt16_dev_calls_wait (implied by gt16_dev_calls_count / _device_ptr / _fetch), which
+ * may be called until 128 further calls have been made on the context.  Record buffers are sized by a bound (one
+ * record per 128 sites + 16,384); a call that finds more is repeated, blocking, inside gt16_dev_calls_wait with
+ * buffers of the size it needs. */
 int gt16_call_sites_device_nowait(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
                                   uint64_t site_begin, uint64_t site_end, gt16_dev_calls **out, gt16_stats *stats);
 int gt16_dev_calls_wait(gt16_ctx *ctx, gt16_dev_calls *calls, gt16_stats *stats);
-uint64_t gt16_dev_calls_count(const gt16_dev_calls *calls);
-const void *gt16_dev_calls_device_ptr(const gt16_dev_calls *calls);   /* gt16_called_site[count] in device memory */
+uint64_t gt16_dev_calls_count(const gt16_dev_calls *calls);            /* completes a pending call first */
+const void *gt16_dev_calls_device_ptr(const gt16_dev_calls *calls);   /* gt16_called_site[count] in device memory, ordered by site */
 int gt16_dev_calls_fetch(gt16_ctx *ctx, const gt16_dev_calls *calls, gt16_calls **out);
 void gt16_dev_calls_free(gt16_dev_calls *calls);
 

@@ -61,6 +61,8 @@ def main():
                      [out + ".snapshot", idx + ".pac", idx + ".ann", idx + ".tra"] + ([region] if region else [])}
             manifest[name] = dict(inputs=files, ini=CONFIGS_ALL[name].get("ini"), rows=txt.count(b"\n") - 1, called=called[0] if called else "",
                                   txt_sha256=hashlib.sha256(txt).hexdigest(), callset_sha256=T.callset_digest(txt)[0])
+            if name in FULL_CONFIGS:
+                manifest[name]["block_sha8"] = T.block_digests(txt)
             print(name, manifest[name]["rows"], "rows")
         finally:
             shutil.rmtree(wd, ignore_errors=True)

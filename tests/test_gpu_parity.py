@@ -120,20 +120,47 @@ def test_full_size_callset_digest(gpu_caller, tmp_path, name, shards):
     size -- 200,000 targets on a 3.1 Gb genome, positions beyond 2^31): the call-set columns of
     every row hash to the digest of the reference's own .txt for the same snapshot, and the number of rows
     whose floating-point columns print differently is bounded."""
-    import hashlib
     idx, out, region = T.regenerate(name, tmp_path)
     inp = T.LoadedInput(idx, out + ".snapshot", region, pinned=0 if name == "stress_full" else 1)   # one of them through the staging ring
     try:
         st = T.call_to_txt(gpu_caller, inp, out + ".txt", shards=shards)
     finally:
         inp.close()
-    m = T.manifest()[name]
     txt = open(out + ".txt", "rb").read()
-    digest, rows = T.callset_digest(txt)
-    assert rows == m["rows"] == sum(s.called for s in st)
-    assert digest == m["callset_sha256"]
-    print("%s: whole .txt %s the reference's" % (name, "IDENTICAL to" if hashlib.sha256(txt).hexdigest() == m["txt_sha256"]
-                                                  else "differs (floating-point columns only) from"))
+    assert T.manifest()[name]["rows"] == sum(s.called for s in st)
+    bad = T.assert_full_size_txt(name, txt)
+    print("%s: whole .txt %s" % (name, "IDENTICAL to the reference's" if not bad else
+                                 "differs from the reference's in %d blocks of %d rows (floating-point print only)" % (bad, T.BLOCK_ROWS)))
+
+
+@pytest.mark.parametrize("name", ["wgs_full", "stress_huge"])
+def test_whole_genome_configs_through_dropin_binary(tmp_path, name):
+    """BASELINE.json configs[2] and configs[4] at FULL size (3.1 Gb, 24 contigs, 370 batches, positions beyond 2^31;
+    25.5 / 26.5 GB snapshots) through the drop-in binary on every visible GPU: .txt identical to the reference's
+    (3,480,483 / 9,235,032 rows; the reference needs 25 / 38 minutes on 8 cores for them)."""
+    import shutil
+    wd = os.environ.get("GT16_HUGE_DIR") or ("/dev/shm" if shutil.disk_usage("/dev/shm").free > (60 << 30) else str(tmp_path))
+    wd = os.path.join(wd, "gt16_huge_" + name)
+    avail_ram = 0
+    for line in open("/proc/meminfo"):
+        if line.startswith("MemAvailable"):
+            avail_ram = int(line.split()[1]) >> 20
+    if shutil.disk_usage(os.path.dirname(wd)).free < (40 << 30) or avail_ram < 70:
+        pytest.skip("needs 40 GiB of scratch space and 70 GiB of RAM")
+    os.makedirs(wd, exist_ok=True)
+    try:
+        idx, out, region = T.regenerate(name, wd, check=False)
+        m = T.manifest()[name]
+        for p in (idx + ".pac", idx + ".ann", idx + ".tra"):
+            assert T.sha256(p) == m["inputs"][os.path.basename(p)], "regenerated input differs from the golden input: " + p
+        r = subprocess.run([T.CLI, "-i", idx, "-o", out, "-v"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1200)
+        assert r.returncode == 0, r.stderr[-2000:]
+        os.remove(out + ".snapshot")
+        assert "Called Entries : %d" % m["rows"] in r.stdout
+        bad = T.assert_full_size_txt(name, open(out + ".txt", "rb").read())
+        print("%s: whole .txt %s" % (name, "IDENTICAL to the reference's" if not bad else "differs in %d blocks" % bad))
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
 
 
 @pytest.mark.parametrize("name", ["wgs_small", "stress_small"])
@@ -259,12 +286,13 @@ def test_device_resident_results(gpu_caller, tmp_path):
         for _ in range(3):
             h, s0 = ctypes.c_void_p(), T.Stats()
             gpu_caller.check(L.gt16_call_sites_device_nowait(gpu_caller.ctx, dev, None, 0, 0, inp.total_sites, ctypes.byref(h), ctypes.byref(s0)))
-            assert L.gt16_dev_calls_count(h) == len(ra) and s0.called == len(ra) and s0.sites == inp.total_sites
+            assert s0.sites == inp.total_sites and s0.kernel_launches > 0      # the count is not known yet: nothing has been waited for
             hs.append(h); sts.append(s0)
         for h in (hs[2], hs[0], hs[1]):
             s1 = T.Stats()
             gpu_caller.check(L.gt16_dev_calls_wait(gpu_caller.ctx, h, ctypes.byref(s1)))
             assert s1.flagged == st.flagged and s1.called == len(ra) and s1.ms_stream > 0 and s1.ms_total_device > 0
+            assert L.gt16_dev_calls_count(h) == len(ra)
             gpu_caller.check(L.gt16_dev_calls_wait(gpu_caller.ctx, h, ctypes.byref(s1)))      # idempotent
         c = ctypes.c_void_p()
         gpu_caller.check(L.gt16_dev_calls_fetch(gpu_caller.ctx, hs[2], ctypes.byref(c)))
