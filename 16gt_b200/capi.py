@@ -96,6 +96,9 @@ def capi():
         "gt16_compute_bias": (i32, [vp, vp, vp, vp, sz, u32, vp, vp]),
         "gt16_snapshot_upload": (i32, [vp, P(View), P(vp)]),
         "gt16_snapshot_release": (None, [vp, vp]),
+        "gt16_snapshot_upload_range": (i32, [vp, P(View), vp, u32, u64, u64, P(vp)]),
+        "gt16_call_sites_host_to": (i32, [vp, P(View), vp, u32, u64, u64, vp, u64, P(u64), P(Stats)]),
+        "gt16_snapshot_read_range": (i32, [cp, i32, u32, u32, P(vp), cp, sz]),
         "gt16_call_sites": (i32, [vp, vp, vp, u32, u64, u64, P(vp), P(Stats)]),
         "gt16_call_sites_host": (i32, [vp, P(View), vp, u32, u64, u64, P(vp), P(Stats)]),
         "gt16_call_sites_device": (i32, [vp, vp, vp, u32, u64, u64, P(vp), P(Stats)]),
@@ -157,28 +160,43 @@ class Caller:
 
 
 class LoadedInput:
-    """index + snapshot read through the library's own readers"""
+    """index + snapshot read through the library's own readers.
 
-    def __init__(self, idx_prefix, snapshot_path, region_bin=None, pinned=1):
+    snapshot_path=None: index (and region list) only.  pos_range=(lo, hi): keep the counters of genome positions
+    [lo, hi) only (gt16_snapshot_read_range: one shard of a sharded genome).  index=<LoadedInput>: share that input's
+    index instead of reading it again."""
+
+    def __init__(self, idx_prefix, snapshot_path, region_bin=None, pinned=1, pos_range=None, index=None):
         L = capi()
         self.L = L
         err = ctypes.create_string_buffer(512)
         self.ix = ctypes.c_void_p()
         self.hs = ctypes.c_void_p()
-        if L.gt16_index_read(idx_prefix.encode(), ctypes.byref(self.ix), err, 512) != 0:
-            raise RuntimeError(err.value.decode())
-        if L.gt16_snapshot_read(snapshot_path.encode(), pinned, ctypes.byref(self.hs), err, 512) != 0:
-            raise RuntimeError(err.value.decode())
-        if pinned:
-            L.gt16_index_pin(self.ix)        # best effort: without a device the reference stays pageable
+        self.owns_index = index is None
+        if index is None:
+            if L.gt16_index_read(idx_prefix.encode(), ctypes.byref(self.ix), err, 512) != 0:
+                raise RuntimeError(err.value.decode())
+            if pinned:
+                L.gt16_index_pin(self.ix)        # best effort: without a device the reference stays pageable
+        else:
+            self.ix = index.ix
+        self.length = L.gt16_index_length(self.ix)
         self.view = View()
-        L.gt16_snapshot_view_of(self.hs, ctypes.byref(self.view))
+        if snapshot_path is not None:
+            if pos_range is None:
+                rc = L.gt16_snapshot_read(snapshot_path.encode(), pinned, ctypes.byref(self.hs), err, 512)
+            else:
+                rc = L.gt16_snapshot_read_range(snapshot_path.encode(), pinned, int(pos_range[0]), int(pos_range[1]),
+                                                ctypes.byref(self.hs), err, 512)
+            if rc != 0:
+                raise RuntimeError(err.value.decode())
+            L.gt16_snapshot_view_of(self.hs, ctypes.byref(self.view))
         n = ctypes.c_uint32()
         self.view.packed_ref = L.gt16_index_packed(self.ix, ctypes.byref(n))
         self.view.packed_ref_words = n.value
         self.regions = None
         self.n_regions = 0
-        self.total_sites = self.view.text_length
+        self.total_sites = self.view.text_length if snapshot_path is not None else self.length
         if region_bin:
             raw = np.fromfile(region_bin, dtype=np.uint32)
             self.n_regions = int(raw[0])
@@ -193,9 +211,9 @@ class LoadedInput:
         if self.hs:
             self.L.gt16_snapshot_free(self.hs)
             self.hs = ctypes.c_void_p()
-        if self.ix:
+        if self.ix and self.owns_index:
             self.L.gt16_index_free(self.ix)
-            self.ix = ctypes.c_void_p()
+        self.ix = ctypes.c_void_p()
 
 
 def call_to_txt(caller, inp, txt_path, shards=1, resident=False):

@@ -85,6 +85,8 @@ struct gt16_ctx {
   uint32_t *hPinned = nullptr;          // the current call's slot: [0] records of a device-resident call, [1] error word, [2] (scan total), [3] sites evaluated exactly
   uint32_t *hCounts = nullptr;          // page-locked copy of dCounts (host-result calls)
   uint32_t recCap = 0;                  // records the candidate buffers (part, rankOf, list, recs, recs2) hold per segment
+  gt16_called_site *extDst = nullptr;   // gt16_call_sites_host_to: the caller's result buffer for the call in progress
+  uint64_t extCap = 0;
   uint32_t recCapWanted = 0;            // set when a call found more candidates than recCap: the retry allocates this many
   bool havePrefill = false, haveDecisions = false, useDecisions = true;
   double balance = 0.01, unbalance = 0.005;
@@ -110,7 +112,10 @@ struct gt16_ctx {
 
 struct gt16_dev_snapshot {
   SnapView v;
-  void *counters = nullptr, *invalid = nullptr, *ovf = nullptr, *ovfBase = nullptr, *pool = nullptr, *ref = nullptr;
+  // `counters` is indexed by genome position but only [winLo, winHi) (+ padding) is backed by memory: the allocation
+  // starts at countersAlloc = counters + winLo (a whole snapshot has the window [0, L))
+  void *counters = nullptr, *countersAlloc = nullptr, *invalid = nullptr, *ovf = nullptr, *ovfBase = nullptr, *pool = nullptr, *ref = nullptr;
+  uint64_t winLo = 0, winHi = 0;
   bool borrowed = false;      // buffers belong to the context's streaming arena
 };
 
@@ -132,10 +137,11 @@ struct gt16_dev_calls {          // records left in the context's record buffer
 };
 
 struct gt16_calls {
-  std::shared_ptr<PinPool> pins;
+  std::shared_ptr<PinPool> pins;      // null: `sites` is the caller's own buffer (gt16_call_sites_host_to)
   gt16_called_site *sites = nullptr;
-  size_t cap = 0;
+  size_t cap = 0;                     // bytes
   uint64_t n = 0;
+  bool tooSmall = false;              // caller's buffer could not take every record
   ~gt16_calls() { if (sites && pins) pins->give(sites, cap); }
 };
 
@@ -523,13 +529,14 @@ static int get_event(gt16_ctx *ctx, size_t k, cudaEvent_t *out) {
 // TMA streaming kernel may copy whole tiles; counters[L] duplicates counters[L-1] (the reference clamps the
 // indel look-ahead of the last position, see decode_indel_refs).
 static int alloc_snapshot(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot *ds,
-                          std::vector<uint32_t> &ovfBase, bool arena) {
+                          std::vector<uint32_t> &ovfBase, bool arena, uint64_t winLo, uint64_t winHi) {
   const uint32_t L = view->text_length;
   size_t nOvf = 0;
   ovfBase.assign(view->n_overflow_regions + 1, 0);
   for (uint32_t r = 0; r < view->n_overflow_regions; ++r) { ovfBase[r] = (uint32_t) nOvf; nOvf += view->overflow_size[r]; }
   ovfBase[view->n_overflow_regions] = (uint32_t) nOvf;
-  const size_t bC = ((size_t) L + kStreamPadSites) * 8, bO = nOvf * 32 + 32, bB = ovfBase.size() * 4,
+  ds->winLo = winLo; ds->winHi = winHi;
+  const size_t bC = ((size_t) (winHi - winLo) + kStreamPadSites) * 8, bO = nOvf * 32 + 32, bB = ovfBase.size() * 4,
                bP = (size_t) view->pool_bytes + 16,
                bR = ((size_t) view->packed_ref_words + kStreamPadSites / 16 + 4) * 4,
                bI = ((((size_t) L + 31) >> 5) + kStreamPadSites / 32 + 4) * 4;
@@ -538,13 +545,14 @@ static int alloc_snapshot(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_de
     CUF(ctx->sCounters.ensure(bC)); CUF(ctx->sOvf.ensure(bO)); CUF(ctx->sOvfBase.ensure(bB)); CUF(ctx->sPool.ensure(bP));
     CUF(ctx->sRef.ensure(bR));
     if (view->invalid_bitmap) CUF(ctx->sInvalid.ensure(bI));
-    ds->counters = ctx->sCounters.p; ds->ovf = ctx->sOvf.p; ds->ovfBase = ctx->sOvfBase.p; ds->pool = ctx->sPool.p;
+    ds->countersAlloc = ctx->sCounters.p; ds->ovf = ctx->sOvf.p; ds->ovfBase = ctx->sOvfBase.p; ds->pool = ctx->sPool.p;
     ds->ref = ctx->sRef.p; ds->invalid = view->invalid_bitmap ? ctx->sInvalid.p : nullptr;
   } else {
-    CUF(cudaMalloc(&ds->counters, bC)); CUF(cudaMalloc(&ds->ovf, bO)); CUF(cudaMalloc(&ds->ovfBase, bB));
+    CUF(cudaMalloc(&ds->countersAlloc, bC)); CUF(cudaMalloc(&ds->ovf, bO)); CUF(cudaMalloc(&ds->ovfBase, bB));
     CUF(cudaMalloc(&ds->pool, bP)); CUF(cudaMalloc(&ds->ref, bR));
     if (view->invalid_bitmap) CUF(cudaMalloc(&ds->invalid, bI));
   }
+  ds->counters = (char *) ds->countersAlloc - (size_t) winLo * 8;     // winLo is a multiple of 4096: alignment is kept
   SnapView &v = ds->v;
   v.counters = (const uint64_t *) ds->counters;
   v.invalid = (const uint32_t *) ds->invalid;
@@ -602,13 +610,21 @@ static int upload_aux(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_sn
       CUF(cudaMemcpyAsync((uint32_t *) ds->invalid + wLo, view->invalid_bitmap + wLo, (wHi - wLo) * 4, cudaMemcpyHostToDevice, s));
     CUF(cudaMemsetAsync((char *) ds->invalid + w * 4, 0, (kStreamPadSites / 32 + 4) * 4, s));
   }
-  CUF(cudaMemsetAsync((char *) ds->counters + (size_t) L * 8, 0, kStreamPadSites * 8, s));
+  CUF(cudaMemsetAsync((char *) ds->counters + (size_t) ds->winHi * 8, 0, kStreamPadSites * 8, s));
   return GT16_OK;
 }
+
+// Counter positions [lo, hi) that calls on the processed range [begin, end) may touch: their own sites; the sites after
+// `end` that the windows / neighbour tests of the last sites walk in processed order when the range does not end on a
+// batch boundary (~360 sites, which in a multi-region list may lie in later regions -- overlapping regions: the highest
+// end so far); 512 positions before the first site (left window margin) and 1,024 after the last (indel look-ahead,
+// right margin).  lo is a multiple of 4096 (TMA source alignment of the biased counter pointer).
+// (touch_range(), below)
 
 // after the counter element L-1 has been copied: counters[L] = counters[L-1]
 static int finish_counters(gt16_ctx *ctx, gt16_dev_snapshot *ds, cudaStream_t s) {
   const uint32_t L = ds->v.L;
+  if (ds->winHi != L) return GT16_OK;
   CUF(cudaMemcpyAsync((char *) ds->counters + (size_t) L * 8, (char *) ds->counters + (size_t) (L - 1) * 8, 8,
                       cudaMemcpyDeviceToDevice, s));
   return GT16_OK;
@@ -626,7 +642,7 @@ extern "C" void gt16_snapshot_release(gt16_ctx *ctx, gt16_dev_snapshot *ds) {
   if (!ds) return;
   if (ctx) cudaSetDevice(ctx->device);
   if (!ds->borrowed) {
-    cudaFree(ds->counters); cudaFree(ds->invalid); cudaFree(ds->ovf); cudaFree(ds->ovfBase); cudaFree(ds->pool); cudaFree(ds->ref);
+    cudaFree(ds->countersAlloc); cudaFree(ds->invalid); cudaFree(ds->ovf); cudaFree(ds->ovfBase); cudaFree(ds->pool); cudaFree(ds->ref);
   }
   delete ds;
 }
@@ -638,7 +654,7 @@ extern "C" int gt16_snapshot_upload(gt16_ctx *ctx, const gt16_snapshot_view *vie
   CU(cudaSetDevice(ctx->device));
   gt16_dev_snapshot *ds = new gt16_dev_snapshot();
   std::vector<uint32_t> ovfBase;
-  rc = alloc_snapshot(ctx, view, ds, ovfBase, false);
+  rc = alloc_snapshot(ctx, view, ds, ovfBase, false, 0, view->text_length);
   if (rc == GT16_OK) rc = upload_aux(ctx, view, ds, ovfBase, ctx->copy, 0, view->text_length - 1);
   if (rc == GT16_OK) {
     const uint32_t L = view->text_length;
@@ -713,6 +729,15 @@ int make_plan(gt16_ctx *ctx, uint32_t L, const gt16_region *regions, uint32_t nR
   return GT16_OK;
 }
 
+void touch_range(const RegionPlan &pl, uint32_t L, uint64_t begin, uint64_t end, uint32_t *loPos, uint32_t *hiPos,
+                 uint64_t *lo, uint64_t *hi) {
+  const uint64_t reachEnd = std::min<uint64_t>(pl.map.totalSites, end + 512);
+  *loPos = pl.ascending ? pl.pos_of(begin) : 0;
+  *hiPos = pl.ascending ? (uint32_t) std::min<uint64_t>(L - 1, pl.hi_pos(reachEnd - 1)) : L - 1;
+  *lo = *loPos > 512 ? (uint64_t) ((*loPos - 512) & ~4095u) : 0;
+  *hi = std::min<uint64_t>((uint64_t) *hiPos + 1024, L);
+}
+
 float ms_between(cudaEvent_t a, cudaEvent_t b) { float m = 0.f; cudaEventElapsedTime(&m, a, b); return m; }
 
 // can [pos(begin), pos(end)) go through the TMA-staged kernel?
@@ -735,6 +760,7 @@ void stream_range(gt16_ctx *ctx, const SnapView &V, const RegionPlan &pl, uint64
 int reserve_results(gt16_ctx *ctx, gt16_calls *calls, uint64_t need, uint64_t hint) {
   const uint64_t want = calls->n + need;
   if (want * sizeof(gt16_called_site) <= calls->cap) return GT16_OK;
+  if (!calls->pins) { calls->tooSmall = true; return GT16_OK; }
   const uint64_t target = std::max<uint64_t>(want + want / 2, hint);
   size_t cap = 0;
   gt16_called_site *fresh = (gt16_called_site *) ctx->pins->take((size_t) target * sizeof(gt16_called_site), &cap);
@@ -867,7 +893,8 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   if (end > pl.map.totalSites) end = pl.map.totalSites;
   if (begin > end) begin = end;
   std::unique_ptr<gt16_calls> calls(new gt16_calls());
-  calls->pins = ctx->pins;
+  if (ctx->extDst) { calls->sites = ctx->extDst; calls->cap = (size_t) ctx->extCap * sizeof(gt16_called_site); }
+  else calls->pins = ctx->pins;
   // an error return must not hand the page-locked result buffer back to the pool while copies into it are queued
   struct DrainD2H {
     gt16_ctx *c; bool armed = true;
@@ -935,29 +962,27 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   std::function<cudaError_t(size_t, const void *, bool)> enqueue_chunk;
   if (resident) {
     V = &resident->v;
+    uint32_t loPos, hiPos; uint64_t lo, hi;
+    touch_range(pl, L, begin, end, &loPos, &hiPos, &lo, &hi);
+    if (lo < resident->winLo || hi > resident->winHi)
+      return fail(ctx, GT16_EINVAL, "site range reaches outside the part of the snapshot that was uploaded (gt16_snapshot_upload_range)");
   } else {
     // counters stream in on the copy stream in genome order (32 MiB chunks, all queued up front)
     std::vector<uint32_t> ovfBase;
-    rc = alloc_snapshot(ctx, hostView, &streamed, ovfBase, true);
-    // positions the call can touch: its own sites, and -- when the range does not end on a batch boundary -- the
-    // sites after `end` that the windows / neighbour tests of its last sites walk in processed order (up to
-    // ~360 sites, which in a multi-region list may lie in later regions); overlapping regions: the highest end so far
-    const uint64_t reachEnd = std::min<uint64_t>(pl.map.totalSites, end + 512);
-    const uint32_t loPos = pl.ascending ? pl.pos_of(begin) : 0;
-    uint32_t hiPos = L - 1;
-    if (pl.ascending) hiPos = (uint32_t) std::min<uint64_t>(L - 1, pl.hi_pos(reachEnd - 1));
+    uint32_t loPos, hiPos;
+    touch_range(pl, L, begin, end, &loPos, &hiPos, &copyLo, &copyHi);
+    rc = alloc_snapshot(ctx, hostView, &streamed, ovfBase, true, copyLo, copyHi);
     if (rc == GT16_OK) rc = upload_aux(ctx, hostView, &streamed, ovfBase, ctx->copy, loPos, hiPos);
     if (rc != GT16_OK) return rc;
     V = &streamed.v;
     // page-locked source: cudaMemcpyAsync straight from the caller's buffer.  Pageable source (what a caller gets
     // from malloc/fread; pinning half a gigabyte costs more than copying it): stager threads move 8 MiB chunks
-    // through a small page-locked ring.
+    // through a small page-locked ring.  (The counters pointer may be biased -- a windowed view -- so it is looked
+    // at where the call starts reading.)
     cudaPointerAttributes pa;
-    staged = !(cudaPointerGetAttributes(&pa, hostView->counters) == cudaSuccess && pa.type == cudaMemoryTypeHost);
+    staged = !(cudaPointerGetAttributes(&pa, hostView->counters + copyLo) == cudaSuccess && pa.type == cudaMemoryTypeHost);
     (void) cudaGetLastError();
     chunkSites = staged ? kStageChunkSites : kCopyChunkSites;
-    copyLo = loPos > 512 ? ((loPos - 512) / chunkSites) * (uint64_t) chunkSites : 0;
-    copyHi = std::min<uint64_t>((uint64_t) hiPos + 1024, L);
     nChunks = (size_t) ((copyHi - copyLo + chunkSites - 1) / chunkSites);
     chunkEv0 = evNext;
     evNext += nChunks;
@@ -1075,10 +1100,12 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
       ctx->recCapWanted = std::max(ctx->recCapWanted, cnt + cnt / 8 + 1024);
     } else if (cnt && !overflow) {
       if ((rc2 = reserve_results(ctx, calls.get(), cnt, resultHint))) return rc2;
-      const gt16_called_site *recs = (const gt16_called_site *) ((sg & 1) ? ctx->recs2.p : ctx->recs.p);
-      CUF(cudaStreamWaitEvent(ctx->d2h, segDone[sg], 0));
-      CUF(cudaMemcpyAsync(calls->sites + calls->n, recs, (size_t) cnt * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->d2h));
-      calls->n += cnt;
+      if (!calls->tooSmall) {
+        const gt16_called_site *recs = (const gt16_called_site *) ((sg & 1) ? ctx->recs2.p : ctx->recs.p);
+        CUF(cudaStreamWaitEvent(ctx->d2h, segDone[sg], 0));
+        CUF(cudaMemcpyAsync(calls->sites + calls->n, recs, (size_t) cnt * sizeof(gt16_called_site), cudaMemcpyDeviceToHost, ctx->d2h));
+        calls->n += cnt;
+      }
       st.called += cnt;
     }
     CUF(cudaEventRecord(done, ctx->d2h));
@@ -1226,6 +1253,56 @@ int gt16_call_sites_host(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt
   int rc = check_view(ctx, view);
   if (rc) return rc;
   return call_with_retry(ctx, view, nullptr, regions, n_regions, site_begin, site_end, out, stats);
+}
+
+int gt16_call_sites_host_to(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt16_region *regions, uint32_t n_regions,
+                            uint64_t site_begin, uint64_t site_end, gt16_called_site *dst, uint64_t dst_capacity,
+                            uint64_t *n_out, gt16_stats *stats) {
+  if (!ctx || !n_out || (!dst && dst_capacity)) return GT16_EINVAL;
+  int rc = check_view(ctx, view);
+  if (rc) return rc;
+  static gt16_called_site none;
+  ctx->extDst = dst ? dst : &none; ctx->extCap = dst_capacity;
+  gt16_calls *calls = nullptr;
+  gt16_stats st;
+  memset(&st, 0, sizeof(st));
+  rc = call_with_retry(ctx, view, nullptr, regions, n_regions, site_begin, site_end, &calls, &st);
+  ctx->extDst = nullptr; ctx->extCap = 0;
+  if (stats) *stats = st;
+  *n_out = st.called;
+  const bool tooSmall = calls && calls->tooSmall;
+  delete calls;
+  if (rc == GT16_OK && tooSmall) return fail(ctx, GT16_EINVAL, "result buffer too small (n_out = records found)");
+  return rc;
+}
+
+int gt16_snapshot_upload_range(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt16_region *regions, uint32_t n_regions,
+                               uint64_t site_begin, uint64_t site_end, gt16_dev_snapshot **out) {
+  if (!ctx || !out) return GT16_EINVAL;
+  int rc = check_view(ctx, view);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t L = view->text_length;
+  RegionPlan pl;
+  if ((rc = make_plan(ctx, L, regions, n_regions, pl))) return rc;
+  if (site_end > pl.map.totalSites) site_end = pl.map.totalSites;
+  if (site_begin >= site_end) return fail(ctx, GT16_EINVAL, "empty site range");
+  uint32_t loPos, hiPos; uint64_t lo, hi;
+  touch_range(pl, L, site_begin, site_end, &loPos, &hiPos, &lo, &hi);
+  gt16_dev_snapshot *ds = new gt16_dev_snapshot();
+  std::vector<uint32_t> ovfBase;
+  rc = alloc_snapshot(ctx, view, ds, ovfBase, false, lo, hi);
+  if (rc == GT16_OK) rc = upload_aux(ctx, view, ds, ovfBase, ctx->copy, loPos, hiPos);
+  for (uint64_t a = lo; a < hi && rc == GT16_OK; a += kCopyChunkSites) {
+    const uint64_t b = std::min<uint64_t>(a + kCopyChunkSites, hi);
+    if (cudaMemcpyAsync((char *) ds->counters + a * 8, view->counters + a, (b - a) * 8, cudaMemcpyHostToDevice, ctx->copy) != cudaSuccess)
+      rc = fail(ctx, GT16_ECUDA, "counter upload failed");
+  }
+  if (rc == GT16_OK) rc = finish_counters(ctx, ds, ctx->copy);
+  if (rc == GT16_OK && cudaStreamSynchronize(ctx->copy) != cudaSuccess) rc = fail(ctx, GT16_ECUDA, "upload synchronize failed");
+  if (rc != GT16_OK) { (void) cudaGetLastError(); gt16_snapshot_release(ctx, ds); return rc; }
+  *out = ds;
+  return GT16_OK;
 }
 
 uint64_t gt16_calls_count(const gt16_calls *c) { return c ? c->n : 0; }

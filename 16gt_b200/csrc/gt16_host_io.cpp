@@ -115,6 +115,7 @@ bool pread_parallel(const char *path, uint64_t off, void *dst, size_t n) {
 
 struct gt16_host_snapshot {
   uint32_t textLength = 0;
+  uint32_t posLo = 0, posHi = 0;           // counters.p holds positions [posLo, posHi) (gt16_snapshot_read_range)
   uint32_t nRegions = 0;
   HostBuf counters, invalid, pool, ovfAll;
   bool hasInvalid = false;
@@ -136,6 +137,11 @@ extern "C" {
 
 // ---- snapshot container (SnapshotHandler.cpp:238-347) -----------------------------------
 int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, char *err, size_t errLen) {
+  return gt16_snapshot_read_range(path, pinned, 0, 0xFFFFFFFFu, out, err, errLen);
+}
+
+int gt16_snapshot_read_range(const char *path, int pinned, uint32_t pos_lo, uint32_t pos_hi, gt16_host_snapshot **out,
+                             char *err, size_t errLen) {
   if (!path || !out) return GT16_EINVAL;
   FILE *f = fopen(path, "rb");
   if (!f) { set_err(err, errLen, "Error opening %s", path); return GT16_EIO; }
@@ -153,17 +159,21 @@ int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, c
     memcpy(&hs->textLength, head + 1, 4);
     const uint32_t L = hs->textLength;
     if (!L) { set_err(err, errLen, "%s: empty snapshot", path); rc = GT16_EDATA; break; }
+    // the window of counters kept in memory (a shard of a sharded genome reads and page-locks its own part only)
+    const uint32_t wLo = pos_lo < L ? pos_lo : 0, wHi = pos_hi > L || pos_hi <= wLo ? L : pos_hi;
+    const size_t W = (size_t) wHi - wLo;
+    hs->posLo = wLo; hs->posHi = wHi;
     // Dense counters of a pageable snapshot are mapped, not read: the only consumer copies them chunk by chunk into
     // page-locked memory on their way to the GPU, so a private copy would just be one more pass over 8 bytes per
     // site of host memory (the slowest resource of the drop-in binary on a 3.1 Gb genome).
-    const bool mapped = (mode & 1) && !pinned && !getenv("GT16_NO_MMAP") && hs->counters.map_file(path, start[1] + 5, (size_t) L * 8);
-    if (!mapped && !hs->counters.alloc((size_t) L * 8 + 16, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
+    const bool mapped = (mode & 1) && !pinned && !getenv("GT16_NO_MMAP") && hs->counters.map_file(path, start[1] + 5 + (uint64_t) wLo * 8, W * 8);
+    if (!mapped && !hs->counters.alloc(W * 8 + 16, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
     if (mapped) {
     } else if (mode & 1) {
-      if (!pread_parallel(path, start[1] + 5, hs->counters.p, (size_t) L * 8)) { set_err(err, errLen, "%s: truncated counters", path); rc = GT16_EIO; break; }
-      memset((char *) hs->counters.p + (size_t) L * 8, 0, 16);
+      if (!pread_parallel(path, start[1] + 5 + (uint64_t) wLo * 8, hs->counters.p, W * 8)) { set_err(err, errLen, "%s: truncated counters", path); rc = GT16_EIO; break; }
+      memset((char *) hs->counters.p + W * 8, 0, 16);
     } else if (mode & 2) {
-      memset(hs->counters.p, 0, (size_t) L * 8 + 16);
+      memset(hs->counters.p, 0, W * 8 + 16);
       uint64_t n = len[1] / 12;
       std::vector<uint8_t> buf((size_t) 12 << 16);
       uint64_t done = 0;
@@ -174,7 +184,8 @@ int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, c
         for (size_t k = 0; k < chunk; ++k) {
           uint32_t pos; memcpy(&pos, &buf[k * 12], 4);
           if (pos >= L) { ok = false; break; }
-          memcpy((char *) hs->counters.p + (size_t) pos * 8, &buf[k * 12 + 4], 8);
+          if (pos < wLo || pos >= wHi) continue;
+          memcpy((char *) hs->counters.p + (size_t) (pos - wLo) * 8, &buf[k * 12 + 4], 8);
         }
         done += chunk;
       }
@@ -238,7 +249,9 @@ int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, c
 
 void gt16_snapshot_view_of(const gt16_host_snapshot *hs, gt16_snapshot_view *v) {
   memset(v, 0, sizeof(*v));
-  v->counters = (const uint64_t *) hs->counters.p;
+  // indexed by genome position whatever the window: with a window the pointer is biased and only positions
+  // [pos_lo, pos_hi) may be dereferenced (calls whose range lies inside the window touch nothing else)
+  v->counters = (const uint64_t *) hs->counters.p - hs->posLo;
   v->text_length = hs->textLength;
   v->invalid_bitmap = hs->hasInvalid ? (const uint32_t *) hs->invalid.p : nullptr;
   v->n_overflow_regions = hs->nRegions;

@@ -150,6 +150,11 @@ typedef struct gt16_stats {
 /* Copy a snapshot to HBM (pinned staging + cudaMemcpyAsync on the copy stream). */
 int gt16_snapshot_upload(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot **out);
 void gt16_snapshot_release(gt16_ctx *ctx, gt16_dev_snapshot *snap);
+/* Copy to HBM what calls on the processed-order range [site_begin, site_end) of `regions` need: that range's counters
+ * (8 B/site) and the side arrays its positions can reach -- one shard of a region-sharded genome.  Calls on the
+ * returned snapshot must stay inside that range (GT16_EINVAL otherwise). */
+int gt16_snapshot_upload_range(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt16_region *regions, uint32_t n_regions,
+                               uint64_t site_begin, uint64_t site_end, gt16_dev_snapshot **out);
 
 /* Call every site of the processed-order range [site_begin, site_end) of the concatenated
  * region list (regions == NULL: the single region [0,text_length), snapshotSnpcaller.cpp
@@ -188,6 +193,13 @@ int gt16_call_sites_host(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt
                          uint32_t n_regions, uint64_t site_begin, uint64_t site_end, gt16_calls **out,
                          gt16_stats *stats);
 
+/* The same with the records written straight into the caller's buffer `dst` (room for dst_capacity records; page-locked
+ * memory -- cudaHostAlloc / cudaHostRegister, e.g. a shared-memory slab that another process reads -- makes the copies
+ * asynchronous DMA).  *n_out = records written; GT16_EINVAL with *n_out = records found when dst is too small. */
+int gt16_call_sites_host_to(gt16_ctx *ctx, const gt16_snapshot_view *view, const gt16_region *regions, uint32_t n_regions,
+                            uint64_t site_begin, uint64_t site_end, gt16_called_site *dst, uint64_t dst_capacity,
+                            uint64_t *n_out, gt16_stats *stats);
+
 uint64_t gt16_calls_count(const gt16_calls *calls);
 const gt16_called_site *gt16_calls_data(const gt16_calls *calls);
 void gt16_calls_free(gt16_calls *calls);
@@ -196,6 +208,13 @@ void gt16_calls_free(gt16_calls *calls);
 typedef struct gt16_host_snapshot gt16_host_snapshot;
 /* readSnpInfoSnapshot (SnapshotHandler.cpp:259-347); buffers are page-locked when pinned != 0 */
 int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, char *err, size_t err_len);
+/* The same with the counters of positions [pos_lo, pos_hi) only (everything else -- overflow arrays, bitmap, pool -- is
+ * read whole): what one shard of a region-sharded genome keeps in (page-locked) memory.  The view's counters pointer
+ * stays indexed by genome position; only the window may be dereferenced, which is all that gt16_call_sites_host /
+ * gt16_snapshot_upload_range touch for a site range whose positions lie at least 4,608 positions inside it (or at the
+ * genome's ends). */
+int gt16_snapshot_read_range(const char *path, int pinned, uint32_t pos_lo, uint32_t pos_hi, gt16_host_snapshot **out,
+                             char *err, size_t err_len);
 void gt16_snapshot_view_of(const gt16_host_snapshot *hs, gt16_snapshot_view *view);  /* packed_ref left NULL */
 void gt16_snapshot_free(gt16_host_snapshot *hs);
 
