@@ -426,6 +426,9 @@ void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint3
 // A site that is NOT a candidate has its bit cleared in the site mask, so that one more ordered
 // compaction of the mask yields the candidate list.
 constexpr int kEvalThreads = 128;
+#ifndef GT16_EVAL_BLOCKS
+#define GT16_EVAL_BLOCKS 8      // resident blocks per SM (register budget 65536 / (128 x blocks)); tools/probes sweeps it: 6 -> 8 = -5 us, 10 = +13 us
+#endif
 constexpr int kEvalQueue = 64;                       // per-warp ring of flagged site indices
 
 // Exact evaluation of up to 32 flagged sites, one per lane (site index i relative to `base`, lanes with !active idle).
@@ -563,7 +566,7 @@ __device__ __forceinline__ void eval_group(const SnapView &V, const DevSiteMap &
 // word w = site 32 w + k relative to `base`).  No compaction pass and no host round trip in front of it: a warp walks
 // chunks of 32 mask words, parks the set bits in a shared-memory ring and evaluates them 32 at a time (flag density is
 // ~0.4 %, so one chunk of 1,024 sites yields ~4 sites).  *flagged += number of sites evaluated.
-__global__ void __launch_bounds__(kEvalThreads, 6) k_eval_mask(SnapView V, DevSiteMap M, uint64_t base, uint32_t wordBegin,
+__global__ void __launch_bounds__(kEvalThreads, GT16_EVAL_BLOCKS) k_eval_mask(SnapView V, DevSiteMap M, uint64_t base, uint32_t wordBegin,
                                                             uint32_t nWords, bool useTables, DecisionTables D, EvalParams P,
                                                             uint32_t *__restrict__ siteMask, uint32_t *errWord,
                                                             uint32_t *flagged, EvalOut *__restrict__ part, uint32_t *count,
@@ -612,7 +615,7 @@ void launch_eval_mask(const SnapView &V, const DevSiteMap &M, uint64_t base, uin
   if (!nSites) return;
   const uint32_t nWords = (nSites + 31) / 32, nChunks = (nWords + 31) / 32;
   unsigned grid = (nChunks + (kEvalThreads / 32) - 1) / (kEvalThreads / 32);
-  if (grid > 148 * 6) grid = 148 * 6;                     // one resident wave (launch bounds: 6 blocks of 128 threads per SM)
+  if (grid > 148 * GT16_EVAL_BLOCKS) grid = 148 * GT16_EVAL_BLOCKS;      // one resident wave (launch bounds)
   k_eval_mask<<<grid, kEvalThreads, 0, s>>>(V, M, base, firstSite / 32, nWords, useTables, D, P, siteMask, errWord, flagged, part, count, cap);
 }
 
@@ -705,11 +708,9 @@ void launch_rank(const uint32_t *siteMask, uint32_t firstSite, const uint32_t *b
 // tests of the record are done by k_bias.  Every leaf routine is the one the serial build_called_site()
 // uses, so the bits are the same.
 constexpr int kCandThreads = 128;
-struct CandWarpSmem {
-  uint32_t sc[2][kWindow + 4];        // window entries: strand count (< 2^20) | valid << 31
-  uint32_t w[2][kWindow + 4];         //                 weighted depth (< 2^18) | flags << 24 (bit0 valid, bit1 C-or-G, bit2 G)
-};
-
+#ifndef GT16_CAND_BLOCKS
+#define GT16_CAND_BLOCKS 8      // resident blocks per SM
+#endif
 // what the window sums need of one position (SNP_Caller.cpp:276-367): strand count, weighted depth, flags
 struct WinLite { uint32_t sc, w, fl; };                      // fl: bit0 valid, bit1 C-or-G seen, bit2 G seen
 
@@ -753,13 +754,111 @@ __device__ __forceinline__ uint32_t region_of(const SiteMap &M, uint64_t i) {   
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }   // one REDUX.SUM
 
-__global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevSiteMap M, uint64_t base,
+// Sums of one 100-entry window of the batch's mwInfo array starting at entry k0 (SNP_Caller.cpp:286-314), by a whole
+// warp: lane l owns the four CONSECUTIVE entries 4 l .. 4 l + 3 (entries 0..100 are needed: the 101st only as the
+// neighbour of the 100th), so the |strand-count difference| of neighbours is an in-lane affair but for one shuffle, the
+// sums are five REDUX and nothing goes through shared memory.  The positions are resolved first, then all the lane's loads
+// are issued together (invalid words + counters: eight independent gathers in flight), then decoded by win_decode.
+// gflags (per lane, not reduced): bit s = entry 4 l + s is valid and saw a G.
+struct WinSums { int strand, delta, depth, gc, valid; uint32_t gflags; };
+__device__ __forceinline__ WinSums window_sums(const SnapView &V, const DevSiteMap &M, const BatchGeom &B, uint32_t k0,
+                                               uint32_t kLo, uint32_t kHi, bool multi, uint32_t lane) {
+  uint32_t pp[4], inv = 0; bool ex[4];                        // inv: bit 31 - s = entry 4 l + s sits on an invalid position
+  uint32_t iw[4] = {0u, 0u, 0u, 0u}; uint64_t cc[4];
+  if (!multi && k0 >= kLo && k0 + 104u <= kHi) {
+    // the common case -- one region, window away from the batch's ends: 101 consecutive positions, all of them there;
+    // the lane's four invalid bits come out of two bitmap words with one funnel shift
+    const uint32_t p0 = B.amb0 - (uint32_t) kWindow + k0 + 4u * lane;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) { pp[it] = p0 + it; ex[it] = 4u * lane + it <= (uint32_t) kWindow; }
+    if (V.invalid && ex[0]) inv = __funnelshift_l(__ldg(V.invalid + (p0 >> 5) + 1), __ldg(V.invalid + (p0 >> 5)), p0 & 31u);
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+      cc[it] = ex[it] ? __ldg(reinterpret_cast<const unsigned long long *>(V.counters) + pp[it]) : 0ull;
+  } else {
+    uint32_t reg = 0;                                         // region of the first in-batch entry (exome): a lower bound
+    if (multi) reg = region_of(M.m, B.first + (k0 >= (uint32_t) kWindow ? k0 - kWindow : 0u));
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const uint32_t t = 4u * lane + it, k = k0 + t;
+      ex[it] = t <= (uint32_t) kWindow && k >= kLo && k < kHi;
+      pp[it] = B.amb0 - (uint32_t) kWindow + k;
+      if (multi && ex[it] && k >= (uint32_t) kWindow) {
+        if (k < (uint32_t) kWindow + B.n) {
+          const uint64_t q = B.first + (k - (uint32_t) kWindow);
+          while (reg + 1 < M.m.nRegions && M.m.regFirst[reg + 1] <= q) ++reg;
+          pp[it] = M.m.regStart[reg] + (uint32_t) (q - M.m.regFirst[reg]);
+        } else {
+          pp[it] = B.ambLast + 1u + (k - (uint32_t) kWindow - B.n);
+        }
+      }
+      ex[it] = ex[it] && pp[it] < V.L;
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      iw[it] = (ex[it] && V.invalid) ? __ldg(V.invalid + (pp[it] >> 5)) : 0u;
+      cc[it] = ex[it] ? __ldg(reinterpret_cast<const unsigned long long *>(V.counters) + pp[it]) : 0ull;
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) inv |= ((iw[it] >> (31 - (pp[it] & 31))) & 1u) << (31 - it);
+  }
+  WinLite e[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    e[it].sc = e[it].w = e[it].fl = 0;
+    if (ex[it] && !((inv >> (31 - it)) & 1u)) e[it] = win_decode(V, pp[it], cc[it]);
+  }
+  // the neighbour of the lane's last entry is the next lane's first one (strand counts stay below 2^31)
+  const uint32_t nextLane = __shfl_down_sync(0xffffffffu, e[0].sc | (e[0].fl << 31), 1);
+  int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+  WinSums r; r.gflags = 0;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const uint32_t nsc = it < 3 ? e[it < 3 ? it + 1 : 3].sc : (nextLane & 0x7FFFFFFFu);
+    const bool nvalid = it < 3 ? (e[it < 3 ? it + 1 : 3].fl & 1u) != 0 : (nextLane >> 31) != 0;
+    if ((e[it].fl & 5u) == 5u) r.gflags |= 1u << it;
+    if ((e[it].fl & 1u) && 4u * lane + it < (uint32_t) kWindow) {
+      const uint32_t sc = e[it].sc;
+      a0 += (int) sc; a1 += (int) e[it].w; a2 += (int) ((e[it].fl >> 1) & 1u); a3 += 1;
+      if (nvalid) a4 += (int) (sc > nsc ? sc - nsc : nsc - sc);
+    }
+  }
+  r.strand = warp_sum(a0); r.depth = warp_sum(a1); r.gc = warp_sum(a2) & 0xFF;      // gcSum / validSum are unsigned char
+  r.valid = warp_sum(a3) & 0xFF; r.delta = warp_sum(a4);
+  return r;
+}
+
+// rare paths of the record kernel, kept out of line so that the loop the common record walks stays small
+__device__ __noinline__ uint32_t left_g_near_batch_start(const SnapView &V, const DevSiteMap &M, const BatchGeom &B, uint32_t idx,
+                                                         uint32_t lane) {
+  bool gbit = false;
+  if (lane < 3) { WinEntry e = window_entry(V, M.m, B, (uint64_t) idx - 3 + lane); gbit = e.valid && e.g; }
+  return __popc(__ballot_sync(0xffffffffu, gbit));
+}
+__device__ __noinline__ void write_indel_patterns(const SnapView &V, gt16_called_site &o, const PatRef &d0, const PatRef &d1,
+                                                  uint32_t isIndel, uint32_t lane) {
+  for (int k = 0; k < 2; ++k) {                                         // indel pattern bytes, two per lane
+    gt16_indel &d = o.indel[k];
+    const PatRef &pr = k ? d1 : d0;
+    const bool have = k == 0 || isIndel == 3;
+    const uint32_t nb = ((uint32_t) pr.len + 3) / 4;
+    for (uint32_t bIdx = lane; bIdx < 64; bIdx += 32) {
+      uint8_t v = 0;
+      if (have && bIdx < nb) {
+        if (pr.type == 'I') v = pr.seq[bIdx];
+        else for (uint32_t q = bIdx * 4; q < bIdx * 4 + 4 && q < pr.len; ++q) v |= (uint8_t) (ref_base(V, pr.delPos + q) << ((q & 3) << 1));
+      }
+      d.seq[bIdx] = v;
+    }
+    if (lane == 0) { d.type = have ? pr.type : (uint8_t) '*'; d.len = have ? pr.len : 0; d.hq = have ? pr.hq : 0; d.lq = have ? pr.lq : 0; }
+  }
+}
+
+__global__ void __launch_bounds__(kCandThreads, GT16_CAND_BLOCKS) k_candidates(SnapView V, DevSiteMap M, uint64_t base,
                                                              const EvalOut *__restrict__ part,
                                                              const uint32_t *__restrict__ rankOf,
                                                              const uint32_t *__restrict__ count, uint32_t cap,
                                                              gt16_called_site *__restrict__ out, uint32_t *errWord) {
-  __shared__ CandWarpSmem smAll[kCandThreads / 32];
-  CandWarpSmem &sm = smAll[threadIdx.x >> 5];
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warpsTotal = gridDim.x * (kCandThreads / 32);
   const uint32_t n = *count < cap ? *count : cap;
@@ -813,125 +912,76 @@ __global__ void __launch_bounds__(kCandThreads, 8) k_candidates(SnapView V, DevS
     const uint32_t idx = (uint32_t) (i - B.first);
 
     // -- windows (reference's un-offset mwInfo indexing)                                 :276-367
-    // Four entries per lane and side.  The positions are resolved first, then all the lane's loads of a side are
-    // issued together (invalid words + counters: eight independent gathers in flight instead of one), then decoded
-    // by win_decode -- only what the window sums need of a position.
-    const bool haveLeft = idx >= (uint32_t) kWindow;
-    const bool multi = M.m.nRegions > 1;
     // entry k of the batch's mwInfo array (k < n + 200; the cases of window_entry()): the left margin [0, 100) holds
     // the positions before the batch's first site -- filled only when amb0 > 100 (VariantCaller.cpp:713-729) --, then
     // the n sites of the batch, then 99 positions after its last site as far as the genome goes (:731-747).  In a
     // single-region call all three are one run of consecutive positions.
+    const bool haveLeft = idx >= (uint32_t) kWindow;
+    const bool multi = M.m.nRegions > 1;
     const uint32_t kLo = B.amb0 > (uint32_t) kWindow ? 0u : (uint32_t) kWindow;
     const uint32_t past = V.L - 1u - B.ambLast;
     const uint32_t kHi = (uint32_t) kWindow + B.n + (past < (uint32_t) kWindow - 1u ? past : (uint32_t) kWindow - 1u);
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      if (side == 0 && !haveLeft) continue;
-      const uint32_t k0 = side == 0 ? idx - (uint32_t) kWindow : idx + nextBp;
-      uint32_t reg = 0;                                       // region of the first in-batch entry (exome): a lower bound
-      if (multi) reg = region_of(M.m, B.first + (k0 >= (uint32_t) kWindow ? k0 - kWindow : 0u));
-      uint32_t pp[4]; bool ex[4];
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const uint32_t t = lane + 32u * it, k = k0 + t;
-        ex[it] = t <= (uint32_t) kWindow && k >= kLo && k < kHi;
-        pp[it] = B.amb0 - (uint32_t) kWindow + k;
-        if (multi && ex[it] && k >= (uint32_t) kWindow) {
-          if (k < (uint32_t) kWindow + B.n) {
-            const uint64_t q = B.first + (k - (uint32_t) kWindow);
-            while (reg + 1 < M.m.nRegions && M.m.regFirst[reg + 1] <= q) ++reg;
-            pp[it] = M.m.regStart[reg] + (uint32_t) (q - M.m.regFirst[reg]);
-          } else {
-            pp[it] = B.ambLast + 1u + (k - (uint32_t) kWindow - B.n);
-          }
-        }
-        ex[it] = ex[it] && pp[it] < V.L;
-      }
-      uint32_t iw[4]; uint64_t cc[4];
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        iw[it] = (ex[it] && V.invalid) ? __ldg(V.invalid + (pp[it] >> 5)) : 0u;
-        cc[it] = ex[it] ? __ldg(reinterpret_cast<const unsigned long long *>(V.counters) + pp[it]) : 0ull;
-      }
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const uint32_t t = lane + 32u * it;
-        if (t > (uint32_t) kWindow) continue;
-        WinLite e; e.sc = e.w = e.fl = 0;
-        if (ex[it] && !((iw[it] >> (31 - (pp[it] & 31))) & 1u)) e = win_decode(V, pp[it], cc[it]);
-        sm.sc[side][t] = e.sc | (e.fl << 31); sm.w[side][t] = e.w | (e.fl << 24);
-      }
-    }
-    __syncwarp();
-    int strandSum[2] = {0, 0}, deltaSum[2] = {0, 0}, depthSum[2] = {0, 0}, gcSum[2] = {0, 0}, validSum[2] = {0, 0};
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      if (side == 0 && !haveLeft) continue;
-      int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-      for (uint32_t t = lane; t < (uint32_t) kWindow; t += 32) {
-        const uint32_t sv = sm.sc[side][t];
-        if (sv >> 31) {
-          const uint32_t sc = sv & 0x7FFFFFFFu, nv = sm.sc[side][t + 1], sn = nv & 0x7FFFFFFFu, wf = sm.w[side][t];
-          a0 += (int) sc; a1 += (int) (wf & 0xFFFFFFu); a2 += (int) ((wf >> 25) & 1); a3 += 1;
-          if (nv >> 31) a4 += (int) (sc > sn ? sc - sn : sn - sc);
-        }
-      }
-      strandSum[side] = warp_sum(a0); depthSum[side] = warp_sum(a1); gcSum[side] = warp_sum(a2) & 0xFF;
-      validSum[side] = warp_sum(a3) & 0xFF; deltaSum[side] = warp_sum(a4);
+    WinSums wl, wr;
+    wl.strand = wl.delta = wl.depth = wl.gc = wl.valid = 0; wl.gflags = 0;
+    wr = wl;
+#pragma unroll 1
+    for (int side = haveLeft ? 0 : 1; side < 2; ++side) {              // one copy of the window code (instruction cache)
+      const WinSums w = window_sums(V, M, B, side ? idx + nextBp : idx - (uint32_t) kWindow, kLo, kHi, multi, lane);
+      if (side) wr = w; else wl = w;
     }
     // G counts of the three sites before / after (:355-367): mwInfo entries idx-3..idx-1 and idx+nextBp..+2, i.e.
-    // entries 97..99 of the left window and 0..2 of the right one (valid bit 0, G bit 2)
-    bool gbit = false;
-    if (lane < 3) {
-      if (haveLeft) gbit = ((sm.w[0][kWindow - 3 + lane] >> 24) & 5u) == 5u;
-      else if (idx >= 3) { WinEntry e = window_entry(V, M.m, B, (uint64_t) idx - 3 + lane); gbit = e.valid && e.g; }
-    } else if (lane < 6) gbit = ((sm.w[1][lane - 3] >> 24) & 5u) == 5u;
-    const uint32_t gb = __ballot_sync(0xffffffffu, gbit);
-    __syncwarp();
+    // entries 97..99 of the left window (lane 24, slots 1..3) and 0..2 of the right one (lane 0, slots 0..2)
+    uint32_t lg = __popc(__shfl_sync(0xffffffffu, wl.gflags, 24) & 0xEu);
+    const uint32_t rg = __popc(__shfl_sync(0xffffffffu, wr.gflags, 0) & 0x7u);
+    if (!haveLeft && idx >= 3) lg = left_g_near_batch_start(V, M, B, idx, lane);   // the first 100 sites of a batch: no left window
     const uint32_t run = polyrun(V, p);
 
     // -- record
-    for (int k = 0; k < 2; ++k) {                                       // indel pattern bytes, two per lane
-      gt16_indel &d = o.indel[k];
-      const PatRef &pr = k ? d1 : d0;
-      const bool have = isIndel && (k == 0 || isIndel == 3);
-      const uint32_t nb = ((uint32_t) pr.len + 3) / 4;
-      for (uint32_t bIdx = lane; bIdx < 64; bIdx += 32) {
-        uint8_t v = 0;
-        if (have && bIdx < nb) {
-          if (pr.type == 'I') v = pr.seq[bIdx];
-          else for (uint32_t q = bIdx * 4; q < bIdx * 4 + 4 && q < pr.len; ++q) v |= (uint8_t) (ref_base(V, pr.delPos + q) << ((q & 3) << 1));
-        }
-        d.seq[bIdx] = v;
-      }
-      if (lane == 0) { d.type = have ? pr.type : (uint8_t) '*'; d.len = have ? pr.len : 0; d.hq = have ? pr.hq : 0; d.lq = have ? pr.lq : 0; }
+    static_assert(offsetof(gt16_called_site, indel) % 4 == 0 && sizeof(gt16_indel) == 70, "indel patterns are written as 35 words");
+    if (!isIndel) {
+      // two empty patterns {'*', 0, 0, 0, zeros}: byte 0 and byte 70 of the 140 hold '*'
+      uint32_t *iw = reinterpret_cast<uint32_t *>(o.indel);
+      iw[lane] = lane == 0 ? 0x2Au : (lane == 17 ? 0x2A0000u : 0u);
+      if (lane < 3) iw[32 + lane] = 0u;
+    } else {
+      write_indel_patterns(V, o, d0, d1, isIndel, lane);
     }
-    if (lane == 0) {
-      o.amb = p; o.ref = (uint8_t) ref; o.genotype = (uint8_t) genotype; o.is_indel = isIndel;
-      o.pD = eo.pD; o.bestD = eo.bestD; o.secondD = eo.secondD;
-      float avgSC[2] = {0.f, 0.f}, avgD[2] = {0.f, 0.f};
-      if (deltaSum[0] | deltaSum[1]) o.rpb = (deltaSum[0] - deltaSum[1] + 0.0f) / (deltaSum[0] + deltaSum[1]);
-      else o.rpb = 0.0f;
-      if (validSum[0]) { o.lgc = (gcSum[0] + 0.0f) / validSum[0]; avgSC[0] = (strandSum[0] + 0.0f) / validSum[0]; avgD[0] = (depthSum[0] + 0.0f) / validSum[0]; }
-      else o.lgc = 0.0f;
-      if (validSum[1]) { o.rgc = (gcSum[1] + 0.0f) / validSum[1]; avgSC[1] = (strandSum[1] + 0.0f) / validSum[1]; avgD[1] = (depthSum[1] + 0.0f) / validSum[1]; }
-      else o.rgc = 0.0f;
-      o.lq = 0.f; o.rq = 0.f; o.rq_assigned = 0;
-      if (fabsf(avgSC[0] + avgSC[1]) > FLT_EPSILON) {
-        o.asc = (avgSC[0] - avgSC[1]) / (avgSC[0] + avgSC[1]);
-        o.lq = fabsf(avgSC[0]) > FLT_EPSILON ? avgD[0] / avgSC[0] : 0.0f;
-        o.rq = fabsf(avgSC[1]) > FLT_EPSILON ? avgD[1] / avgSC[1] : 0.0f;
-        o.rq_assigned = 1;
-      } else {
-        o.asc = 0.0f;
+    // window features (:316-353): ten float divisions, spread over the lanes instead of lined up on one.  Round 1, lanes
+    // 0..6: rpb, lgc, avgSC[0], avgD[0], rgc, avgSC[1], avgD[1] -- (int + 0.0f) / int, IEEE division, the same bits on
+    // any lane; round 2, lanes 0..2: asc, lq, rq.  rpb/lgc/rgc and asc/lq/rq are six consecutive floats of the record.
+    {
+      const bool right = lane >= 4;
+      const int sel = right ? (int) lane - 3 : (int) lane;             // sel 1..3: gc, strand, depth
+      int num = right ? wr.gc : wl.gc, den = right ? wr.valid : wl.valid;
+      if (sel == 2) num = right ? wr.strand : wl.strand;
+      if (sel == 3) num = right ? wr.depth : wl.depth;
+      if (lane == 0) { num = wl.delta - wr.delta; den = wl.delta + wr.delta; }
+      float q1 = 0.0f;
+      if (lane < 7 && den != 0) q1 = (num + 0.0f) / den;
+      const float avgSC0 = __shfl_sync(0xffffffffu, q1, 2), avgD0 = __shfl_sync(0xffffffffu, q1, 3);
+      const float avgSC1 = __shfl_sync(0xffffffffu, q1, 5), avgD1 = __shfl_sync(0xffffffffu, q1, 6);
+      const bool assigned = fabsf(avgSC0 + avgSC1) > FLT_EPSILON;
+      float a = avgSC0 - avgSC1, bden = avgSC0 + avgSC1;
+      bool ok = assigned;
+      if (lane == 1) { a = avgD0; bden = avgSC0; ok = assigned && fabsf(avgSC0) > FLT_EPSILON; }
+      if (lane == 2) { a = avgD1; bden = avgSC1; ok = assigned && fabsf(avgSC1) > FLT_EPSILON; }
+      float q2 = 0.0f;
+      if (lane < 3 && ok) q2 = a / bden;
+      float *feat = &o.rpb;                                             // rpb, lgc, rgc, asc, lq, rq
+      if (lane == 0) { feat[0] = q1; feat[3] = q2; }
+      if (lane == 1) { feat[1] = q1; feat[4] = q2; }
+      if (lane == 2) feat[5] = q2;
+      if (lane == 4) feat[2] = q1;
+      if (lane == 0) {
+        o.amb = p; o.ref = (uint8_t) ref; o.genotype = (uint8_t) genotype; o.is_indel = isIndel;
+        o.rq_assigned = assigned ? 1 : 0;
+        o.pD = eo.pD; o.bestD = eo.bestD; o.secondD = eo.secondD;
+        o.lg = (uint8_t) lg; o.rg = (uint8_t) rg;
+        o.polyrun = (uint16_t) run;
+        o.total_hq = ii.hqTotal; o.total_lq = ii.lqTotal;
+        if (err) atomicOr(errWord, err);
       }
-      o.lg = (uint8_t) __popc(gb & 0x7u); o.rg = (uint8_t) __popc(gb & 0x38u);
-      o.polyrun = (uint16_t) run;
-      o.total_hq = ii.hqTotal; o.total_lq = ii.lqTotal;
-      if (err) atomicOr(errWord, err);
     }
-    __syncwarp();
   }
 }
 void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
@@ -940,7 +990,7 @@ void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, co
   // persistent grid: the number of records is only known on the device; 8 blocks of 4 warps per SM (launch bounds), and a
   // small call (cap is a bound on its records) does not need more warps than records
   unsigned grid = (cap + (kCandThreads / 32) - 1) / (kCandThreads / 32);
-  const unsigned full = (unsigned) numSMs * 8u;
+  const unsigned full = (unsigned) numSMs * GT16_CAND_BLOCKS;
   if (grid > full) grid = full;
   k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, part, rankOf, count, cap, out, errWord);
 }
