@@ -96,7 +96,7 @@ struct gt16_ctx {
   uint2 *biasCache = nullptr;             // memoised Fisher tests (k_bias), kBiasCacheEntries entries
   int numSMs = 148;
   // persistent scratch of the fused path
-  DevBuf mask, counts, part, rankOf, list, recs, recs2, planStart, planFirst;
+  DevBuf mask, counts, part, rankOf, list, recs, recs2, planStart, planFirst, planTile;
   std::vector<uint32_t> lastPlanStart;   // host copy of what planStart / planFirst hold (make_plan)
   std::vector<uint64_t> lastPlanFirst;
   DevBuf sCounters, sInvalid, sOvf, sOvfBase, sPool, sRef;      // streamed (host-fed) snapshot
@@ -288,7 +288,7 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   cudaFree(ctx->biasCache);
   if (ctx->hPinnedRing) cudaFreeHost(ctx->hPinnedRing);
   if (ctx->hCounts) cudaFreeHost(ctx->hCounts);
-  for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->part, &ctx->rankOf, &ctx->list, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst,
+  for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->part, &ctx->rankOf, &ctx->list, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst, &ctx->planTile,
                     &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
   for (auto &pool : ctx->evPool) for (auto e : pool) cudaEventDestroy(e);
   if (ctx->stagePin) cudaFreeHost(ctx->stagePin);
@@ -718,6 +718,21 @@ int make_plan(gt16_ctx *ctx, uint32_t L, const gt16_region *regions, uint32_t nR
     CUF(ctx->planFirst.ensure(pl.first.size() * 8));
     CUF(cudaMemcpyAsync(ctx->planStart.p, pl.start.data(), pl.start.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
     CUF(cudaMemcpyAsync(ctx->planFirst.p, pl.first.data(), pl.first.size() * 8, cudaMemcpyHostToDevice, ctx->compute));
+    if (pl.start.size() > 1) {
+      // cursor of the streaming kernel: the region that holds processed site 256 t
+      const size_t nTiles = (size_t) ((acc + kCursorTile - 1) / kCursorTile);
+      std::vector<uint32_t> tile(nTiles + 1);
+      size_t r = 0;
+      for (size_t t = 0; t < nTiles; ++t) {
+        const uint64_t i = (uint64_t) t * kCursorTile;
+        while (r + 1 < pl.start.size() && pl.first[r + 1] <= i) ++r;
+        tile[t] = (uint32_t) r;
+      }
+      tile[nTiles] = (uint32_t) (pl.start.size() - 1);
+      CUF(ctx->planTile.ensure(tile.size() * 4));
+      CUF(cudaMemcpyAsync(ctx->planTile.p, tile.data(), tile.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
+      CUF(cudaStreamSynchronize(ctx->compute));
+    }
     CUF(cudaStreamSynchronize(ctx->compute));     // the host vectors may be pageable
     ctx->lastPlanStart = pl.start;
     ctx->lastPlanFirst = pl.first;
@@ -725,6 +740,7 @@ int make_plan(gt16_ctx *ctx, uint32_t L, const gt16_region *regions, uint32_t nR
   pl.map.m.regStart = (const uint32_t *) ctx->planStart.p;
   pl.map.m.regFirst = (const uint64_t *) ctx->planFirst.p;
   pl.map.m.nRegions = (uint32_t) pl.start.size();
+  pl.map.m.tileReg = pl.start.size() > 1 ? (const uint32_t *) ctx->planTile.p : nullptr;
   pl.map.totalSites = acc;
   return GT16_OK;
 }
@@ -800,8 +816,9 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
   launch_eval_mask(V, pl.map, begin, off, n, usedTables, D, P, maskAll, ctx->errWord, ctx->dFlagged, part, dCount, cap, ctx->compute);
   CUF(cudaEventRecord(ev[1], ctx->compute));
   launch_mask_count(maskAll + off / 32, n, counts, ctx->compute);
-  launch_scan_counts(counts, scan_blocks(n), ctx->dTotal, ctx->compute);
-  launch_rank(maskAll, off, counts, part, dCount, cap, rankOf, list, ctx->compute);
+  uint32_t *chunkOffsets = counts + scan_blocks(n) + 1;        // behind the block counts (counts.ensure)
+  launch_scan_counts(counts, scan_blocks(n), chunkOffsets, ctx->dTotal, ctx->compute);
+  launch_rank(maskAll, off, counts, chunkOffsets, part, dCount, cap, rankOf, list, ctx->compute);
   CUF(cudaEventRecord(ev[2], ctx->compute));
   // record buffers alternate between segments: a segment's copy home may still be in flight while the next one is written
   gt16_called_site *recs = (gt16_called_site *) ((seg & 1) ? ctx->recs2.p : ctx->recs.p);
@@ -812,7 +829,7 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
   CUF(cudaStreamWaitEvent(ctx->aux, ev[2], 0));
   launch_candidates(V, pl.map, begin, part, rankOf, dCount, cap, recs, ctx->errWord, ctx->numSMs, ctx->compute);
   launch_bias(V, pl.map, begin, part, rankOf, dCount, cap, P, ctx->biasCache, kBiasCacheEntries - 1, recs, ctx->numSMs, ctx->aux);
-  ctx->launches += 6;
+  ctx->launches += 7;
   CUF(cudaEventRecord(auxDone, ctx->aux));
   CUF(cudaStreamWaitEvent(ctx->compute, auxDone, 0));         // part / rankOf / list are reused by the next segment
   CUF(cudaEventRecord(ev[3], ctx->compute));
@@ -929,7 +946,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   if (const char *e = getenv("GT16_SEG_BATCHES")) { int v = atoi(e); if (v >= 1 && v <= 64) segBatches = (uint32_t) v; }
   const uint64_t segSites = devOutHandle ? (uint64_t) n : (uint64_t) segBatches * kBatch;
   const uint64_t segLongest = std::min<uint64_t>(segSites, n);
-  CUF(ctx->counts.ensure(((size_t) scan_blocks((uint32_t) segLongest) + 1) * 4));
+  CUF(ctx->counts.ensure(((size_t) scan_blocks((uint32_t) segLongest) + 1 + 1024) * 4));    // block counts + chunk offsets
   {
     const uint32_t capWant = std::max(std::max(ctx->recCap, ctx->recCapWanted), record_bound(segLongest));
     ctx->recCap = capWant;

@@ -602,9 +602,21 @@ struct SiteMap {
   const uint32_t *regStart;     // [nRegions] start position of each region
   const uint64_t *regFirst;     // [nRegions + 1] processed index of each region's first site
   uint32_t nRegions;
+  const uint32_t *tileReg;      // cursor for the streaming kernel, may be null: [ceil(total / 256) + 1] region that holds
+                                // processed site 256 t (the last entry repeats the last region)
 };
+constexpr uint32_t kCursorTile = 256;
 GT16_HD uint32_t pos_of(const SiteMap &M, uint64_t i) {
   uint32_t lo = 0, hi = M.nRegions;              // last region with regFirst <= i
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (M.regFirst[mid] <= i) lo = mid; else hi = mid; }
+  return M.regStart[lo] + (uint32_t) (i - M.regFirst[lo]);
+}
+
+// the same through the per-tile cursor: the search is confined to the regions that overlap site i's tile of 256 processed
+// sites (one or two for exome targets), not the whole list
+GT16_HD uint32_t pos_of_cursor(const SiteMap &M, uint64_t i) {
+  const uint64_t t = i / kCursorTile;
+  uint32_t lo = M.tileReg[t], hi = M.tileReg[t + 1] + 1;      // last region with regFirst <= i lies in [lo, hi)
   while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (M.regFirst[mid] <= i) lo = mid; else hi = mid; }
   return M.regStart[lo] + (uint32_t) (i - M.regFirst[lo]);
 }

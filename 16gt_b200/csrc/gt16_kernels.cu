@@ -108,18 +108,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
+#ifndef GT16_WAIT_HINT
+#define GT16_WAIT_HINT 1000      // ns; tools/probes: polling with __nanosleep 0.1291 ms, hint 1 us 0.1280, hint 10 ms 0.1284
+#endif
+// try_wait with a suspend-time hint: the warp is parked by the hardware until the phase completes (or the hint runs out)
+// instead of polling -- waiting warps must not take issue slots from working ones
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(40);                             // waiting warps must not take issue slots from working ones (0..200 ns: no difference)
-    if (++spins > (1u << 22)) __trap();          // a lost bulk copy must not hang the device
-  }
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t) GT16_WAIT_HINT) : "memory");
+    if (!ok && ++spins > (1u << 22)) __trap();     // a lost bulk copy must not hang the device
+  } while (!ok);
 }
 
 // Streaming classification of a dense, single-region range of positions [pBeg, pEnd) -- the HBM-bound
@@ -368,7 +368,8 @@ __global__ void __launch_bounds__(256) k_stream(SnapView V, DevSiteMap M, uint64
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool flag = false;
   if (i < n) {
-    uint32_t p = site_pos(M, first + i);
+    // multi-region (exome) lists: the region is found through the per-tile cursor, not by a search over the whole list
+    const uint32_t p = (M.m.nRegions > 1 && M.m.tileReg) ? pos_of_cursor(M.m, first + i) : site_pos(M, first + i);
     if (!kUseTables) {
       uint32_t e = 0;
       flag = site_is_candidate(V, P, p, e);
@@ -640,42 +641,53 @@ void launch_mask_count(const uint32_t *mask, uint32_t nItems, uint32_t *blockCou
   if (nb) k_mask_count<<<nb, kScanBlock, 0, s>>>(mask, (nItems + 31) / 32, blockCounts);
 }
 
-// in-place exclusive scan of up to a few 10^5 block counts by one CTA; total -> *total
-__global__ void __launch_bounds__(1024) k_scan_counts(uint32_t *counts, uint32_t n, uint32_t *total) {
-  __shared__ uint32_t warpTot[32];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
+// Exclusive scan of the block counts in two levels, so that a whole-genome call (380 K blocks) costs what a chromosome
+// costs: k_scan_chunks -- one CTA per chunk of 1024 counts, exclusive scan in place + the chunk's total --, then
+// k_scan_top -- one CTA scans the (at most 512) chunk totals.  A block's offset is counts[b] + chunkOffsets[b >> 10].
+__device__ __forceinline__ uint32_t cta_exclusive_scan_1024(uint32_t v, uint32_t *warpTot, uint32_t *total) {
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+  if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = x;
   __syncthreads();
-  for (uint32_t base = 0; base < n; base += 1024) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t v = i < n ? counts[i] : 0, x = v;
+  if (threadIdx.x < 32) {
+    uint32_t w = warpTot[threadIdx.x], z = w;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-    if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      uint32_t w = warpTot[threadIdx.x], z = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, z, o); if (threadIdx.x >= o) z += y; }
-      warpTot[threadIdx.x] = z - w;   // exclusive warp offsets
-    }
-    __syncthreads();
-    uint32_t excl = carry + warpTot[threadIdx.x >> 5] + x - v;
-    if (i < n) counts[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
-    __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, z, o); if (threadIdx.x >= o) z += y; }
+    warpTot[threadIdx.x] = z - w;   // exclusive warp offsets
+    if (threadIdx.x == 31) *total = z;
   }
-  if (threadIdx.x == 0) *total = carry;
+  __syncthreads();
+  return warpTot[threadIdx.x >> 5] + x - v;
 }
-void launch_scan_counts(uint32_t *blockCounts, uint32_t nBlocks, uint32_t *total, cudaStream_t s) {
-  k_scan_counts<<<1, 1024, 0, s>>>(blockCounts, nBlocks, total);
+__global__ void __launch_bounds__(1024) k_scan_chunks(uint32_t *counts, uint32_t n, uint32_t *chunkTotals) {
+  __shared__ uint32_t warpTot[32];
+  __shared__ uint32_t tot;
+  const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+  const uint32_t v = i < n ? counts[i] : 0u;
+  const uint32_t excl = cta_exclusive_scan_1024(v, warpTot, &tot);
+  if (i < n) counts[i] = excl;
+  if (threadIdx.x == 0) chunkTotals[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(1024) k_scan_top(uint32_t *chunkTotals, uint32_t nChunks, uint32_t *total) {
+  __shared__ uint32_t warpTot[32];
+  __shared__ uint32_t tot;
+  const uint32_t v = threadIdx.x < nChunks ? chunkTotals[threadIdx.x] : 0u;
+  const uint32_t excl = cta_exclusive_scan_1024(v, warpTot, &tot);
+  if (threadIdx.x < nChunks) chunkTotals[threadIdx.x] = excl;
+  if (threadIdx.x == 0) *total = tot;
+}
+void launch_scan_counts(uint32_t *blockCounts, uint32_t nBlocks, uint32_t *chunkOffsets, uint32_t *total, cudaStream_t s) {
+  const uint32_t nChunks = (nBlocks + 1023) / 1024;                 // <= 512 for any 32-bit site count
+  k_scan_chunks<<<nChunks, 1024, 0, s>>>(blockCounts, nBlocks, chunkOffsets);
+  k_scan_top<<<1, 1024, 0, s>>>(chunkOffsets, nChunks, total);
 }
 
 // Place of every candidate in the ordered output: rank = number of set mask bits before its site, from the scanned block
 // counts plus the (at most kScanBlock) words of its own block.  One warp per candidate; the count is read on the device.
 __global__ void __launch_bounds__(256) k_rank(const uint32_t *__restrict__ mask, uint32_t firstWord,
-                                              const uint32_t *__restrict__ blockOffsets, const EvalOut *__restrict__ part,
+                                              const uint32_t *__restrict__ blockOffsets,
+                                              const uint32_t *__restrict__ chunkOffsets, const EvalOut *__restrict__ part,
                                               const uint32_t *__restrict__ count, uint32_t cap,
                                               uint32_t *__restrict__ rankOf, uint32_t *__restrict__ list) {
   const uint32_t n = *count < cap ? *count : cap;
@@ -687,17 +699,18 @@ __global__ void __launch_bounds__(256) k_rank(const uint32_t *__restrict__ mask,
     for (uint32_t k = w0 + lane; k < w; k += 32) c += __popc(mask[firstWord + k]);
     c = __reduce_add_sync(0xffffffffu, c);
     if (lane == 0) {
-      const uint32_t r = blockOffsets[w / kScanBlock] + c + __popc(mask[firstWord + w] & ((1u << (site & 31)) - 1u));
+      const uint32_t blk = w / kScanBlock;
+      const uint32_t r = chunkOffsets[blk >> 10] + blockOffsets[blk] + c + __popc(mask[firstWord + w] & ((1u << (site & 31)) - 1u));
       rankOf[j] = r;
       list[r] = site;
     }
   }
 }
-void launch_rank(const uint32_t *siteMask, uint32_t firstSite, const uint32_t *blockOffsets, const EvalOut *part,
-                 const uint32_t *count, uint32_t cap, uint32_t *rankOf, uint32_t *list, cudaStream_t s) {
+void launch_rank(const uint32_t *siteMask, uint32_t firstSite, const uint32_t *blockOffsets, const uint32_t *chunkOffsets,
+                 const EvalOut *part, const uint32_t *count, uint32_t cap, uint32_t *rankOf, uint32_t *list, cudaStream_t s) {
   unsigned grid = (cap + 7) / 8;
   if (grid > 148 * 8) grid = 148 * 8;
-  k_rank<<<grid, 256, 0, s>>>(siteMask, firstSite / 32, blockOffsets, part, count, cap, rankOf, list);
+  k_rank<<<grid, 256, 0, s>>>(siteMask, firstSite / 32, blockOffsets, chunkOffsets, part, count, cap, rankOf, list);
 }
 
 // ------------------------------------------------------------------------------ candidates

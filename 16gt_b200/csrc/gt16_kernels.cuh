@@ -73,18 +73,16 @@ void launch_eval_mask(const SnapView &V, const DevSiteMap &M, uint64_t base, uin
                       uint32_t *errWord, uint32_t *flagged, EvalOut *part, uint32_t *count, uint32_t cap, cudaStream_t s);
 // rankOf[j] = number of set mask bits before part[j].site among sites [firstSite, ...) (its place in the ordered output),
 // list[rank] = part[j].site; blockOffsets = scanned block counts of the same mask range
-void launch_rank(const uint32_t *siteMask, uint32_t firstSite, const uint32_t *blockOffsets, const EvalOut *part,
-                 const uint32_t *count, uint32_t cap, uint32_t *rankOf, uint32_t *list, cudaStream_t s);
+void launch_rank(const uint32_t *siteMask, uint32_t firstSite, const uint32_t *blockOffsets, const uint32_t *chunkOffsets,
+                 const EvalOut *part, const uint32_t *count, uint32_t cap, uint32_t *rankOf, uint32_t *list, cudaStream_t s);
 
 // ordered compaction of a bit mask over nItems items
 constexpr int kScanBlock = 256;                       // mask words per block
 inline uint32_t scan_blocks(uint32_t nItems) { return ((nItems + 31) / 32 + kScanBlock - 1) / kScanBlock; }
 void launch_mask_count(const uint32_t *mask, uint32_t nItems, uint32_t *blockCounts, cudaStream_t s);
-void launch_scan_counts(uint32_t *blockCounts, uint32_t nBlocks, uint32_t *total, cudaStream_t s);
-// out[k] = (values ? values[i] : i + offset) for the k-th set bit i
-void launch_mask_scatter(const uint32_t *mask, uint32_t nItems, const uint32_t *blockOffsets,
-                         const uint32_t *values, uint32_t offset, uint32_t *out, cudaStream_t s);
-
+// exclusive scan in two levels: blockCounts[b] becomes the offset within its chunk of 1024 blocks, chunkOffsets[c]
+// (room for (nBlocks + 1023) / 1024 words) the offset of the chunk; *total = number of set bits
+void launch_scan_counts(uint32_t *blockCounts, uint32_t nBlocks, uint32_t *chunkOffsets, uint32_t *total, cudaStream_t s);
 // full records of the candidates in part[0, min(*count, cap)): out[rankOf[j]] (persistent grid, the count is read on the device)
 void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
                        const uint32_t *count, uint32_t cap, gt16_called_site *out, uint32_t *errWord, int numSMs,

@@ -118,7 +118,7 @@ int emu_run(const char *indexPrefix, const char *snapshotPath, const char *regio
     fclose(f);
   } else { rs.push_back(0); rf.push_back(0); acc = V.L; }
   rf.push_back(acc);
-  DevSiteMap M; M.m.regStart = rs.data(); M.m.regFirst = rf.data(); M.m.nRegions = (uint32_t) rs.size(); M.totalSites = acc;
+  DevSiteMap M; M.m.regStart = rs.data(); M.m.regFirst = rf.data(); M.m.nRegions = (uint32_t) rs.size(); M.m.tileReg = nullptr; M.totalSites = acc;
   double prior[256]; uint32_t g2i[16];
   EvalParams P = make_params(lc, balance, unbalance, prior, g2i);
   std::vector<gt16_called_site> calls;
