@@ -123,44 +123,58 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 // Streaming classification of a dense, single-region range of positions [pBeg, pEnd) -- the HBM-bound
-// pass of the path.  Persistent CTAs (one per SM); each walks tiles of kStreamTile positions that an
-// elected thread stages into shared memory with three 1-D TMA bulk copies per tile (counters + one
-// look-ahead entry, packed reference, invalid bitmap) through a kStreamStages-deep mbarrier ring, so
-// ~100 KB per SM is in flight independent of the warps' progress.
+// pass of the path.  Persistent CTAs (one per SM); each walks tiles of kTile positions that an elected
+// thread stages into shared memory with three 1-D TMA bulk copies per tile (counters + one look-ahead
+// entry, packed reference, invalid bitmap) through an mbarrier ring, so ~200 KB per SM is in flight
+// independent of the warps' progress.
 //
-// The integer ALU pipe is what bounds this kernel once the loads are asynchronous (every LOP3/SHF/ISETP
-// occupies it for two cycles per warp), so the per-site work is split by how common the site shape is:
-//   simple  (~90 %): no coverage, or only the reference allele seen with a compact counter -> one byte
-//                    lookup in a 16 KB shared-memory table indexed by the weight (~25 ALU ops);
-//   special (~0.4 %): overflow-type counter, or the successor carries indel records -> flagged for
-//                    the exact evaluator without further work;
-//   complex (~9 %) : anything else (a non-reference allele in a compact counter).  The lane parks the
-//                    counter in a per-warp shared-memory queue; whenever 32 are parked the whole warp
-//                    runs the general role-indexed bitmap test, one site per lane, and ORs the verdicts
-//                    into the mask words the warp wrote earlier.
+// The integer ALU pipe and the issue slots are what bound this kernel once the loads are asynchronous
+// (every LOP3/SHF/ISETP occupies the pipe for two cycles per warp), so the row code does ONE thing: it
+// decides whether a site is *settled* -- certainly not a candidate, by a handful of mask tests on its
+// counter word (and, in the table-driven variant, one byte lookup) -- and parks the index of every other
+// site (~1.5 %) in a per-warp shared-memory queue.  The flag bitmap is written as zeros per tile visit;
+// whenever 32 sites are parked the whole warp settles them, one per lane: the counter, its successor and the
+// reference base are read again from global memory (they have just come through L2), the general role-indexed
+// bitmap test runs, and the verdicts are OR-ed into the bitmap.  One ballot per 32-site row, no store.
+//   settled: no coverage; or the reference allele in slot 1 with slot 2 dead (table-driven: and the (Wr) table
+//            says hom-ref); shortcut variant: ... or slot 2 holding one allele of weight <= bound
+//   parked : overflow-type counter, successor with indel records (-> flagged), a non-reference allele in a
+//            compact counter (-> bitmap test), invalid positions never
 // Requires pBeg % 128 == 0 (16-byte alignment of all three sources) and arrays padded by one tile.
-struct StreamQueueEntry { uint32_t x, y, bit, ref; };
-// The ring is as deep as shared memory allows: what bounds the kernel once the per-site work is small is the number
-// of bytes in flight per SM (a stage is requested again only after all 32 warps have left it, and HBM latency under
-// load is ~3 us), so the shortcut variant -- which never reads the (Wr) byte table -- spends those 16 KB on a fifth stage.
-template <bool kShortcut>
+//
+// kShortcut (chosen at launch when the decision bitmaps allow it, see stream_shortcut_bound): the bitmap (Wr) is all
+// zero -- a position where only the reference allele was seen is never a candidate -- and every row
+// (Wr < 1024, alt <= altBound >> 16) of the two-allele bitmaps is zero.  Then "reference allele in slot 1, plus
+// at most one more allele of weight <= bound in slot 2" is settled with mask tests and no table read; that
+// is ~99 % of all positions of a 30x snapshot (a sequencing error adds one read of weight <= 4).
+#ifndef GT16_ROW_V
+#define GT16_ROW_V 1
+#endif
+#ifndef GT16_STREAM_CTAS
+#define GT16_STREAM_CTAS 1      // resident CTAs per SM (each with its own ring)
+#endif
+template <bool kShortcut, int kRows>
 struct StreamSmemT {
-  static constexpr int kStages = kShortcut ? kStreamStages + 1 : kStreamStages;
-  uint64_t counters[kStages][kStreamTile + 2];
-  uint32_t ref[kStages][kStreamTile / 16];
-  uint32_t bm[kStages][kStreamTile / 32];
+  static constexpr int kTile = kStreamThreads * kRows;     // positions per tile
+#ifdef GT16_STREAM_STAGES
+  static constexpr int kStages = GT16_STREAM_STAGES;
+#else
+  static constexpr int kStages = kRows >= 8 ? 3 : (kShortcut ? 5 : 4);
+#endif
+  uint64_t counters[kStages][kTile + 2];
+  uint32_t ref[kStages][kTile / 16];
+  uint32_t bm[kStages][kTile / 32];
   uint8_t s1[kShortcut ? 16 : kS1Bits];                  // byte per weight: 1 = needs exact evaluation (all zero when kShortcut)
-  uint32_t s2[2 * kS2Words];                             // bitmaps (Wr, Wp) and (Wr, Wq)
-  StreamQueueEntry queue[kStreamThreads / 32][64];
+  uint32_t queue[kStreamThreads / 32][64];               // parked sites (index relative to pBeg)
   uint64_t full[kStages];                                // TMA bytes have landed
   uint32_t released[kStages];                            // warps that are done reading the stage
 };
-static_assert(sizeof(uint64_t) * (kStreamTile + 2) % 16 == 0, "bulk copy sizes must be multiples of 16 bytes");
-static_assert(sizeof(StreamSmemT<false>) <= 227 * 1024 && sizeof(StreamSmemT<true>) <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(StreamSmemT<false, GT16_STREAM_ROWS>) <= 227 * 1024 && sizeof(StreamSmemT<true, GT16_STREAM_ROWS>) <= 227 * 1024, "shared memory budget");
+static_assert((size_t) kStreamThreads * GT16_STREAM_ROWS + 64 <= kStreamPadSites, "arrays are padded by one tile");
 
 // general role-indexed test of one compact (non-overflow) counter; same verdict as lookup_needs_exact
 template <bool kShortcut>
-__device__ __forceinline__ bool compact_needs_exact(const uint32_t *__restrict__ s2, const uint8_t *__restrict__ s1,
+__device__ __forceinline__ bool compact_needs_exact(const DecisionTables &D, const uint8_t *__restrict__ s1,
                                                     uint32_t x, uint32_t y, uint32_t ref) {
   uint32_t v1 = (y & 0xFFFFu) ? (x & 0x3FFFu) : 0u, v2 = (y >> 16) ? ((x >> 16) & 0x3FFFu) : 0u;
   const uint32_t r1 = ((x >> 14) & 3u) ^ ref, r2 = (x >> 30) ^ ref;
@@ -169,31 +183,27 @@ __device__ __forceinline__ bool compact_needs_exact(const uint32_t *__restrict__
   const uint32_t a1 = r1 ? v1 : 0u, a2 = r2 ? v2 : 0u, alt = a1 | a2, ar = a1 ? r1 : r2;
   if (alt == 0) return kShortcut ? false : s1[wr] != 0;      // kShortcut: the (Wr) bitmap is all zero
   if ((a1 && a2) || wr >= (uint32_t) kS2R || alt >= (uint32_t) kS2A) return true;
-  const uint32_t idx = (ar == 2 ? 0u : (uint32_t) (kS2R * kS2A)) + alt * kS2R + wr;
-  return (s2[idx >> 5] >> (idx & 31)) & 1u;
+  return tab_bit(ar == 2 ? D.s2p : D.s2q, alt * kS2R + wr);
 }
 
-// kShortcut (chosen at launch when the decision bitmaps allow it, see StreamShortcut): the bitmap (Wr) is all
-// zero -- a position where only the reference allele was seen is never a candidate -- and every row
-// (Wr < 1024, alt <= altBound >> 16) of the two-allele bitmaps is zero.  Then "reference allele in slot 1, plus
-// at most one more allele of weight <= bound in slot 2" is decided with two mask tests and no table read; that
-// is ~99 % of all positions of a 30x snapshot (a sequencing error adds one read of weight <= 4).
-template <bool kShortcut>
-__global__ void __launch_bounds__(kStreamThreads, 1)
+template <bool kShortcut, int kRows>
+__global__ void __launch_bounds__(kStreamThreads, GT16_STREAM_CTAS)
 k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__ packedRef,
              const uint32_t *__restrict__ invalid, uint32_t pBeg, uint32_t pEnd, DecisionTables D,
              uint32_t altBound, uint32_t *__restrict__ mask) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
-  using Smem = StreamSmemT<kShortcut>;
+  using Smem = StreamSmemT<kShortcut, kRows>;
   constexpr int kStages = Smem::kStages;
+  constexpr uint32_t kTile = Smem::kTile;
   Smem &S = *reinterpret_cast<Smem *>(smemRaw);
-  const uint32_t nTiles = (pEnd - pBeg + kStreamTile - 1) / kStreamTile;
+  const uint32_t nTiles = (pEnd - pBeg + kTile - 1) / kTile;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr uint32_t kBytesC = sizeof(uint64_t) * (kStreamTile + 2), kBytesR = kStreamTile / 4, kBytesB = kStreamTile / 8;
+  constexpr uint32_t kBytesC = sizeof(uint64_t) * (kTile + 2), kBytesR = kTile / 4, kBytesB = kTile / 8;
+  static_assert(kBytesC % 16 == 0, "bulk copy sizes must be multiples of 16 bytes");
   const uint32_t txBytes = kBytesC + kBytesR + (invalid ? kBytesB : 0);
 
   auto issue = [&](uint32_t stage, uint32_t tile) {        // elected thread only
-    const uint32_t pT = pBeg + tile * kStreamTile;
+    const uint32_t pT = pBeg + tile * kTile;
     mbar_expect_tx(&S.full[stage], txBytes);
     bulk_g2s(S.counters[stage], counters + pT, kBytesC, &S.full[stage]);
     bulk_g2s(S.ref[stage], packedRef + (pT >> 4), kBytesR, &S.full[stage]);
@@ -209,10 +219,8 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
       const uint32_t bits = (__ldg(D.s1 + (k >> 3)) >> ((k & 7) << 2)) & 0xFu;
       reinterpret_cast<uint32_t *>(S.s1)[k] = (bits & 1u) | ((bits & 2u) << 7) | ((bits & 4u) << 14) | ((bits & 8u) << 21);
     }
-  for (uint32_t k = tid; k < 2 * kS2Words; k += kStreamThreads)
-    S.s2[k] = k < kS2Words ? __ldg(D.s2p + k) : __ldg(D.s2q + (k - kS2Words));
   if (!invalid)
-    for (uint32_t k = tid; k < kStages * (kStreamTile / 32); k += kStreamThreads) (&S.bm[0][0])[k] = 0;
+    for (uint32_t k = tid; k < kStages * (kTile / 32); k += kStreamThreads) (&S.bm[0][0])[k] = 0;
   __syncthreads();
   if (tid == 0)
     for (uint32_t s = 0; s < (uint32_t) kStages; ++s) {
@@ -220,100 +228,102 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
       if (t < nTiles) issue(s, t);
     }
 
-  // per-warp ring of parked (complex) sites
-  StreamQueueEntry *q = S.queue[warp];
+  // per-warp ring of parked sites
+  uint32_t *q = S.queue[warp];
   uint32_t qhead = 0, qtail = 0;
-  auto drain = [&](uint32_t count) {                        // lanes < count run one parked site each
+  auto drain = [&](uint32_t count) {                        // lanes < count settle one parked site each
     if (lane < count) {
-      const StreamQueueEntry e = q[(qhead + lane) & 63u];
-      if (compact_needs_exact<kShortcut>(S.s2, S.s1, e.x, e.y, e.ref)) atomicOr(mask + (e.bit >> 5), 1u << (e.bit & 31));
+      const uint32_t b = q[(qhead + lane) & 63u], p = pBeg + b;
+      const uint2 c = __ldg(reinterpret_cast<const uint2 *>(counters + p));
+      const uint32_t n = __ldg(reinterpret_cast<const uint32_t *>(counters + p + 1));      // successor, low word
+      const uint32_t ref = (__ldg(packedRef + (p >> 4)) >> (30u - ((p & 15u) << 1))) & 3u;
+      // an overflow-type counter, or a successor that is overflow-type AND carries indel records: exact evaluator.  The
+      // successor test is ONE compare: with m = n & 0xE000E000, m >= 0xC000E000 holds for the three true patterns (C000E000,
+      // E000C000, E000E000) and otherwise only for a compact successor whose slot 2 holds base T with weight >= 8192 --
+      // such a site is flagged needlessly and settled by the exact evaluator.
+      const bool special = ((c.x & 0xC000C000u) == 0xC000C000u) | ((n & 0xE000E000u) >= 0xC000E000u);
+      if (special || compact_needs_exact<kShortcut>(D, S.s1, c.x, c.y, ref)) atomicOr(mask + (b >> 5), 1u << (b & 31));
     }
     qhead += count;
   };
-  constexpr int kRows = kStreamTile / kStreamThreads;       // 32-site rows per warp and tile
   // the lane's reference base sits in bits (31 - 2l, 30 - 2l) of its packed word, l = lane % 16: rotated to bits 15:14 it
   // lines up with the base of counter slot 1
   const uint32_t rsh = (48u - ((lane & 15u) << 1)) & 31u, ltMask = (1u << lane) - 1u;
   const uint32_t site0 = warp * (32 * kRows) + lane;        // this lane's site in row 0 of a tile
-  const uint32_t refIdx0 = site0 >> 4, bmIdx0 = warp * kRows;
   const bool deadBit = kShortcut ? false : S.s1[0] != 0;    // verdict for a position without coverage
 
   uint32_t stage = 0, parity = 0;
   for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
     mbar_wait(&S.full[stage], parity);
-    const uint2 *sc = reinterpret_cast<const uint2 *>(S.counters[stage]) + site0;
-    const uint32_t *sr = S.ref[stage] + refIdx0, *sb = S.bm[stage] + bmIdx0;
-    const uint32_t pT = pBeg + tile * kStreamTile;
-    const uint32_t lim = (pEnd - pT) < (uint32_t) kStreamTile ? pEnd - pT : (uint32_t) kStreamTile;
-    uint2 c[kRows]; uint32_t nlo[kRows], rw[kRows], bw[kRows];
+    const uint32_t pT = pBeg + tile * kTile;
+    const uint32_t lim = (pEnd - pT) < kTile ? pEnd - pT : kTile;
+    // the warp's words of the flag bitmap start out as zeros; parked sites set their bits later (same warp)
+    if (lane < (uint32_t) kRows && (warp * kRows + lane) * 32u < lim) mask[((pT - pBeg) >> 5) + warp * kRows + lane] = 0u;
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) { c[r] = sc[32 * r]; nlo[r] = sc[32 * r + 1].x; rw[r] = sr[2 * r]; bw[r] = sb[r]; }
-    uint32_t *mw = mask + ((pT - pBeg) >> 5) + warp * kRows;
-    // masked: some position of this warp's rows is invalid, or (partial) the range ends inside this tile -- decided
-    // once per tile visit, so that the common rows carry no validity test at all
-    auto row = [&](int r, bool partial, bool masked) {
-      const uint32_t site = site0 + 32 * r;
-      const uint32_t x = c[r].x, y = c[r].y, n = nlo[r];
-      const uint32_t rot = __funnelshift_r(rw[r], rw[r], rsh);
-      const bool isRef1 = ((x ^ rot) & 0xC000u) == 0;
-      const bool dead = y == 0;
-      // special: an overflow-type counter, or a successor that is overflow-type AND carries indel records.  The successor
-      // test is ONE compare: with m = n & 0xE000E000, m >= 0xC000E000 holds for the three true patterns (C000E000,
-      // E000C000, E000E000) and otherwise only for a compact successor whose slot 2 holds base T with weight >= 8192 --
-      // such a site is flagged needlessly and settled by the exact evaluator.
-      const bool special = ((x & 0xC000C000u) == 0xC000C000u) | ((n & 0xE000E000u) >= 0xC000E000u);
-      bool flag, cplx;
-      if (kShortcut) {
-        const bool live1 = (y & 0xFFFFu) != 0;
-        const bool oneAllele = y < 0x10000u;                   // slot 2 dead
-        const bool tinyAlt = ((x & 0x3FFF0000u) <= altBound) & ((x & 0x3C00u) == 0);   // slot-2 weight <= bound, slot-1 weight < 1024
-        const bool settled = isRef1 & live1 & (oneAllele | tinyAlt);                   // certainly hom-ref
-        flag = special;
-        cplx = !special & !settled & !dead;
-      } else {
-        const bool oneSlot = (y - 1u) < 0xFFFFu;               // slot 1 live, slot 2 dead
-        const bool simple1 = oneSlot & isRef1;
-        const bool bit = S.s1[x & 0x3FFFu] != 0;
-        flag = special | (simple1 & bit) | (dead & deadBit);
-        cplx = !special & !simple1 & !dead;
-      }
-      if (masked) {                                            // invalid positions / positions beyond the range in this tile visit
-        bool valid = (bw[r] & (0x80000000u >> lane)) == 0;     // bitmap word of the row, MSB first
-        if (partial) valid &= site < lim;
-        flag &= valid; cplx &= valid;
-      }
-      const uint32_t word = __ballot_sync(0xffffffffu, flag);
-      const uint32_t cw = __ballot_sync(0xffffffffu, cplx);
-      if (partial) { if (lane == 0 && site < lim) mw[r] = word; }
-      else mw[r] = word;                                       // every lane, same address, same value: one transaction
-      if (cw) {
-        if ((cw >> lane) & 1u) {
-          StreamQueueEntry e; e.x = x; e.y = y; e.bit = pT - pBeg + site; e.ref = (rot >> 14) & 3u;
-          q[(qtail + __popc(cw & ltMask)) & 63u] = e;
+    for (int h = 0; h < kRows / 4; ++h) {                      // four rows at a time (registers)
+      const uint32_t siteH = site0 + 128u * h;
+      const uint2 *sc = reinterpret_cast<const uint2 *>(S.counters[stage]) + siteH;
+      const uint32_t *sr = S.ref[stage] + (siteH >> 4), *sb = S.bm[stage] + warp * kRows + 4 * h;
+      uint2 c[4]; uint32_t nlo[4], rw[4], bw[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { c[r] = sc[32 * r]; nlo[r] = sc[32 * r + 1].x; rw[r] = sr[2 * r]; bw[r] = sb[r]; }
+      // masked: some position of these rows is invalid, or (partial) the range ends inside this tile -- decided
+      // once per visit, so that the common rows carry no validity test at all
+      auto row = [&](int r, bool partial, bool masked) {
+        const uint32_t site = siteH + 32 * r;
+        const uint32_t x = c[r].x, y = c[r].y, n = nlo[r];
+        const uint32_t rot = __funnelshift_r(rw[r], rw[r], rsh);
+        const bool isRef1 = ((x ^ rot) & 0xC000u) == 0;
+        const bool dead = y == 0;
+        const bool special = ((x & 0xC000C000u) == 0xC000C000u) | ((n & 0xE000E000u) >= 0xC000E000u);
+        bool settled;
+        if (kShortcut) {
+#if GT16_ROW_V == 1
+          // shifts by constants are IMADs (fma pipe); the logic ops they replace sit on the alu pipe, which is the busy one
+          const bool live1 = (y << 16) != 0;
+          const bool oneAllele = y < 0x10000u;                   // slot 2 dead
+          const bool tinyAlt = ((x << 2) <= ((altBound << 2) | 0x3FFFFu)) & ((x & 0x3C00u) == 0);
+#else
+          const bool live1 = (y & 0xFFFFu) != 0;
+          const bool oneAllele = y < 0x10000u;                   // slot 2 dead
+          const bool tinyAlt = ((x & 0x3FFF0000u) <= altBound) & ((x & 0x3C00u) == 0);   // slot-2 weight <= bound, slot-1 weight < 1024
+#endif
+          settled = dead | (isRef1 & live1 & (oneAllele | tinyAlt));                     // certainly hom-ref
+        } else {
+          const bool oneSlot = (y - 1u) < 0xFFFFu;               // slot 1 live, slot 2 dead
+          const bool bit = S.s1[x & 0x3FFFu] != 0;
+          settled = (dead & !deadBit) | (oneSlot & isRef1 & !bit);
         }
-        qtail += __popc(cw);
-        __syncwarp();                                         // entries and the row's mask word are visible to the warp
-        if (qtail - qhead >= 32u) { drain(32); __syncwarp(); }
-      }
-    };
-    if (lim == (uint32_t) kStreamTile) {                       // all tiles but the last: no per-site range test
-      uint32_t anyInvalid = 0;
+        bool park = special | !settled;
+        if (masked) {                                            // invalid positions / positions beyond the range
+          bool valid = (bw[r] & (0x80000000u >> lane)) == 0;     // bitmap word of the row, MSB first
+          if (partial) valid &= site < lim;
+          park &= valid;
+        }
+        const uint32_t cw = __ballot_sync(0xffffffffu, park);
+        if (cw) {
+          if ((cw >> lane) & 1u) q[(qtail + __popc(cw & ltMask)) & 63u] = pT - pBeg + site;
+          qtail += __popc(cw);
+          __syncwarp();                                         // entries (and the zeroed mask words) are visible to the warp
+          if (qtail - qhead >= 32u) { drain(32); __syncwarp(); }
+        }
+      };
+      if (lim == kTile) {                                        // all tiles but the last: no per-site range test
+        if ((bw[0] | bw[1] | bw[2] | bw[3]) == 0) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) anyInvalid |= bw[r];
-      if (anyInvalid == 0) {
+          for (int r = 0; r < 4; ++r) row(r, false, false);
+        } else {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) row(r, false, false);
+          for (int r = 0; r < 4; ++r) row(r, false, true);
+        }
       } else {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) row(r, false, true);
+        for (int r = 0; r < 4; ++r) row(r, true, true);
       }
-    } else {
-#pragma unroll
-      for (int r = 0; r < kRows; ++r) row(r, true, true);
     }
     __syncwarp();
     // This warp no longer reads the stage.  The LAST warp to say so refills it (no producer warp, nobody waits
-    // for a release): the stage's next tile is kStreamStages rounds ahead.
+    // for a release): the stage's next tile is kStages rounds ahead.
     if (lane == 0) {
       __threadfence_block();
       if (atomicAdd(&S.released[stage], 1u) == kStreamThreads / 32 - 1) {
@@ -331,9 +341,10 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
 
 // function attributes are per device: called once per context, with its device current
 cudaError_t configure_kernels() {
-  cudaError_t e = cudaFuncSetAttribute(k_stream_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmemT<false>));
+  constexpr int R = GT16_STREAM_ROWS;
+  cudaError_t e = cudaFuncSetAttribute(k_stream_tma<false, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmemT<false, R>));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_stream_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmemT<true>));
+  return cudaFuncSetAttribute(k_stream_tma<true, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmemT<true, R>));
 }
 
 // what the decision bitmaps (host copies) allow the streaming kernel to skip: returns the largest alt weight A
@@ -353,12 +364,15 @@ uint32_t stream_shortcut_bound(const uint32_t *s1, const uint32_t *s2p, const ui
 void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const DecisionTables &D, uint32_t shortcutAlt,
                        uint32_t *mask, int numSMs, cudaStream_t s) {
   if (pEnd <= pBeg) return;
-  uint32_t nTiles = (pEnd - pBeg + kStreamTile - 1) / kStreamTile;
-  unsigned grid = nTiles < (uint32_t) numSMs ? nTiles : (unsigned) numSMs;
+  constexpr int R = GT16_STREAM_ROWS;
+  constexpr uint32_t tileSites = kStreamThreads * R;
+  uint32_t nTiles = (pEnd - pBeg + tileSites - 1) / tileSites;
+  const uint32_t ctas = (uint32_t) numSMs * GT16_STREAM_CTAS;
+  unsigned grid = nTiles < ctas ? nTiles : ctas;
   if (shortcutAlt)
-    k_stream_tma<true><<<grid, kStreamThreads, sizeof(StreamSmemT<true>), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, shortcutAlt << 16, mask);
+    k_stream_tma<true, R><<<grid, kStreamThreads, sizeof(StreamSmemT<true, R>), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, shortcutAlt << 16, mask);
   else
-    k_stream_tma<false><<<grid, kStreamThreads, sizeof(StreamSmemT<false>), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, 0, mask);
+    k_stream_tma<false, R><<<grid, kStreamThreads, sizeof(StreamSmemT<false, R>), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, 0, mask);
 }
 
 template <bool kUseTables>
@@ -722,7 +736,13 @@ void launch_rank(const uint32_t *siteMask, uint32_t firstSite, const uint32_t *b
 // uses, so the bits are the same.
 constexpr int kCandThreads = 128;
 #ifndef GT16_CAND_BLOCKS
-#define GT16_CAND_BLOCKS 8      // resident blocks per SM
+#define GT16_CAND_BLOCKS 8      // resident blocks per SM (register budget)
+#endif
+#ifndef GT16_CAND_GRID
+#define GT16_CAND_GRID GT16_CAND_BLOCKS      // blocks per SM that are launched
+#endif
+#ifndef GT16_BIAS_GRID
+#define GT16_BIAS_GRID 4        // blocks of the Fisher-test kernel per SM
 #endif
 // what the window sums need of one position (SNP_Caller.cpp:276-367): strand count, weighted depth, flags
 struct WinLite { uint32_t sc, w, fl; };                      // fl: bit0 valid, bit1 C-or-G seen, bit2 G seen
@@ -1003,7 +1023,7 @@ void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, co
   // persistent grid: the number of records is only known on the device; 8 blocks of 4 warps per SM (launch bounds), and a
   // small call (cap is a bound on its records) does not need more warps than records
   unsigned grid = (cap + (kCandThreads / 32) - 1) / (kCandThreads / 32);
-  const unsigned full = (unsigned) numSMs * GT16_CAND_BLOCKS;
+  const unsigned full = (unsigned) numSMs * GT16_CAND_GRID;
   if (grid > full) grid = full;
   k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, part, rankOf, count, cap, out, errWord);
 }
@@ -1215,7 +1235,7 @@ void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const Ev
   // resident warps as the device holds (4 blocks of 8 warps per SM); blocks beyond the device-side count leave at once
   const uint32_t chunks = (uint32_t) (((uint64_t) cap * 12u + 31) / 32), perBlock = kBiasThreads / 32;
   unsigned grid = (chunks + perBlock - 1) / perBlock;
-  if (grid > (unsigned) numSMs * 4u) grid = (unsigned) numSMs * 4u;
+  if (grid > (unsigned) numSMs * GT16_BIAS_GRID) grid = (unsigned) numSMs * GT16_BIAS_GRID;
   if (grid < 1) grid = 1;
   k_bias<<<grid, kBiasThreads, 0, s>>>(V, M, base, part, rankOf, count, cap, P.lnfact, cache, cacheMask, out);
 }

@@ -23,14 +23,15 @@ struct DecisionTables {
 };
 
 // TMA-staged streaming kernel geometry
-constexpr int kStreamTile = 4096;      // positions per tile (32 KB of counters)
-constexpr int kStreamStages = 4;       // mbarrier ring depth
 #ifndef GT16_STREAM_THREADS
 #define GT16_STREAM_THREADS 1024
 #endif
+#ifndef GT16_STREAM_ROWS
+#define GT16_STREAM_ROWS 8             // 32-site rows per warp and tile visit: tiles of 8,192 positions (64 KB of counters), 3 stages
+#endif
 constexpr int kStreamThreads = GT16_STREAM_THREADS;
-// bytes by which every streamed array must be over-allocated so that full tiles can be copied
-constexpr size_t kStreamPadSites = kStreamTile + 64;
+// positions by which every streamed array must be over-allocated so that full tiles can be copied
+constexpr size_t kStreamPadSites = 8192 + 64;
 
 cudaError_t configure_kernels();   // per-device kernel attributes (dynamic shared memory opt-in)
 void launch_build_table(double *out, float err, cudaStream_t s);
