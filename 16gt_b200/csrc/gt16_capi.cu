@@ -78,7 +78,7 @@ struct gt16_ctx {
   uint32_t *g2i = nullptr;
   float *lnfact = nullptr;
   uint32_t *s1 = nullptr, *s2p = nullptr, *s2q = nullptr, *g4 = nullptr;
-  uint32_t *errWord = nullptr, *dTotal = nullptr, *dFlagged = nullptr;   // one allocation: error bits, compaction total, sites evaluated exactly, ...
+  uint32_t *errWord = nullptr, *dTotal = nullptr, *dFlagged = nullptr, *dMissed = nullptr;   // one allocation: error bits, compaction total, sites evaluated exactly, Fisher tests left to the walk kernel, ...
   uint32_t *dCounts = nullptr;          // ... and kMaxSegs per-segment candidate counters (written by k_eval_mask, read by the kernels behind it)
   static const int kMaxSegs = 512;
   uint32_t *hPinnedRing = nullptr;      // kCallRing slots of 4 words
@@ -96,7 +96,7 @@ struct gt16_ctx {
   uint2 *biasCache = nullptr;             // memoised Fisher tests (k_bias), kBiasCacheEntries entries
   int numSMs = 148;
   // persistent scratch of the fused path
-  DevBuf mask, counts, part, rankOf, list, recs, recs2, planStart, planFirst, planTile;
+  DevBuf mask, counts, part, rankOf, list, missed, recs, recs2, planStart, planFirst, planTile;
   std::vector<uint32_t> lastPlanStart;   // host copy of what planStart / planFirst hold (make_plan)
   std::vector<uint64_t> lastPlanFirst;
   DevBuf sCounters, sInvalid, sOvf, sOvfBase, sPool, sRef;      // streamed (host-fed) snapshot
@@ -253,6 +253,7 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   if ((e = cudaMalloc(&ctx->errWord, (4 + gt16_ctx::kMaxSegs) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   ctx->dTotal = ctx->errWord + 1;
   ctx->dFlagged = ctx->errWord + 2;
+  ctx->dMissed = ctx->errWord + 3;
   ctx->dCounts = ctx->errWord + 4;
   if ((e = cudaHostAlloc(&ctx->hCounts, gt16_ctx::kMaxSegs * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
   if ((e = cudaHostAlloc(&ctx->hPinnedRing, gt16_ctx::kCallRing * 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
@@ -288,7 +289,7 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   cudaFree(ctx->biasCache);
   if (ctx->hPinnedRing) cudaFreeHost(ctx->hPinnedRing);
   if (ctx->hCounts) cudaFreeHost(ctx->hCounts);
-  for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->part, &ctx->rankOf, &ctx->list, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst, &ctx->planTile,
+  for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->part, &ctx->rankOf, &ctx->list, &ctx->missed, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst, &ctx->planTile,
                     &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
   for (auto &pool : ctx->evPool) for (auto e : pool) cudaEventDestroy(e);
   if (ctx->stagePin) cudaFreeHost(ctx->stagePin);
@@ -564,6 +565,7 @@ static int alloc_snapshot(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_de
   v.nOvfRegions = view->n_overflow_regions;
   v.poolBytes = view->pool_bytes;
   v.refWords = view->packed_ref_words;
+  set_ovf_geometry(v);
   return GT16_OK;
 }
 
@@ -796,8 +798,9 @@ int reserve_results(gt16_ctx *ctx, gt16_calls *calls, uint64_t need, uint64_t hi
 //                 leaves likelihoods / posteriors of the candidates in part[] (device-side counter dCounts[seg])
 //   count + scan  block counts of what is left in the mask
 //   k_rank        place of every candidate in the ordered output
-//   k_candidates (compute stream) || k_bias (aux stream): records and their Fisher tests, both persistent grids that
-//                 read the count on the device and write disjoint fields of recs[rank]
+//   k_candidates  records (persistent grid that reads the count on the device), with every strand-bias / base-quality
+//                 Fisher test the memo cache holds; the others go to a list
+//   k_bias        the walks of the listed tests (persistent grid, device-side count; next to nothing once the cache is warm)
 // `mask` is the flag bitmap of the whole call (bit 0 = site `begin`).
 int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t begin, uint64_t a, uint64_t b,
                    bool usedTables, const DecisionTables &D, size_t &evNext, uint32_t seg, cudaEvent_t evStream0,
@@ -808,10 +811,9 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
   uint32_t *dCount = ctx->dCounts + seg;
   EvalOut *part = (EvalOut *) ctx->part.p;
   uint32_t *rankOf = (uint32_t *) ctx->rankOf.p, *list = (uint32_t *) ctx->list.p;
-  cudaEvent_t ev[4], auxDone;
+  cudaEvent_t ev[4];
   int rc;
   for (int k = 0; k < 4; ++k) if ((rc = get_event(ctx, evNext++, &ev[k]))) return rc;
-  if ((rc = get_event(ctx, evNext++, &auxDone))) return rc;
   CUF(cudaEventRecord(ev[0], ctx->compute));
   launch_eval_mask(V, pl.map, begin, off, n, usedTables, D, P, maskAll, ctx->errWord, ctx->dFlagged, part, dCount, cap, ctx->compute);
   CUF(cudaEventRecord(ev[1], ctx->compute));
@@ -822,16 +824,12 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
   CUF(cudaEventRecord(ev[2], ctx->compute));
   // record buffers alternate between segments: a segment's copy home may still be in flight while the next one is written
   gt16_called_site *recs = (gt16_called_site *) ((seg & 1) ? ctx->recs2.p : ctx->recs.p);
-  if (seg >= 2) {                                             // this buffer's previous contents are on the host
-    CUF(cudaStreamWaitEvent(ctx->compute, segCopied[seg - 2], 0));
-    CUF(cudaStreamWaitEvent(ctx->aux, segCopied[seg - 2], 0));
-  }
-  CUF(cudaStreamWaitEvent(ctx->aux, ev[2], 0));
-  launch_candidates(V, pl.map, begin, part, rankOf, dCount, cap, recs, ctx->errWord, ctx->numSMs, ctx->compute);
-  launch_bias(V, pl.map, begin, part, rankOf, dCount, cap, P, ctx->biasCache, kBiasCacheEntries - 1, recs, ctx->numSMs, ctx->aux);
+  if (seg >= 2) CUF(cudaStreamWaitEvent(ctx->compute, segCopied[seg - 2], 0));   // this buffer's previous contents are on the host
+  CUF(cudaMemsetAsync(ctx->dMissed, 0, 4, ctx->compute));
+  launch_candidates(V, pl.map, begin, part, rankOf, dCount, cap, P, ctx->biasCache, kBiasCacheEntries - 1,
+                    (BiasTask *) ctx->missed.p, ctx->dMissed, cap, recs, ctx->errWord, ctx->numSMs, ctx->compute);
+  launch_bias((BiasTask *) ctx->missed.p, ctx->dMissed, cap, P, ctx->biasCache, kBiasCacheEntries - 1, recs, ctx->numSMs, ctx->compute);
   ctx->launches += 7;
-  CUF(cudaEventRecord(auxDone, ctx->aux));
-  CUF(cudaStreamWaitEvent(ctx->compute, auxDone, 0));         // part / rankOf / list are reused by the next segment
   CUF(cudaEventRecord(ev[3], ctx->compute));
   timing.push_back(evStream0); timing.push_back(evStream1);
   for (int k = 0; k < 4; ++k) timing.push_back(ev[k]);
@@ -953,6 +951,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     CUF(ctx->part.ensure((size_t) capWant * sizeof(EvalOut)));
     CUF(ctx->rankOf.ensure((size_t) capWant * 4));
     CUF(ctx->list.ensure((size_t) capWant * 4));
+    CUF(ctx->missed.ensure((size_t) capWant * sizeof(BiasTask)));
     CUF(ctx->recs.ensure((size_t) capWant * sizeof(gt16_called_site)));
     if (!devOutHandle && n > kBatch) CUF(ctx->recs2.ensure((size_t) capWant * sizeof(gt16_called_site)));   // more than one segment
   }

@@ -413,7 +413,13 @@ struct SnapView {
   uint32_t nOvfRegions;       // numOfCPUThreads of the snapshot (SnapshotHandler.cpp:297)
   uint32_t poolBytes;
   uint32_t refWords;
+  uint32_t ovfLen;            // L / nOvfRegions, positions per overflow region (set_ovf_geometry)
+  double ovfInv;              // 1.0 / ovfLen
 };
+inline void set_ovf_geometry(SnapView &V) {
+  V.ovfLen = V.nOvfRegions ? V.L / V.nOvfRegions : 0;
+  V.ovfInv = V.ovfLen ? 1.0 / (double) V.ovfLen : 0.0;
+}
 
 GT16_HD uint32_t ref_base(const SnapView &V, uint32_t p) {            // VariantCaller.cpp:629
   uint32_t w = p >> 4;
@@ -425,10 +431,14 @@ GT16_HD bool is_invalid(const SnapView &V, uint32_t p) {              // :39
   if (!V.invalid) return false;
   return (V.invalid[p >> 5] >> (31 - (p & 31))) & 1;
 }
-GT16_HD uint32_t ovf_region(const SnapView &V, uint32_t p) {          // findRegionByPosition
-  uint32_t n = V.nOvfRegions, len = V.L / n;
+GT16_HD uint32_t ovf_region(const SnapView &V, uint32_t p) {          // findRegionByPosition: min(p / (L / n), n - 1)
+  const uint32_t n = V.nOvfRegions, len = V.ovfLen;
   if (len == 0) return n - 1;
-  uint32_t r = p / len;
+  // p / len without an integer division (the region length is fixed per snapshot): the product with the reciprocal is
+  // within one of the quotient, one comparison on either side makes it exact
+  uint32_t r = (uint32_t) ((double) p * V.ovfInv);
+  if ((uint64_t) r * len > p) --r;
+  else if ((uint64_t) (r + 1) * len <= p) ++r;
   return r < n - 1 ? r : n - 1;
 }
 GT16_HD bool is_overflow_type(uint64_t c) { return (((uint32_t) c & (uint32_t) (c >> 16)) & 0xC000u) == 0xC000u; }

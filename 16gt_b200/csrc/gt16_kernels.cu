@@ -887,14 +887,41 @@ __device__ __noinline__ void write_indel_patterns(const SnapView &V, gt16_called
   }
 }
 
+// ---- Fisher tests of the records (strand bias / base-quality bias, SNPFunctions.cpp:137-159) -------------------
+// SB and BQB for the four bases of the site itself (SNP rows) or of the three sites {index-1, index+nextBp, index}
+// (indel rows, SNP_Caller.cpp:248-274).
+// A test is a pure function of its three counts, and a genome repeats the same (F, R) and (W, F+R) pairs
+// endlessly, so finished tests are memoised in a direct-mapped cache in global memory (L2-resident, owned by the
+// context, kept across calls): {key, result} in one aligned 8-byte word.  A hit returns the very value a walk
+// would produce; a miss runs the walk and stores it.  Keys that do not fit 32 bits (W >= 32768 or F+R >= 65536)
+// are simply not cached.
+__device__ __forceinline__ uint32_t bias_key(bool bqb, uint32_t W, uint32_t F, uint32_t R) {
+  if (bqb) { const uint32_t S = F + R; return (W < 32768u && S < 65536u && !(W == 32767u && S == 65535u)) ? (0x80000000u | (W << 16) | S) : 0xFFFFFFFFu; }
+  return (F < 32768u && R < 65536u) ? ((F << 16) | R) : 0xFFFFFFFFu;
+}
+__device__ __forceinline__ uint32_t bias_slot(uint32_t key, uint32_t mask) { return ((key * 0x9E3779B1u) ^ (key >> 15)) & mask; }
+
+// A test the cache does not hold goes to the walk kernel (k_bias) through a list in global memory.
+struct BiasList { BiasTask *tasks; uint32_t *count; uint32_t cap; };
+
+// the list is full (it holds one test per record of the bound, far more than a warmed-up cache ever misses): the lane
+// walks the test itself
+__device__ __noinline__ float bias_inline(const LnFact &G, bool bqb, uint32_t W, uint32_t F, uint32_t R) {
+  LnFact L; L.tab = G.tab; L.size = G.size; L.far = G.tab; L.farSize = G.size;
+  return bqb ? base_quality_bias(L, W, F, R) : strand_bias(L, F, R);
+}
+
 __global__ void __launch_bounds__(kCandThreads, GT16_CAND_BLOCKS) k_candidates(SnapView V, DevSiteMap M, uint64_t base,
                                                              const EvalOut *__restrict__ part,
                                                              const uint32_t *__restrict__ rankOf,
                                                              const uint32_t *__restrict__ count, uint32_t cap,
+                                                             LnFact G, uint2 *__restrict__ cache, uint32_t cacheMask, BiasList missed,
+                                                             float sbEmpty, float bqbEmpty,
                                                              gt16_called_site *__restrict__ out, uint32_t *errWord) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warpsTotal = gridDim.x * (kCandThreads / 32);
   const uint32_t n = *count < cap ? *count : cap;
+
   for (uint32_t j = blockIdx.x * (kCandThreads / 32) + (threadIdx.x >> 5); j < n; j += warpsTotal) {
     const EvalOut &eo = part[j];
     const uint64_t i = base + eo.site;
@@ -905,35 +932,10 @@ __global__ void __launch_bounds__(kCandThreads, GT16_CAND_BLOCKS) k_candidates(S
     //    to decide that this site is a candidate
     if (lane < 16) { o.lh[lane] = eo.lh[lane]; o.flh[lane] = eo.flh[lane]; }
     const int genotype = eo.genotype;
-    // -- counts of the site: base `lane` on lanes 0..3 (decode_bases, one base per lane), the two deepest indel
-    //    patterns on lanes 4 and 5
     const int ref = (int) ref_base(V, p);
     IndelInfo ii; PatRef d0, d1;
     decode_indel_refs(V, p, ii, d0, d1);
     if (ii.bad) err |= kErrBadSnapshot;
-    {
-      uint32_t w = 0, f = 0, r = 0;
-      bool bad = false;
-      if (lane < 4 && !is_invalid(V, p)) {
-        const uint64_t c = V.counters[p];
-        const uint32_t lo = (uint32_t) c, hi = (uint32_t) (c >> 32);
-        if (!is_overflow_type(c)) {
-          if ((hi & 0xFFFFu) && ((lo >> 14) & 3u) == lane) { w = lo & 0x3FFFu; f = hi & 0xFFu; r = (hi >> 8) & 0xFFu; }
-          if ((hi >> 16) && (lo >> 30) == lane) { w = (lo >> 16) & 0x3FFFu; f = (hi >> 16) & 0xFFu; r = hi >> 24; }   // second slot wins
-        } else {
-          const uint8_t *rec = ovf_record(V, ovf_region(V, p), hi);
-          if (!rec) bad = true;
-          else {
-            f = rd16(rec + 8 + 2 * lane); r = rd16(rec + 16 + 2 * lane);
-            if (f | r) w = rd16(rec + 2 * lane);
-          }
-        }
-      }
-      if (lane == 4) { w = ii.W4; f = ii.F4; r = ii.R4; }
-      if (lane == 5) { w = ii.W5; f = ii.F5; r = ii.R5; }
-      if (__any_sync(0xffffffffu, bad)) err |= kErrBadSnapshot;
-      if (lane < 6) { o.W[lane] = w; o.F[lane] = f; o.R[lane] = r; }
-    }
     const uint8_t isIndel = eo.isIndel, nextBp = eo.nextBp;             // SNP_Caller.cpp:228-239 (decided by the evaluator)
     if (genotype > 9 && !isIndel) err |= kErrGenotype;
     BatchGeom B;
@@ -943,6 +945,79 @@ __global__ void __launch_bounds__(kCandThreads, GT16_CAND_BLOCKS) k_candidates(S
     B.amb0 = site_pos(M, B.first);
     B.ambLast = site_pos(M, B.first + B.n - 1);
     const uint32_t idx = (uint32_t) (i - B.first);
+    // -- counts and Fisher tests: lane 4 k + b holds base b of the k-th site whose strand / base-quality bias the row
+    //    carries -- the site itself (SNP rows, k = 0) or {index-1, index+nextBp, index} (indel rows) :248-274 -- decoded
+    //    one base per lane (decode_bases); the site's own counts go into the record, and every lane looks its two
+    //    tests up in the memo cache: a hit is written at once, a miss is left to the walk kernel.
+    {
+      const uint32_t k = lane >> 2, b = lane & 3u;
+      bool have = false; uint64_t si = i;
+      if (lane < 12) {
+        if (isIndel) {
+          if (k == 0) { have = idx != 0; si = i - 1; }
+          else if (k == 1) { have = idx + nextBp < B.n; si = i + nextBp; }
+          else have = true;
+        } else have = k == 0;
+      }
+      const bool own = have && si == i;
+      uint32_t w = 0, f = 0, r = 0;
+      bool bad = false;
+      if (have) {
+        const uint32_t ps = own ? p : site_pos(M, si);
+        if (!is_invalid(V, ps)) {
+          const uint64_t c = V.counters[ps];
+          const uint32_t lo = (uint32_t) c, hi = (uint32_t) (c >> 32);
+          if (!is_overflow_type(c)) {
+            if ((hi & 0xFFFFu) && ((lo >> 14) & 3u) == b) { w = lo & 0x3FFFu; f = hi & 0xFFu; r = (hi >> 8) & 0xFFu; }
+            if ((hi >> 16) && (lo >> 30) == b) { w = (lo >> 16) & 0x3FFFu; f = (hi >> 16) & 0xFFu; r = hi >> 24; }   // second slot wins
+          } else {
+            const uint8_t *rec = ovf_record(V, ovf_region(V, ps), hi);
+            if (!rec) bad = own;                              // a neighbour with a bad index counts as empty, like decode_bases
+            else {
+              f = rd16(rec + 8 + 2 * b); r = rd16(rec + 16 + 2 * b);
+              if (f | r) w = rd16(rec + 2 * b);
+            }
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, bad)) err |= kErrBadSnapshot;
+      if (own) { o.W[b] = w; o.F[b] = f; o.R[b] = r; }
+      if (lane == 12) { o.W[4] = ii.W4; o.F[4] = ii.F4; o.R[4] = ii.R4; }
+      if (lane == 13) { o.W[5] = ii.W5; o.F[5] = ii.F5; o.R[5] = ii.R5; }
+      if (lane < 12) {
+        float sbv = 0.f, bqv = 0.f;
+        bool needS = false, needB = false;
+        if (have) {
+          sbv = sbEmpty; bqv = bqbEmpty;
+          if (w | f | r) {
+            const uint32_t kS = bias_key(false, w, f, r), kB = bias_key(true, w, f, r);
+            unsigned long long eS = ~0ull, eB = ~0ull;
+            if (kS != 0xFFFFFFFFu) eS = *reinterpret_cast<const volatile unsigned long long *>(cache + bias_slot(kS, cacheMask));
+            if (kB != 0xFFFFFFFFu) eB = *reinterpret_cast<const volatile unsigned long long *>(cache + bias_slot(kB, cacheMask));
+            needS = !(kS != 0xFFFFFFFFu && (uint32_t) eS == kS);
+            needB = !(kB != 0xFFFFFFFFu && (uint32_t) eB == kB);
+            sbv = __uint_as_float((uint32_t) (eS >> 32)); bqv = __uint_as_float((uint32_t) (eB >> 32));
+          }
+        }
+        if (needS | needB) {                                  // rare once the cache is warm
+          const uint32_t dst = rankOf[j] * 12u + lane;
+          const uint32_t want = (needS ? 1u : 0u) + (needB ? 1u : 0u);
+          const uint32_t at = atomicAdd(missed.count, want);
+          if (at + want <= missed.cap) {
+            uint32_t q = at;
+            if (needS) { BiasTask t; t.W = w; t.F = f; t.R = r; t.dst = dst; missed.tasks[q++] = t; }
+            if (needB) { BiasTask t; t.W = w; t.F = f; t.R = r; t.dst = dst | 0x80000000u; missed.tasks[q] = t; }
+          } else {
+            atomicSub(missed.count, want);
+            if (needS) { sbv = bias_inline(G, false, w, f, r); needS = false; }
+            if (needB) { bqv = bias_inline(G, true, w, f, r); needB = false; }
+          }
+        }
+        if (!needS) o.sb[k][b] = sbv;
+        if (!needB) o.bqb[k][b] = bqv;
+      }
+    }
+
 
     // -- windows (reference's un-offset mwInfo indexing)                                 :276-367
     // entry k of the batch's mwInfo array (k < n + 200; the cases of window_entry()): the left margin [0, 100) holds
@@ -1018,14 +1093,21 @@ __global__ void __launch_bounds__(kCandThreads, GT16_CAND_BLOCKS) k_candidates(S
   }
 }
 void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
-                       const uint32_t *count, uint32_t cap, gt16_called_site *out, uint32_t *errWord, int numSMs,
-                       cudaStream_t s) {
+                       const uint32_t *count, uint32_t cap, const EvalParams &P, uint2 *cache, uint32_t cacheMask,
+                       BiasTask *missed, uint32_t *missedCount, uint32_t missedCap, gt16_called_site *out, uint32_t *errWord,
+                       int numSMs, cudaStream_t s) {
   // persistent grid: the number of records is only known on the device; 8 blocks of 4 warps per SM (launch bounds), and a
   // small call (cap is a bound on its records) does not need more warps than records
   unsigned grid = (cap + (kCandThreads / 32) - 1) / (kCandThreads / 32);
   const unsigned full = (unsigned) numSMs * GT16_CAND_GRID;
   if (grid > full) grid = full;
-  k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, part, rankOf, count, cap, out, errWord);
+  BiasList ml; ml.tasks = missed; ml.count = missedCount; ml.cap = missedCap;
+  // the tests of a base that was never seen (all counts zero) need lnfactC(0) only: evaluated here, by the same routines,
+  // with the host libm's lgammaf(1) the device table starts with
+  static const float lg1 = lgammaf(1.0f);
+  LnFact H; H.tab = &lg1; H.size = 1; H.far = nullptr; H.farSize = 0;
+  const float sbEmpty = strand_bias(H, 0, 0), bqbEmpty = base_quality_bias(H, 0, 0, 0);
+  k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, part, rankOf, count, cap, P.lnfact, cache, cacheMask, ml, sbEmpty, bqbEmpty, out, errWord);
 }
 
 // ------------------------------------------------------------------------------ Fisher tests of the candidates
@@ -1046,7 +1128,6 @@ constexpr int kBiasThreads = 256;
 constexpr int kLnSmem = 4096;
 constexpr int kBiasQueue = 128;
 constexpr int kBiasStepsPerRefill = 12;
-struct BiasTask { uint32_t W, F, R, dst; };      // dst = record * 12 + k * 4 + base, bit 31 = base-quality test
 
 struct FisherWalk {                               // state of one fisher2tailC evaluation
   int n1_, n_1, n, x, lo, hi, n11;
@@ -1095,25 +1176,10 @@ __device__ __forceinline__ void walk_step(FisherWalk &w) {
   }
 }
 
-// A test is a pure function of its three counts, and a genome repeats the same (F, R) and (W, F+R) pairs
-// endlessly, so finished tests are memoised in a direct-mapped cache in global memory (L2-resident, owned by the
-// context, kept across calls): {key, result} in one aligned 8-byte word.  A hit returns the very value a walk
-// would produce; a miss runs the walk and stores it.  Keys that do not fit 32 bits (W >= 32768 or F+R >= 65536)
-// are simply not cached.
-__device__ __forceinline__ uint32_t bias_key(bool bqb, uint32_t W, uint32_t F, uint32_t R) {
-  if (bqb) { const uint32_t S = F + R; return (W < 32768u && S < 65536u && !(W == 32767u && S == 65535u)) ? (0x80000000u | (W << 16) | S) : 0xFFFFFFFFu; }
-  return (F < 32768u && R < 65536u) ? ((F << 16) | R) : 0xFFFFFFFFu;
-}
-__device__ __forceinline__ uint32_t bias_slot(uint32_t key, uint32_t mask) { return ((key * 0x9E3779B1u) ^ (key >> 15)) & mask; }
-
-__global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M, uint64_t base,
-                                                       const EvalOut *__restrict__ part,
-                                                       const uint32_t *__restrict__ rankOf,
-                                                       const uint32_t *__restrict__ count, uint32_t cap, LnFact G,
-                                                       uint2 *__restrict__ cache, uint32_t cacheMask,
+__global__ void __launch_bounds__(kBiasThreads) k_bias(BiasList missed, LnFact G, uint2 *__restrict__ cache, uint32_t cacheMask,
                                                        gt16_called_site *__restrict__ out) {
-  const uint32_t n = *count < cap ? *count : cap;
-  if (blockIdx.x * (kBiasThreads / 32) * 32u >= n * 12u) return;     // persistent grid sized for the bound, not the count
+  const uint32_t n = *missed.count < missed.cap ? *missed.count : missed.cap;
+  if (blockIdx.x * (kBiasThreads / 32) * 32u >= n) return;          // persistent grid sized for the bound, not the count
   __shared__ float lnS[kLnSmem];
   __shared__ BiasTask queue[kBiasThreads / 32][kBiasQueue];
   const uint32_t nS = G.size < (uint32_t) kLnSmem ? G.size : (uint32_t) kLnSmem;
@@ -1121,7 +1187,6 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
   __syncthreads();
   LnFact L;
   L.tab = lnS; L.size = nS; L.far = G.tab; L.farSize = G.size;
-  const float sbEmpty = strand_bias(L, 0, 0), bqbEmpty = base_quality_bias(L, 0, 0, 0);   // a base that was never seen
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
   BiasTask *q = queue[warp];
   uint32_t qhead = 0, qtail = 0;                   // ring indices (monotonic), entries live in q[i % kBiasQueue]
@@ -1163,59 +1228,14 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
     __syncwarp();
   };
 
-  const uint32_t nSlots = n * 12u, warpsTotal = gridDim.x * (kBiasThreads / 32);
-  for (uint32_t chunk = blockIdx.x * (kBiasThreads / 32) + warp; chunk * 32u < nSlots; chunk += warpsTotal) {
-    const uint32_t slot = chunk * 32u + lane;
-    bool pending = false;
-    BiasTask t; t.W = t.F = t.R = 0; t.dst = 0;
-    uint32_t rec = 0;                                 // the record this slot belongs to (ordered output)
-    if (slot < nSlots) {
-      const uint32_t j = slot / 12, k = (slot % 12) >> 2, b = slot & 3;
-      const EvalOut &eo = part[j];
-      rec = rankOf[j];
-      t.dst = rec * 12u + (slot % 12);
-      const uint32_t isIndel = eo.isIndel;
-      const uint32_t nextBp = eo.nextBp;
-      const uint64_t i = base + eo.site;
-      const uint64_t bFirst = (i / kBatch) * (uint64_t) kBatch;
-      const uint64_t left = M.totalSites - bFirst;
-      const uint32_t bn = left < kBatch ? (uint32_t) left : kBatch, idx = (uint32_t) (i - bFirst);
-      bool have; uint64_t si = i;
-      if (isIndel) {
-        if (k == 0) { have = idx != 0; si = i - 1; }
-        else if (k == 1) { have = idx + nextBp < bn; si = i + nextBp; }
-        else have = true;
-      } else have = (k == 0);
-      float sbv = 0.f, bqv = 0.f;
-      if (have) {
-        BaseCounts nb;
-        decode_bases(V, site_pos(M, si), nb);
-        t.W = b == 0 ? nb.W[0] : b == 1 ? nb.W[1] : b == 2 ? nb.W[2] : nb.W[3];
-        t.F = b == 0 ? nb.F[0] : b == 1 ? nb.F[1] : b == 2 ? nb.F[2] : nb.F[3];
-        t.R = b == 0 ? nb.R[0] : b == 1 ? nb.R[1] : b == 2 ? nb.R[2] : nb.R[3];
-        pending = (t.W | t.F | t.R) != 0;
-        sbv = sbEmpty; bqv = bqbEmpty;
-      }
-      if (!pending) { out[rec].sb[k][b] = sbv; out[rec].bqb[k][b] = bqv; }
-    }
-    BiasTask tb = t; tb.dst |= 0x80000000u;
-    bool needS = pending, needB = pending;
-    if (pending) {                                  // memoised?
-      const uint32_t kS = bias_key(false, t.W, t.F, t.R), kB = bias_key(true, t.W, t.F, t.R);
-      const uint32_t k = (slot % 12) >> 2, b = slot & 3;
-      if (kS != 0xFFFFFFFFu) {
-        const unsigned long long e = *reinterpret_cast<const volatile unsigned long long *>(cache + bias_slot(kS, cacheMask));
-        if ((uint32_t) e == kS) { out[rec].sb[k][b] = __uint_as_float((uint32_t) (e >> 32)); needS = false; }
-      }
-      if (kB != 0xFFFFFFFFu) {
-        const unsigned long long e = *reinterpret_cast<const volatile unsigned long long *>(cache + bias_slot(kB, cacheMask));
-        if ((uint32_t) e == kB) { out[rec].bqb[k][b] = __uint_as_float((uint32_t) (e >> 32)); needB = false; }
-      }
-    }
-    push(needS, t);                                 // strand test
-    push(needB, tb);                                // base-quality test
-    // keep room for the next chunk's (up to 64) tests
-    while (qtail - qhead > (uint32_t) (kBiasQueue - 64)) {
+  const uint32_t warpsTotal = gridDim.x * (kBiasThreads / 32);
+  for (uint32_t chunk = blockIdx.x * (kBiasThreads / 32) + warp; chunk * 32u < n; chunk += warpsTotal) {
+    const uint32_t t = chunk * 32u + lane;
+    BiasTask task; task.W = task.F = task.R = task.dst = 0;
+    if (t < n) task = missed.tasks[t];
+    push(t < n, task);
+    // keep room for the next chunk's tests
+    while (qtail - qhead > (uint32_t) (kBiasQueue - 32)) {
       refill();
 #pragma unroll 1
       for (int it = 0; it < kBiasStepsPerRefill; ++it) walk_step(w);
@@ -1228,16 +1248,16 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(SnapView V, DevSiteMap M,
     for (int it = 0; it < kBiasStepsPerRefill; ++it) walk_step(w);
   }
 }
-void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
-                 const uint32_t *count, uint32_t cap, const EvalParams &P, uint2 *cache, uint32_t cacheMask,
-                 gt16_called_site *out, int numSMs, cudaStream_t s) {
+void launch_bias(BiasTask *missed, const uint32_t *missedCount, uint32_t missedCap, const EvalParams &P, uint2 *cache,
+                 uint32_t cacheMask, gt16_called_site *out, int numSMs, cudaStream_t s) {
   // the walks are long dependent chains: what matters is how many run at once, so spread the chunks over as many
   // resident warps as the device holds (4 blocks of 8 warps per SM); blocks beyond the device-side count leave at once
-  const uint32_t chunks = (uint32_t) (((uint64_t) cap * 12u + 31) / 32), perBlock = kBiasThreads / 32;
+  const uint32_t chunks = (missedCap + 31) / 32, perBlock = kBiasThreads / 32;
   unsigned grid = (chunks + perBlock - 1) / perBlock;
   if (grid > (unsigned) numSMs * GT16_BIAS_GRID) grid = (unsigned) numSMs * GT16_BIAS_GRID;
   if (grid < 1) grid = 1;
-  k_bias<<<grid, kBiasThreads, 0, s>>>(V, M, base, part, rankOf, count, cap, P.lnfact, cache, cacheMask, out);
+  BiasList ml; ml.tasks = missed; ml.count = const_cast<uint32_t *>(missedCount); ml.cap = missedCap;
+  k_bias<<<grid, kBiasThreads, 0, s>>>(ml, P.lnfact, cache, cacheMask, out);
 }
 
 // ------------------------------------------------------------------------------ operator seam

@@ -84,17 +84,22 @@ void launch_mask_count(const uint32_t *mask, uint32_t nItems, uint32_t *blockCou
 // exclusive scan in two levels: blockCounts[b] becomes the offset within its chunk of 1024 blocks, chunkOffsets[c]
 // (room for (nBlocks + 1023) / 1024 words) the offset of the chunk; *total = number of set bits
 void launch_scan_counts(uint32_t *blockCounts, uint32_t nBlocks, uint32_t *chunkOffsets, uint32_t *total, cudaStream_t s);
-// full records of the candidates in part[0, min(*count, cap)): out[rankOf[j]] (persistent grid, the count is read on the device)
-void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
-                       const uint32_t *count, uint32_t cap, gt16_called_site *out, uint32_t *errWord, int numSMs,
-                       cudaStream_t s);
+// One Fisher test (strand bias or base-quality bias) that the memo cache did not hold: three counts and where the result
+// goes (dst = record * 12 + k * 4 + base, bit 31 = base-quality test).
+struct BiasTask { uint32_t W, F, R, dst; };
 
-// strand-bias / base-quality-bias Fisher tests of the same candidates, written into out[rankOf[j]].sb / .bqb; may run
-// beside launch_candidates (the two kernels write disjoint fields)
-// cache: (cacheMask + 1) 8-byte {key, result} entries, all bytes 0xFF when empty (see k_bias)
-void launch_bias(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
-                 const uint32_t *count, uint32_t cap, const EvalParams &P, uint2 *cache, uint32_t cacheMask,
-                 gt16_called_site *out, int numSMs, cudaStream_t s);
+// full records of the candidates in part[0, min(*count, cap)): out[rankOf[j]] (persistent grid, the count is read on the
+// device) -- counts, window features, indel patterns and the strand-bias / base-quality-bias tests the memo cache holds
+// (cache: (cacheMask + 1) 8-byte {key, result} entries, all bytes 0xFF when empty); tests it does not hold are appended to
+// missed[0, missedCap) (*missedCount, zeroed by the caller) for launch_bias, and walked in place when that list is full
+void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
+                       const uint32_t *count, uint32_t cap, const EvalParams &P, uint2 *cache, uint32_t cacheMask,
+                       BiasTask *missed, uint32_t *missedCount, uint32_t missedCap, gt16_called_site *out, uint32_t *errWord,
+                       int numSMs, cudaStream_t s);
+
+// the Fisher-test walks of missed[0, min(*missedCount, missedCap)): results into out[dst / 12].sb / .bqb and into the cache
+void launch_bias(BiasTask *missed, const uint32_t *missedCount, uint32_t missedCap, const EvalParams &P, uint2 *cache,
+                 uint32_t cacheMask, gt16_called_site *out, int numSMs, cudaStream_t s);
 
 // operator seam kernels
 void launch_op_likelihood(const EvalParams &P, const uint8_t *w, size_t wStride, const uint8_t *ref,

@@ -109,6 +109,7 @@ int emu_run(const char *indexPrefix, const char *snapshotPath, const char *regio
   V.counters = v.counters; V.invalid = v.invalid_bitmap; V.ovf = ovf.data(); V.ovfBase = ovfBase.data();
   V.pool = v.pool; V.packedRef = packed; V.L = v.text_length; V.nOvfRegions = v.n_overflow_regions;
   V.poolBytes = v.pool_bytes; V.refWords = nWords;
+  set_ovf_geometry(V);
   std::vector<uint32_t> rs; std::vector<uint64_t> rf;
   uint64_t acc = 0;
   if (regionBin && *regionBin) {
