@@ -26,7 +26,8 @@ class View(ctypes.Structure):
     _fields_ = [("counters", ctypes.c_void_p), ("text_length", ctypes.c_uint32), ("invalid_bitmap", ctypes.c_void_p),
                 ("n_overflow_regions", ctypes.c_uint32), ("overflow", ctypes.c_void_p),
                 ("overflow_size", ctypes.c_void_p), ("pool", ctypes.c_void_p), ("pool_bytes", ctypes.c_uint32),
-                ("packed_ref", ctypes.c_void_p), ("packed_ref_words", ctypes.c_uint32)]
+                ("packed_ref", ctypes.c_void_p), ("packed_ref_words", ctypes.c_uint32),
+                ("sparse_entries", ctypes.c_void_p), ("n_sparse_entries", ctypes.c_uint64)]
 
 
 class Indel(ctypes.Structure):
@@ -112,6 +113,7 @@ def capi():
         "gt16_calls_data": (vp, [vp]),
         "gt16_calls_free": (None, [vp]),
         "gt16_snapshot_read": (i32, [cp, i32, P(vp), cp, sz]),
+        "gt16_snapshot_read_ex": (i32, [cp, i32, u32, u32, P(vp), cp, sz]),
         "gt16_snapshot_view_of": (None, [vp, P(View)]),
         "gt16_snapshot_free": (None, [vp]),
         "gt16_index_read": (i32, [cp, P(vp), cp, sz]),
@@ -166,7 +168,7 @@ class LoadedInput:
     [lo, hi) only (gt16_snapshot_read_range: one shard of a sharded genome).  index=<LoadedInput>: share that input's
     index instead of reading it again."""
 
-    def __init__(self, idx_prefix, snapshot_path, region_bin=None, pinned=1, pos_range=None, index=None):
+    def __init__(self, idx_prefix, snapshot_path, region_bin=None, pinned=1, pos_range=None, index=None, keep_sparse=False):
         L = capi()
         self.L = L
         err = ctypes.create_string_buffer(512)
@@ -183,7 +185,10 @@ class LoadedInput:
         self.length = L.gt16_index_length(self.ix)
         self.view = View()
         if snapshot_path is not None:
-            if pos_range is None:
+            if keep_sparse:      # a sparse snapshot stays the list of {position, counter} records it is (GT16_READ_KEEP_SPARSE)
+                lo, hi = (0, 0xFFFFFFFF) if pos_range is None else (int(pos_range[0]), int(pos_range[1]))
+                rc = L.gt16_snapshot_read_ex(snapshot_path.encode(), (1 if pinned else 0) | 2, lo, hi, ctypes.byref(self.hs), err, 512)
+            elif pos_range is None:
                 rc = L.gt16_snapshot_read(snapshot_path.encode(), pinned, ctypes.byref(self.hs), err, 512)
             else:
                 rc = L.gt16_snapshot_read_range(snapshot_path.encode(), pinned, int(pos_range[0]), int(pos_range[1]),

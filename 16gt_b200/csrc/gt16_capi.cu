@@ -97,9 +97,10 @@ struct gt16_ctx {
   int numSMs = 148;
   // persistent scratch of the fused path
   DevBuf mask, counts, part, rankOf, list, missed, recs, recs2, planStart, planFirst, planTile;
-  std::vector<uint32_t> lastPlanStart;   // host copy of what planStart / planFirst hold (make_plan)
-  std::vector<uint64_t> lastPlanFirst;
+  std::shared_ptr<const void> planCache; // host side of what planStart / planFirst / planTile hold (PlanData, make_plan)
   DevBuf sCounters, sInvalid, sOvf, sOvfBase, sPool, sRef;      // streamed (host-fed) snapshot
+  DevBuf sSparse;                                               // records of a sparse view on their way into the counter array
+  cudaEvent_t sparseCopied = nullptr;                           // ... and the event that orders a chunk's scatter behind its copy
   // events and the small pinned read-back slot of a call come from ring entry evCur: a call that returns before its tail
   // has run (gt16_call_sites_device_nowait) keeps its entry until kCallRing further calls have been made
   static const int kCallRing = 128;
@@ -246,6 +247,7 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->sparseCopied, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
   if ((e = cudaMalloc(&ctx->prior, 256 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->g2i, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->ycsq, kYcsqN * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -290,11 +292,12 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
   if (ctx->hPinnedRing) cudaFreeHost(ctx->hPinnedRing);
   if (ctx->hCounts) cudaFreeHost(ctx->hCounts);
   for (DevBuf *b : {&ctx->mask, &ctx->counts, &ctx->part, &ctx->rankOf, &ctx->list, &ctx->missed, &ctx->recs, &ctx->recs2, &ctx->planStart, &ctx->planFirst, &ctx->planTile,
-                    &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef}) b->release();
+                    &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef, &ctx->sSparse}) b->release();
   for (auto &pool : ctx->evPool) for (auto e : pool) cudaEventDestroy(e);
   if (ctx->stagePin) cudaFreeHost(ctx->stagePin);
   for (auto e : ctx->stageEv) if (e) cudaEventDestroy(e);
   for (cudaStream_t st : {ctx->compute, ctx->copy, ctx->d2h, ctx->aux}) if (st) cudaStreamDestroy(st);
+  if (ctx->sparseCopied) cudaEventDestroy(ctx->sparseCopied);
   (void) cudaGetLastError();
   delete ctx;
 }
@@ -632,9 +635,72 @@ static int finish_counters(gt16_ctx *ctx, gt16_dev_snapshot *ds, cudaStream_t s)
   return GT16_OK;
 }
 
+// ---- sparse views: {u32 position; u64 counter} records, 12 bytes each, ascending positions -----------------------
+static const uint64_t kSparseChunk = 1u << 21;          // records per cudaMemcpyAsync (24 MiB)
+static inline uint32_t sparse_pos(const gt16_snapshot_view *v, uint64_t k) {
+  uint32_t p;
+  memcpy(&p, (const char *) v->sparse_entries + k * 12, 4);
+  return p;
+}
+// first record whose position is >= pos
+static uint64_t sparse_lower_bound(const gt16_snapshot_view *v, uint64_t pos) {
+  uint64_t lo = 0, hi = v->n_sparse_entries;
+  while (lo < hi) { const uint64_t mid = (lo + hi) / 2; if ((uint64_t) sparse_pos(v, mid) < pos) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+// copy records [eLo, eHi) to the context's staging buffer and scatter them into ds->counters (positions in the window
+// only) on stream s, in sparse_chunks(eLo, eHi) chunks; chunkDone (optional) holds one event per chunk, recorded behind
+// its scatter (the last one also behind counters[L] = counters[L-1])
+static size_t sparse_chunks(uint64_t eLo, uint64_t eHi) { return eHi > eLo ? (size_t) ((eHi - eLo + kSparseChunk - 1) / kSparseChunk) : 1; }
+static int finish_counters(gt16_ctx *ctx, gt16_dev_snapshot *ds, cudaStream_t s);
+static int upload_sparse(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot *ds, uint64_t eLo, uint64_t eHi,
+                         cudaStream_t s, const std::vector<cudaEvent_t> *chunkDone) {
+  if (eHi < eLo) eHi = eLo;
+  CUF(ctx->sSparse.ensure((size_t) (eHi - eLo) * 12 + 16));
+  const size_t nChunks = sparse_chunks(eLo, eHi);
+  for (size_t c = 0; c < nChunks; ++c) {
+    const uint64_t a = eLo + c * kSparseChunk, b = std::min<uint64_t>(a + kSparseChunk, eHi);
+    // the copies queue up back to back on s; the scatter of a chunk runs on the aux stream behind its copy
+    if (b > a) {
+      char *dst = (char *) ctx->sSparse.p + (size_t) (a - eLo) * 12;
+      CUF(cudaMemcpyAsync(dst, (const char *) view->sparse_entries + a * 12, (size_t) (b - a) * 12, cudaMemcpyHostToDevice, s));
+      CUF(cudaEventRecord(ctx->sparseCopied, s));
+      CUF(cudaStreamWaitEvent(ctx->aux, ctx->sparseCopied, 0));
+      launch_scatter_sparse(dst, b - a, (uint64_t *) ds->counters, view->text_length, (uint32_t) ds->winLo,
+                            (uint32_t) std::min<uint64_t>(ds->winHi, view->text_length), a ? sparse_pos(view, a - 1) : 0xFFFFFFFFu,
+                            ctx->errWord, ctx->aux);
+      ctx->launches++;
+    } else if (c == 0) {                       // no records at all: the aux stream still has to stand behind the zeroing
+      CUF(cudaEventRecord(ctx->sparseCopied, s));
+      CUF(cudaStreamWaitEvent(ctx->aux, ctx->sparseCopied, 0));
+    }
+    if (c + 1 == nChunks) { int rc = finish_counters(ctx, ds, ctx->aux); if (rc) return rc; }
+    if (chunkDone) CUF(cudaEventRecord((*chunkDone)[c], ctx->aux));
+  }
+  CUF(cudaEventRecord(ctx->sparseCopied, ctx->aux));       // whoever synchronises s next also waits for the scatters
+  CUF(cudaStreamWaitEvent(s, ctx->sparseCopied, 0));
+  return GT16_OK;
+}
+// a whole window from a sparse view: zeros, then the records that fall into it
+static int upload_sparse_window(gt16_ctx *ctx, const gt16_snapshot_view *view, gt16_dev_snapshot *ds, cudaStream_t s) {
+  CUF(cudaMemsetAsync((char *) ds->counters + (size_t) ds->winLo * 8, 0, (size_t) (ds->winHi - ds->winLo) * 8, s));
+  return upload_sparse(ctx, view, ds, sparse_lower_bound(view, ds->winLo), sparse_lower_bound(view, ds->winHi), s, nullptr);
+}
+
+// after a synchronised sparse upload: did a record lie out of order or beyond the genome?
+static int sparse_upload_errors(gt16_ctx *ctx) {
+  uint32_t errw = 0;
+  CUF(cudaMemcpy(&errw, ctx->errWord, 4, cudaMemcpyDeviceToHost));
+  if (errw & kErrBadSnapshot) {
+    CUF(cudaMemset(ctx->errWord, 0, 4));
+    return fail(ctx, GT16_EDATA, "sparse snapshot records are not in ascending position order or lie beyond the genome");
+  }
+  return GT16_OK;
+}
+
 static int check_view(gt16_ctx *ctx, const gt16_snapshot_view *v) {
-  if (!v || !v->counters || !v->text_length || !v->packed_ref || !v->n_overflow_regions || !v->overflow_size ||
-      !v->overflow)
+  if (!v || (!v->counters && !v->sparse_entries) || !v->text_length || !v->packed_ref || !v->n_overflow_regions ||
+      !v->overflow_size || !v->overflow)
     return fail(ctx, GT16_EINVAL, "incomplete snapshot view");
   if ((size_t) v->packed_ref_words * 16 < v->text_length) return fail(ctx, GT16_EINVAL, "packed reference shorter than the snapshot");
   return GT16_OK;
@@ -658,7 +724,8 @@ extern "C" int gt16_snapshot_upload(gt16_ctx *ctx, const gt16_snapshot_view *vie
   std::vector<uint32_t> ovfBase;
   rc = alloc_snapshot(ctx, view, ds, ovfBase, false, 0, view->text_length);
   if (rc == GT16_OK) rc = upload_aux(ctx, view, ds, ovfBase, ctx->copy, 0, view->text_length - 1);
-  if (rc == GT16_OK) {
+  if (rc == GT16_OK && !view->counters) rc = upload_sparse_window(ctx, view, ds, ctx->copy);
+  else if (rc == GT16_OK) {
     const uint32_t L = view->text_length;
     for (uint64_t a = 0; a < L && rc == GT16_OK; a += kCopyChunkSites) {
       uint64_t b = std::min<uint64_t>(a + kCopyChunkSites, L);
@@ -668,6 +735,7 @@ extern "C" int gt16_snapshot_upload(gt16_ctx *ctx, const gt16_snapshot_view *vie
   }
   if (rc == GT16_OK) rc = finish_counters(ctx, ds, ctx->copy);
   if (rc == GT16_OK && cudaStreamSynchronize(ctx->copy) != cudaSuccess) rc = fail(ctx, GT16_ECUDA, "upload synchronize failed");
+  if (rc == GT16_OK && !view->counters) rc = sparse_upload_errors(ctx);
   if (rc != GT16_OK) { gt16_snapshot_release(ctx, ds); return rc; }
   *out = ds;
   return GT16_OK;
@@ -675,83 +743,98 @@ extern "C" int gt16_snapshot_upload(gt16_ctx *ctx, const gt16_snapshot_view *vie
 
 namespace {
 
-struct RegionPlan {
+// The region list of a call in processed order.  The host arrays are shared with the context's cache: a call with the
+// same list as the previous one (every call of a bench loop, every piece of a shard; 200,000 targets for an exome) builds
+// nothing and copies nothing.
+struct PlanData {
+  std::vector<gt16_region> source;  // the caller's list as it was passed (cache key)
+  uint32_t L = 0;
   std::vector<uint32_t> start;
   std::vector<uint64_t> first;      // nRegions + 1
   std::vector<uint64_t> maxEnd;     // running maximum of the region ends (regions may overlap)
   bool ascending = true;
+};
+struct RegionPlan {
+  std::shared_ptr<const PlanData> d;
   DevSiteMap map;
-  uint32_t pos_of(uint64_t i) const {
-    size_t lo = 0, hi = start.size();
-    while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (first[mid] <= i) lo = mid; else hi = mid; }
-    return start[lo] + (uint32_t) (i - first[lo]);
+  const std::vector<uint32_t> &start() const { return d->start; }
+  const std::vector<uint64_t> &first() const { return d->first; }
+  const std::vector<uint64_t> &maxEnd() const { return d->maxEnd; }
+  bool ascending() const { return d->ascending; }
+  uint32_t region_of(uint64_t i) const {           // index (in start / first) of the region that holds processed site i
+    size_t lo = 0, hi = d->start.size();
+    while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (d->first[mid] <= i) lo = mid; else hi = mid; }
+    return (uint32_t) lo;
   }
+  uint32_t pos_of(uint64_t i) const { const uint32_t r = region_of(i); return d->start[r] + (uint32_t) (i - d->first[r]); }
+  uint64_t max_end_upto(uint64_t i) const { return d->maxEnd[region_of(i)]; }   // highest region end among the regions up to the one holding site i
   uint64_t hi_pos(uint64_t i) const {              // highest position any site up to processed index i can have
     const uint64_t p = pos_of(i);
-    return start.size() > 1 ? std::max<uint64_t>(p, max_end_upto(i) - 1) : p;
-  }
-  uint64_t max_end_upto(uint64_t i) const {        // highest region end among the regions up to the one holding site i
-    size_t lo = 0, hi = start.size();
-    while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (first[mid] <= i) lo = mid; else hi = mid; }
-    return maxEnd[lo];
+    return d->start.size() > 1 ? std::max<uint64_t>(p, max_end_upto(i) - 1) : p;
   }
 };
 
 int make_plan(gt16_ctx *ctx, uint32_t L, const gt16_region *regions, uint32_t nRegions, RegionPlan &pl) {
   gt16_region whole = {0, L};
   if (!regions || !nRegions) { regions = &whole; nRegions = 1; }
-  uint64_t acc = 0;
-  for (uint32_t r = 0; r < nRegions; ++r) {
-    if (regions[r].start >= L || regions[r].end > L)       // VariantCaller.cpp:623-627
-      return fail(ctx, GT16_EINVAL, "[Error] Positions in exome region are incompatible with the index, please generate the exome list with the correct index.");
-    if (regions[r].end <= regions[r].start) continue;      // empty loop body in the reference
-    if (!pl.start.empty() && regions[r].start < pl.start.back()) pl.ascending = false;
-    pl.start.push_back(regions[r].start);
-    pl.first.push_back(acc);
-    pl.maxEnd.push_back(std::max<uint64_t>(pl.maxEnd.empty() ? 0 : pl.maxEnd.back(), regions[r].end));
-    acc += regions[r].end - regions[r].start;
-  }
-  if (pl.start.empty()) { pl.start.push_back(0); pl.first.push_back(0); pl.maxEnd.push_back(0); }
-  pl.first.push_back(acc);
-  // the device copy of the plan survives between calls: the same region list (every call of a bench loop, every piece
-  // of a shard) costs neither a copy nor a host round trip
-  if (!(ctx->planStart.p && pl.start == ctx->lastPlanStart && pl.first == ctx->lastPlanFirst)) {
-    CUF(ctx->planStart.ensure(pl.start.size() * 4));
-    CUF(ctx->planFirst.ensure(pl.first.size() * 8));
-    CUF(cudaMemcpyAsync(ctx->planStart.p, pl.start.data(), pl.start.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
-    CUF(cudaMemcpyAsync(ctx->planFirst.p, pl.first.data(), pl.first.size() * 8, cudaMemcpyHostToDevice, ctx->compute));
-    if (pl.start.size() > 1) {
+  const PlanData *cached = static_cast<const PlanData *>(ctx->planCache.get());
+  if (!(cached && ctx->planStart.p && cached->L == L && cached->source.size() == nRegions &&
+        memcmp(cached->source.data(), regions, (size_t) nRegions * sizeof(gt16_region)) == 0)) {
+    std::shared_ptr<PlanData> fresh = std::make_shared<PlanData>();
+    PlanData &d = *fresh;
+    d.L = L;
+    d.source.assign(regions, regions + nRegions);
+    uint64_t acc = 0;
+    for (uint32_t r = 0; r < nRegions; ++r) {
+      if (regions[r].start >= L || regions[r].end > L)       // VariantCaller.cpp:623-627
+        return fail(ctx, GT16_EINVAL, "[Error] Positions in exome region are incompatible with the index, please generate the exome list with the correct index.");
+      if (regions[r].end <= regions[r].start) continue;      // empty loop body in the reference
+      if (!d.start.empty() && regions[r].start < d.start.back()) d.ascending = false;
+      d.start.push_back(regions[r].start);
+      d.first.push_back(acc);
+      d.maxEnd.push_back(std::max<uint64_t>(d.maxEnd.empty() ? 0 : d.maxEnd.back(), regions[r].end));
+      acc += regions[r].end - regions[r].start;
+    }
+    if (d.start.empty()) { d.start.push_back(0); d.first.push_back(0); d.maxEnd.push_back(0); }
+    d.first.push_back(acc);
+    // the device copy of the plan
+    ctx->planCache.reset();
+    CUF(ctx->planStart.ensure(d.start.size() * 4));
+    CUF(ctx->planFirst.ensure(d.first.size() * 8));
+    CUF(cudaMemcpyAsync(ctx->planStart.p, d.start.data(), d.start.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
+    CUF(cudaMemcpyAsync(ctx->planFirst.p, d.first.data(), d.first.size() * 8, cudaMemcpyHostToDevice, ctx->compute));
+    std::vector<uint32_t> tile;
+    if (d.start.size() > 1) {
       // cursor of the streaming kernel: the region that holds processed site 256 t
       const size_t nTiles = (size_t) ((acc + kCursorTile - 1) / kCursorTile);
-      std::vector<uint32_t> tile(nTiles + 1);
+      tile.resize(nTiles + 1);
       size_t r = 0;
       for (size_t t = 0; t < nTiles; ++t) {
         const uint64_t i = (uint64_t) t * kCursorTile;
-        while (r + 1 < pl.start.size() && pl.first[r + 1] <= i) ++r;
+        while (r + 1 < d.start.size() && d.first[r + 1] <= i) ++r;
         tile[t] = (uint32_t) r;
       }
-      tile[nTiles] = (uint32_t) (pl.start.size() - 1);
+      tile[nTiles] = (uint32_t) (d.start.size() - 1);
       CUF(ctx->planTile.ensure(tile.size() * 4));
       CUF(cudaMemcpyAsync(ctx->planTile.p, tile.data(), tile.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
-      CUF(cudaStreamSynchronize(ctx->compute));
     }
     CUF(cudaStreamSynchronize(ctx->compute));     // the host vectors may be pageable
-    ctx->lastPlanStart = pl.start;
-    ctx->lastPlanFirst = pl.first;
+    ctx->planCache = fresh;
   }
+  pl.d = std::static_pointer_cast<const PlanData>(ctx->planCache);
   pl.map.m.regStart = (const uint32_t *) ctx->planStart.p;
   pl.map.m.regFirst = (const uint64_t *) ctx->planFirst.p;
-  pl.map.m.nRegions = (uint32_t) pl.start.size();
-  pl.map.m.tileReg = pl.start.size() > 1 ? (const uint32_t *) ctx->planTile.p : nullptr;
-  pl.map.totalSites = acc;
+  pl.map.m.nRegions = (uint32_t) pl.d->start.size();
+  pl.map.m.tileReg = pl.d->start.size() > 1 ? (const uint32_t *) ctx->planTile.p : nullptr;
+  pl.map.totalSites = pl.d->first.back();
   return GT16_OK;
 }
 
 void touch_range(const RegionPlan &pl, uint32_t L, uint64_t begin, uint64_t end, uint32_t *loPos, uint32_t *hiPos,
                  uint64_t *lo, uint64_t *hi) {
   const uint64_t reachEnd = std::min<uint64_t>(pl.map.totalSites, end + 512);
-  *loPos = pl.ascending ? pl.pos_of(begin) : 0;
-  *hiPos = pl.ascending ? (uint32_t) std::min<uint64_t>(L - 1, pl.hi_pos(reachEnd - 1)) : L - 1;
+  *loPos = pl.ascending() ? pl.pos_of(begin) : 0;
+  *hiPos = pl.ascending() ? (uint32_t) std::min<uint64_t>(L - 1, pl.hi_pos(reachEnd - 1)) : L - 1;
   *lo = *loPos > 512 ? (uint64_t) ((*loPos - 512) & ~4095u) : 0;
   *hi = std::min<uint64_t>((uint64_t) *hiPos + 1024, L);
 }
@@ -760,13 +843,13 @@ float ms_between(cudaEvent_t a, cudaEvent_t b) { float m = 0.f; cudaEventElapsed
 
 // can [pos(begin), pos(end)) go through the TMA-staged kernel?
 bool tma_eligible(const gt16_ctx *ctx, const RegionPlan &pl, uint64_t begin, bool useTables) {
-  return useTables && pl.start.size() == 1 && ((pl.start[0] + (begin - pl.first[0])) % 128) == 0 && ctx->s1 != nullptr;
+  return useTables && pl.start().size() == 1 && ((pl.start()[0] + (begin - pl.first()[0])) % 128) == 0 && ctx->s1 != nullptr;
 }
 
 void stream_range(gt16_ctx *ctx, const SnapView &V, const RegionPlan &pl, uint64_t a, uint64_t b, bool useTables,
                   const DecisionTables &D, const EvalParams &P, uint32_t *mask) {
   if (tma_eligible(ctx, pl, a, useTables)) {
-    uint32_t pBeg = pl.start[0] + (uint32_t) (a - pl.first[0]);
+    uint32_t pBeg = pl.start()[0] + (uint32_t) (a - pl.first()[0]);
     launch_stream_tma(V, pBeg, pBeg + (uint32_t) (b - a), D, ctx->shortcutAlt, mask, ctx->numSMs, ctx->compute);
   } else {
     launch_stream(V, pl.map, a, (uint32_t) (b - a), useTables, D, P, mask, ctx->errWord, ctx->compute);
@@ -970,6 +1053,8 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   size_t nChunks = 0, chunkEv0 = 0;
   uint32_t chunkSites = kCopyChunkSites;
   bool staged = false;
+  const bool sparse = !resident && hostView && !hostView->counters;
+  std::vector<uint32_t> sparseLastPos;          // position of the last record of each chunk of a sparse view
   std::unique_ptr<std::atomic<int>[]> enqueued;
   std::atomic<int> stageError{0};
   std::vector<std::thread> stagers;
@@ -995,24 +1080,48 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     // from malloc/fread; pinning half a gigabyte costs more than copying it): stager threads move 8 MiB chunks
     // through a small page-locked ring.  (The counters pointer may be biased -- a windowed view -- so it is looked
     // at where the call starts reading.)
-    cudaPointerAttributes pa;
-    staged = !(cudaPointerGetAttributes(&pa, hostView->counters + copyLo) == cudaSuccess && pa.type == cudaMemoryTypeHost);
-    (void) cudaGetLastError();
-    chunkSites = staged ? kStageChunkSites : kCopyChunkSites;
-    nChunks = (size_t) ((copyHi - copyLo + chunkSites - 1) / chunkSites);
+    uint64_t eLo = 0, eHi = 0;
+    if (sparse) {
+      // a sparse view: its records (12 B per covered position) travel as they are and are expanded on the device
+      eLo = sparse_lower_bound(hostView, copyLo); eHi = sparse_lower_bound(hostView, copyHi);
+      nChunks = sparse_chunks(eLo, eHi);
+      for (size_t c = 0; c < nChunks; ++c) {
+        const uint64_t b = std::min<uint64_t>(eLo + (c + 1) * kSparseChunk, eHi);
+        sparseLastPos.push_back(b > eLo + c * kSparseChunk ? sparse_pos(hostView, b - 1) : 0u);
+      }
+    } else {
+      cudaPointerAttributes pa;
+      staged = !(cudaPointerGetAttributes(&pa, hostView->counters + copyLo) == cudaSuccess && pa.type == cudaMemoryTypeHost);
+      (void) cudaGetLastError();
+      chunkSites = staged ? kStageChunkSites : kCopyChunkSites;
+      nChunks = (size_t) ((copyHi - copyLo + chunkSites - 1) / chunkSites);
+    }
     chunkEv0 = evNext;
     evNext += nChunks;
     chunkEvents.resize(nChunks);      // own copy: stager threads must not look into evPool while it grows
     for (size_t c = 0; c < nChunks; ++c) { rc = get_event(ctx, chunkEv0 + c, &chunkEvents[c]); if (rc) return rc; }
+    if (sparse) {
+      // positions without a record hold zero counters: the targets' spans (and what windows, look-ahead and batch margins
+      // reach around them) are cleared, or the whole window when the call is not a list of ascending targets
+      if (pl.ascending() && pl.start().size() > 1) {
+        const uint32_t rA = pl.region_of(begin), rB = pl.region_of(std::min<uint64_t>(pl.map.totalSites, end + 512) - 1);
+        launch_zero_spans(pl.map.m.regStart, pl.map.m.regFirst, rA, rB, (uint64_t *) streamed.counters, (uint32_t) copyLo,
+                          (uint32_t) copyHi, kSideReach, ctx->copy);
+        ctx->launches++;
+      } else {
+        CUF(cudaMemsetAsync((char *) streamed.counters + copyLo * 8, 0, (size_t) (copyHi - copyLo) * 8, ctx->copy));
+      }
+      if ((rc = upload_sparse(ctx, hostView, &streamed, eLo, eHi, ctx->copy, &chunkEvents))) return rc;
+    }
     chunk_needed = [&](uint64_t a, uint64_t b) -> bool {
-      if (!(pl.ascending && pl.start.size() > 1)) return true;
-      size_t lo = 0, hi = pl.start.size();                 // sparse targets: skip chunks no region touches
-      while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if ((uint64_t) pl.start[mid] <= a + 0) lo = mid; else hi = mid; }
+      if (!(pl.ascending() && pl.start().size() > 1)) return true;
+      size_t lo = 0, hi = pl.start().size();                 // sparse targets: skip chunks no region touches
+      while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if ((uint64_t) pl.start()[mid] <= a + 0) lo = mid; else hi = mid; }
       // regions may nest or overlap (starts ascend, ends need not: the reference's merge can emit such lists,
       // buildRegionList.cpp:199-216): an earlier region reaches into [a, b) iff the running maximum of the ends does
-      if (lo > 0 && pl.maxEnd[lo - 1] + 512 > a) return true;
-      for (size_t r = lo; r < pl.start.size(); ++r) {
-        uint64_t rs = pl.start[r], re = rs + (pl.first[r + 1] - pl.first[r]);
+      if (lo > 0 && pl.maxEnd()[lo - 1] + 512 > a) return true;
+      for (size_t r = lo; r < pl.start().size(); ++r) {
+        uint64_t rs = pl.start()[r], re = rs + (pl.first()[r + 1] - pl.first()[r]);
         if (rs > b + 512) break;
         if (re + 512 > a && rs < b + 512) return true;
       }
@@ -1029,7 +1138,8 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
       if (e == cudaSuccess) e = cudaEventRecord(chunkEvents[c], ctx->copy);
       return e;
     };
-    if (!staged) {
+    if (sparse) {
+    } else if (!staged) {
       for (size_t c = 0; c < nChunks; ++c) {
         const uint64_t a = copyLo + c * (uint64_t) chunkSites, b = std::min<uint64_t>(a + chunkSites, copyHi);
         CUF(enqueue_chunk(c, hostView->counters + a, chunk_needed(a, b)));
@@ -1082,9 +1192,10 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   auto wait_chunks = [&](uint64_t need) -> int {
     if (resident) return GT16_OK;
     size_t c = nChunks - 1;
-    if (pl.ascending) {
+    if (pl.ascending()) {
       need = std::min<uint64_t>(std::max<uint64_t>(need, copyLo + 1), copyHi);
-      c = std::min((size_t) ((need - 1 - copyLo) / chunkSites), nChunks - 1);
+      if (sparse) c = std::min((size_t) (std::lower_bound(sparseLastPos.begin(), sparseLastPos.end(), (uint32_t) (need - 1)) - sparseLastPos.begin()), nChunks - 1);
+      else c = std::min((size_t) ((need - 1 - copyLo) / chunkSites), nChunks - 1);
     }
     for (; chunksWaited <= c; ++chunksWaited) {
       host_wait_enqueued(chunksWaited);
@@ -1136,13 +1247,13 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     CUF(cudaEventRecord(es0, ctx->compute));
     for (uint64_t c = a; c < b; c += kBatch) {           // classification of a batch waits for the chunk with its last position + 1
       const uint64_t d = std::min<uint64_t>(c + kBatch, b);
-      if ((rc = wait_chunks(pl.ascending ? pl.hi_pos(d - 1) + 2 : copyHi))) return rc;
+      if ((rc = wait_chunks(pl.ascending() ? pl.hi_pos(d - 1) + 2 : copyHi))) return rc;
       if (resident) { stream_range(ctx, *V, pl, a, b, useTables, D, P, mask + (a - begin) / 32); break; }
       stream_range(ctx, *V, pl, c, d, useTables, D, P, mask + (c - begin) / 32);
     }
     CUF(cudaEventRecord(es1, ctx->compute));
     // windows, neighbours' Fisher tests and the indel look-ahead reach up to ~360 positions past the segment
-    if ((rc = wait_chunks(pl.ascending ? pl.hi_pos(std::min<uint64_t>(pl.map.totalSites, b + 512) - 1) + 600 : copyHi))) return rc;
+    if ((rc = wait_chunks(pl.ascending() ? pl.hi_pos(std::min<uint64_t>(pl.map.totalSites, b + 512) - 1) + 600 : copyHi))) return rc;
     rc = finish_segment(ctx, *V, pl, begin, a, b, useTables, D, evNext, seg, es0, es1, timing, segCopied);
     if (rc != GT16_OK) return rc;
     if (!devOutHandle) {
@@ -1309,13 +1420,15 @@ int gt16_snapshot_upload_range(gt16_ctx *ctx, const gt16_snapshot_view *view, co
   std::vector<uint32_t> ovfBase;
   rc = alloc_snapshot(ctx, view, ds, ovfBase, false, lo, hi);
   if (rc == GT16_OK) rc = upload_aux(ctx, view, ds, ovfBase, ctx->copy, loPos, hiPos);
-  for (uint64_t a = lo; a < hi && rc == GT16_OK; a += kCopyChunkSites) {
+  if (rc == GT16_OK && !view->counters) rc = upload_sparse_window(ctx, view, ds, ctx->copy);
+  for (uint64_t a = lo; view->counters && a < hi && rc == GT16_OK; a += kCopyChunkSites) {
     const uint64_t b = std::min<uint64_t>(a + kCopyChunkSites, hi);
     if (cudaMemcpyAsync((char *) ds->counters + a * 8, view->counters + a, (b - a) * 8, cudaMemcpyHostToDevice, ctx->copy) != cudaSuccess)
       rc = fail(ctx, GT16_ECUDA, "counter upload failed");
   }
   if (rc == GT16_OK) rc = finish_counters(ctx, ds, ctx->copy);
   if (rc == GT16_OK && cudaStreamSynchronize(ctx->copy) != cudaSuccess) rc = fail(ctx, GT16_ECUDA, "upload synchronize failed");
+  if (rc == GT16_OK && !view->counters) rc = sparse_upload_errors(ctx);
   if (rc != GT16_OK) { (void) cudaGetLastError(); gt16_snapshot_release(ctx, ds); return rc; }
   *out = ds;
   return GT16_OK;

@@ -682,7 +682,7 @@ struct DevSiteMap {          // SiteMap + total number of processed sites
 
 GT16_HD uint32_t site_pos(const DevSiteMap &M, uint64_t i) {
   if (M.m.nRegions == 1) return M.m.regStart[0] + (uint32_t) (i - M.m.regFirst[0]);
-  return pos_of(M.m, i);
+  return M.m.tileReg ? pos_of_cursor(M.m, i) : pos_of(M.m, i);
 }
 
 // exact candidate predicate of one site: getSnpMetrics + computeGenotypeLikelihood +

@@ -117,7 +117,8 @@ struct gt16_host_snapshot {
   uint32_t textLength = 0;
   uint32_t posLo = 0, posHi = 0;           // counters.p holds positions [posLo, posHi) (gt16_snapshot_read_range)
   uint32_t nRegions = 0;
-  HostBuf counters, invalid, pool, ovfAll;
+  HostBuf counters, invalid, pool, ovfAll, sparse;   // sparse: the {position, counter} records of a mode-2 snapshot kept as they are
+  uint64_t nSparse = 0;
   bool hasInvalid = false;
   uint32_t poolBytes = 0;
   std::vector<const void *> ovfPtr;
@@ -142,6 +143,13 @@ int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, c
 
 int gt16_snapshot_read_range(const char *path, int pinned, uint32_t pos_lo, uint32_t pos_hi, gt16_host_snapshot **out,
                              char *err, size_t errLen) {
+  return gt16_snapshot_read_ex(path, pinned ? GT16_READ_PINNED : 0, pos_lo, pos_hi, out, err, errLen);
+}
+
+int gt16_snapshot_read_ex(const char *path, int flags, uint32_t pos_lo, uint32_t pos_hi, gt16_host_snapshot **out,
+                          char *err, size_t errLen) {
+  const int pinned = (flags & GT16_READ_PINNED) ? 1 : 0;
+  const bool keepSparse = (flags & GT16_READ_KEEP_SPARSE) != 0;
   if (!path || !out) return GT16_EINVAL;
   FILE *f = fopen(path, "rb");
   if (!f) { set_err(err, errLen, "Error opening %s", path); return GT16_EIO; }
@@ -167,8 +175,22 @@ int gt16_snapshot_read_range(const char *path, int pinned, uint32_t pos_lo, uint
     // page-locked memory on their way to the GPU, so a private copy would just be one more pass over 8 bytes per
     // site of host memory (the slowest resource of the drop-in binary on a 3.1 Gb genome).
     const bool mapped = (mode & 1) && !pinned && !getenv("GT16_NO_MMAP") && hs->counters.map_file(path, start[1] + 5 + (uint64_t) wLo * 8, W * 8);
-    if (!mapped && !hs->counters.alloc(W * 8 + 16, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
+    const bool asRecords = !(mode & 1) && (mode & 2) && keepSparse;
+    if (!mapped && !asRecords && !hs->counters.alloc(W * 8 + 16, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
     if (mapped) {
+    } else if (asRecords) {
+      // the records stay as the producer wrote them (12 bytes each, ascending positions): they are expanded in HBM, not
+      // here -- a whole-genome array of zeros for an exome's worth of counters would cost 8 B per genome position of host
+      // memory and of host-link traffic
+      if (len[1] < 5 || (len[1] - 5) % 12) { set_err(err, errLen, "%s: bad sparse counter subfile", path); rc = GT16_EDATA; break; }
+      hs->nSparse = (len[1] - 5) / 12;
+      const size_t bytes = (size_t) hs->nSparse * 12;
+      const bool mappedRecords = !pinned && !getenv("GT16_NO_MMAP") && bytes && hs->sparse.map_file(path, start[1] + 5, bytes);
+      if (!mappedRecords) {
+        if (!hs->sparse.alloc(bytes + 16, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
+        if (bytes && !pread_parallel(path, start[1] + 5, hs->sparse.p, bytes)) { set_err(err, errLen, "%s: truncated counters", path); rc = GT16_EIO; break; }
+      }
+      if (fseeko(f, (off_t) (start[1] + len[1]), SEEK_SET) != 0) { set_err(err, errLen, "%s: bad sparse counter subfile", path); rc = GT16_EIO; break; }
     } else if (mode & 1) {
       if (!pread_parallel(path, start[1] + 5 + (uint64_t) wLo * 8, hs->counters.p, W * 8)) { set_err(err, errLen, "%s: truncated counters", path); rc = GT16_EIO; break; }
       memset((char *) hs->counters.p + W * 8, 0, 16);
@@ -251,7 +273,9 @@ void gt16_snapshot_view_of(const gt16_host_snapshot *hs, gt16_snapshot_view *v) 
   memset(v, 0, sizeof(*v));
   // indexed by genome position whatever the window: with a window the pointer is biased and only positions
   // [pos_lo, pos_hi) may be dereferenced (calls whose range lies inside the window touch nothing else)
-  v->counters = (const uint64_t *) hs->counters.p - hs->posLo;
+  v->counters = hs->counters.p ? (const uint64_t *) hs->counters.p - hs->posLo : nullptr;
+  v->sparse_entries = hs->counters.p ? nullptr : hs->sparse.p;
+  v->n_sparse_entries = hs->counters.p ? 0 : hs->nSparse;
   v->text_length = hs->textLength;
   v->invalid_bitmap = hs->hasInvalid ? (const uint32_t *) hs->invalid.p : nullptr;
   v->n_overflow_regions = hs->nRegions;
@@ -263,7 +287,7 @@ void gt16_snapshot_view_of(const gt16_host_snapshot *hs, gt16_snapshot_view *v) 
 
 void gt16_snapshot_free(gt16_host_snapshot *hs) {
   if (!hs) return;
-  hs->counters.release(); hs->invalid.release(); hs->pool.release(); hs->ovfAll.release();
+  hs->counters.release(); hs->invalid.release(); hs->pool.release(); hs->ovfAll.release(); hs->sparse.release();
   delete hs;
 }
 

@@ -181,7 +181,7 @@ __device__ __forceinline__ bool compact_needs_exact(const DecisionTables &D, con
   if (r1 == r2 && (y >> 16)) v1 = 0;                       // the second slot overwrites the first
   const uint32_t wr = (r1 == 0 ? v1 : 0u) | (r2 == 0 ? v2 : 0u);
   const uint32_t a1 = r1 ? v1 : 0u, a2 = r2 ? v2 : 0u, alt = a1 | a2, ar = a1 ? r1 : r2;
-  if (alt == 0) return kShortcut ? false : s1[wr] != 0;      // kShortcut: the (Wr) bitmap is all zero
+  if (alt == 0) return kShortcut ? false : (s1 ? s1[wr] != 0 : tab_bit(D.s1, wr));   // kShortcut: the (Wr) bitmap is all zero
   if ((a1 && a2) || wr >= (uint32_t) kS2R || alt >= (uint32_t) kS2A) return true;
   return tab_bit(ar == 2 ? D.s2p : D.s2q, alt * kS2R + wr);
 }
@@ -375,50 +375,112 @@ void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const De
     k_stream_tma<false, R><<<grid, kStreamThreads, sizeof(StreamSmemT<false, R>), s>>>(V.counters, V.packedRef, V.invalid, pBeg, pEnd, D, 0, mask);
 }
 
-template <bool kUseTables>
-__global__ void __launch_bounds__(256) k_stream(SnapView V, DevSiteMap M, uint64_t first, uint32_t n,
-                                                DecisionTables D, EvalParams P, uint32_t *__restrict__ mask,
-                                                uint32_t *errWord) {
+// Table-driven classification of a range of PROCESSED sites [first, first + n) of a region list (exome targets: a few
+// hundred positions each; also a dense range whose start is not tile-aligned).  A CTA takes 1,024 consecutive processed
+// sites; the regions they fall into (three or four for exome targets) are found through the per-tile cursor and staged
+// in shared memory once, so a thread maps a site to its position with a short scan over shared memory instead of a
+// binary search over the whole list; every thread then issues the loads of its four sites together (counter,
+// successor, reference word, invalid word: coalesced within a region), classifies them with the same tests the parked
+// sites of k_stream_tma go through, and the warp's ballots are the words of the flag bitmap.
+constexpr int kRegThreads = 256, kRegRows = 4, kRegTile = kRegThreads * kRegRows, kRegTable = 64;
+static_assert(kRegTile % kCursorTile == 0, "a CTA's sites start on a cursor tile");
+__global__ void __launch_bounds__(kRegThreads) k_stream_regions(SnapView V, DevSiteMap M, uint64_t first, uint32_t n,
+                                                                DecisionTables D, uint32_t *__restrict__ mask, uint32_t *errWord) {
+  __shared__ uint64_t sFirst[kRegTable + 1];
+  __shared__ uint32_t sStart[kRegTable];
+  __shared__ uint32_t qCount, qPos[kRegTile], qIdx[kRegTile];      // parked overflow-type sites: position, record index,
+  __shared__ uint16_t qSite[kRegTile];                             // site within the tile | reference base << 12
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) qCount = 0;
+  const uint64_t i0 = first + (uint64_t) blockIdx.x * kRegTile;
+  const uint32_t done = blockIdx.x * (uint32_t) kRegTile, cnt = n - done < (uint32_t) kRegTile ? n - done : (uint32_t) kRegTile;
+  // regions that hold sites i0 .. i0 + cnt - 1: [r0, rHi]
+  uint32_t r0 = 0, rHi = 0;
+  if (M.m.tileReg) { r0 = M.m.tileReg[i0 / kCursorTile]; rHi = M.m.tileReg[(i0 + cnt - 1) / kCursorTile + 1]; }
+  else if (M.m.nRegions > 1) rHi = M.m.nRegions - 1;
+  const uint32_t nr = rHi - r0 + 1;
+  const bool staged = nr <= (uint32_t) kRegTable;
+  if (staged) {
+    if (tid < nr) { sFirst[tid] = M.m.regFirst[r0 + tid]; sStart[tid] = M.m.regStart[r0 + tid]; }
+    if (tid == nr) sFirst[nr] = M.m.regFirst[r0 + nr];
+  }
+  __syncthreads();
+  uint32_t p[kRegRows], r = 0;
+  bool in[kRegRows];
+#pragma unroll
+  for (int k = 0; k < kRegRows; ++k) {
+    const uint32_t s = tid + kRegThreads * k;
+    in[k] = s < cnt;
+    p[k] = 0;
+    if (in[k]) {
+      const uint64_t i = i0 + s;
+      if (staged) {
+        while (r + 1 < nr && sFirst[r + 1] <= i) ++r;          // the thread's sites ascend: the scan never goes back
+        p[k] = sStart[r] + (uint32_t) (i - sFirst[r]);
+      } else {
+        p[k] = M.m.tileReg ? pos_of_cursor(M.m, i) : pos_of(M.m, i);
+      }
+    }
+  }
+  uint2 c[kRegRows]; uint32_t nx[kRegRows], rw[kRegRows], iw[kRegRows];
+#pragma unroll
+  for (int k = 0; k < kRegRows; ++k) {
+    c[k] = make_uint2(0u, 0u); nx[k] = 0; rw[k] = 0; iw[k] = 0;
+    if (in[k]) {
+      c[k] = __ldg(reinterpret_cast<const uint2 *>(V.counters + p[k]));
+      nx[k] = __ldg(reinterpret_cast<const uint32_t *>(V.counters + (p[k] + 1 < V.L ? p[k] + 1 : V.L - 1)));
+      rw[k] = (p[k] >> 4) < V.refWords ? __ldg(V.packedRef + (p[k] >> 4)) : 0u;
+      if (V.invalid) iw[k] = __ldg(V.invalid + (p[k] >> 5));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kRegRows; ++k) {
+    bool flag = false;
+    if (in[k] && !((iw[k] >> (31 - (p[k] & 31))) & 1u)) {
+      const uint32_t ref = (rw[k] >> (30u - ((p[k] & 15u) << 1))) & 3u;
+      if ((nx[k] & 0xE000E000u) >= 0xC000E000u) flag = true;              // the successor carries indel records: exact evaluator
+      else if ((c[k].x & 0xC000C000u) != 0xC000C000u) flag = compact_needs_exact<false>(D, nullptr, c[k].x, c[k].y, ref);
+      else {
+        // overflow-type counter (three or more alleles seen, or deep coverage: a few per cent of the sites at exome
+        // depth): parked, and settled below by the whole CTA, one site per thread, instead of by a divergent branch here
+        const uint32_t q = atomicAdd(&qCount, 1u);
+        qPos[q] = p[k]; qIdx[q] = c[k].y; qSite[q] = (uint16_t) ((tid + kRegThreads * k) | (ref << 12));
+      }
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, flag);
+    const uint32_t s0 = kRegThreads * k + (tid & ~31u);          // the warp's first site of this row
+    if (lane == 0 && s0 < cnt) mask[(done + s0) >> 5] = word;
+  }
+  __syncthreads();
+  for (uint32_t q = tid; q < qCount; q += kRegThreads) {         // the general role-indexed test on the record's weights
+    const uint32_t ref = qSite[q] >> 12, site = qSite[q] & 0xFFFu;
+    const uint8_t *rec = ovf_record(V, ovf_region(V, qPos[q]), qIdx[q]);
+    if (!rec) { atomicOr(errWord, kErrBadSnapshot); continue; }
+    const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(rec));           // W[4], F[4]
+    const uint2 hi = __ldg(reinterpret_cast<const uint2 *>(rec + 16));      // R[4]
+    const uint32_t Wv[4] = {lo.x & 0xFFFFu, lo.x >> 16, lo.y & 0xFFFFu, lo.y >> 16};
+    const uint32_t Fv[4] = {lo.z & 0xFFFFu, lo.z >> 16, lo.w & 0xFFFFu, lo.w >> 16};
+    const uint32_t Rv[4] = {hi.x & 0xFFFFu, hi.x >> 16, hi.y & 0xFFFFu, hi.y >> 16};
+    uint32_t wr[4] = {0u, 0u, 0u, 0u};                                      // weights indexed by role = base ^ ref
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const uint32_t w = (Fv[b] | Rv[b]) ? Wv[b] : 0u, role = (uint32_t) b ^ ref;
+      if (role == 0) wr[0] = w; else if (role == 1) wr[1] = w; else if (role == 2) wr[2] = w; else wr[3] = w;
+    }
+    if (lookup_needs_exact(D, wr[0], wr[2], wr[1], wr[3])) atomicOr(mask + ((done + site) >> 5), 1u << (site & 31u));
+  }
+}
+
+// exact inline mode (no decision tables): one thread per site, the full evaluator
+__global__ void __launch_bounds__(256) k_stream_exact(SnapView V, DevSiteMap M, uint64_t first, uint32_t n, EvalParams P,
+                                                      uint32_t *__restrict__ mask, uint32_t *errWord) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool flag = false;
   if (i < n) {
-    // multi-region (exome) lists: the region is found through the per-tile cursor, not by a search over the whole list
     const uint32_t p = (M.m.nRegions > 1 && M.m.tileReg) ? pos_of_cursor(M.m, first + i) : site_pos(M, first + i);
-    if (!kUseTables) {
-      uint32_t e = 0;
-      flag = site_is_candidate(V, P, p, e);
-      if (e) atomicOr(errWord, e);
-    } else if (!is_invalid(V, p)) {
-      uint64_t c = __ldg(V.counters + p);
-      uint32_t q = p + 1 < V.L ? p + 1 : V.L - 1;
-      uint64_t cn = __ldg(V.counters + q);
-      uint32_t ref = ref_base(V, p);
-      bool nextIndel = is_overflow_type(cn) && (((uint32_t) cn | (uint32_t) (cn >> 16)) & 0x2000u);
-      if (nextIndel) {
-        flag = true;                                   // W[4] / W[5] may be non-zero: exact path
-      } else {
-        uint32_t wr[4] = {0, 0, 0, 0};                 // weights indexed by role = base ^ ref
-        bool ok = true;
-        if (!is_overflow_type(c)) {
-          uint32_t w1 = (uint32_t) c & 0xFFFF, w2 = (uint32_t) (c >> 16) & 0xFFFF;
-          if ((uint32_t) (c >> 32) & 0xFFFFu) wr[(w1 >> 14) ^ ref] = w1 & 0x3FFF;
-          if ((uint32_t) (c >> 48) & 0xFFFFu) wr[(w2 >> 14) ^ ref] = w2 & 0x3FFF;
-        } else {
-          const uint8_t *r = ovf_record(V, ovf_region(V, p), (uint32_t) (c >> 32));
-          if (!r) { atomicOr(errWord, kErrBadSnapshot); ok = false; }
-          else {
-            const uint4 lo = __ldg((const uint4 *) r);           // W[4], F[4]
-            const uint2 hi = __ldg((const uint2 *) (r + 16));    // R[4]
-            uint32_t Wv[4] = {lo.x & 0xFFFF, lo.x >> 16, lo.y & 0xFFFF, lo.y >> 16};
-            uint32_t Fv[4] = {lo.z & 0xFFFF, lo.z >> 16, lo.w & 0xFFFF, lo.w >> 16};
-            uint32_t Rv[4] = {hi.x & 0xFFFF, hi.x >> 16, hi.y & 0xFFFF, hi.y >> 16};
-#pragma unroll
-            for (int b = 0; b < 4; ++b) if (Fv[b] | Rv[b]) wr[b ^ ref] = Wv[b];
-          }
-        }
-        if (ok) flag = lookup_needs_exact(D, wr[0], wr[2], wr[1], wr[3]);
-      }
-    }
+    uint32_t e = 0;
+    flag = site_is_candidate(V, P, p, e);
+    if (e) atomicOr(errWord, e);
   }
   uint32_t word = __ballot_sync(0xffffffffu, flag);
   if ((threadIdx.x & 31) == 0 && i < n) mask[i >> 5] = word;
@@ -428,9 +490,37 @@ void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint3
                    const DecisionTables &D, const EvalParams &P, uint32_t *mask, uint32_t *errWord,
                    cudaStream_t s) {
   if (!n) return;
-  unsigned grid = (n + 255) / 256;
-  if (useTables) k_stream<true><<<grid, 256, 0, s>>>(V, M, first, n, D, P, mask, errWord);
-  else k_stream<false><<<grid, 256, 0, s>>>(V, M, first, n, D, P, mask, errWord);
+  if (useTables) k_stream_regions<<<(n + kRegTile - 1) / kRegTile, kRegThreads, 0, s>>>(V, M, first, n, D, mask, errWord);
+  else k_stream_exact<<<(n + 255) / 256, 256, 0, s>>>(V, M, first, n, P, mask, errWord);
+}
+
+// ---- sparse snapshots (mode 2, SnapshotHandler.cpp:178-236: {u32 position; SnpCounter} records of 12 bytes) ----------
+// counters[pos] = counter for every record whose position lies in [lo, hi); positions must ascend strictly.
+__global__ void __launch_bounds__(256) k_scatter_sparse(const uint32_t *__restrict__ rec, uint64_t n, uint64_t *counters,
+                                                        uint32_t L, uint32_t lo, uint32_t hi, uint32_t prevPos, uint32_t *errWord) {
+  const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t pos = rec[3 * t];
+  const uint32_t before = t ? rec[3 * (t - 1)] : prevPos;
+  if (pos >= L || (pos <= before && !(t == 0 && prevPos == 0xFFFFFFFFu))) { atomicOr(errWord, kErrBadSnapshot); return; }
+  if (pos >= lo && pos < hi) counters[pos] = (uint64_t) rec[3 * t + 1] | ((uint64_t) rec[3 * t + 2] << 32);
+}
+void launch_scatter_sparse(const void *rec, uint64_t n, uint64_t *counters, uint32_t L, uint32_t lo, uint32_t hi,
+                           uint32_t prevPos, uint32_t *errWord, cudaStream_t s) {
+  if (n) k_scatter_sparse<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>((const uint32_t *) rec, n, counters, L, lo, hi, prevPos, errWord);
+}
+// zero counters of regions [rA, rB] of the list, widened by `margin` positions on either side and clamped to [lo, hi)
+__global__ void __launch_bounds__(256) k_zero_spans(const uint32_t *__restrict__ regStart, const uint64_t *__restrict__ regFirst,
+                                                    uint32_t rA, uint64_t *counters, uint32_t lo, uint32_t hi, uint32_t margin) {
+  const uint32_t r = rA + blockIdx.x;
+  const uint64_t a0 = regStart[r], len = regFirst[r + 1] - regFirst[r];
+  const uint64_t a = a0 > margin ? a0 - margin : 0, b = a0 + len + margin;
+  const uint64_t x = a < lo ? lo : a, y = b > hi ? hi : b;
+  for (uint64_t q = x + threadIdx.x; q < y; q += blockDim.x) counters[q] = 0ull;
+}
+void launch_zero_spans(const uint32_t *regStart, const uint64_t *regFirst, uint32_t rA, uint32_t rB, uint64_t *counters,
+                       uint32_t lo, uint32_t hi, uint32_t margin, cudaStream_t s) {
+  if (rB >= rA) k_zero_spans<<<rB - rA + 1, 256, 0, s>>>(regStart, regFirst, rA, counters, lo, hi, margin);
 }
 
 // Exact predicate for the flagged sites.  Lane phase: every lane decodes one listed site (overflow
@@ -781,6 +871,7 @@ __device__ __forceinline__ WinLite win_decode(const SnapView &V, uint32_t p, uin
 
 __device__ __forceinline__ uint32_t region_of(const SiteMap &M, uint64_t i) {      // last region with regFirst <= i
   uint32_t lo = 0, hi = M.nRegions;
+  if (M.tileReg) { lo = M.tileReg[i / kCursorTile]; hi = M.tileReg[i / kCursorTile + 1] + 1; }   // the cursor confines the search to the site's tile
   while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (M.regFirst[mid] <= i) lo = mid; else hi = mid; }
   return lo;
 }

@@ -44,6 +44,14 @@ void launch_build_decisions(const EvalParams &P, uint32_t *s1, uint32_t *s2p, ui
 void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint32_t n, bool useTables,
                    const DecisionTables &D, const EvalParams &P, uint32_t *mask, uint32_t *errWord,
                    cudaStream_t s);
+// sparse snapshots: scatter n {u32 position; u64 counter} records (12 bytes each, strictly ascending positions; prevPos =
+// position of the record before rec[0], 0xFFFFFFFF if none) into the position-indexed counter array, positions in
+// [lo, hi) only; a record out of order or beyond L raises kErrBadSnapshot
+void launch_scatter_sparse(const void *rec, uint64_t n, uint64_t *counters, uint32_t L, uint32_t lo, uint32_t hi,
+                           uint32_t prevPos, uint32_t *errWord, cudaStream_t s);
+// counters of regions [rA, rB] (device copies of the plan), widened by `margin` positions, clamped to [lo, hi) := 0
+void launch_zero_spans(const uint32_t *regStart, const uint64_t *regFirst, uint32_t rA, uint32_t rB, uint64_t *counters,
+                       uint32_t lo, uint32_t hi, uint32_t margin, cudaStream_t s);
 // same contract for a dense single-region range of positions [pBeg,pEnd), pBeg % 128 == 0, arrays padded
 // by kStreamPadSites: persistent CTAs, TMA bulk copies into a shared-memory ring
 // shortcutAlt: stream_shortcut_bound() of the bitmaps in D (0 = take the table-driven path for every site)

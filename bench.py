@@ -347,7 +347,8 @@ def main():
         r1 = int(np.searchsorted(first, max(begin, min(total, end + 512) - 1), side="right") - 1)
         r0, r1 = min(r0, len(regs) - 1), min(r1, len(regs) - 1)
         pos_lo, pos_hi = max(0, int(regs[r0, 0]) - 8192), min(meta.length, int(regs[:r1 + 1, 1].max()) + 8192)
-    inp = capi.LoadedInput(idx, out + ".snapshot", region, pinned=1, pos_range=(pos_lo, pos_hi), index=meta)
+    # (a sparse -- exome -- snapshot stays the list of records it is: 12 B per covered position travel, not 8 B per genome position)
+    inp = capi.LoadedInput(idx, out + ".snapshot", region, pinned=1, pos_range=(pos_lo, pos_hi), index=meta, keep_sparse=True)
     dev = ctypes.c_void_p()
     if shard:
         caller.check(L.gt16_snapshot_upload_range(caller.ctx, ctypes.byref(inp.view), inp.regions_ptr(), inp.n_regions, begin, end,
@@ -512,7 +513,15 @@ def main():
         arr = (ctypes.c_uint32 * v.n_overflow_regions).from_address(v.overflow_size)
         ovf_records = sum(arr)
     # bytes this rank moves per e2e step (counters of its shard + the side arrays its positions reach), summed over ranks
-    h2d_rank = shard * 8 + shard // 8 + shard // 4 + (ovf_records * 32) // world + v.pool_bytes
+    if v.counters:
+        h2d_rank = shard * 8 + shard // 8 + shard // 4 + (ovf_records * 32) // world + v.pool_bytes
+    else:                                # sparse view: the records whose positions lie in this rank's window, 12 bytes each
+        k = v.n_sparse_entries
+        raw = np.ctypeslib.as_array(ctypes.cast(v.sparse_entries, ctypes.POINTER(ctypes.c_uint8)), (k * 12,)).reshape(k, 12)
+        pos = raw[:, :4].copy().view(np.uint32)[:, 0]
+        in_window = int(np.searchsorted(pos, pos_hi) - np.searchsorted(pos, pos_lo)) if shard else 0
+        # ... and the packed reference of the genome span its targets lie in (2 bits per position of the span, not per site)
+        h2d_rank = in_window * 12 + (pos_hi - pos_lo) // 4 + (ovf_records * 32) // world + v.pool_bytes
     h2d_t = torch.tensor([h2d_rank], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(h2d_t)
@@ -553,14 +562,15 @@ def main():
         "gpu_launches": launches,
         "device_ms_per_step_rank0": parts["ms_total_device"],
         "device_ms_breakdown_rank0": {k: parts[k] for k in ("ms_stream", "ms_eval", "ms_scan", "ms_candidates", "ms_d2h")},
-        "roofline": {"bound": "hbm", "kernel": "k_stream_tma (decode + 16-genotype classification of every site), rank 0's launch",
+        "roofline": {"bound": "hbm", "kernel": ("k_stream_regions (decode + 16-genotype classification of every target site, region list staged in shared memory), rank 0's launches"
+                                                if region else "k_stream_tma (decode + 16-genotype classification of every site), rank 0's launch"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": shard * BYTES_PER_SITE, "avg_launch_ms": ms_stream},
         "clocks": clocks,
     }
     tr = os.path.join(ROOT, "profiles", "stream_kernel_traffic.json")
-    if os.path.exists(tr):
+    if os.path.exists(tr) and not region:
         try:
             t = json.load(open(tr))
             # measured by ncu on one launch of `sites_per_launch` sites: bytes per site carry over to a launch of any length

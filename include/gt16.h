@@ -105,6 +105,12 @@ typedef struct gt16_snapshot_view {
   uint32_t pool_bytes;             /* curPtr: bytes in use */
   const uint32_t *packed_ref;      /* 16 bases / word, first base in bits 31..30 */
   uint32_t packed_ref_words;
+  /* A sparse (mode 2) snapshot may be passed as it lies in the file instead of expanded: counters == NULL and
+   * sparse_entries -> n_sparse_entries packed records {u32 position; SnpCounter} of 12 bytes, positions strictly
+   * ascending (bam2snapshot.cpp:527-589 writes them so); a position without a record holds a zero counter.  The records
+   * are copied to HBM as they are (12 B per covered position instead of 8 B per genome position) and expanded there. */
+  const void *sparse_entries;
+  uint64_t n_sparse_entries;
 } gt16_snapshot_view;
 
 typedef struct gt16_region { uint32_t start, end; } gt16_region;   /* [start,end), struct.h:5-13 */
@@ -215,6 +221,14 @@ int gt16_snapshot_read(const char *path, int pinned, gt16_host_snapshot **out, c
  * genome's ends). */
 int gt16_snapshot_read_range(const char *path, int pinned, uint32_t pos_lo, uint32_t pos_hi, gt16_host_snapshot **out,
                              char *err, size_t err_len);
+/* The same with flags: GT16_READ_PINNED page-locks the buffers; GT16_READ_KEEP_SPARSE leaves the counters of a sparse
+ * (mode 2) snapshot as the packed records they are in the file (view: counters == NULL, sparse_entries set) instead of
+ * expanding them into a position-indexed array -- gt16_call_sites_host / gt16_snapshot_upload* expand them in HBM.  A
+ * dense snapshot is read as before whatever the flag. */
+#define GT16_READ_PINNED 1
+#define GT16_READ_KEEP_SPARSE 2
+int gt16_snapshot_read_ex(const char *path, int flags, uint32_t pos_lo, uint32_t pos_hi, gt16_host_snapshot **out,
+                          char *err, size_t err_len);
 void gt16_snapshot_view_of(const gt16_host_snapshot *hs, gt16_snapshot_view *view);  /* packed_ref left NULL */
 void gt16_snapshot_free(gt16_host_snapshot *hs);
 

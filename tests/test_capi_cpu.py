@@ -78,6 +78,36 @@ def test_index_and_snapshot_readers(tmp_path):
     assert b"Error opening" in err.value
 
 
+@pytest.mark.parametrize("mapped", [True, False])
+def test_sparse_snapshot_kept_as_records(tmp_path, mapped, monkeypatch):
+    """GT16_READ_KEEP_SPARSE: the counter subfile of a mode-2 snapshot stays the {u32 position; u64 counter} records the
+    producer wrote (mapped or read); scattered into an array of zeros they give exactly what the expanding reader gives"""
+    if not mapped:
+        monkeypatch.setenv("GT16_NO_MMAP", "1")
+    idx, out, region = T.regenerate("exome_small", tmp_path)
+    dense = T.LoadedInput(idx, out + ".snapshot", region, pinned=0)
+    recs = T.LoadedInput(idx, out + ".snapshot", region, pinned=0, keep_sparse=True)
+    try:
+        n = dense.view.text_length
+        assert recs.view.text_length == n and not recs.view.counters and dense.view.counters and not dense.view.n_sparse_entries
+        k = recs.view.n_sparse_entries
+        raw = np.ctypeslib.as_array(ctypes.cast(recs.view.sparse_entries, ctypes.POINTER(ctypes.c_uint8)), (k * 12,)).reshape(k, 12)
+        pos = raw[:, :4].copy().view(np.uint32)[:, 0]
+        val = raw[:, 4:].copy().view(np.uint64)[:, 0]
+        assert np.all(pos[1:] > pos[:-1]) and pos[-1] < n
+        want = np.ctypeslib.as_array(ctypes.cast(dense.view.counters, ctypes.POINTER(ctypes.c_uint64)), (n,))
+        got = np.zeros(n, dtype=np.uint64)
+        got[pos] = val
+        assert np.array_equal(got, want)
+        # a dense snapshot is read as before whatever the flag
+        idx2, out2, _ = T.regenerate("wgs_small", tmp_path)
+        d2 = T.LoadedInput(idx2, out2 + ".snapshot", None, pinned=0, keep_sparse=True)
+        assert d2.view.counters and not d2.view.sparse_entries
+        d2.close()
+    finally:
+        dense.close(); recs.close()
+
+
 def test_region_index_builder_matches_reference(tmp_path):
     """RegionIndexBuilder (buildRegionList.cpp): byte-identical region.bin for the seeded BED and GFF lists of
     tests/golden/regions (made by the unmodified reference tool, tests/golden/make_region_golden.py); plus the

@@ -40,6 +40,36 @@ def test_fused_path_matches_reference(gpu_caller, tmp_path, name, mode):
     assert nonident <= max(2, rows * 98 // 1000), "too many fields differ in the last digit: %d" % nonident
 
 
+@pytest.mark.parametrize("mode", ["host_stream", "host_pageable", "resident", "resident_range"])
+def test_sparse_snapshot_as_records(gpu_caller, tmp_path, mode):
+    """A sparse (mode 2, exome) snapshot handed over as the {position, counter} records it consists of
+    (GT16_READ_KEEP_SPARSE; view.counters == NULL): copied to HBM as they are and expanded there -- from page-locked
+    records, from pageable (mapped) ones, into a resident snapshot (whole genome / one shard's range)."""
+    import ctypes
+    name = "exome_small"
+    idx, out, region = T.regenerate(name, tmp_path)
+    inp = T.LoadedInput(idx, out + ".snapshot", region, pinned=0 if mode == "host_pageable" else 1, keep_sparse=True)
+    assert not inp.view.counters and inp.view.n_sparse_entries > 0
+    try:
+        if mode == "resident_range":
+            L = gpu_caller.L
+            dev, calls, st = ctypes.c_void_p(), ctypes.c_void_p(), T.Stats()
+            gpu_caller.check(L.gt16_snapshot_upload_range(gpu_caller.ctx, ctypes.byref(inp.view), inp.regions_ptr(), inp.n_regions,
+                                                          0, inp.total_sites, ctypes.byref(dev)))
+            gpu_caller.check(L.gt16_call_sites(gpu_caller.ctx, dev, inp.regions_ptr(), inp.n_regions, 0, inp.total_sites,
+                                               ctypes.byref(calls), ctypes.byref(st)))
+            assert L.gt16_write_txt((out + ".txt").encode(), inp.ix, L.gt16_calls_data(calls), L.gt16_calls_count(calls), 0, None) == 0
+            L.gt16_calls_free(calls)
+            L.gt16_snapshot_release(gpu_caller.ctx, dev)
+            st = [st]
+        else:
+            st = T.call_to_txt(gpu_caller, inp, out + ".txt", resident=(mode == "resident"))
+    finally:
+        inp.close()
+    assert sum(s.called for s in st) == T.manifest()[name]["rows"]
+    assert T.compare_txt(open(out + ".txt", "rb").read(), T.golden_txt(name)) <= 2
+
+
 @pytest.mark.parametrize("name", ["wgs_small", "two_batch"])
 def test_exact_inline_mode_matches_reference(tmp_path, name):
     """DecisionTables=0: every site goes through the exact evaluator in the streaming kernel."""
@@ -121,7 +151,8 @@ def test_full_size_callset_digest(gpu_caller, tmp_path, name, shards):
     every row hash to the digest of the reference's own .txt for the same snapshot, and the number of rows
     whose floating-point columns print differently is bounded."""
     idx, out, region = T.regenerate(name, tmp_path)
-    inp = T.LoadedInput(idx, out + ".snapshot", region, pinned=0 if name == "stress_full" else 1)   # one of them through the staging ring
+    # one of them through the staging ring; the full-size exome as the sparse records it is written as (expanded in HBM)
+    inp = T.LoadedInput(idx, out + ".snapshot", region, pinned=0 if name == "stress_full" else 1, keep_sparse=(name == "exome_full"))
     try:
         st = T.call_to_txt(gpu_caller, inp, out + ".txt", shards=shards)
     finally:
