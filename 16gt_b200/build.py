@@ -49,9 +49,9 @@ def build(force=False, verbose=True):
     os.makedirs(os.path.join(PKG, "lib"), exist_ok=True)
     os.makedirs(os.path.join(PKG, "bin"), exist_ok=True)
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
-    hdrs = [os.path.join(CSRC, h) for h in ("gt16_core.cuh", "gt16_kernels.cuh")] + [os.path.join(ROOT, "include", "gt16.h")]
+    hdrs = [os.path.join(CSRC, h) for h in ("gt16_core.cuh", "gt16_kernels.cuh", "gt16_pileup.cuh")] + [os.path.join(ROOT, "include", "gt16.h")]
     lib = os.path.join(PKG, "lib", "libgt16.so")
-    units = ["gt16_kernels.cu", "gt16_capi.cu", "gt16_host_io.cpp"]
+    units = ["gt16_kernels.cu", "gt16_capi.cu", "gt16_pileup.cu", "gt16_host_io.cpp", "gt16_sam.cpp"]
     objs = []
     for u in units:
         src = os.path.join(CSRC, u)
@@ -78,6 +78,13 @@ def build(force=False, verbose=True):
         _run([HOST_CXX, "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), rib_src, "-o", rib,
               "-L", os.path.join(PKG, "lib"), "-lgt16", "-Wl,-rpath,$ORIGIN/../lib",
               "-Wl,-rpath-link,/usr/local/cuda/lib64", "-lpthread"])
+    b2s_src = os.path.join(PKG, "host", "bam2snapshot.cpp")
+    b2s = os.path.join(PKG, "bin", "bam2snapshot")
+    if os.path.exists(b2s_src) and (force or not _newer(b2s, [b2s_src, lib] + hdrs)):
+        _run([HOST_CXX, "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), b2s_src, "-o", b2s,
+              "-L", os.path.join(PKG, "lib"), "-lgt16", "-Wl,-rpath,$ORIGIN/../lib",
+              "-Wl,-rpath-link,/usr/local/cuda/lib64", "-lpthread"])
+        shutil.copyfile(os.path.join(PKG, "host", "bam2snapshot.ini"), b2s + ".ini")
     t2v_src = os.path.join(PKG, "host", "txt2vcf.cpp")
     t2v = os.path.join(PKG, "bin", "txt2vcf")
     if os.path.exists(t2v_src) and (force or not _newer(t2v, [t2v_src])):

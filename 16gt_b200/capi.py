@@ -30,6 +30,22 @@ class View(ctypes.Structure):
                 ("sparse_entries", ctypes.c_void_p), ("n_sparse_entries", ctypes.c_uint64)]
 
 
+class Reads(ctypes.Structure):            # gt16_reads
+    _fields_ = [("n_reads", ctypes.c_uint64), ("start", ctypes.c_void_p), ("reverse", ctypes.c_void_p), ("length", ctypes.c_void_p),
+                ("seq_off", ctypes.c_void_p), ("cigar_off", ctypes.c_void_p), ("n_cigar", ctypes.c_void_p),
+                ("n_bases", ctypes.c_uint64), ("n_cigar_ops", ctypes.c_uint64), ("bases", ctypes.c_void_p),
+                ("quals", ctypes.c_void_p), ("cigar", ctypes.c_void_p)]
+
+
+class PileupParams(ctypes.Structure):     # gt16_pileup_params
+    _fields_ = [("weight_map", ctypes.c_uint8 * 41), ("trim_size", ctypes.c_uint32),
+                ("indel_weight_threshold", ctypes.c_uint32), ("n_overflow_regions", ctypes.c_uint32)]
+
+
+class BuiltSnapshot(ctypes.Structure):    # gt16_built_snapshot
+    _fields_ = [("view", View), ("overflow_storage", ctypes.c_void_p)]
+
+
 class Indel(ctypes.Structure):
     _fields_ = [("type", ctypes.c_uint8), ("len", ctypes.c_uint8), ("hq", ctypes.c_uint16), ("lq", ctypes.c_uint16),
                 ("seq", ctypes.c_uint8 * 64)]
@@ -125,6 +141,17 @@ def capi():
         "gt16_format_number": (i32, [ctypes.c_double, i32, cp]),
         "gt16_index_free": (None, [vp]),
         "gt16_write_txt": (i32, [cp, vp, vp, u64, i32, vp]),
+        "gt16_index_sequences": (u32, [vp]),
+        "gt16_index_sequence_id": (i32, [vp, cp]),
+        "gt16_index_locate_id": (i32, [vp, i32, u32, P(u32)]),
+        "gt16_pileup_default_params": (None, [vp]),
+        "gt16_build_snapshot": (i32, [vp, vp, u32, vp, vp]),
+        "gt16_built_snapshot_free": (None, [vp]),
+        "gt16_snapshot_write": (i32, [cp, P(View), cp, sz]),
+        "gt16_sam_read": (i32, [cp, vp, u32, P(vp), cp, sz]),
+        "gt16_sam_reads": (None, [vp, vp]),
+        "gt16_sam_total_alignments": (u64, [vp]),
+        "gt16_sam_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -158,6 +158,12 @@ struct gt16_calls {
   } while (0)
 
 static int fail(gt16_ctx *ctx, int code, const char *msg) { if (ctx) ctx->err = msg; return code; }
+// for gt16_pileup.cu (the producer lives in its own translation unit)
+int gt16_pileup_set_error(gt16_ctx *ctx, int code, const char *msg) { return fail(ctx, code, msg); }
+int gt16_pileup_device(gt16_ctx *ctx) {
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { (void) cudaGetLastError(); return fail(ctx, GT16_ECUDA, "cudaSetDevice failed"); }
+  return GT16_OK;
+}
 
 static EvalParams eval_params(const gt16_ctx *ctx, double balance, double unbalance) {
   EvalParams P;

@@ -367,6 +367,7 @@ int gt16_index_read(const char *prefix, gt16_index **out, char *err, size_t errL
 }
 
 uint32_t gt16_index_length(const gt16_index *ix) { return ix->length; }
+uint32_t gt16_index_sequences(const gt16_index *ix) { return ix ? (uint32_t) ix->names.size() : 0; }
 const uint32_t *gt16_index_packed(const gt16_index *ix, uint32_t *nWords) {
   if (nWords) *nWords = (uint32_t) ix->packed.size();
   return ix->packed.data();
@@ -395,24 +396,32 @@ const char *gt16_index_translate(const gt16_index *ix, uint32_t amb, uint32_t *c
   return c < ix->names.size() ? ix->names[c].c_str() : "?";
 }
 
-int gt16_index_locate(const gt16_index *ix, const char *chrName, uint32_t chrPos, uint32_t *amb) {
-  if (!ix || !chrName || !amb) return -1;
+int gt16_index_sequence_id(const gt16_index *ix, const char *chrName) {
+  if (!ix || !chrName) return -1;
   // getChrIDFromName: exact name, else the name without a leading "chr" (indexFunction.cpp:42-66; its third
   // attempt compares the unprefixed name again and so never matches anything new)
   size_t id = ix->names.size();
   for (size_t i = 0; i < ix->names.size(); ++i) if (ix->names[i] == chrName) { id = i; break; }
   if (id == ix->names.size() && strncmp(chrName, "chr", 3) == 0)
     for (size_t i = 0; i < ix->names.size(); ++i) if (ix->names[i] == chrName + 3) { id = i; break; }
-  if (id == ix->names.size()) return -1;
-  // getAmbPos: the concatenated position whose translation is (id + 1, chrPos)
+  return id == ix->names.size() ? -1 : (int) id + 1;
+}
+
+int gt16_index_locate_id(const gt16_index *ix, int chrID, uint32_t chrPos, uint32_t *amb) {
+  if (!ix || !amb || chrID < 1) return -1;
+  // getAmbPos: the concatenated position whose translation is (chrID, chrPos)
   for (size_t k = 0; k < ix->translate.size(); ++k) {
     const gt16_index::Tr &t = ix->translate[k];
-    if ((size_t) t.chrID != id + 1) continue;
+    if ((int) t.chrID != chrID) continue;
     const uint32_t a = chrPos + t.correction;
     const uint64_t next = k + 1 < ix->translate.size() ? ix->translate[k + 1].startPos : (uint64_t) ix->length;
     if (a >= t.startPos && (uint64_t) a < next && a < ix->length) { *amb = a; return 0; }
   }
   return -1;
+}
+
+int gt16_index_locate(const gt16_index *ix, const char *chrName, uint32_t chrPos, uint32_t *amb) {
+  return gt16_index_locate_id(ix, gt16_index_sequence_id(ix, chrName), chrPos, amb);
 }
 
 void gt16_index_free(gt16_index *ix) {

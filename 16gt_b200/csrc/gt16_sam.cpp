@@ -1,0 +1,245 @@
+// gt16_sam.cpp -- host side of the producer: SAM text -> aligned reads as bam2snapshot hands them to
+// updateSnpCounterForReads (bam2snapshot.cpp:79-206), and the snapshot container writer (writeSnpInfoSnapshot,
+// SnapshotHandler.cpp:83-236).  Plain C++; the counter construction itself is gt16_pileup.cu.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <unistd.h>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/gt16.h"
+
+namespace {
+void set_err(char *err, size_t n, const char *fmt, ...) {
+  if (!err || !n) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err, n, fmt, ap);
+  va_end(ap);
+}
+}  // namespace
+
+struct gt16_sam {
+  std::vector<uint32_t> start, length, nCigar, cigar;
+  std::vector<uint8_t> reverse, bases, quals;
+  std::vector<uint64_t> seqOff, cigarOff;
+  uint64_t total = 0;
+};
+
+extern "C" {
+
+void gt16_pileup_default_params(gt16_pileup_params *p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  // bam2snapshot.cpp:352-363 with Weight0..3 = 10 13 17 20
+  const int bound[4] = {10, 13, 17, 20};
+  for (int q = 0; q < 41; ++q) p->weight_map[q] = q <= bound[0] ? 0 : q <= bound[1] ? 1 : q <= bound[2] ? 2 : q <= bound[3] ? 3 : 4;
+  p->trim_size = 5;
+  p->indel_weight_threshold = 1;      // IndelQualityThreshold 13 >= Weight1 (:364-368)
+  p->n_overflow_regions = 16;
+}
+
+// SEQ character -> the reference's 2-bit code through BAM's 4-bit code (bam_nt16_table, then bamcode2snpcode,
+// bam2snapshot.h:52-58): A C G T keep their codes, N becomes G (code 15 -> 2), every other IUPAC letter A
+static inline uint8_t snp_code(char c) {
+  switch (c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    case 'N': case 'n': return 2;
+    default: break;
+  }
+  // ambiguity codes: bam_nt16_table gives M=3 R=5 S=6 V=7 W=9 Y=10 H=11 K=12 D=13 B=14 (all -> 0), anything else 15 (-> 2)
+  switch (c) {
+    case 'M': case 'R': case 'S': case 'V': case 'W': case 'Y': case 'H': case 'K': case 'D': case 'B':
+    case 'm': case 'r': case 's': case 'v': case 'w': case 'y': case 'h': case 'k': case 'd': case 'b':
+    case '=': return 0;
+    default: return 2;
+  }
+}
+
+int gt16_sam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold, gt16_sam **out, char *err, size_t errLen) {
+  if (!path || !ix || !out) return GT16_EINVAL;
+  FILE *f = fopen(path, "r");
+  if (!f) { set_err(err, errLen, "[ERROR] Failed accessing %s.", path); return GT16_EIO; }
+  gt16_sam *S = new gt16_sam();
+  std::unordered_map<std::string, int> ids;            // RNAME -> chromosome id (chrIdMap, bam2snapshot.cpp:157-158)
+  const uint32_t L = gt16_index_length(ix);
+  char *line = nullptr;
+  size_t cap = 0;
+  ssize_t n;
+  int rc = GT16_OK;
+  std::vector<uint32_t> ops;
+  while ((n = getline(&line, &cap, f)) > 0) {
+    if (line[0] == '@') continue;
+    while (n > 0 && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
+    if (!n) continue;
+    // QNAME FLAG RNAME POS MAPQ CIGAR RNEXT PNEXT TLEN SEQ QUAL
+    char *fld[11];
+    int nf = 0;
+    char *p = line;
+    while (nf < 11) {
+      fld[nf++] = p;
+      char *t = strchr(p, '\t');
+      if (!t) break;
+      *t = 0; p = t + 1;
+    }
+    if (nf < 11) { set_err(err, errLen, "%s: alignment line with fewer than 11 fields", path); rc = GT16_EDATA; break; }
+    S->total++;
+    const unsigned flag = (unsigned) strtoul(fld[1], nullptr, 10);
+    const long pos1 = strtol(fld[3], nullptr, 10);
+    const unsigned mapq = (unsigned) strtoul(fld[4], nullptr, 10);
+    if (mapq < mapqThreshold) continue;                                    // bam2snapshot.cpp:84-87
+    if (fld[2][0] == '*' || pos1 <= 0) continue;                           // :91-94 (tid < 0 or pos < 0)
+    if (flag & 0x400) continue;                                            // :171-174
+    const char *seq = fld[9], *qual = fld[10];
+    const size_t lseq = (seq[0] == '*' && seq[1] == 0) ? 0 : strlen(seq);
+    if (!lseq) continue;                                                   // readLength <= 0 (:181)
+    // CIGAR: the reference string is rebuilt from the BAM operations (:132-141); l_qseq must equal M + I + S (:181)
+    ops.clear();
+    size_t fromCigar = 0;
+    bool bad = fld[5][0] == '*' || fld[5][0] == 0;
+    for (const char *c = fld[5]; *c && !bad;) {
+      char *e;
+      const unsigned long len = strtoul(c, &e, 10);
+      if (e == c || !*e) { bad = true; break; }
+      int op;
+      switch (*e) {
+        case 'M': op = 0; break; case 'I': op = 1; break; case 'D': op = 2; break; case 'N': op = 3; break;
+        case 'S': op = 4; break; case 'H': op = 5; break; case 'P': op = 6; break; case '=': op = 7; break;
+        case 'X': op = 8; break; default: op = -1;
+      }
+      if (op < 0 || len >= (1ul << 28)) { bad = true; break; }
+      if (op == 0 || op == 1 || op == 4) fromCigar += len;                 // getLenFromCigar (:55-77) counts M, I and S
+      ops.push_back((uint32_t) (len << 4) | (uint32_t) op);
+      c = e + 1;
+    }
+    if (bad || fromCigar != lseq) continue;                                // :181-184, :186-188 (empty CIGAR)
+    int id;
+    {
+      auto it = ids.find(fld[2]);
+      if (it == ids.end()) { id = gt16_index_sequence_id(ix, fld[2]); ids.emplace(fld[2], id); }
+      else id = it->second;
+    }
+    uint32_t amb;
+    if (id < 1 || gt16_index_locate_id(ix, id, (uint32_t) pos1, &amb) != 0 || amb >= L) continue;   // :186
+    const bool haveQual = !(qual[0] == '*' && qual[1] == 0) && strlen(qual) == lseq;
+    S->start.push_back(amb);
+    S->reverse.push_back((flag & 16) ? 1 : 0);
+    S->length.push_back((uint32_t) lseq);
+    S->seqOff.push_back(S->bases.size());
+    S->cigarOff.push_back(S->cigar.size());
+    S->nCigar.push_back((uint32_t) ops.size());
+    S->cigar.insert(S->cigar.end(), ops.begin(), ops.end());
+    for (size_t k = 0; k < lseq; ++k) {
+      S->bases.push_back(snp_code(seq[k]));
+      S->quals.push_back(haveQual ? (uint8_t) (qual[k] - 33) : (uint8_t) 0xFF);
+    }
+  }
+  free(line);
+  fclose(f);
+  if (rc != GT16_OK) { delete S; return rc; }
+  *out = S;
+  return GT16_OK;
+}
+
+void gt16_sam_reads(const gt16_sam *S, gt16_reads *r) {
+  memset(r, 0, sizeof(*r));
+  r->n_reads = S->start.size();
+  r->start = S->start.data(); r->reverse = S->reverse.data(); r->length = S->length.data();
+  r->seq_off = S->seqOff.data(); r->cigar_off = S->cigarOff.data(); r->n_cigar = S->nCigar.data();
+  r->n_bases = S->bases.size(); r->n_cigar_ops = S->cigar.size();
+  r->bases = S->bases.data(); r->quals = S->quals.data(); r->cigar = S->cigar.data();
+}
+uint64_t gt16_sam_total_alignments(const gt16_sam *S) { return S ? S->total : 0; }
+void gt16_sam_free(gt16_sam *S) { delete S; }
+
+// ---- writeSnpInfoSnapshot (SnapshotHandler.cpp:83-236) ---------------------------------------------------------
+int gt16_snapshot_write(const char *path, const gt16_snapshot_view *v, char *err, size_t errLen) {
+  if (!path || !v || !v->counters || !v->text_length) return GT16_EINVAL;
+  const uint32_t L = v->text_length;
+  const size_t page = (size_t) sysconf(_SC_PAGE_SIZE);
+  // populated positions (isLowPopulation, bam2snapshot.cpp:527-561): overflow-type, or any non-zero field
+  size_t populated = 0;
+  for (uint32_t p = 0; p < L; ++p) if (v->counters[p]) ++populated;
+  const bool sparse = (double) populated / L < 0.1;
+  std::vector<uint32_t> keep;                       // sparse: positions within 100 of a populated one (writeHeader :103-122)
+  if (sparse) {
+    uint64_t next = 0;                              // first position not yet kept
+    for (uint32_t p = 0; p < L; ++p) if (v->counters[p]) {
+      const uint64_t s = p > 100 ? p - 100 : 0, e = p < L - 100 ? (uint64_t) p + 100 : (uint64_t) L - 1;
+      for (uint64_t j = s > next ? s : next; j <= e; ++j) keep.push_back((uint32_t) j);
+      if (e + 1 > next) next = e + 1;
+    }
+  }
+  const size_t poolCap = ((size_t) v->pool_bytes + page) / page * page;
+  size_t len[5], start[5];
+  len[0] = 4 + 8 + poolCap;
+  len[1] = 1 + 4 + (sparse ? keep.size() * 12 : (size_t) L * 8);
+  len[2] = 4;
+  for (uint32_t r = 0; r < v->n_overflow_regions; ++r) len[2] += 8 + (size_t) v->overflow_size[r] * 32;
+  len[3] = sparse ? 0 : (((size_t) L + 31) >> 5) * 4;
+  len[4] = 0;                                       // directional soft-clip counters: not used by the caller
+  size_t cur = page;
+  for (int i = 0; i < 5; ++i) { start[i] = cur; cur += (len[i] + page - 1) / page * page; }
+  FILE *f = fopen(path, "wb");
+  if (!f) { set_err(err, errLen, "cannot write %s", path); return GT16_EIO; }
+  bool ok = true;
+  std::vector<uint8_t> hdr(page, 0);
+  const int pg = (int) page;
+  memcpy(&hdr[0], &pg, 4);
+  for (int i = 0; i < 5; ++i) { memcpy(&hdr[4 + i * 16], &start[i], 8); memcpy(&hdr[12 + i * 16], &len[i], 8); }
+  ok = ok && fwrite(hdr.data(), 1, page, f) == page;
+  // subfile 0: pool
+  ok = ok && fseeko(f, (off_t) start[0], SEEK_SET) == 0;
+  const uint32_t curPtr = v->pool_bytes;
+  const uint64_t cap64 = poolCap;
+  ok = ok && fwrite(&curPtr, 4, 1, f) == 1 && fwrite(&cap64, 8, 1, f) == 1;
+  if (curPtr) ok = ok && fwrite(v->pool, 1, curPtr, f) == curPtr;
+  { std::vector<uint8_t> z(poolCap - curPtr, 0); if (!z.empty()) ok = ok && fwrite(z.data(), 1, z.size(), f) == z.size(); }
+  // subfile 1: counters
+  ok = ok && fseeko(f, (off_t) start[1], SEEK_SET) == 0;
+  const char mode = sparse ? 2 : 1;
+  ok = ok && fwrite(&mode, 1, 1, f) == 1 && fwrite(&L, 4, 1, f) == 1;
+  if (!sparse) ok = ok && fwrite(v->counters, 8, L, f) == L;
+  else {
+    std::vector<uint8_t> buf;
+    buf.reserve((size_t) 12 << 16);
+    for (size_t i = 0; i < keep.size(); ++i) {
+      const uint32_t p = keep[i];
+      const uint64_t c = v->counters[p];
+      const size_t at = buf.size();
+      buf.resize(at + 12);
+      memcpy(&buf[at], &p, 4); memcpy(&buf[at + 4], &c, 8);
+      if (buf.size() >= ((size_t) 12 << 16) || i + 1 == keep.size()) { ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size(); buf.clear(); }
+    }
+  }
+  // subfile 2: overflow arrays
+  ok = ok && fseeko(f, (off_t) start[2], SEEK_SET) == 0;
+  const uint32_t nr = v->n_overflow_regions;
+  ok = ok && fwrite(&nr, 4, 1, f) == 1;
+  for (uint32_t r = 0; r < nr; ++r) {
+    const uint32_t sz = v->overflow_size[r], lim = sz + 16;
+    ok = ok && fwrite(&sz, 4, 1, f) == 1 && fwrite(&lim, 4, 1, f) == 1;
+    if (sz) ok = ok && fwrite(v->overflow[r], 32, sz, f) == sz;
+  }
+  // subfile 3: invalid bitmap
+  if (!sparse) {
+    ok = ok && fseeko(f, (off_t) start[3], SEEK_SET) == 0;
+    const size_t w = ((size_t) L + 31) >> 5;
+    if (v->invalid_bitmap) ok = ok && fwrite(v->invalid_bitmap, 4, w, f) == w;
+    else { std::vector<uint32_t> z(w, 0); ok = ok && fwrite(z.data(), 4, w, f) == w; }
+  }
+  // every subfile is addressable up to its page-rounded end
+  ok = ok && fseeko(f, 0, SEEK_END) == 0;
+  const off_t endNow = ftello(f);
+  if (ok && (size_t) endNow < cur) { std::vector<uint8_t> z(cur - (size_t) endNow, 0); ok = fwrite(z.data(), 1, z.size(), f) == z.size(); }
+  if (fclose(f) != 0) ok = false;
+  if (!ok) { set_err(err, errLen, "error writing %s", path); return GT16_EIO; }
+  return GT16_OK;
+}
+
+}  // extern "C"

@@ -236,6 +236,7 @@ typedef struct gt16_index gt16_index;
 /* <prefix>.pac/.ann/.tra as HSPLoad reads them (readIndex.cpp:24-60,96-115) */
 int gt16_index_read(const char *prefix, gt16_index **out, char *err, size_t err_len);
 uint32_t gt16_index_length(const gt16_index *ix);
+uint32_t gt16_index_sequences(const gt16_index *ix);   /* number of sequences (numOfSeq) */
 const uint32_t *gt16_index_packed(const gt16_index *ix, uint32_t *n_words);
 /* Page-lock the packed reference in place (optional; worthwhile when the index serves many gt16_call_sites_host
  * calls: the copy to HBM then is an asynchronous DMA).  GT16_ECUDA when there is no device. */
@@ -246,6 +247,9 @@ const char *gt16_index_translate(const gt16_index *ix, uint32_t amb, uint32_t *c
  * leniency) and 1-based position -> concatenated position; returns 0 and *amb, or -1 when there is no such
  * position (unknown sequence, beyond its end, inside a removed stretch) */
 int gt16_index_locate(const gt16_index *ix, const char *chr_name, uint32_t chr_pos, uint32_t *amb);
+/* its two halves: getChrIDFromName (1-based id, -1 when unknown) and getAmbPos */
+int gt16_index_sequence_id(const gt16_index *ix, const char *chr_name);
+int gt16_index_locate_id(const gt16_index *ix, int chr_id, uint32_t chr_pos, uint32_t *amb);
 void gt16_index_free(gt16_index *ix);
 /* Test hook: the emitter's own "%.4e" (kind 0) / "%.4f" (kind 1) formatting of v into out (>= 64 bytes); returns the
  * length.  Must equal printf's output byte for byte. */
@@ -254,6 +258,64 @@ int gt16_format_number(double v, int kind, char *out);
 /* printHeader + printPossibleSNP (interpreter.cpp:8-31,107-156): byte-identical layout */
 int gt16_write_txt(const char *path, const gt16_index *ix, const gt16_called_site *sites, uint64_t n, int append,
                    float *lq_rq_carry /* [2] in/out, may be NULL */);
+
+/* ---- the producer in front of the path: aligned reads -> snapshot (bam2snapshot's counter construction) ---------- */
+
+/* Aligned reads as bamToAlignment (bam2snapshot.cpp:79-143) hands them to updateSnpCounterForReads (SNP.cpp:438), as
+ * host arrays.  Reads that the reference skips (unmapped, duplicates, MAPQ below the threshold, length mismatch with
+ * the CIGAR; bam2snapshot.cpp:84-186) are not in the list.  Any order; the order decides which of two equally deep indel
+ * patterns of a position is listed first, as it does in the reference. */
+typedef struct gt16_reads {
+  uint64_t n_reads;
+  const uint32_t *start;        /* concatenated-coordinate position of the first aligned base (getAmbPos of POS) */
+  const uint8_t *reverse;       /* 1: the read is on the reverse strand (FLAG & 16) */
+  const uint32_t *length;       /* l_qseq */
+  const uint64_t *seq_off;      /* first base of the read in bases[] / quals[] */
+  const uint64_t *cigar_off;    /* first operation of the read in cigar[] */
+  const uint32_t *n_cigar;
+  uint64_t n_bases, n_cigar_ops;
+  const uint8_t *bases;         /* 0..3 = A C G T as in SEQ, i.e. in reference orientation (N and IUPAC codes as bamcode2snpcode maps them, bam2snapshot.h:52-58) */
+  const uint8_t *quals;         /* phred scores as in QUAL (0xFF: absent) */
+  const uint32_t *cigar;        /* BAM encoding: length << 4 | op, op = 0 M, 1 I, 2 D, 3 N, 4 S, 5 H, 6 P, 7 =, 8 X */
+} gt16_reads;
+
+/* what loadBam2snapshotParas (bam2snapshot.cpp:336-369) derives from bam2snapshot.ini */
+typedef struct gt16_pileup_params {
+  uint8_t weight_map[41];          /* quality -> weight 0..4 (Weight0..Weight3) */
+  uint32_t trim_size;              /* statTrimSize: bases ignored at either end of a read */
+  uint32_t indel_weight_threshold; /* from IndelQualityThreshold */
+  uint32_t n_overflow_regions;     /* NumOfCpuThreads: number of overflow arrays of the snapshot */
+} gt16_pileup_params;
+/* defaults of the shipped bam2snapshot.ini (Weight 10/13/17/20, trim 5, IndelQualityThreshold 13, 16 regions) */
+void gt16_pileup_default_params(gt16_pileup_params *p);
+
+/* A snapshot built in memory: `view` is what gt16_call_sites_host / gt16_snapshot_upload / gt16_snapshot_write take
+ * (packed_ref left NULL).  Released with gt16_built_snapshot_free. */
+typedef struct gt16_built_snapshot {
+  gt16_snapshot_view view;
+  void *overflow_storage;
+} gt16_built_snapshot;
+
+/* updateSnpCounterForReads over all reads + readFilesForOverflow (bam2snapshot.cpp:221-330; SNP.cpp:438-891,893-1688):
+ * per-position base counters, overflow promotion, invalid bits, pooled insertion / deletion patterns, built on the GPU
+ * as one histogram pass (gt16_pileup.cu).  The decoded content equals the reference producer's; slot order, array
+ * indices and pool offsets -- which depend on the order in which the reference's threads get there -- need not. */
+int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint32_t text_length, const gt16_pileup_params *params,
+                        gt16_built_snapshot *out);
+void gt16_built_snapshot_free(gt16_built_snapshot *s);
+
+/* writeSnpInfoSnapshot (SnapshotHandler.cpp:83-236): the container with its page-aligned subfiles; dense (mode 1) when
+ * at least 10 % of the positions carry data, else sparse (mode 2: positions within 100 of a populated one,
+ * bam2snapshot.cpp:527-589).  The pool is written at its used size rounded up to a page, not at 1 GiB. */
+int gt16_snapshot_write(const char *path, const gt16_snapshot_view *view, char *err, size_t err_len);
+
+/* SAM text -> gt16_reads with the reference's filters (bam2snapshot.cpp:79-186: MAPQ threshold, unmapped, FLAG 0x400,
+ * l_qseq against the CIGAR); sequence names are resolved against the index like getChrIDFromName / getAmbPos. */
+typedef struct gt16_sam gt16_sam;
+int gt16_sam_read(const char *path, const gt16_index *ix, uint32_t mapq_threshold, gt16_sam **out, char *err, size_t err_len);
+void gt16_sam_reads(const gt16_sam *sam, gt16_reads *reads);
+uint64_t gt16_sam_total_alignments(const gt16_sam *sam);   /* lines read, including the skipped ones */
+void gt16_sam_free(gt16_sam *sam);
 
 #ifdef __cplusplus
 }

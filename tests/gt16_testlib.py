@@ -226,7 +226,66 @@ def snapshot_content_digest(path):
     return h.hexdigest()
 
 
-def producer_pipeline(name, workdir):
+def decode_snapshot(path):
+    """What a snapshot MEANS, position by position (the comparison bar of the producer): the invalid bitmap,
+    which positions are overflow-type, the weight / forward / reverse totals of the four bases, and the insertion and
+    deletion pattern lists (pattern, hq, lq) in list order.  Slot order, array indices and pool offsets are gone."""
+    c = parse_snapshot_container(path)
+    L, nreg = c["L"], len(c["ovf"])
+    cnt = c["counters"]
+    lo = (cnt & 0xFFFFFFFF).astype(np.uint32)
+    hi = (cnt >> 32).astype(np.uint32)
+    w1, w2 = lo & 0xFFFF, lo >> 16
+    ovf = ((w1 & w2) & 0xC000) == 0xC000
+    W = np.zeros((L, 4), np.uint32); F = np.zeros((L, 4), np.uint32); R = np.zeros((L, 4), np.uint32)
+    idx = np.arange(L)
+    for w, f, r in ((w1, hi & 0xFF, (hi >> 8) & 0xFF), (w2, (hi >> 16) & 0xFF, hi >> 24)):
+        live = (~ovf) & ((f | r) != 0)
+        b = (w >> 14)[live]
+        W[idx[live], b] = (w & 0x3FFF)[live]; F[idx[live], b] = f[live]; R[idx[live], b] = r[live]
+    recs = [np.frombuffer(o, np.uint8).reshape(-1, 32) for o in c["ovf"]]
+    seg = L // nreg
+    ins, dele = {}, {}
+    pool = c["pool"]
+    for p in np.nonzero(ovf)[0]:
+        p = int(p)
+        r = min(p // seg, nreg - 1) if seg else nreg - 1
+        rec = recs[r][int(hi[p])]
+        u16 = rec[:24].view("<u2")
+        f, rv = u16[4:8].astype(np.uint32), u16[8:12].astype(np.uint32)
+        seen = (f | rv) != 0
+        W[p] = np.where(seen, u16[0:4], 0); F[p] = f; R[p] = rv
+        a, b = int(w1[p]), int(w2[p])
+        if a & 0x2000:
+            lst = []
+            if a & 0x1000:
+                ptr, size, i = int(rec[24:28].view("<u4")[0]), a & 0xFFF, 0
+                info = pool[ptr:ptr + size]
+                while i < size:
+                    n = info[i]; nb = (n + 3) // 4
+                    lst.append((n, bytes(info[i + 1:i + 1 + nb]), info[i + 1 + nb] | info[i + 2 + nb] << 8, info[i + 3 + nb] | info[i + 4 + nb] << 8))
+                    i += 1 + nb + 4
+            else:
+                n = (a >> 8) & 0xF
+                lst.append((n, bytes(rec[24:24 + (n + 3) // 4]), a & 0xFF, int(rec[27])))
+            ins[p] = lst
+        if b & 0x2000:
+            lst = []
+            if b & 0x1000:
+                ptr, size, i = int(rec[28:32].view("<u4")[0]), b & 0xFFF, 0
+                info = pool[ptr:ptr + size]
+                while i < size:
+                    lst.append((info[i], info[i + 1] | info[i + 2] << 8, info[i + 3] | info[i + 4] << 8))
+                    i += 5
+            else:
+                lst.append((int(rec[28]), int(rec[29]), int(rec[30])))
+            dele[p] = lst
+    bitmap = c["bitmap"] if c["bitmap"] is not None else np.zeros((L + 31) >> 5, np.uint32)
+    bits = np.unpackbits(bitmap.astype(">u4").view(np.uint8))[:L].astype(bool)      # bit 31 - (p & 31) of word p >> 5
+    return dict(L=L, invalid=bits, overflow=ovf, W=W, F=F, R=R, ins=ins, dele=dele, mode=c["mode"], nreg=nreg)
+
+
+def producer_pipeline(name, workdir, keep_sam=False):
     """reads -> index -> snapshot with the reference's own tools; returns (index_prefix, out_prefix)"""
     cfg = PRODUCER_CONFIGS[name]
     wd = str(workdir)
@@ -238,7 +297,8 @@ def producer_pipeline(name, workdir):
     out = os.path.join(wd, "out", name)
     subprocess.run([REF_BAM2SNAPSHOT, "-i", idx, "-s", pre + ".sam", "-o", out], check=True, stdout=subprocess.DEVNULL,
                    stderr=subprocess.DEVNULL)
-    os.remove(pre + ".sam")
+    if not keep_sam:
+        os.remove(pre + ".sam")
     return idx, out
 
 

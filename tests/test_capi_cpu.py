@@ -199,3 +199,68 @@ def test_cli_usage_errors():
     assert r.returncode == 1 and "Missing index" in r.stderr
     r = subprocess.run([T.CLI, "-q"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "Invalid arguments" in r.stderr
+
+
+@pytest.mark.parametrize("name", ["stress_small", "exome_small"])
+def test_snapshot_writer_round_trip(tmp_path, name):
+    """gt16_snapshot_write (writeSnpInfoSnapshot, SnapshotHandler.cpp:83-236): a snapshot read by the library and written
+    again means the same (dense stays dense, a sparsely populated one is written as mode-2 records)"""
+    idx, out, region = T.regenerate(name, tmp_path)
+    inp = T.LoadedInput(idx, out + ".snapshot", region, pinned=0)
+    err = ctypes.create_string_buffer(256)
+    again = str(tmp_path / "again.snapshot")
+    try:
+        assert T.capi().gt16_snapshot_write(again.encode(), ctypes.byref(inp.view), err, 256) == 0, err.value
+    finally:
+        inp.close()
+    a, b = T.decode_snapshot(out + ".snapshot"), T.decode_snapshot(again)
+    assert a["mode"] == b["mode"] and a["L"] == b["L"] and a["nreg"] == b["nreg"]
+    for k in ("invalid", "overflow", "W", "F", "R"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["ins"] == b["ins"] and a["dele"] == b["dele"] and len(a["ins"]) + len(a["dele"]) > 0
+    assert T.snapshot_content_digest(out + ".snapshot") == T.snapshot_content_digest(again) or name == "exome_small"
+
+
+def test_sam_reader_filters(tmp_path):
+    """gt16_sam_read applies bamToAlignment / updateSnapshotForFile's filters (bam2snapshot.cpp:79-186)"""
+    idx, out, region = T.regenerate("wgs_small", tmp_path)
+    L = T.capi()
+    sam = tmp_path / "r.sam"
+    seq, q = "ACGTACGTAC", "IIIIIIIII#"
+    rows = [
+        ("ok_fwd", 0, "chrA", 11, 60, "10M", seq, q),
+        ("ok_rev", 16, "chrA", 21, 60, "2S3M1I2M1D2M", seq, q),
+        ("dup", 0x400, "chrA", 31, 60, "10M", seq, q),            # duplicate: skipped
+        ("lowq", 0, "chrA", 41, 3, "10M", seq, q),                # MAPQ below the threshold: skipped
+        ("unmapped", 4, "*", 0, 0, "*", seq, q),                  # skipped
+        ("lenmiss", 0, "chrA", 51, 60, "9M", seq, q),             # l_qseq != M + I + S: skipped
+        ("chrB", 0, "chrB", 1, 60, "10M", "NNNNNNNNNN", "*"),     # second contig, N bases, no qualities
+        ("offend", 0, "chrA", 999999999, 60, "10M", seq, q),      # beyond the contig: skipped
+    ]
+    with open(sam, "w") as f:
+        f.write("@HD\tVN:1.0\n@SQ\tSN:chrA\tLN:180000\n@SQ\tSN:chrB\tLN:70000\n")
+        for n, fl, rn, pos, mq, cg, s, ql in rows:
+            f.write("%s\t%d\t%s\t%d\t%d\t%s\t*\t0\t0\t%s\t%s\n" % (n, fl, rn, pos, mq, cg, s, ql))
+    err = ctypes.create_string_buffer(256)
+    ix = ctypes.c_void_p(); h = ctypes.c_void_p()
+    assert L.gt16_index_read(idx.encode(), ctypes.byref(ix), err, 256) == 0
+    assert L.gt16_sam_read(str(sam).encode(), ix, 10, ctypes.byref(h), err, 256) == 0, err.value
+    r = T.capi_mod.Reads()
+    L.gt16_sam_reads(h, ctypes.byref(r))
+    assert L.gt16_sam_total_alignments(h) == 8 and r.n_reads == 3
+    start = np.ctypeslib.as_array(ctypes.cast(r.start, ctypes.POINTER(ctypes.c_uint32)), (3,))
+    rev = np.ctypeslib.as_array(ctypes.cast(r.reverse, ctypes.POINTER(ctypes.c_uint8)), (3,))
+    amb = ctypes.c_uint32()
+    assert L.gt16_index_locate(ix, b"chrB", 1, ctypes.byref(amb)) == 0
+    assert list(start) == [10, 20, amb.value] and list(rev) == [0, 1, 0]
+    bases = np.ctypeslib.as_array(ctypes.cast(r.bases, ctypes.POINTER(ctypes.c_uint8)), (30,))
+    quals = np.ctypeslib.as_array(ctypes.cast(r.quals, ctypes.POINTER(ctypes.c_uint8)), (30,))
+    assert list(bases[:10]) == [0, 1, 2, 3, 0, 1, 2, 3, 0, 1] and list(bases[20:]) == [2] * 10      # N -> G (bamcode2snpcode[15])
+    assert list(quals[:10]) == [40] * 9 + [2] and list(quals[20:]) == [255] * 10
+    cig = np.ctypeslib.as_array(ctypes.cast(r.cigar, ctypes.POINTER(ctypes.c_uint32)), (int(r.n_cigar_ops),))
+    assert list(cig) == [10 << 4, (2 << 4) | 4, 3 << 4, (1 << 4) | 1, 2 << 4, (1 << 4) | 2, 2 << 4, 10 << 4]
+    L.gt16_sam_free(h)
+    L.gt16_index_free(ix)
+    p = T.capi_mod.PileupParams()
+    L.gt16_pileup_default_params(ctypes.byref(p))
+    assert list(p.weight_map)[9:22] == [0, 0, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4] and (p.trim_size, p.indel_weight_threshold, p.n_overflow_regions) == (5, 1, 16)

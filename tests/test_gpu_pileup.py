@@ -1,0 +1,78 @@
+"""SURVEY 8(f)3, the producer in front of the path: 16gt_b200/bin/bam2snapshot (SAM -> snapshot, counters built on the
+GPU by gt16_pileup.cu) against the reference's own bam2snapshot (oracle/_ref/ref_bam2snapshot, unmodified) on the same
+reads.  The bar: the DECODED snapshots are equal -- invalid bits, overflow-type positions, per-base weight /
+forward / reverse totals, insertion and deletion pattern lists in order -- and the caller turns ours into the very .txt
+the reference pipeline produced (tests/golden/prod_*.txt.gz)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import gt16_testlib as T
+
+pytestmark = pytest.mark.gpu
+B2S = os.path.join(T.PKG, "bin", "bam2snapshot")
+
+
+@pytest.fixture(scope="module")
+def built(tmp_path_factory):
+    made = {}
+
+    def make(name):
+        if name not in made:
+            for exe in (T.REF_MKINDEX, T.REF_BAM2SNAPSHOT, T.READSIM):
+                if not os.path.exists(exe):
+                    pytest.skip("%s not built" % os.path.relpath(exe, T.ROOT))
+            wd = str(tmp_path_factory.mktemp(name))
+            idx, out = T.producer_pipeline(name, wd, keep_sam=True)          # the reference's tools
+            sam = os.path.join(wd, name + ".sam")
+            mine = os.path.join(wd, "mine")
+            r = subprocess.run([B2S, "-i", idx, "-s", sam, "-o", mine], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1200)
+            assert r.returncode == 0, r.stderr + r.stdout
+            for marker in ("Loading reference...", "Updating snapshot...", "Total number of alignments:", "Dealing with overflows...",
+                           "Writing snapshot..."):
+                assert marker in r.stdout, marker
+            os.remove(sam)
+            made[name] = (idx, out, mine, r.stdout)
+        return made[name]
+    return make
+
+
+@pytest.mark.parametrize("name", list(T.PRODUCER_CONFIGS))
+def test_decoded_snapshot_equals_the_reference_producers(built, name):
+    idx, out, mine, log = built(name)
+    ref = T.decode_snapshot(out + ".snapshot")
+    got = T.decode_snapshot(mine + ".snapshot")
+    assert got["L"] == ref["L"] and got["nreg"] == ref["nreg"] and got["mode"] == ref["mode"]
+    assert np.array_equal(got["invalid"], ref["invalid"]), "invalid bitmaps differ at %s" % np.nonzero(got["invalid"] != ref["invalid"])[0][:10]
+    ok = ~ref["invalid"]                                # what an invalid position holds is whatever was there when it saturated
+    assert np.array_equal(got["overflow"][ok], ref["overflow"][ok]), "overflow-type positions differ at %s" % np.nonzero((got["overflow"] != ref["overflow"]) & ok)[0][:10]
+    for k in ("W", "F", "R"):
+        bad = np.nonzero((got[k] != ref[k]).any(axis=1) & ok)[0]
+        assert len(bad) == 0, "%s differs at %s: %s vs %s" % (k, bad[:5], got[k][bad[:5]], ref[k][bad[:5]])
+    for k in ("ins", "dele"):
+        a = {p: v for p, v in got[k].items() if ok[p]}
+        b = {p: v for p, v in ref[k].items() if ok[p]}
+        assert sorted(a) == sorted(b), "%s positions differ: %s" % (k, sorted(set(a) ^ set(b))[:10])
+        diff = [p for p in a if a[p] != b[p]]
+        assert not diff, "%s lists differ at %s: %s vs %s" % (k, diff[:3], [a[p] for p in diff[:3]], [b[p] for p in diff[:3]])
+    assert len(got["ins"]) + len(got["dele"]) > 100 and got["overflow"].sum() > 1000      # the config does exercise the rules
+
+
+@pytest.mark.parametrize("name", list(T.PRODUCER_CONFIGS))
+def test_caller_output_from_our_snapshot_equals_the_reference_pipelines(built, name):
+    """reads -> OUR bam2snapshot -> OUR snapshotSnpcaller  ==  reads -> reference bam2snapshot -> reference caller"""
+    idx, out, mine, log = built(name)
+    r = subprocess.run([T.CLI, "-i", idx, "-o", mine], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "Called Entries : %d" % T.manifest()[name]["rows"] in r.stdout
+    assert T.compare_txt(open(mine + ".txt", "rb").read(), T.golden_txt(name)) == 0
+    # and the reference's own reader (readSnpInfoSnapshot), producer loop and .txt writer accept the container we wrote:
+    # its harness with the libgt16 operator shim in place of FisherExactTest.o (no 26 s CPU prefill)
+    exe = os.path.join(T.REF_DIR, "ref_caller_gt16")
+    if name == "prod_5mb" and os.path.exists(exe):
+        os.remove(mine + ".txt")
+        r = subprocess.run([exe, idx, mine], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert T.compare_txt(open(mine + ".txt", "rb").read(), T.golden_txt(name)) == 0
