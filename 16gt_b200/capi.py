@@ -43,7 +43,8 @@ class PileupParams(ctypes.Structure):     # gt16_pileup_params
 
 
 class BuiltSnapshot(ctypes.Structure):    # gt16_built_snapshot
-    _fields_ = [("view", View), ("overflow_storage", ctypes.c_void_p)]
+    _fields_ = [("view", View), ("overflow_storage", ctypes.c_void_p), ("ms_pack", ctypes.c_float), ("ms_h2d", ctypes.c_float),
+                ("ms_kernel", ctypes.c_float), ("ms_d2h", ctypes.c_float), ("aligned_bases", ctypes.c_uint64)]
 
 
 class Indel(ctypes.Structure):

@@ -20,6 +20,10 @@ using namespace gt16;
 
 static thread_local std::string g_createError;      // per thread: the drop-in creates one context per shard thread
 static const uint32_t kBiasCacheEntries = 1u << 20;     // 8 MB, stays in L2
+// room in the list of Fisher tests the memo cache did not hold: four per record of the bound.  A context's first call finds
+// the cache empty and lists every test (~8 per SNP row); the record bound is ~7x the called fraction of a 30x genome, so
+// that fits; whatever does not is walked in place by the record kernel.
+static const uint32_t kMissedPerRecord = 4;
 
 namespace {
 
@@ -915,9 +919,10 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
   gt16_called_site *recs = (gt16_called_site *) ((seg & 1) ? ctx->recs2.p : ctx->recs.p);
   if (seg >= 2) CUF(cudaStreamWaitEvent(ctx->compute, segCopied[seg - 2], 0));   // this buffer's previous contents are on the host
   CUF(cudaMemsetAsync(ctx->dMissed, 0, 4, ctx->compute));
+  const uint32_t missedCap = (uint32_t) std::min<uint64_t>((uint64_t) cap * kMissedPerRecord, 0x7FFFFFF0ull);
   launch_candidates(V, pl.map, begin, part, rankOf, dCount, cap, P, ctx->biasCache, kBiasCacheEntries - 1,
-                    (BiasTask *) ctx->missed.p, ctx->dMissed, cap, recs, ctx->errWord, ctx->numSMs, ctx->compute);
-  launch_bias((BiasTask *) ctx->missed.p, ctx->dMissed, cap, P, ctx->biasCache, kBiasCacheEntries - 1, recs, ctx->numSMs, ctx->compute);
+                    (BiasTask *) ctx->missed.p, ctx->dMissed, missedCap, recs, ctx->errWord, ctx->numSMs, ctx->compute);
+  launch_bias((BiasTask *) ctx->missed.p, ctx->dMissed, missedCap, P, ctx->biasCache, kBiasCacheEntries - 1, recs, ctx->numSMs, ctx->compute);
   ctx->launches += 7;
   CUF(cudaEventRecord(ev[3], ctx->compute));
   timing.push_back(evStream0); timing.push_back(evStream1);
@@ -1040,7 +1045,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     CUF(ctx->part.ensure((size_t) capWant * sizeof(EvalOut)));
     CUF(ctx->rankOf.ensure((size_t) capWant * 4));
     CUF(ctx->list.ensure((size_t) capWant * 4));
-    CUF(ctx->missed.ensure((size_t) capWant * sizeof(BiasTask)));
+    CUF(ctx->missed.ensure((size_t) capWant * kMissedPerRecord * sizeof(BiasTask)));
     CUF(ctx->recs.ensure((size_t) capWant * sizeof(gt16_called_site)));
     if (!devOutHandle && n > kBatch) CUF(ctx->recs2.ensure((size_t) capWant * sizeof(gt16_called_site)));   // more than one segment
   }

@@ -1304,7 +1304,16 @@ __global__ void __launch_bounds__(kBiasThreads) k_bias(BiasList missed, LnFact G
       if (w.phase == 0 && rank < avail) {
         const BiasTask t = q[(qhead + rank) % kBiasQueue];
         w.key = bias_key(t.dst >> 31, t.W, t.F, t.R);
-        if (t.dst >> 31) { const int S = (int) ((t.F + t.R) * 4); walk_begin(L, w, (int) t.W, S, S, S, t.dst); }      // getBaseQualityBias
+        // the same test may have been finished by another lane since the record kernel looked (a cold cache lists every
+        // test of the call, most of them many times over): look again before walking
+        unsigned long long e = ~0ull;
+        if (w.key != 0xFFFFFFFFu) e = *reinterpret_cast<const volatile unsigned long long *>(cache + bias_slot(w.key, cacheMask));
+        if (w.key != 0xFFFFFFFFu && (uint32_t) e == w.key) {
+          const uint32_t d = t.dst & 0x7FFFFFFFu;
+          gt16_called_site &o = out[d / 12];
+          const float v = __uint_as_float((uint32_t) (e >> 32));
+          if (t.dst >> 31) o.bqb[(d % 12) >> 2][d & 3] = v; else o.sb[(d % 12) >> 2][d & 3] = v;
+        } else if (t.dst >> 31) { const int S = (int) ((t.F + t.R) * 4); walk_begin(L, w, (int) t.W, S, S, S, t.dst); }      // getBaseQualityBias
         else { const int S = (int) (t.F + t.R); walk_begin(L, w, (int) t.F, (int) t.R, (int) (S * 0.5), (int) (S * 0.5), t.dst); }  // getStrandBiasC
       }
       const uint32_t taken = __popc(idle) < avail ? __popc(idle) : avail;

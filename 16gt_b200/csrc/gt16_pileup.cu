@@ -23,6 +23,7 @@
 //
 // No CPU path: gt16_build_snapshot needs a context.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -372,6 +373,8 @@ extern "C" int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint3
   int rc = gt16_pileup_device(ctx);
   if (rc) return rc;
   memset(out, 0, sizeof(*out));
+  auto clock0 = std::chrono::steady_clock::now();
+  auto ms_since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
   const uint64_t n = reads->n_reads;
   const uint32_t L = text_length;
   // ---- sort the reads by start (stable: the input order decides which pattern appears first), pack what the kernel reads
@@ -406,6 +409,8 @@ extern "C" int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint3
     if (q > 40) q = 40;
     hBases[k] = (uint8_t) ((reads->bases[k] & 3u) | (params->weight_map[q] << 2));
   }
+  const float msPack = ms_since(clock0);
+  clock0 = std::chrono::steady_clock::now();
   Dev<uint32_t> dStart, dLen, dOrder, dNCig, dCigar, dInvalid, dOvfCount, dPoolPtr, dErr;
   Dev<uint64_t> dSeq, dCig, dCounters;
   Dev<uint8_t> dBases, dOvf, dPool;
@@ -422,6 +427,11 @@ extern "C" int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint3
   uint32_t poolCap = 16u << 20;
   std::vector<uint32_t> hCount(nReg);
   uint32_t hPool = 0;
+  const float msH2d = ms_since(clock0);
+  float msKernel = 0.f;
+  cudaEvent_t e0, e1;
+  PCU(cudaEventCreate(&e0)); PCU(cudaEventCreate(&e1));
+  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evGuard{e0, e1};
   for (int attempt = 0;; ++attempt) {
     if (dOvf.p) { cudaFree(dOvf.p); dOvf.p = nullptr; }
     if (dPool.p) { cudaFree(dPool.p); dPool.p = nullptr; }
@@ -435,9 +445,12 @@ extern "C" int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint3
     A.nRegions = nReg; A.ovfLen = regLen; A.ovfInv = regLen ? 1.0 / (double) regLen : 0.0;
     A.pool = dPool.p; A.poolPtr = dPoolPtr.p; A.poolCap = poolCap; A.errWord = dErr.p;
     const unsigned tiles = (unsigned) (((uint64_t) L + kPileTile - 1) / kPileTile);
+    PCU(cudaEventRecord(e0, 0));
     k_pileup<<<tiles, kPileThreads, sizeof(PileSmem)>>>(A);
     PCU(cudaGetLastError());
+    PCU(cudaEventRecord(e1, 0));
     PCU(cudaDeviceSynchronize());
+    PCU(cudaEventElapsedTime(&msKernel, e0, e1));
     uint32_t err = 0;
     PCU(cudaMemcpy(&err, dErr.p, 4, cudaMemcpyDeviceToHost));
     PCU(cudaMemcpy(hCount.data(), dOvfCount.p, nReg * 4, cudaMemcpyDeviceToHost));
@@ -450,6 +463,7 @@ extern "C" int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint3
     if (err & kErrPilePool) poolCap = std::max(poolCap * 2, hPool + (1u << 20));
   }
   // ---- results to the host
+  clock0 = std::chrono::steady_clock::now();
   uint64_t *counters = (uint64_t *) malloc(((size_t) L + 2) * 8);
   uint32_t *invalid = (uint32_t *) malloc((words + 1) * 4);
   uint8_t *pool = (uint8_t *) malloc((size_t) hPool + 16);
@@ -482,6 +496,8 @@ extern "C" int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint3
   out->view.n_overflow_regions = nReg; out->view.overflow = ovfPtr; out->view.overflow_size = ovfSize;
   out->view.pool = pool; out->view.pool_bytes = hPool;
   out->overflow_storage = ovf;
+  out->ms_pack = msPack; out->ms_h2d = msH2d; out->ms_kernel = msKernel; out->ms_d2h = ms_since(clock0);
+  out->aligned_bases = nBases;
   return GT16_OK;
 }
 

@@ -294,6 +294,10 @@ void gt16_pileup_default_params(gt16_pileup_params *p);
 typedef struct gt16_built_snapshot {
   gt16_snapshot_view view;
   void *overflow_storage;
+  /* how the time went: host (sorting / packing the reads), host->device copies, the k_pileup launch (CUDA events),
+   * device->host copies of the result; aligned bases in the reads */
+  float ms_pack, ms_h2d, ms_kernel, ms_d2h;
+  uint64_t aligned_bases;
 } gt16_built_snapshot;
 
 /* updateSnpCounterForReads over all reads + readFilesForOverflow (bam2snapshot.cpp:221-330; SNP.cpp:438-891,893-1688):

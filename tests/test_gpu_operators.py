@@ -104,13 +104,15 @@ def test_custom_prior_and_genotype_table(gpu_caller):
         gpu_caller.check(L.gt16_configure(gpu_caller.ctx, 0.01, 0.005, 1))
 
 
-def test_called_site_records_against_oracle(gpu_caller, tmp_path):
-    """the raw records behind the .txt rows: doubles within 1e-6 in log space of the C oracle's operator outputs
-    for the same W vectors, integer fields consistent"""
+@pytest.mark.parametrize("name", ["stress_small", "chr20_full", "stress_full"])
+def test_called_site_records_against_oracle(gpu_caller, tmp_path, name):
+    """the raw records behind the .txt rows -- of the small stress config and of the two full-size dense configs (the
+    bench workload and the config-5 flavour): doubles within 1e-6 in log space of the C oracle's operator outputs for the
+    same W vectors (the .txt prints five significant digits only), integer fields consistent"""
     O = ctypes.CDLL(T.ORACLE_LIB)
     vp = ctypes.c_void_p
     O.oracle_call.argtypes = [ctypes.c_double, ctypes.c_double, vp, vp, ctypes.c_uint] + [vp] * 6
-    idx, out, region = T.regenerate("stress_small", tmp_path)
+    idx, out, region = T.regenerate(name, tmp_path)
     inp = T.LoadedInput(idx, out + ".snapshot", region)
     L = gpu_caller.L
     calls = ctypes.c_void_p(); st = T.Stats()
@@ -120,7 +122,7 @@ def test_called_site_records_against_oracle(gpu_caller, tmp_path):
     L.gt16_calls_free(calls)
     inp.close()
     n = len(recs)
-    assert n == T.manifest()["stress_small"]["rows"]
+    assert n == T.manifest()[name]["rows"]
     W = np.ascontiguousarray(recs["W"]); ref = np.ascontiguousarray(recs["ref"])
     lh = np.zeros((n, 16)); flh = np.zeros((n, 16)); pD = np.zeros(n); b = np.zeros(n); s = np.zeros(n)
     gt = np.zeros(n, dtype=np.int32)
