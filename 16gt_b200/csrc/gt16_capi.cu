@@ -83,10 +83,11 @@ struct gt16_ctx {
   float *lnfact = nullptr;
   uint32_t *s1 = nullptr, *s2p = nullptr, *s2q = nullptr, *g4 = nullptr;
   uint32_t *errWord = nullptr, *dTotal = nullptr, *dFlagged = nullptr, *dMissed = nullptr;   // one allocation: error bits, compaction total, sites evaluated exactly, Fisher tests left to the walk kernel, ...
-  uint32_t *dCounts = nullptr;          // ... and kMaxSegs per-segment candidate counters (written by k_eval_mask, read by the kernels behind it)
+  uint32_t *dCounts = nullptr;          // ... and per segment a pair: [2 seg] side-buffer entries the evaluator reserved (its device-side counter, read by the
+                                        // kernels behind it; includes entries reserved and left unused), [2 seg + 1] the number of candidates (the scan's total)
   static const int kMaxSegs = 512;
-  uint32_t *hPinnedRing = nullptr;      // kCallRing slots of 4 words
-  uint32_t *hPinned = nullptr;          // the current call's slot: [0] records of a device-resident call, [1] error word, [2] (scan total), [3] sites evaluated exactly
+  uint32_t *hPinnedRing = nullptr;      // kCallRing slots of 8 words
+  uint32_t *hPinned = nullptr;          // the current call's slot: [0] entries reserved / [1] records of a device-resident call, [2] error word, [3] -, [4] sites evaluated exactly
   uint32_t *hCounts = nullptr;          // page-locked copy of dCounts (host-result calls)
   uint32_t recCap = 0;                  // records the candidate buffers (part, rankOf, list, recs, recs2) hold per segment
   gt16_called_site *extDst = nullptr;   // gt16_call_sites_host_to: the caller's result buffer for the call in progress
@@ -262,15 +263,15 @@ int gt16_ctx_create(int device, gt16_ctx **out) {
   if ((e = cudaMalloc(&ctx->g2i, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->ycsq, kYcsqN * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->lnfact, (size_t) kLnFactTab * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMalloc(&ctx->errWord, (4 + gt16_ctx::kMaxSegs) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->errWord, (4 + 2 * gt16_ctx::kMaxSegs) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   ctx->dTotal = ctx->errWord + 1;
   ctx->dFlagged = ctx->errWord + 2;
   ctx->dMissed = ctx->errWord + 3;
-  ctx->dCounts = ctx->errWord + 4;
-  if ((e = cudaHostAlloc(&ctx->hCounts, gt16_ctx::kMaxSegs * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
-  if ((e = cudaHostAlloc(&ctx->hPinnedRing, gt16_ctx::kCallRing * 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  ctx->dCounts = ctx->errWord + 4;       // 8-byte aligned: a segment's pair is read back with one copy
+  if ((e = cudaHostAlloc(&ctx->hCounts, 2 * gt16_ctx::kMaxSegs * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  if ((e = cudaHostAlloc(&ctx->hPinnedRing, gt16_ctx::kCallRing * 8 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
   ctx->hPinned = ctx->hPinnedRing;
-  if ((e = cudaMemset(ctx->errWord, 0, (4 + gt16_ctx::kMaxSegs) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMemset(ctx->errWord, 0, (4 + 2 * gt16_ctx::kMaxSegs) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = cudaMalloc(&ctx->biasCache, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(ctx->biasCache, 0xFF, (size_t) kBiasCacheEntries * sizeof(uint2))) != cudaSuccess) return bail("cudaMemset", e);
   if ((e = install_default_tables(ctx)) != cudaSuccess) return bail("cudaMemcpy", e);
@@ -512,7 +513,9 @@ static int stage_threads() {                              // GT16_STAGE_THREADS,
 // candidate per 128 sites plus a floor -- about seven times the called fraction of a 30x genome, 2.5 times that of the
 // 60x stress configs.  A call that finds more raises kErrRecordOverflow, and is repeated once with buffers of the size
 // it asked for (the buffers only grow, so this happens at most once per context and workload).
-static uint32_t record_bound(uint64_t segSites) { return (uint32_t) std::min<uint64_t>(segSites / 128 + 16384, 0x7FFFFFFFull / 12); }
+// (The floor also covers the side-buffer entries the evaluator's warps reserve in chunks of 8 and leave unused: at most 7
+// per warp of its grid, 33,152 in all.)
+static uint32_t record_bound(uint64_t segSites) { return (uint32_t) std::min<uint64_t>(segSites / 128 + 65536, 0x7FFFFFFFull / 12); }
 static const int kRetryLargerBuffers = 1;             // internal return code of call_common
 static const uint32_t kSegBatchesDefault = 2;         // batches per segment of a host-fed range (GT16_SEG_BATCHES overrides)
 
@@ -901,7 +904,7 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
   EvalParams P = eval_params(ctx);
   const uint32_t n = (uint32_t) (b - a), off = (uint32_t) (a - begin), cap = ctx->recCap;
   uint32_t *maskAll = (uint32_t *) ctx->mask.p, *counts = (uint32_t *) ctx->counts.p;
-  uint32_t *dCount = ctx->dCounts + seg;
+  uint32_t *dCount = ctx->dCounts + 2 * seg;
   EvalOut *part = (EvalOut *) ctx->part.p;
   uint32_t *rankOf = (uint32_t *) ctx->rankOf.p, *list = (uint32_t *) ctx->list.p;
   cudaEvent_t ev[4];
@@ -910,17 +913,18 @@ int finish_segment(gt16_ctx *ctx, const SnapView &V, RegionPlan &pl, uint64_t be
   CUF(cudaEventRecord(ev[0], ctx->compute));
   launch_eval_mask(V, pl.map, begin, off, n, usedTables, D, P, maskAll, ctx->errWord, ctx->dFlagged, part, dCount, cap, ctx->compute);
   CUF(cudaEventRecord(ev[1], ctx->compute));
-  launch_mask_count(maskAll + off / 32, n, counts, ctx->compute);
   uint32_t *chunkOffsets = counts + scan_blocks(n) + 1;        // behind the block counts (counts.ensure)
-  launch_scan_counts(counts, scan_blocks(n), chunkOffsets, ctx->dTotal, ctx->compute);
-  launch_rank(maskAll, off, counts, chunkOffsets, part, dCount, cap, rankOf, list, ctx->compute);
+  uint32_t *subCounts = chunkOffsets + 1024;                   // ... and the counts of the blocks' runs of 32 words behind those
+  launch_mask_count(maskAll + off / 32, n, counts, subCounts, ctx->compute);
+  launch_scan_counts(counts, scan_blocks(n), chunkOffsets, ctx->dCounts + 2 * seg + 1, ctx->compute);
+  launch_rank(maskAll, off, counts, chunkOffsets, subCounts, part, dCount, cap, rankOf, list, ctx->compute);
   CUF(cudaEventRecord(ev[2], ctx->compute));
   // record buffers alternate between segments: a segment's copy home may still be in flight while the next one is written
   gt16_called_site *recs = (gt16_called_site *) ((seg & 1) ? ctx->recs2.p : ctx->recs.p);
   if (seg >= 2) CUF(cudaStreamWaitEvent(ctx->compute, segCopied[seg - 2], 0));   // this buffer's previous contents are on the host
   CUF(cudaMemsetAsync(ctx->dMissed, 0, 4, ctx->compute));
   const uint32_t missedCap = (uint32_t) std::min<uint64_t>((uint64_t) cap * kMissedPerRecord, 0x7FFFFFF0ull);
-  launch_candidates(V, pl.map, begin, part, rankOf, dCount, cap, P, ctx->biasCache, kBiasCacheEntries - 1,
+  launch_candidates(V, pl.map, begin, part, list, dCount, cap, P, ctx->biasCache, kBiasCacheEntries - 1,
                     (BiasTask *) ctx->missed.p, ctx->dMissed, missedCap, recs, ctx->errWord, ctx->numSMs, ctx->compute);
   launch_bias((BiasTask *) ctx->missed.p, ctx->dMissed, missedCap, P, ctx->biasCache, kBiasCacheEntries - 1, recs, ctx->numSMs, ctx->compute);
   ctx->launches += 7;
@@ -963,11 +967,11 @@ static int finish_dev_call(gt16_ctx *ctx, gt16_dev_calls *c) {
   CUF(cudaEventSynchronize(c->evEnd));
   CUF(cudaGetLastError());
   c->pending = false;
-  const uint32_t found = c->slot[0], errw = c->slot[1];
-  if (found > c->cap) {
+  const uint32_t reserved = c->slot[0], found = c->slot[1], errw = c->slot[2];
+  if (reserved > c->cap) {
     CUF(cudaDeviceSynchronize());                                 // later calls on the context may be in flight
     CUF(cudaMemset(ctx->errWord, 0, 4));
-    ctx->recCapWanted = found + found / 8 + 1024;
+    ctx->recCapWanted = reserved + reserved / 8 + 1024;
     gt16_dev_calls *again = nullptr;
     gt16_stats st2;
     int rc = call_common(ctx, nullptr, c->snap, c->regions.empty() ? nullptr : c->regions.data(), (uint32_t) c->regions.size(),
@@ -979,7 +983,7 @@ static int finish_dev_call(gt16_ctx *ctx, gt16_dev_calls *c) {
   }
   c->n = found;
   c->st.called = found;
-  c->st.flagged = c->slot[3];
+  c->st.flagged = c->slot[4];
   int rc = report_device_errors(ctx, errw);
   if (rc != GT16_OK) return rc;
   fill_timings(c->st, c->evBegin, c->evEnd, c->timing);
@@ -991,7 +995,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
                        gt16_calls **out, gt16_stats *stats, gt16_dev_calls **devOutHandle, bool nowait) {
   if (!ctx || (!out && !devOutHandle)) return GT16_EINVAL;
   ctx->evCur = (ctx->evCur + 1) % gt16_ctx::kCallRing;
-  ctx->hPinned = ctx->hPinnedRing + 4 * ctx->evCur;
+  ctx->hPinned = ctx->hPinnedRing + 8 * ctx->evCur;
   if (!ctx->havePrefill) return fail(ctx, GT16_ESTATE, "gt16_configure / gt16_prefill_likelihood_cache must run first");
   std::unique_ptr<gt16_dev_calls> devOut(devOutHandle ? new gt16_dev_calls() : nullptr);
   CU(cudaSetDevice(ctx->device));
@@ -1038,7 +1042,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   if (const char *e = getenv("GT16_SEG_BATCHES")) { int v = atoi(e); if (v >= 1 && v <= 64) segBatches = (uint32_t) v; }
   const uint64_t segSites = devOutHandle ? (uint64_t) n : (uint64_t) segBatches * kBatch;
   const uint64_t segLongest = std::min<uint64_t>(segSites, n);
-  CUF(ctx->counts.ensure(((size_t) scan_blocks((uint32_t) segLongest) + 1 + 1024) * 4));    // block counts + chunk offsets
+  CUF(ctx->counts.ensure(((size_t) scan_blocks((uint32_t) segLongest) * (1 + kScanBlock / 32) + 1 + 1024) * 4));    // block counts + chunk offsets + run counts
   {
     const uint32_t capWant = std::max(std::max(ctx->recCap, ctx->recCapWanted), record_bound(segLongest));
     ctx->recCap = capWant;
@@ -1055,7 +1059,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   const uint32_t nSegsBound = (uint32_t) ((n + segSites - 1) / segSites) + 1;
   if (nSegsBound > (uint32_t) gt16_ctx::kMaxSegs) return fail(ctx, GT16_EINVAL, "range too long for GT16_SEG_BATCHES");
   CUF(cudaMemsetAsync(ctx->dFlagged, 0, 4, ctx->compute));
-  CUF(cudaMemsetAsync(ctx->dCounts, 0, nSegsBound * 4, ctx->compute));
+  CUF(cudaMemsetAsync(ctx->dCounts, 0, nSegsBound * 8, ctx->compute));
   CUF(cudaEventRecord(evBegin, ctx->compute));
 
   gt16_dev_snapshot streamed;
@@ -1229,13 +1233,13 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   bool overflow = false;
   auto collect = [&](uint32_t sg) -> int {
     CUF(cudaEventSynchronize(segDone[sg]));
-    const uint32_t cnt = ctx->hCounts[sg];
+    const uint32_t reserved = ctx->hCounts[2 * sg], cnt = ctx->hCounts[2 * sg + 1];
     cudaEvent_t done;
     int rc2 = get_event(ctx, evNext++, &done);
     if (rc2) return rc2;
-    if (cnt > ctx->recCap) {
+    if (reserved > ctx->recCap) {
       overflow = true;
-      ctx->recCapWanted = std::max(ctx->recCapWanted, cnt + cnt / 8 + 1024);
+      ctx->recCapWanted = std::max(ctx->recCapWanted, reserved + reserved / 8 + 1024);
     } else if (cnt && !overflow) {
       if ((rc2 = reserve_results(ctx, calls.get(), cnt, resultHint))) return rc2;
       if (!calls->tooSmall) {
@@ -1270,7 +1274,7 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     if (!devOutHandle) {
       cudaEvent_t sd;
       if ((rc = get_event(ctx, evNext++, &sd))) return rc;
-      CUF(cudaMemcpyAsync(ctx->hCounts + seg, ctx->dCounts + seg, 4, cudaMemcpyDeviceToHost, ctx->compute));
+      CUF(cudaMemcpyAsync(ctx->hCounts + 2 * seg, ctx->dCounts + 2 * seg, 8, cudaMemcpyDeviceToHost, ctx->compute));
       CUF(cudaEventRecord(sd, ctx->compute));
       segDone.push_back(sd);
       if (seg >= 1 && (rc = collect(seg - 1))) return rc;
@@ -1287,8 +1291,8 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
     for (auto &t : stagers) t.join();
     if (stageError.load()) { ctx->err = std::string("staged upload failed: ") + cudaGetErrorString((cudaError_t) stageError.load()); return GT16_ECUDA; }
   }
-  if (devOutHandle) CUF(cudaMemcpyAsync(ctx->hPinned, ctx->dCounts, 4, cudaMemcpyDeviceToHost, ctx->compute));   // records of the (single) segment
-  CUF(cudaMemcpyAsync(ctx->hPinned + 1, ctx->errWord, 12, cudaMemcpyDeviceToHost, ctx->compute));   // error bits, (total), sites evaluated
+  if (devOutHandle) CUF(cudaMemcpyAsync(ctx->hPinned, ctx->dCounts, 8, cudaMemcpyDeviceToHost, ctx->compute));   // entries reserved / records of the (single) segment
+  CUF(cudaMemcpyAsync(ctx->hPinned + 2, ctx->errWord, 12, cudaMemcpyDeviceToHost, ctx->compute));   // error bits, -, sites evaluated
   CUF(cudaEventRecord(evEnd, ctx->compute));
   st.kernel_launches = ctx->launches - launches0;
   if (devOutHandle) {
@@ -1309,8 +1313,8 @@ static int call_common(gt16_ctx *ctx, const gt16_snapshot_view *hostView, const 
   }
   CUF(cudaStreamSynchronize(ctx->compute));
   CUF(cudaGetLastError());
-  const uint32_t errw = ctx->hPinned[1];
-  st.flagged = ctx->hPinned[3];
+  const uint32_t errw = ctx->hPinned[2];
+  st.flagged = ctx->hPinned[4];
   if (overflow) {                                   // more candidates than the record buffers hold: again, with larger ones
     CUF(cudaDeviceSynchronize());
     CUF(cudaMemset(ctx->errWord, 0, 4));

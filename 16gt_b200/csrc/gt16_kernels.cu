@@ -535,6 +535,10 @@ constexpr int kEvalThreads = 128;
 #define GT16_EVAL_BLOCKS 8      // resident blocks per SM (register budget 65536 / (128 x blocks)); tools/probes sweeps it: 6 -> 8 = -5 us, 10 = +13 us
 #endif
 constexpr int kEvalQueue = 64;                       // per-warp ring of flagged site indices
+#ifndef GT16_EVAL_CHUNK
+#define GT16_EVAL_CHUNK 8
+#endif
+constexpr int kEvalSlotChunk = GT16_EVAL_CHUNK;      // side-buffer entries a warp reserves at a time (unused ones are marked)
 
 // Exact evaluation of up to 32 flagged sites, one per lane (site index i relative to `base`, lanes with !active idle).
 // Lane phase: decode + the general bitmap test; warp phase: the sites that still need the full evaluator are taken
@@ -544,7 +548,8 @@ __device__ __forceinline__ void eval_group(const SnapView &V, const DevSiteMap &
                                            bool useTables, const DecisionTables &D, const EvalParams &P,
                                            uint32_t *__restrict__ siteMask, uint32_t *errWord,
                                            double (*lhS)[16], uint32_t (*wpS)[6],
-                                           EvalOut *__restrict__ part, uint32_t *count, uint32_t cap) {
+                                           EvalOut *__restrict__ part, uint32_t *count, uint32_t cap,
+                                           uint32_t &slotNext, uint32_t &slotEnd) {
   const uint32_t lane = threadIdx.x & 31, half = lane >> 4, g = lane & 15;
   {
     uint32_t e = 0;
@@ -637,9 +642,18 @@ __device__ __forceinline__ void eval_group(const SnapView &V, const DevSiteMap &
           const double w = __shfl_xor_sync(0xffffffffu, f1, o);
           if (w > f1) f1 = w;
         }
-        uint32_t slot = 0;
-        if (emit && g == 0) slot = atomicAdd(count, 1u);
-        slot = __shfl_sync(0xffffffffu, slot, half << 4);
+        // entries of the side buffer are handed out from a chunk the warp reserves with ONE atomic (the reply of a
+        // contended global atomic takes a microsecond: per candidate it was a fifth of this kernel's stall samples)
+        const uint32_t emits = __ballot_sync(0xffffffffu, emit && g == 0);          // bit 0 and / or bit 16
+        if (slotEnd - slotNext < (uint32_t) __popc(emits)) {
+          if (slotNext < slotEnd && lane == 0 && slotNext < cap) part[slotNext].site = 0xFFFFFFFFu;   // at most one entry is left: unused
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(count, (uint32_t) kEvalSlotChunk);
+          slotNext = __shfl_sync(0xffffffffu, base, 0);
+          slotEnd = slotNext + (uint32_t) kEvalSlotChunk;
+        }
+        const uint32_t slot = slotNext + ((half && (emits & 1u)) ? 1u : 0u);
+        slotNext += (uint32_t) __popc(emits);
         if (emit) {
           if (slot < cap) {
             EvalOut &eo = part[slot];
@@ -683,6 +697,7 @@ __global__ void __launch_bounds__(kEvalThreads, GT16_EVAL_BLOCKS) k_eval_mask(Sn
   uint32_t *ring = ringS[warp];
   const uint32_t warpsTotal = gridDim.x * (kEvalThreads / 32), nChunks = (nWords + 31) / 32;
   uint32_t head = 0, tail = 0, seen = 0;
+  uint32_t slotNext = 0, slotEnd = 0;                   // the warp's reserved entries of part[]: [slotNext, slotEnd)
   for (uint32_t c = blockIdx.x * (kEvalThreads / 32) + warp; c < nChunks; c += warpsTotal) {
     const uint32_t wi = c * 32 + lane;
     // plain load: the words are cleared by atomics of this very launch (other warps' sites never share a word with ours
@@ -700,7 +715,7 @@ __global__ void __launch_bounds__(kEvalThreads, GT16_EVAL_BLOCKS) k_eval_mask(Sn
       tail += __popc(any);
       __syncwarp();
       if (tail - head >= 32u) {
-        eval_group(V, M, base, ring[(head + lane) & (kEvalQueue - 1)], true, useTables, D, P, siteMask, errWord, lhS[warp], wpS[warp], part, count, cap);
+        eval_group(V, M, base, ring[(head + lane) & (kEvalQueue - 1)], true, useTables, D, P, siteMask, errWord, lhS[warp], wpS[warp], part, count, cap, slotNext, slotEnd);
         head += 32;
         __syncwarp();
       }
@@ -709,8 +724,9 @@ __global__ void __launch_bounds__(kEvalThreads, GT16_EVAL_BLOCKS) k_eval_mask(Sn
   }
   if (tail != head) {
     const bool active = lane < tail - head;
-    eval_group(V, M, base, active ? ring[(head + lane) & (kEvalQueue - 1)] : 0u, active, useTables, D, P, siteMask, errWord, lhS[warp], wpS[warp], part, count, cap);
+    eval_group(V, M, base, active ? ring[(head + lane) & (kEvalQueue - 1)] : 0u, active, useTables, D, P, siteMask, errWord, lhS[warp], wpS[warp], part, count, cap, slotNext, slotEnd);
   }
+  for (uint32_t k = slotNext + lane; k < slotEnd; k += 32) if (k < cap) part[k].site = 0xFFFFFFFFu;   // reserved, not used
   seen = __reduce_add_sync(0xffffffffu, seen);
   if (lane == 0 && seen) atomicAdd(flagged, seen);
 }
@@ -725,14 +741,14 @@ void launch_eval_mask(const SnapView &V, const DevSiteMap &M, uint64_t base, uin
 }
 
 // ------------------------------------------------------------------------------ ordered compaction
+// blockCounts[b] = set bits of the block's kScanBlock words; subCounts[b * 8 + k] = set bits of its k-th run of 32 words
 __global__ void __launch_bounds__(kScanBlock) k_mask_count(const uint32_t *__restrict__ mask, uint32_t nWords,
-                                                          uint32_t *__restrict__ blockCounts) {
+                                                          uint32_t *__restrict__ blockCounts, uint32_t *__restrict__ subCounts) {
   __shared__ uint32_t warpSum[kScanBlock / 32];
   uint32_t w = blockIdx.x * kScanBlock + threadIdx.x;
   uint32_t c = w < nWords ? __popc(mask[w]) : 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0) warpSum[threadIdx.x >> 5] = c;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) { warpSum[threadIdx.x >> 5] = c; subCounts[blockIdx.x * (kScanBlock / 32) + (threadIdx.x >> 5)] = c; }
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t t = 0;
@@ -740,9 +756,9 @@ __global__ void __launch_bounds__(kScanBlock) k_mask_count(const uint32_t *__res
     blockCounts[blockIdx.x] = t;
   }
 }
-void launch_mask_count(const uint32_t *mask, uint32_t nItems, uint32_t *blockCounts, cudaStream_t s) {
+void launch_mask_count(const uint32_t *mask, uint32_t nItems, uint32_t *blockCounts, uint32_t *subCounts, cudaStream_t s) {
   uint32_t nb = scan_blocks(nItems);
-  if (nb) k_mask_count<<<nb, kScanBlock, 0, s>>>(mask, (nItems + 31) / 32, blockCounts);
+  if (nb) k_mask_count<<<nb, kScanBlock, 0, s>>>(mask, (nItems + 31) / 32, blockCounts, subCounts);
 }
 
 // Exclusive scan of the block counts in two levels, so that a whole-genome call (380 K blocks) costs what a chromosome
@@ -788,33 +804,41 @@ void launch_scan_counts(uint32_t *blockCounts, uint32_t nBlocks, uint32_t *chunk
 }
 
 // Place of every candidate in the ordered output: rank = number of set mask bits before its site, from the scanned block
-// counts plus the (at most kScanBlock) words of its own block.  One warp per candidate; the count is read on the device.
+// counts plus the (at most kScanBlock) words of its own block.  One warp per side-buffer entry; the count is read on the
+// device.  list[rank] = entry: the record kernel walks the ranks, so entries a warp of the evaluator reserved and did not
+// use cost nothing there, and neighbouring warps write neighbouring records.
 __global__ void __launch_bounds__(256) k_rank(const uint32_t *__restrict__ mask, uint32_t firstWord,
                                               const uint32_t *__restrict__ blockOffsets,
-                                              const uint32_t *__restrict__ chunkOffsets, const EvalOut *__restrict__ part,
+                                              const uint32_t *__restrict__ chunkOffsets,
+                                              const uint32_t *__restrict__ subCounts, const EvalOut *__restrict__ part,
                                               const uint32_t *__restrict__ count, uint32_t cap,
                                               uint32_t *__restrict__ rankOf, uint32_t *__restrict__ list) {
   const uint32_t n = *count < cap ? *count : cap;
   const uint32_t lane = threadIdx.x & 31, warpsTotal = gridDim.x * (blockDim.x >> 5);
   for (uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += warpsTotal) {
     const uint32_t site = part[j].site;
-    const uint32_t w = (site >> 5) - firstWord, w0 = (w / kScanBlock) * kScanBlock;
+    if (site == 0xFFFFFFFFu) continue;                                  // an entry a warp reserved and did not use
+    // set bits before the site's word inside its block: whole runs of 32 words from the sub-counts (lanes 0..7), the
+    // words of its own run one per lane
+    const uint32_t w = (site >> 5) - firstWord, run = w / 32, w0 = run * 32;
     uint32_t c = 0;
-    for (uint32_t k = w0 + lane; k < w; k += 32) c += __popc(mask[firstWord + k]);
+    if (lane < (run & (kScanBlock / 32 - 1))) c = subCounts[(run & ~(uint32_t) (kScanBlock / 32 - 1)) + lane];
+    if (w0 + lane < w) c += __popc(mask[firstWord + w0 + lane]);
     c = __reduce_add_sync(0xffffffffu, c);
     if (lane == 0) {
       const uint32_t blk = w / kScanBlock;
       const uint32_t r = chunkOffsets[blk >> 10] + blockOffsets[blk] + c + __popc(mask[firstWord + w] & ((1u << (site & 31)) - 1u));
       rankOf[j] = r;
-      list[r] = site;
+      list[r] = j;
     }
   }
 }
 void launch_rank(const uint32_t *siteMask, uint32_t firstSite, const uint32_t *blockOffsets, const uint32_t *chunkOffsets,
-                 const EvalOut *part, const uint32_t *count, uint32_t cap, uint32_t *rankOf, uint32_t *list, cudaStream_t s) {
+                 const uint32_t *subCounts, const EvalOut *part, const uint32_t *count, uint32_t cap, uint32_t *rankOf,
+                 uint32_t *list, cudaStream_t s) {
   unsigned grid = (cap + 7) / 8;
   if (grid > 148 * 8) grid = 148 * 8;
-  k_rank<<<grid, 256, 0, s>>>(siteMask, firstSite / 32, blockOffsets, chunkOffsets, part, count, cap, rankOf, list);
+  k_rank<<<grid, 256, 0, s>>>(siteMask, firstSite / 32, blockOffsets, chunkOffsets, subCounts, part, count, cap, rankOf, list);
 }
 
 // ------------------------------------------------------------------------------ candidates
@@ -1004,20 +1028,22 @@ __device__ __noinline__ float bias_inline(const LnFact &G, bool bqb, uint32_t W,
 
 __global__ void __launch_bounds__(kCandThreads, GT16_CAND_BLOCKS) k_candidates(SnapView V, DevSiteMap M, uint64_t base,
                                                              const EvalOut *__restrict__ part,
-                                                             const uint32_t *__restrict__ rankOf,
+                                                             const uint32_t *__restrict__ entryOf,
                                                              const uint32_t *__restrict__ count, uint32_t cap,
                                                              LnFact G, uint2 *__restrict__ cache, uint32_t cacheMask, BiasList missed,
                                                              float sbEmpty, float bqbEmpty,
                                                              gt16_called_site *__restrict__ out, uint32_t *errWord) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warpsTotal = gridDim.x * (kCandThreads / 32);
-  const uint32_t n = *count < cap ? *count : cap;
-
-  for (uint32_t j = blockIdx.x * (kCandThreads / 32) + (threadIdx.x >> 5); j < n; j += warpsTotal) {
-    const EvalOut &eo = part[j];
+  // count[0]: side-buffer entries the evaluator reserved, count[1]: candidates (the scan's total).  More entries than the
+  // buffers hold: some candidates were dropped, the call is going to be repeated with larger buffers.
+  if (count[0] > cap) return;
+  const uint32_t n = count[1];
+  for (uint32_t rk = blockIdx.x * (kCandThreads / 32) + (threadIdx.x >> 5); rk < n; rk += warpsTotal) {
+    const EvalOut &eo = part[entryOf[rk]];
     const uint64_t i = base + eo.site;
     const uint32_t p = site_pos(M, i);
-    gt16_called_site &o = out[rankOf[j]];
+    gt16_called_site &o = out[rk];
     uint32_t err = 0;
     // -- the likelihoods, posteriors and the call itself come from the exact evaluator (k_eval_mask), which computed them
     //    to decide that this site is a candidate
@@ -1091,7 +1117,7 @@ __global__ void __launch_bounds__(kCandThreads, GT16_CAND_BLOCKS) k_candidates(S
           }
         }
         if (needS | needB) {                                  // rare once the cache is warm
-          const uint32_t dst = rankOf[j] * 12u + lane;
+          const uint32_t dst = rk * 12u + lane;
           const uint32_t want = (needS ? 1u : 0u) + (needB ? 1u : 0u);
           const uint32_t at = atomicAdd(missed.count, want);
           if (at + want <= missed.cap) {
@@ -1183,7 +1209,7 @@ __global__ void __launch_bounds__(kCandThreads, GT16_CAND_BLOCKS) k_candidates(S
     }
   }
 }
-void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
+void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *entryOf,
                        const uint32_t *count, uint32_t cap, const EvalParams &P, uint2 *cache, uint32_t cacheMask,
                        BiasTask *missed, uint32_t *missedCount, uint32_t missedCap, gt16_called_site *out, uint32_t *errWord,
                        int numSMs, cudaStream_t s) {
@@ -1198,7 +1224,7 @@ void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, co
   static const float lg1 = lgammaf(1.0f);
   LnFact H; H.tab = &lg1; H.size = 1; H.far = nullptr; H.farSize = 0;
   const float sbEmpty = strand_bias(H, 0, 0), bqbEmpty = base_quality_bias(H, 0, 0, 0);
-  k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, part, rankOf, count, cap, P.lnfact, cache, cacheMask, ml, sbEmpty, bqbEmpty, out, errWord);
+  k_candidates<<<grid, kCandThreads, 0, s>>>(V, M, base, part, entryOf, count, cap, P.lnfact, cache, cacheMask, ml, sbEmpty, bqbEmpty, out, errWord);
 }
 
 // ------------------------------------------------------------------------------ Fisher tests of the candidates

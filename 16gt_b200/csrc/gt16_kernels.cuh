@@ -81,14 +81,17 @@ void launch_eval_mask(const SnapView &V, const DevSiteMap &M, uint64_t base, uin
                       bool useTables, const DecisionTables &D, const EvalParams &P, uint32_t *siteMask,
                       uint32_t *errWord, uint32_t *flagged, EvalOut *part, uint32_t *count, uint32_t cap, cudaStream_t s);
 // rankOf[j] = number of set mask bits before part[j].site among sites [firstSite, ...) (its place in the ordered output),
-// list[rank] = part[j].site; blockOffsets = scanned block counts of the same mask range
+// list[rank] = j; entries with site 0xFFFFFFFF (reserved, unused) are skipped; blockOffsets = scanned block counts of the
+// same mask range
 void launch_rank(const uint32_t *siteMask, uint32_t firstSite, const uint32_t *blockOffsets, const uint32_t *chunkOffsets,
-                 const EvalOut *part, const uint32_t *count, uint32_t cap, uint32_t *rankOf, uint32_t *list, cudaStream_t s);
+                 const uint32_t *subCounts, const EvalOut *part, const uint32_t *count, uint32_t cap, uint32_t *rankOf,
+                 uint32_t *list, cudaStream_t s);
 
 // ordered compaction of a bit mask over nItems items
 constexpr int kScanBlock = 256;                       // mask words per block
 inline uint32_t scan_blocks(uint32_t nItems) { return ((nItems + 31) / 32 + kScanBlock - 1) / kScanBlock; }
-void launch_mask_count(const uint32_t *mask, uint32_t nItems, uint32_t *blockCounts, cudaStream_t s);
+// subCounts: 8 per block (set bits of each run of 32 words), so that a rank needs one run of words, not a block's worth
+void launch_mask_count(const uint32_t *mask, uint32_t nItems, uint32_t *blockCounts, uint32_t *subCounts, cudaStream_t s);
 // exclusive scan in two levels: blockCounts[b] becomes the offset within its chunk of 1024 blocks, chunkOffsets[c]
 // (room for (nBlocks + 1023) / 1024 words) the offset of the chunk; *total = number of set bits
 void launch_scan_counts(uint32_t *blockCounts, uint32_t nBlocks, uint32_t *chunkOffsets, uint32_t *total, cudaStream_t s);
@@ -96,11 +99,11 @@ void launch_scan_counts(uint32_t *blockCounts, uint32_t nBlocks, uint32_t *chunk
 // goes (dst = record * 12 + k * 4 + base, bit 31 = base-quality test).
 struct BiasTask { uint32_t W, F, R, dst; };
 
-// full records of the candidates in part[0, min(*count, cap)): out[rankOf[j]] (persistent grid, the count is read on the
-// device) -- counts, window features, indel patterns and the strand-bias / base-quality-bias tests the memo cache holds
+// full records of the candidates: out[r] from part[entryOf[r]], r < count[1] (persistent grid; count[0] = side-buffer entries
+// reserved, count[1] = candidates, both read on the device; nothing is done when count[0] > cap) -- counts, window features, indel patterns and the strand-bias / base-quality-bias tests the memo cache holds
 // (cache: (cacheMask + 1) 8-byte {key, result} entries, all bytes 0xFF when empty); tests it does not hold are appended to
 // missed[0, missedCap) (*missedCount, zeroed by the caller) for launch_bias, and walked in place when that list is full
-void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *rankOf,
+void launch_candidates(const SnapView &V, const DevSiteMap &M, uint64_t base, const EvalOut *part, const uint32_t *entryOf,
                        const uint32_t *count, uint32_t cap, const EvalParams &P, uint2 *cache, uint32_t cacheMask,
                        BiasTask *missed, uint32_t *missedCount, uint32_t missedCap, gt16_called_site *out, uint32_t *errWord,
                        int numSMs, cudaStream_t s);

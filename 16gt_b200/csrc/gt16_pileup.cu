@@ -27,6 +27,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 #include "gt16_kernels.cuh"
 #include "gt16_pileup.cuh"
@@ -403,11 +404,18 @@ extern "C" int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint3
   // base | weight << 2 per base (weightMap of the ini, bam2snapshot.cpp:352-363; quality correction :478-481)
   const uint64_t nBases = reads->n_bases;
   std::vector<uint8_t> hBases(nBases);
-  for (uint64_t k = 0; k < nBases; ++k) {
-    int q = (int) (int8_t) reads->quals[k];
-    if (q < 0) q = 0;
-    if (q > 40) q = 40;
-    hBases[k] = (uint8_t) ((reads->bases[k] & 3u) | (params->weight_map[q] << 2));
+  {
+    uint8_t lut[256];                                // quality byte -> weight << 2 (0xFF = absent = negative = 0)
+    for (int q = 0; q < 256; ++q) lut[q] = (uint8_t) (params->weight_map[q >= 128 ? 0 : q > 40 ? 40 : q] << 2);
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = std::max(1u, std::min(16u, nt ? nt : 4u));
+    if (nBases < (1u << 22)) nt = 1;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() {
+      const uint64_t a = nBases * t / nt, b = nBases * (t + 1) / nt;
+      for (uint64_t k = a; k < b; ++k) hBases[k] = (uint8_t) ((reads->bases[k] & 3u) | lut[reads->quals[k]]);
+    });
+    for (auto &x : th) x.join();
   }
   const float msPack = ms_since(clock0);
   clock0 = std::chrono::steady_clock::now();

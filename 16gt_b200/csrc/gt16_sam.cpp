@@ -6,7 +6,12 @@
 #include <string.h>
 #include <stdarg.h>
 #include <unistd.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 #include "../../include/gt16.h"
@@ -61,87 +66,141 @@ static inline uint8_t snp_code(char c) {
   }
 }
 
+// one alignment line (NUL-terminated, tabs still in place) into S; false = malformed line
+static bool parse_alignment(char *line, const gt16_index *ix, uint32_t L, uint32_t mapqThreshold,
+                            std::unordered_map<std::string, int> &ids, std::vector<uint32_t> &ops, gt16_sam *S) {
+  // QNAME FLAG RNAME POS MAPQ CIGAR RNEXT PNEXT TLEN SEQ QUAL
+  char *fld[11];
+  int nf = 0;
+  char *p = line;
+  while (nf < 11) {
+    fld[nf++] = p;
+    char *t = strchr(p, '\t');
+    if (!t) break;
+    *t = 0; p = t + 1;
+  }
+  if (nf < 11) return false;
+  S->total++;
+  const unsigned flag = (unsigned) strtoul(fld[1], nullptr, 10);
+  const long pos1 = strtol(fld[3], nullptr, 10);
+  const unsigned mapq = (unsigned) strtoul(fld[4], nullptr, 10);
+  if (mapq < mapqThreshold) return true;                                 // bam2snapshot.cpp:84-87
+  if (fld[2][0] == '*' || pos1 <= 0) return true;                        // :91-94 (tid < 0 or pos < 0)
+  if (flag & 0x400) return true;                                         // :171-174
+  const char *seq = fld[9], *qual = fld[10];
+  const size_t lseq = (seq[0] == '*' && seq[1] == 0) ? 0 : strlen(seq);
+  if (!lseq) return true;                                                // readLength <= 0 (:181)
+  // CIGAR: the reference string is rebuilt from the BAM operations (:132-141); l_qseq must equal M + I + S (:181)
+  ops.clear();
+  size_t fromCigar = 0;
+  bool bad = fld[5][0] == '*' || fld[5][0] == 0;
+  for (const char *c = fld[5]; *c && !bad;) {
+    char *e;
+    const unsigned long len = strtoul(c, &e, 10);
+    if (e == c || !*e) { bad = true; break; }
+    int op;
+    switch (*e) {
+      case 'M': op = 0; break; case 'I': op = 1; break; case 'D': op = 2; break; case 'N': op = 3; break;
+      case 'S': op = 4; break; case 'H': op = 5; break; case 'P': op = 6; break; case '=': op = 7; break;
+      case 'X': op = 8; break; default: op = -1;
+    }
+    if (op < 0 || len >= (1ul << 28)) { bad = true; break; }
+    if (op == 0 || op == 1 || op == 4) fromCigar += len;                 // getLenFromCigar (:55-77) counts M, I and S
+    ops.push_back((uint32_t) (len << 4) | (uint32_t) op);
+    c = e + 1;
+  }
+  if (bad || fromCigar != lseq) return true;                             // :181-184, :186-188 (empty CIGAR)
+  int id;
+  {
+    auto it = ids.find(fld[2]);
+    if (it == ids.end()) { id = gt16_index_sequence_id(ix, fld[2]); ids.emplace(fld[2], id); }
+    else id = it->second;
+  }
+  uint32_t amb;
+  if (id < 1 || gt16_index_locate_id(ix, id, (uint32_t) pos1, &amb) != 0 || amb >= L) return true;   // :186
+  const bool haveQual = !(qual[0] == '*' && qual[1] == 0) && strlen(qual) == lseq;
+  S->start.push_back(amb);
+  S->reverse.push_back((flag & 16) ? 1 : 0);
+  S->length.push_back((uint32_t) lseq);
+  S->seqOff.push_back(S->bases.size());
+  S->cigarOff.push_back(S->cigar.size());
+  S->nCigar.push_back((uint32_t) ops.size());
+  S->cigar.insert(S->cigar.end(), ops.begin(), ops.end());
+  const size_t at = S->bases.size();
+  S->bases.resize(at + lseq); S->quals.resize(at + lseq);
+  for (size_t k = 0; k < lseq; ++k) {
+    S->bases[at + k] = snp_code(seq[k]);
+    S->quals[at + k] = haveQual ? (uint8_t) (qual[k] - 33) : (uint8_t) 0xFF;
+  }
+  return true;
+}
+
+// The file is mapped and cut into slices at line ends; worker threads parse their slices into lists of their own, which
+// are then joined in file order (the order of the reads decides which of two indel patterns is listed first).
 int gt16_sam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold, gt16_sam **out, char *err, size_t errLen) {
   if (!path || !ix || !out) return GT16_EINVAL;
-  FILE *f = fopen(path, "r");
-  if (!f) { set_err(err, errLen, "[ERROR] Failed accessing %s.", path); return GT16_EIO; }
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) { set_err(err, errLen, "[ERROR] Failed accessing %s.", path); return GT16_EIO; }
+  struct stat st;
+  if (fstat(fd, &st) != 0) { close(fd); set_err(err, errLen, "[ERROR] Failed accessing %s.", path); return GT16_EIO; }
+  const size_t size = (size_t) st.st_size;
   gt16_sam *S = new gt16_sam();
-  std::unordered_map<std::string, int> ids;            // RNAME -> chromosome id (chrIdMap, bam2snapshot.cpp:157-158)
+  if (!size) { close(fd); *out = S; return GT16_OK; }
+  const char *data = (const char *) mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (data == MAP_FAILED) { delete S; set_err(err, errLen, "[ERROR] Failed accessing %s.", path); return GT16_EIO; }
   const uint32_t L = gt16_index_length(ix);
-  char *line = nullptr;
-  size_t cap = 0;
-  ssize_t n;
-  int rc = GT16_OK;
-  std::vector<uint32_t> ops;
-  while ((n = getline(&line, &cap, f)) > 0) {
-    if (line[0] == '@') continue;
-    while (n > 0 && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
-    if (!n) continue;
-    // QNAME FLAG RNAME POS MAPQ CIGAR RNEXT PNEXT TLEN SEQ QUAL
-    char *fld[11];
-    int nf = 0;
-    char *p = line;
-    while (nf < 11) {
-      fld[nf++] = p;
-      char *t = strchr(p, '\t');
-      if (!t) break;
-      *t = 0; p = t + 1;
-    }
-    if (nf < 11) { set_err(err, errLen, "%s: alignment line with fewer than 11 fields", path); rc = GT16_EDATA; break; }
-    S->total++;
-    const unsigned flag = (unsigned) strtoul(fld[1], nullptr, 10);
-    const long pos1 = strtol(fld[3], nullptr, 10);
-    const unsigned mapq = (unsigned) strtoul(fld[4], nullptr, 10);
-    if (mapq < mapqThreshold) continue;                                    // bam2snapshot.cpp:84-87
-    if (fld[2][0] == '*' || pos1 <= 0) continue;                           // :91-94 (tid < 0 or pos < 0)
-    if (flag & 0x400) continue;                                            // :171-174
-    const char *seq = fld[9], *qual = fld[10];
-    const size_t lseq = (seq[0] == '*' && seq[1] == 0) ? 0 : strlen(seq);
-    if (!lseq) continue;                                                   // readLength <= 0 (:181)
-    // CIGAR: the reference string is rebuilt from the BAM operations (:132-141); l_qseq must equal M + I + S (:181)
-    ops.clear();
-    size_t fromCigar = 0;
-    bool bad = fld[5][0] == '*' || fld[5][0] == 0;
-    for (const char *c = fld[5]; *c && !bad;) {
-      char *e;
-      const unsigned long len = strtoul(c, &e, 10);
-      if (e == c || !*e) { bad = true; break; }
-      int op;
-      switch (*e) {
-        case 'M': op = 0; break; case 'I': op = 1; break; case 'D': op = 2; break; case 'N': op = 3; break;
-        case 'S': op = 4; break; case 'H': op = 5; break; case 'P': op = 6; break; case '=': op = 7; break;
-        case 'X': op = 8; break; default: op = -1;
-      }
-      if (op < 0 || len >= (1ul << 28)) { bad = true; break; }
-      if (op == 0 || op == 1 || op == 4) fromCigar += len;                 // getLenFromCigar (:55-77) counts M, I and S
-      ops.push_back((uint32_t) (len << 4) | (uint32_t) op);
-      c = e + 1;
-    }
-    if (bad || fromCigar != lseq) continue;                                // :181-184, :186-188 (empty CIGAR)
-    int id;
-    {
-      auto it = ids.find(fld[2]);
-      if (it == ids.end()) { id = gt16_index_sequence_id(ix, fld[2]); ids.emplace(fld[2], id); }
-      else id = it->second;
-    }
-    uint32_t amb;
-    if (id < 1 || gt16_index_locate_id(ix, id, (uint32_t) pos1, &amb) != 0 || amb >= L) continue;   // :186
-    const bool haveQual = !(qual[0] == '*' && qual[1] == 0) && strlen(qual) == lseq;
-    S->start.push_back(amb);
-    S->reverse.push_back((flag & 16) ? 1 : 0);
-    S->length.push_back((uint32_t) lseq);
-    S->seqOff.push_back(S->bases.size());
-    S->cigarOff.push_back(S->cigar.size());
-    S->nCigar.push_back((uint32_t) ops.size());
-    S->cigar.insert(S->cigar.end(), ops.begin(), ops.end());
-    for (size_t k = 0; k < lseq; ++k) {
-      S->bases.push_back(snp_code(seq[k]));
-      S->quals.push_back(haveQual ? (uint8_t) (qual[k] - 33) : (uint8_t) 0xFF);
-    }
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::max(1u, std::min(16u, nt ? nt : 4u));
+  if (size < (4u << 20)) nt = 1;
+  std::vector<size_t> cut(nt + 1, size);
+  cut[0] = 0;
+  for (unsigned t = 1; t < nt; ++t) {
+    size_t c = size / nt * t;
+    const char *nl = (const char *) memchr(data + c, '\n', size - c);
+    cut[t] = nl ? (size_t) (nl - data) + 1 : size;
   }
-  free(line);
-  fclose(f);
-  if (rc != GT16_OK) { delete S; return rc; }
+  std::vector<gt16_sam> part(nt);
+  std::vector<char> ok(nt, 1);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() {
+    std::unordered_map<std::string, int> ids;          // RNAME -> chromosome id (chrIdMap, bam2snapshot.cpp:157-158)
+    std::vector<uint32_t> ops;
+    std::string line;
+    gt16_sam &P = part[t];
+    for (size_t a = cut[t]; a < cut[t + 1];) {
+      const char *nl = (const char *) memchr(data + a, '\n', cut[t + 1] - a);
+      size_t b = nl ? (size_t) (nl - data) : cut[t + 1];
+      size_t e = b;
+      while (e > a && (data[e - 1] == '\r')) --e;
+      if (e > a && data[a] != '@') {
+        line.assign(data + a, e - a);
+        if (!parse_alignment(&line[0], ix, L, mapqThreshold, ids, ops, &P)) { ok[t] = 0; return; }
+      }
+      a = b + 1;
+    }
+  });
+  for (auto &x : th) x.join();
+  munmap((void *) data, size);
+  for (unsigned t = 0; t < nt; ++t) if (!ok[t]) { delete S; set_err(err, errLen, "%s: alignment line with fewer than 11 fields", path); return GT16_EDATA; }
+  size_t nr = 0, nb = 0, nc = 0;
+  for (unsigned t = 0; t < nt; ++t) { nr += part[t].start.size(); nb += part[t].bases.size(); nc += part[t].cigar.size(); }
+  S->start.reserve(nr); S->reverse.reserve(nr); S->length.reserve(nr); S->seqOff.reserve(nr); S->cigarOff.reserve(nr); S->nCigar.reserve(nr);
+  S->bases.reserve(nb); S->quals.reserve(nb); S->cigar.reserve(nc);
+  for (unsigned t = 0; t < nt; ++t) {
+    const gt16_sam &P = part[t];
+    const uint64_t b0 = S->bases.size(), c0 = S->cigar.size();
+    S->total += P.total;
+    S->start.insert(S->start.end(), P.start.begin(), P.start.end());
+    S->reverse.insert(S->reverse.end(), P.reverse.begin(), P.reverse.end());
+    S->length.insert(S->length.end(), P.length.begin(), P.length.end());
+    S->nCigar.insert(S->nCigar.end(), P.nCigar.begin(), P.nCigar.end());
+    for (size_t i = 0; i < P.seqOff.size(); ++i) { S->seqOff.push_back(b0 + P.seqOff[i]); S->cigarOff.push_back(c0 + P.cigarOff[i]); }
+    S->bases.insert(S->bases.end(), P.bases.begin(), P.bases.end());
+    S->quals.insert(S->quals.end(), P.quals.begin(), P.quals.end());
+    S->cigar.insert(S->cigar.end(), P.cigar.begin(), P.cigar.end());
+    part[t] = gt16_sam();
+  }
   *out = S;
   return GT16_OK;
 }

@@ -183,7 +183,7 @@ int gt16_call_sites_device(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const g
  * gt16_call_sites_device.  stats at return: sites and kernel_launches; called, flagged, the ms_* fields and any error
  * found on the device arrive with gt16_dev_calls_wait (implied by gt16_dev_calls_count / _device_ptr / _fetch), which
  * may be called until 128 further calls have been made on the context.  Record buffers are sized by a bound (one
- * record per 128 sites + 16,384); a call that finds more is repeated, blocking, inside gt16_dev_calls_wait with
+ * record per 128 sites + 65,536); a call that finds more is repeated, blocking, inside gt16_dev_calls_wait with
  * buffers of the size it needs. */
 int gt16_call_sites_device_nowait(gt16_ctx *ctx, const gt16_dev_snapshot *snap, const gt16_region *regions, uint32_t n_regions,
                                   uint64_t site_begin, uint64_t site_end, gt16_dev_calls **out, gt16_stats *stats);
