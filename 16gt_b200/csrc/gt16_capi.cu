@@ -19,7 +19,10 @@
 using namespace gt16;
 
 static thread_local std::string g_createError;      // per thread: the drop-in creates one context per shard thread
-static const uint32_t kBiasCacheEntries = 1u << 20;     // 8 MB, stays in L2
+#ifndef GT16_BIAS_CACHE_LOG2
+#define GT16_BIAS_CACHE_LOG2 20
+#endif
+static const uint32_t kBiasCacheEntries = 1u << GT16_BIAS_CACHE_LOG2;     // 8 MB, stays in L2
 // room in the list of Fisher tests the memo cache did not hold: four per record of the bound.  A context's first call finds
 // the cache empty and lists every test (~8 per SNP row); the record bound is ~7x the called fraction of a 30x genome, so
 // that fits; whatever does not is walked in place by the record kernel.
