@@ -63,7 +63,7 @@ def build(force=False, verbose=True):
             _run([NVCC] + NVCC_FLAGS + ["-x", "cu", "-c", src, "-o", obj], log=obj + ".log")
     if force or not _newer(lib, objs):
         _run([NVCC, "-shared", "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a"] + objs +
-             ["-o", lib, "-cudart", "static", "-lpthread", "-ldl", "-lrt"])
+             ["-o", lib, "-cudart", "static", "-lpthread", "-ldl", "-lrt", "-lz"])
     # drop-in CLI
     cli_src = os.path.join(PKG, "host", "snapshotSnpcaller.cpp")
     cli = os.path.join(PKG, "bin", "snapshotSnpcaller")

@@ -44,7 +44,8 @@ class PileupParams(ctypes.Structure):     # gt16_pileup_params
 
 class BuiltSnapshot(ctypes.Structure):    # gt16_built_snapshot
     _fields_ = [("view", View), ("overflow_storage", ctypes.c_void_p), ("ms_pack", ctypes.c_float), ("ms_h2d", ctypes.c_float),
-                ("ms_kernel", ctypes.c_float), ("ms_d2h", ctypes.c_float), ("aligned_bases", ctypes.c_uint64)]
+                ("ms_kernel", ctypes.c_float), ("ms_d2h", ctypes.c_float), ("aligned_bases", ctypes.c_uint64),
+                ("heavy_tiles", ctypes.c_uint32)]
 
 
 class Indel(ctypes.Structure):
@@ -150,6 +151,7 @@ def capi():
         "gt16_built_snapshot_free": (None, [vp]),
         "gt16_snapshot_write": (i32, [cp, P(View), cp, sz]),
         "gt16_sam_read": (i32, [cp, vp, u32, P(vp), cp, sz]),
+        "gt16_bam_read": (i32, [cp, vp, u32, P(vp), cp, sz]),
         "gt16_sam_reads": (None, [vp, vp]),
         "gt16_sam_total_alignments": (u64, [vp]),
         "gt16_sam_free": (None, [vp]),

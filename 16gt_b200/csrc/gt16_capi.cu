@@ -868,7 +868,7 @@ void stream_range(gt16_ctx *ctx, const SnapView &V, const RegionPlan &pl, uint64
     uint32_t pBeg = pl.start()[0] + (uint32_t) (a - pl.first()[0]);
     launch_stream_tma(V, pBeg, pBeg + (uint32_t) (b - a), D, ctx->shortcutAlt, mask, ctx->numSMs, ctx->compute);
   } else {
-    launch_stream(V, pl.map, a, (uint32_t) (b - a), useTables, D, P, mask, ctx->errWord, ctx->compute);
+    launch_stream(V, pl.map, a, (uint32_t) (b - a), useTables, D, ctx->shortcutAlt, P, mask, ctx->errWord, ctx->compute);
   }
   ctx->launches++;
 }

@@ -385,10 +385,12 @@ void launch_stream_tma(const SnapView &V, uint32_t pBeg, uint32_t pEnd, const De
 constexpr int kRegThreads = 256, kRegRows = 4, kRegTile = kRegThreads * kRegRows, kRegTable = 64;
 static_assert(kRegTile % kCursorTile == 0, "a CTA's sites start on a cursor tile");
 __global__ void __launch_bounds__(kRegThreads) k_stream_regions(SnapView V, DevSiteMap M, uint64_t first, uint32_t n,
-                                                                DecisionTables D, uint32_t *__restrict__ mask, uint32_t *errWord) {
+                                                                DecisionTables D, uint32_t altBound, uint32_t *__restrict__ mask,
+                                                                uint32_t *errWord) {
   __shared__ uint64_t sFirst[kRegTable + 1];
   __shared__ uint32_t sStart[kRegTable];
-  __shared__ uint32_t qCount, qPos[kRegTile], qIdx[kRegTile];      // parked overflow-type sites: position, record index,
+  // parked sites (everything the mask tests below do not settle): position, both words of the counter,
+  __shared__ uint32_t qCount, qPos[kRegTile], qX[kRegTile], qY[kRegTile];
   __shared__ uint16_t qSite[kRegTile];                             // site within the tile | reference base << 12
   const uint32_t tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) qCount = 0;
@@ -438,13 +440,22 @@ __global__ void __launch_bounds__(kRegThreads) k_stream_regions(SnapView V, DevS
     bool flag = false;
     if (in[k] && !((iw[k] >> (31 - (p[k] & 31))) & 1u)) {
       const uint32_t ref = (rw[k] >> (30u - ((p[k] & 15u) << 1))) & 3u;
+      const uint32_t x = c[k].x, y = c[k].y;
       if ((nx[k] & 0xE000E000u) >= 0xC000E000u) flag = true;              // the successor carries indel records: exact evaluator
-      else if ((c[k].x & 0xC000C000u) != 0xC000C000u) flag = compact_needs_exact<false>(D, nullptr, c[k].x, c[k].y, ref);
       else {
-        // overflow-type counter (three or more alleles seen, or deep coverage: a few per cent of the sites at exome
-        // depth): parked, and settled below by the whole CTA, one site per thread, instead of by a divergent branch here
-        const uint32_t q = atomicAdd(&qCount, 1u);
-        qPos[q] = p[k]; qIdx[q] = c[k].y; qSite[q] = (uint16_t) ((tid + kRegThreads * k) | (ref << 12));
+        // the mask tests of k_stream_tma's rows: no coverage, or the reference allele in slot 1 with at most one more
+        // allele of weight <= bound (altBound != 0: the decision bitmaps say such a site is never a candidate)
+        const bool isRef1 = ((x >> 14) & 3u) == ref, live1 = (y & 0xFFFFu) != 0;
+        const bool tinyAlt = ((x & 0x3FFF0000u) <= altBound) & ((x & 0x3C00u) == 0);
+        const bool compact = (x & 0xC000C000u) != 0xC000C000u;
+        const bool settled = altBound != 0 && compact && (y == 0 || (isRef1 & live1 & ((y < 0x10000u) | tinyAlt)));
+        if (!settled) {
+          // everything else -- a non-reference allele, an overflow-type counter (three or more alleles, or deep coverage: a
+          // few per cent of the sites at exome depth) -- is parked and settled below by the whole CTA, one site per
+          // thread, instead of by a divergent branch here
+          const uint32_t q = atomicAdd(&qCount, 1u);
+          qPos[q] = p[k]; qX[q] = x; qY[q] = y; qSite[q] = (uint16_t) ((tid + kRegThreads * k) | (ref << 12));
+        }
       }
     }
     const uint32_t word = __ballot_sync(0xffffffffu, flag);
@@ -452,9 +463,13 @@ __global__ void __launch_bounds__(kRegThreads) k_stream_regions(SnapView V, DevS
     if (lane == 0 && s0 < cnt) mask[(done + s0) >> 5] = word;
   }
   __syncthreads();
-  for (uint32_t q = tid; q < qCount; q += kRegThreads) {         // the general role-indexed test on the record's weights
+  for (uint32_t q = tid; q < qCount; q += kRegThreads) {         // the general role-indexed test
     const uint32_t ref = qSite[q] >> 12, site = qSite[q] & 0xFFFu;
-    const uint8_t *rec = ovf_record(V, ovf_region(V, qPos[q]), qIdx[q]);
+    if ((qX[q] & 0xC000C000u) != 0xC000C000u) {                    // compact counter: its two slots
+      if (compact_needs_exact<false>(D, nullptr, qX[q], qY[q], ref)) atomicOr(mask + ((done + site) >> 5), 1u << (site & 31u));
+      continue;
+    }
+    const uint8_t *rec = ovf_record(V, ovf_region(V, qPos[q]), qY[q]);     // overflow-type: the record's weights
     if (!rec) { atomicOr(errWord, kErrBadSnapshot); continue; }
     const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(rec));           // W[4], F[4]
     const uint2 hi = __ldg(reinterpret_cast<const uint2 *>(rec + 16));      // R[4]
@@ -487,10 +502,10 @@ __global__ void __launch_bounds__(256) k_stream_exact(SnapView V, DevSiteMap M, 
 }
 
 void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint32_t n, bool useTables,
-                   const DecisionTables &D, const EvalParams &P, uint32_t *mask, uint32_t *errWord,
+                   const DecisionTables &D, uint32_t shortcutAlt, const EvalParams &P, uint32_t *mask, uint32_t *errWord,
                    cudaStream_t s) {
   if (!n) return;
-  if (useTables) k_stream_regions<<<(n + kRegTile - 1) / kRegTile, kRegThreads, 0, s>>>(V, M, first, n, D, mask, errWord);
+  if (useTables) k_stream_regions<<<(n + kRegTile - 1) / kRegTile, kRegThreads, 0, s>>>(V, M, first, n, D, shortcutAlt << 16, mask, errWord);
   else k_stream_exact<<<(n + 255) / 256, 256, 0, s>>>(V, M, first, n, P, mask, errWord);
 }
 

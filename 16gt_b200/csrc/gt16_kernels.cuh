@@ -41,8 +41,9 @@ void launch_build_decisions(const EvalParams &P, uint32_t *s1, uint32_t *s2p, ui
 
 // streaming classification of processed sites [first, first+n): bit i of mask = site first+i must be
 // evaluated exactly (useTables) / is a candidate (exact inline mode)
+// (shortcutAlt: stream_shortcut_bound() of the bitmaps, as for launch_stream_tma)
 void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint32_t n, bool useTables,
-                   const DecisionTables &D, const EvalParams &P, uint32_t *mask, uint32_t *errWord,
+                   const DecisionTables &D, uint32_t shortcutAlt, const EvalParams &P, uint32_t *mask, uint32_t *errWord,
                    cudaStream_t s);
 // sparse snapshots: scatter n {u32 position; u64 counter} records (12 bytes each, strictly ascending positions; prevPos =
 // position of the record before rec[0], 0xFFFFFFFF if none) into the position-indexed counter array, positions in

@@ -74,6 +74,14 @@ struct PileArgs {
   uint32_t *poolPtr;
   uint32_t poolCap;
   uint32_t *errWord;
+  // Tiles whose indel events do not fit the shared-memory list (deep amplicons: tens of thousands of reads over an indel)
+  // are left out by the first launch -- it notes them and how many events they have -- and done by a second launch of the
+  // same kernel, one CTA per noted tile, with the event list in global memory.
+  uint32_t *heavyTiles, *heavyEvents, *heavyCount;    // first launch: tiles noted, their event counts, how many
+  uint32_t heavyCap;
+  const uint32_t *tileList;                           // second launch: the tiles to do (null in the first)
+  PileEvent *heavyList;                               // ... their event lists, tile k at heavyOff[k]
+  const uint64_t *heavyOff;
 };
 
 __device__ __forceinline__ uint32_t pile_region(const PileArgs &A, uint32_t p) {   // findRegionByPosition, coreStruct.h:141-154
@@ -85,7 +93,7 @@ __device__ __forceinline__ uint32_t pile_region(const PileArgs &A, uint32_t p) {
 }
 
 // one read into the tile's histogram and event list (whole warp; control flow is warp-uniform)
-__device__ void pile_read(const PileArgs &A, PileSmem &S, uint64_t r, uint32_t tileLo, uint32_t lane) {
+__device__ void pile_read(const PileArgs &A, PileSmem &S, PileEvent *ev, uint32_t evCap, uint64_t r, uint32_t tileLo, uint32_t lane) {
   const uint32_t readLength = A.length[r], nOps = A.nCigar[r];
   const uint32_t *ops = A.cigar + A.cigarOff[r];
   const uint8_t *sq = A.bases + A.seqOff[r];
@@ -96,12 +104,12 @@ __device__ void pile_read(const PileArgs &A, PileSmem &S, uint64_t r, uint32_t t
   auto emit = [&](uint32_t pos, uint32_t kind, uint32_t len, bool hq, uint64_t seq) {   // lane 0
     if (pos < tileLo || pos >= tileLo + (uint32_t) kPileTile || pos >= A.L) return;
     const uint32_t at = atomicAdd(&S.nEvents, 1u);
-    if (at >= (uint32_t) kPileEvents) { atomicOr(A.errWord, kErrPileEvents); return; }
+    if (at >= evCap) return;                                   // counted: the tile goes to the second launch
     PileEvent e;
     e.key = ((uint64_t) (((pos - tileLo) << 1) | kind) << 32) | (A.order[r] & 0x7FFFFFFFu);
     e.seq = seq; e.rep = at; e.hq = 0; e.lq = 0; e.len = (uint8_t) len; e.isHq = hq ? 1 : 0;
     for (int k = 0; k < 6; ++k) e.pad[k] = 0;
-    S.ev[at] = e;
+    ev[at] = e;
   };
   // An indel reaches the snapshot only if an applied match base follows it in the read: the reference writes a read's
   // overflow bytes up to its last match base (lastMPos, :735-741).  Indels closed by another indel wait here for one.
@@ -185,7 +193,10 @@ __global__ void __launch_bounds__(kPileThreads, 1) k_pileup(PileArgs A) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   PileSmem &S = *reinterpret_cast<PileSmem *>(smemRaw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tileLo = blockIdx.x * (uint32_t) kPileTile;
+  const uint32_t tile = A.tileList ? A.tileList[blockIdx.x] : blockIdx.x;
+  const uint32_t tileLo = tile * (uint32_t) kPileTile;
+  PileEvent *ev = A.tileList ? A.heavyList + A.heavyOff[blockIdx.x] : S.ev;
+  const uint32_t evCap = A.tileList ? (uint32_t) (A.heavyOff[blockIdx.x + 1] - A.heavyOff[blockIdx.x]) : (uint32_t) kPileEvents;
   const uint32_t tileHi = tileLo + (uint32_t) kPileTile < A.L ? tileLo + (uint32_t) kPileTile : A.L;
   // reads with start in (tileLo - maxSpan, tileHi)
   uint64_t rLo, rHi;
@@ -206,41 +217,51 @@ __global__ void __launch_bounds__(kPileThreads, 1) k_pileup(PileArgs A) {
   if (tid < (uint32_t) kPileTile / 32) S.evFlags[tid] = 0u;
   if (tid == 0) S.nEvents = 0;
   __syncthreads();
-  for (uint64_t r = rLo + warp; r < rHi; r += kPileThreads / 32) pile_read(A, S, r, tileLo, lane);
+  for (uint64_t r = rLo + warp; r < rHi; r += kPileThreads / 32) pile_read(A, S, ev, evCap, r, tileLo, lane);
   __syncthreads();
+  if (S.nEvents > evCap) {                          // more events than the list holds: noted for the second launch
+    if (tid == 0) {
+      if (A.tileList) atomicOr(A.errWord, kErrPileEvents);            // cannot happen: the list was sized by the first launch's count
+      else {
+        const uint32_t k = atomicAdd(A.heavyCount, 1u);
+        if (k < A.heavyCap) { A.heavyTiles[k] = tile; A.heavyEvents[k] = S.nEvents; }
+      }
+    }
+    return;
+  }
 
   // ---- indel events: sort by (position, kind, read number), fold equal patterns onto their first appearance
-  const uint32_t nEv = S.nEvents < (uint32_t) kPileEvents ? S.nEvents : (uint32_t) kPileEvents;
+  const uint32_t nEv = S.nEvents;
   if (nEv > 1) {
     uint32_t n2 = 2; while (n2 < nEv) n2 <<= 1;
-    for (uint32_t k = nEv + tid; k < n2; k += kPileThreads) S.ev[k].key = ~0ull;          // padding sorts last
+    for (uint32_t k = nEv + tid; k < n2; k += kPileThreads) ev[k].key = ~0ull;          // padding sorts last
     __syncthreads();
     for (uint32_t size = 2; size <= n2; size <<= 1)
       for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
         for (uint32_t t = tid; t < n2 / 2; t += kPileThreads) {
           const uint32_t i = 2 * t - (t & (stride - 1)), j = i + stride;
           const bool up = (i & size) == 0;
-          if ((S.ev[i].key > S.ev[j].key) == up) { const PileEvent x = S.ev[i]; S.ev[i] = S.ev[j]; S.ev[j] = x; }
+          if ((ev[i].key > ev[j].key) == up) { const PileEvent x = ev[i]; ev[i] = ev[j]; ev[j] = x; }
         }
         __syncthreads();
       }
   }
   // group leaders: the first event of each (position, kind)
   for (uint32_t g = tid; g < nEv; g += kPileThreads) {
-    const uint32_t gk = (uint32_t) (S.ev[g].key >> 32);
-    if (g > 0 && (uint32_t) (S.ev[g - 1].key >> 32) == gk) continue;
-    for (uint32_t e = g; e < nEv && (uint32_t) (S.ev[e].key >> 32) == gk; ++e) {
+    const uint32_t gk = (uint32_t) (ev[g].key >> 32);
+    if (g > 0 && (uint32_t) (ev[g - 1].key >> 32) == gk) continue;
+    for (uint32_t e = g; e < nEv && (uint32_t) (ev[e].key >> 32) == gk; ++e) {
       uint32_t rep = e;
       for (uint32_t f = g; f < e; ++f) {
-        if (S.ev[f].rep != f || S.ev[f].len != S.ev[e].len) continue;
+        if (ev[f].rep != f || ev[f].len != ev[e].len) continue;
         bool same = true;
         if (!(gk & 1u))                                                                  // insertions: same bases
-          for (uint32_t k = 0; k < S.ev[e].len && same; ++k) same = ((A.bases[S.ev[f].seq + k] ^ A.bases[S.ev[e].seq + k]) & 3u) == 0;
+          for (uint32_t k = 0; k < ev[e].len && same; ++k) same = ((A.bases[ev[f].seq + k] ^ A.bases[ev[e].seq + k]) & 3u) == 0;
         if (same) { rep = f; break; }
       }
-      S.ev[e].rep = rep;
-      PileEvent &R = S.ev[rep];
-      if (S.ev[e].isHq) { if (R.hq < 0xFFFFu) ++R.hq; } else { if (R.lq < 0xFFFFu) ++R.lq; }
+      ev[e].rep = rep;
+      PileEvent &R = ev[rep];
+      if (ev[e].isHq) { if (R.hq < 0xFFFFu) ++R.hq; } else { if (R.lq < 0xFFFFu) ++R.lq; }
     }
     const uint32_t p = gk >> 1;
     atomicOr(&S.evFlags[p >> 5], 0x80000000u >> (p & 31));
@@ -283,18 +304,18 @@ __global__ void __launch_bounds__(kPileThreads, 1) k_pileup(PileArgs A) {
           for (uint32_t kind = 0; kind < 2; ++kind) {
             const uint32_t gk = (pr << 1) | kind;
             uint32_t lo = 0, hi = nEv;
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t) (S.ev[mid].key >> 32) < gk) lo = mid + 1; else hi = mid; }
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t) (ev[mid].key >> 32) < gk) lo = mid + 1; else hi = mid; }
             uint32_t g = lo, nPat = 0, bytes = 0, one = 0;
-            for (uint32_t e = g; e < nEv && (uint32_t) (S.ev[e].key >> 32) == gk; ++e)
-              if (S.ev[e].rep == e) {
+            for (uint32_t e = g; e < nEv && (uint32_t) (ev[e].key >> 32) == gk; ++e)
+              if (ev[e].rep == e) {
                 if (!nPat) one = e;
                 ++nPat;
-                bytes += kind ? 5u : 1u + ((uint32_t) S.ev[e].len + 3) / 4 + 4u;
-                if (S.ev[e].hq >= 0xFFFFu || S.ev[e].lq >= 0xFFFFu) invalidBit = true;    // :1343-1372
+                bytes += kind ? 5u : 1u + ((uint32_t) ev[e].len + 3) / 4 + 4u;
+                if (ev[e].hq >= 0xFFFFu || ev[e].lq >= 0xFFFFu) invalidBit = true;    // :1343-1372
               }
             if (!nPat) continue;
             if (bytes >= 4096u) { invalidBit = true; continue; }                          // :1408-1419, :1445-1456
-            const PileEvent &E = S.ev[one];
+            const PileEvent &E = ev[one];
             const bool inlineOk = nPat == 1 && E.hq < 0xFFu && E.lq < 0xFFu && (kind || E.len <= 12);
             uint32_t &w = kind ? w2 : w1;
             w |= 0x2000u;
@@ -310,9 +331,9 @@ __global__ void __launch_bounds__(kPileThreads, 1) k_pileup(PileArgs A) {
               if (at + bytes > A.poolCap) { atomicOr(A.errWord, kErrPilePool); continue; }
               uint8_t *dst = A.pool + at;
               uint32_t q = 0;
-              for (uint32_t e = g; e < nEv && (uint32_t) (S.ev[e].key >> 32) == gk; ++e) {
-                if (S.ev[e].rep != e) continue;
-                const PileEvent &X = S.ev[e];
+              for (uint32_t e = g; e < nEv && (uint32_t) (ev[e].key >> 32) == gk; ++e) {
+                if (ev[e].rep != e) continue;
+                const PileEvent &X = ev[e];
                 dst[q++] = X.len;
                 if (!kind) {
                   const uint32_t nb = ((uint32_t) X.len + 3) / 4;
@@ -453,18 +474,44 @@ extern "C" int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint3
     A.nRegions = nReg; A.ovfLen = regLen; A.ovfInv = regLen ? 1.0 / (double) regLen : 0.0;
     A.pool = dPool.p; A.poolPtr = dPoolPtr.p; A.poolCap = poolCap; A.errWord = dErr.p;
     const unsigned tiles = (unsigned) (((uint64_t) L + kPileTile - 1) / kPileTile);
+    Dev<uint32_t> dHeavyTiles, dHeavyEvents, dHeavyCount;
+    PCU(dHeavyTiles.alloc(tiles)); PCU(dHeavyEvents.alloc(tiles)); PCU(dHeavyCount.alloc(1));
+    PCU(cudaMemset(dHeavyCount.p, 0, 4));
+    A.heavyTiles = dHeavyTiles.p; A.heavyEvents = dHeavyEvents.p; A.heavyCount = dHeavyCount.p; A.heavyCap = tiles;
+    A.tileList = nullptr; A.heavyList = nullptr; A.heavyOff = nullptr;
     PCU(cudaEventRecord(e0, 0));
     k_pileup<<<tiles, kPileThreads, sizeof(PileSmem)>>>(A);
     PCU(cudaGetLastError());
     PCU(cudaEventRecord(e1, 0));
     PCU(cudaDeviceSynchronize());
     PCU(cudaEventElapsedTime(&msKernel, e0, e1));
+    // tiles whose events did not fit the shared-memory list: again, with lists in global memory sized by their counts
+    uint32_t nHeavy = 0;
+    PCU(cudaMemcpy(&nHeavy, dHeavyCount.p, 4, cudaMemcpyDeviceToHost));
+    if (nHeavy) {
+      std::vector<uint32_t> hv(nHeavy);
+      std::vector<uint64_t> off(nHeavy + 1, 0);
+      PCU(cudaMemcpy(hv.data(), dHeavyEvents.p, (size_t) nHeavy * 4, cudaMemcpyDeviceToHost));
+      for (uint32_t k = 0; k < nHeavy; ++k) { uint64_t c = 2; while (c < hv[k]) c <<= 1; off[k + 1] = off[k] + c; }   // the sort pads to a power of two
+      Dev<PileEvent> dList;
+      Dev<uint64_t> dOff;
+      PCU(dList.alloc((size_t) off[nHeavy])); PCU(dOff.put(off.data(), off.size()));
+      A.tileList = dHeavyTiles.p; A.heavyList = dList.p; A.heavyOff = dOff.p;
+      float ms2 = 0.f;
+      PCU(cudaEventRecord(e0, 0));
+      k_pileup<<<nHeavy, kPileThreads, sizeof(PileSmem)>>>(A);
+      PCU(cudaGetLastError());
+      PCU(cudaEventRecord(e1, 0));
+      PCU(cudaDeviceSynchronize());
+      PCU(cudaEventElapsedTime(&ms2, e0, e1));
+      msKernel += ms2;
+    }
+    out->heavy_tiles = nHeavy;
     uint32_t err = 0;
     PCU(cudaMemcpy(&err, dErr.p, 4, cudaMemcpyDeviceToHost));
     PCU(cudaMemcpy(hCount.data(), dOvfCount.p, nReg * 4, cudaMemcpyDeviceToHost));
     PCU(cudaMemcpy(&hPool, dPoolPtr.p, 4, cudaMemcpyDeviceToHost));
-    if (err & kErrPileEvents)
-      return gt16_pileup_set_error(ctx, GT16_EDATA, "more than 2,048 insertions / deletions reported inside one tile of 2,048 positions");
+    if (err & kErrPileEvents) return gt16_pileup_set_error(ctx, GT16_ECUDA, "indel event list of a tile overflowed in the second launch");
     if (!(err & (kErrPileOvf | kErrPilePool))) break;
     if (attempt >= 4) return gt16_pileup_set_error(ctx, GT16_ECUDA, "overflow arrays / pattern pool could not be sized");
     if (err & kErrPileOvf) ovfCap = *std::max_element(hCount.begin(), hCount.end()) + 4096;

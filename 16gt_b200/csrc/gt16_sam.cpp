@@ -13,6 +13,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <zlib.h>
 #include <vector>
 #include "../../include/gt16.h"
 
@@ -200,6 +201,116 @@ int gt16_sam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold
     S->quals.insert(S->quals.end(), P.quals.begin(), P.quals.end());
     S->cigar.insert(S->cigar.end(), P.cigar.begin(), P.cigar.end());
     part[t] = gt16_sam();
+  }
+  *out = S;
+  return GT16_OK;
+}
+
+// ---- BAM (the reference reads it through samtools' bgzf / bam_read1: bam2snapshot.cpp:159-163) --------------------
+// BGZF is a series of gzip members; zlib inflates them one after the other.  The decompressed stream: "BAM\1", header
+// text, reference names, then the alignment records bamToAlignment looks at (SAM specification, section 4.2).
+namespace {
+struct BgzfReader {
+  FILE *f = nullptr;
+  z_stream z;
+  std::vector<uint8_t> in;
+  bool eof = false, bad = false, open = false;
+  bool start(const char *path) {
+    f = fopen(path, "rb");
+    if (!f) return false;
+    in.resize(1u << 20);
+    memset(&z, 0, sizeof(z));
+    if (inflateInit2(&z, 15 + 16) != Z_OK) return false;      // gzip wrapper
+    open = true;
+    return true;
+  }
+  // exactly n bytes, false at a clean end of file (with none read) or on error (bad set)
+  bool get(void *dst, size_t n) {
+    z.next_out = (Bytef *) dst;
+    z.avail_out = (uInt) n;
+    while (z.avail_out) {
+      if (!z.avail_in && !eof) {
+        const size_t k = fread(in.data(), 1, in.size(), f);
+        if (k < in.size()) eof = true;
+        z.next_in = in.data(); z.avail_in = (uInt) k;
+      }
+      if (!z.avail_in && eof) { if (z.avail_out != n) bad = true; return false; }
+      const int rc = inflate(&z, Z_NO_FLUSH);
+      if (rc == Z_STREAM_END) { if (inflateReset(&z) != Z_OK) { bad = true; return false; } }
+      else if (rc != Z_OK && rc != Z_BUF_ERROR) { bad = true; return false; }
+    }
+    return true;
+  }
+  ~BgzfReader() { if (open) inflateEnd(&z); if (f) fclose(f); }
+};
+}  // namespace
+
+int gt16_bam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold, gt16_sam **out, char *err, size_t errLen) {
+  if (!path || !ix || !out) return GT16_EINVAL;
+  BgzfReader R;
+  if (!R.start(path)) { set_err(err, errLen, "[ERROR] Failed accessing %s.", path); return GT16_EIO; }
+  auto fail = [&](const char *what) { set_err(err, errLen, "%s: %s", path, what); return GT16_EDATA; };
+  char magic[4];
+  int32_t lText = 0, nRef = 0;
+  if (!R.get(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) return fail("not a BAM file");
+  if (!R.get(&lText, 4) || lText < 0) return fail("truncated BAM header");
+  { std::vector<char> text((size_t) lText + 1); if (lText && !R.get(text.data(), (size_t) lText)) return fail("truncated BAM header"); }
+  if (!R.get(&nRef, 4) || nRef < 0) return fail("truncated BAM header");
+  std::vector<int> chrId((size_t) nRef, 0);                     // 0: not looked up yet (chrIdMap, bam2snapshot.cpp:157-158)
+  std::vector<std::string> names((size_t) nRef);
+  for (int32_t r = 0; r < nRef; ++r) {
+    int32_t lName = 0, lRef = 0;
+    if (!R.get(&lName, 4) || lName <= 0 || lName > (1 << 16)) return fail("bad reference name in the BAM header");
+    std::vector<char> nm((size_t) lName);
+    if (!R.get(nm.data(), (size_t) lName) || !R.get(&lRef, 4)) return fail("truncated BAM header");
+    names[r] = std::string(nm.data());
+  }
+  gt16_sam *S = new gt16_sam();
+  const uint32_t L = gt16_index_length(ix);
+  static const uint8_t code[16] = {0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 2};   // bamcode2snpcode, bam2snapshot.h:52-58
+  std::vector<uint8_t> rec;
+  for (;;) {
+    int32_t blockSize = 0;
+    if (!R.get(&blockSize, 4)) { if (R.bad) { delete S; return fail("corrupt BGZF stream"); } break; }
+    if (blockSize < 32) { delete S; return fail("bad alignment record"); }
+    rec.resize((size_t) blockSize);
+    if (!R.get(rec.data(), (size_t) blockSize)) { delete S; return fail("truncated alignment record"); }
+    S->total++;
+    int32_t tid, pos, lSeq;
+    memcpy(&tid, &rec[0], 4); memcpy(&pos, &rec[4], 4);
+    const uint32_t lName = rec[8], mapq = rec[9];
+    uint16_t nCig, flag;
+    memcpy(&nCig, &rec[12], 2); memcpy(&flag, &rec[14], 2); memcpy(&lSeq, &rec[16], 4);
+    const size_t need = 32 + (size_t) lName + (size_t) nCig * 4 + ((size_t) (lSeq > 0 ? lSeq : 0) + 1) / 2 + (size_t) (lSeq > 0 ? lSeq : 0);
+    if (need > rec.size()) { delete S; return fail("bad alignment record"); }
+    if (mapq < mapqThreshold) continue;                                           // bam2snapshot.cpp:84-87
+    if (tid < 0 || tid >= nRef || pos < 0 || pos == INT32_MAX) continue;          // :91-94
+    if (flag & 0x400) continue;                                                   // :171-174
+    if (lSeq <= 0) continue;                                                      // :181
+    const uint8_t *cig = &rec[32 + lName], *seq = cig + (size_t) nCig * 4, *qual = seq + ((size_t) lSeq + 1) / 2;
+    size_t fromCigar = 0;
+    for (uint32_t c = 0; c < nCig; ++c) {
+      uint32_t v; memcpy(&v, cig + 4 * c, 4);
+      const uint32_t op = v & 15u;
+      if (op == 0 || op == 1 || op == 4) fromCigar += v >> 4;                     // getLenFromCigar (:55-77)
+    }
+    if (!nCig || fromCigar != (size_t) lSeq) continue;                            // :181-188
+    if (!chrId[tid]) { const int id = gt16_index_sequence_id(ix, names[tid].c_str()); chrId[tid] = id < 1 ? -1 : id; }
+    uint32_t amb;
+    if (chrId[tid] < 1 || gt16_index_locate_id(ix, chrId[tid], (uint32_t) pos + 1, &amb) != 0 || amb >= L) continue;
+    S->start.push_back(amb);
+    S->reverse.push_back((flag & 16) ? 1 : 0);
+    S->length.push_back((uint32_t) lSeq);
+    S->seqOff.push_back(S->bases.size());
+    S->cigarOff.push_back(S->cigar.size());
+    S->nCigar.push_back(nCig);
+    for (uint32_t c = 0; c < nCig; ++c) { uint32_t v; memcpy(&v, cig + 4 * c, 4); S->cigar.push_back(v); }
+    const size_t at = S->bases.size();
+    S->bases.resize(at + (size_t) lSeq); S->quals.resize(at + (size_t) lSeq);
+    for (int32_t k = 0; k < lSeq; ++k) {
+      S->bases[at + k] = code[(seq[k >> 1] >> ((~k & 1) << 2)) & 15u];            // bam1_seqi
+      S->quals[at + k] = qual[k];
+    }
   }
   *out = S;
   return GT16_OK;

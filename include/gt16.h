@@ -298,6 +298,7 @@ typedef struct gt16_built_snapshot {
    * device->host copies of the result; aligned bases in the reads */
   float ms_pack, ms_h2d, ms_kernel, ms_d2h;
   uint64_t aligned_bases;
+  uint32_t heavy_tiles;     /* tiles of 2,048 positions with more than 2,048 indel events: done in a second launch */
 } gt16_built_snapshot;
 
 /* updateSnpCounterForReads over all reads + readFilesForOverflow (bam2snapshot.cpp:221-330; SNP.cpp:438-891,893-1688):
@@ -317,6 +318,8 @@ int gt16_snapshot_write(const char *path, const gt16_snapshot_view *view, char *
  * l_qseq against the CIGAR); sequence names are resolved against the index like getChrIDFromName / getAmbPos. */
 typedef struct gt16_sam gt16_sam;
 int gt16_sam_read(const char *path, const gt16_index *ix, uint32_t mapq_threshold, gt16_sam **out, char *err, size_t err_len);
+/* The same from a BAM file (BGZF inflated with zlib; the records bam_read1 hands to bamToAlignment). */
+int gt16_bam_read(const char *path, const gt16_index *ix, uint32_t mapq_threshold, gt16_sam **out, char *err, size_t err_len);
 void gt16_sam_reads(const gt16_sam *sam, gt16_reads *reads);
 uint64_t gt16_sam_total_alignments(const gt16_sam *sam);   /* lines read, including the skipped ones */
 void gt16_sam_free(gt16_sam *sam);

@@ -311,3 +311,70 @@ def regenerate_producer(name, workdir, check=True):
             assert sha256(p) == want[os.path.basename(p)], "regenerated input differs from golden input: " + p
         assert snapshot_content_digest(out + ".snapshot") == want["snapshot_content"], "producer-written snapshot differs"
     return idx, out
+
+
+# ---- SAM -> BAM (test fixture: the producer's -b input) ---------------------------------------------
+def sam_to_bam(sam_path, bam_path):
+    """Write the alignments of a SAM file as BAM (SAM specification 4.2: BGZF blocks of a binary header and records; no
+    optional fields).  The reference's bam2snapshot -b (samtools' reader) and gt16_bam_read both take the result."""
+    import struct
+    import zlib
+    nib = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+    ops = {c: i for i, c in enumerate("MIDNSHP=X")}
+
+    def reg2bin(beg, end):
+        end -= 1
+        for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+            if beg >> shift == end >> shift:
+                return base + (beg >> shift)
+        return 0
+
+    header, refs, body = [], [], bytearray()
+    ref_id = {}
+    with open(sam_path) as f:
+        for line in f:
+            if line.startswith("@"):
+                header.append(line)
+                if line.startswith("@SQ"):
+                    d = dict(x.split(":", 1) for x in line.rstrip("\n").split("\t")[1:])
+                    ref_id[d["SN"]] = len(refs)
+                    refs.append((d["SN"], int(d["LN"])))
+                continue
+            t = line.rstrip("\n").split("\t")
+            if len(t) < 11:
+                continue
+            qname, flag, rname, pos, mapq, cigar, rnext, pnext, tlen, seq, qual = t[:11]
+            flag, pos, mapq, pnext, tlen = int(flag), int(pos), int(mapq), int(pnext), int(tlen)
+            rid = ref_id.get(rname, -1)
+            nrid = rid if rnext == "=" else ref_id.get(rnext, -1)
+            cig = []
+            if cigar != "*":
+                num = ""
+                for ch in cigar:
+                    if ch.isdigit():
+                        num += ch
+                    else:
+                        cig.append((int(num) << 4) | ops[ch]); num = ""
+            lseq = 0 if seq == "*" else len(seq)
+            span = sum(c >> 4 for c in cig if (c & 15) in (0, 2, 3, 7, 8)) or 1
+            name = qname.encode() + b"\0"
+            rec = struct.pack("<iiBBHHHiiii", rid, pos - 1, len(name), mapq, reg2bin(max(pos - 1, 0), max(pos - 1, 0) + span) & 0xFFFF, len(cig), flag,
+                              lseq, nrid, pnext - 1, tlen) + name + struct.pack("<%dI" % len(cig), *cig)
+            packed = bytearray((lseq + 1) // 2)
+            for k in range(lseq):
+                packed[k >> 1] |= nib.get(seq[k].upper(), 15) << (4 if k % 2 == 0 else 0)
+            rec += bytes(packed) + (b"\xff" * lseq if qual == "*" else bytes(ord(c) - 33 for c in qual))
+            body += struct.pack("<i", len(rec)) + rec
+    text = "".join(header).encode()
+    head = b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))
+    for name, ln in refs:
+        head += struct.pack("<i", len(name) + 1) + name.encode() + b"\0" + struct.pack("<i", ln)
+    data = head + bytes(body)
+    with open(bam_path, "wb") as out:
+        for a in range(0, len(data), 0xFF00):
+            chunk = data[a:a + 0xFF00]
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            comp = c.compress(chunk) + c.flush()
+            out.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp +
+                      struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+        out.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))      # the BGZF end-of-file block

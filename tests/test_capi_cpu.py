@@ -259,6 +259,22 @@ def test_sam_reader_filters(tmp_path):
     assert list(quals[:10]) == [40] * 9 + [2] and list(quals[20:]) == [255] * 10
     cig = np.ctypeslib.as_array(ctypes.cast(r.cigar, ctypes.POINTER(ctypes.c_uint32)), (int(r.n_cigar_ops),))
     assert list(cig) == [10 << 4, (2 << 4) | 4, 3 << 4, (1 << 4) | 1, 2 << 4, (1 << 4) | 2, 2 << 4, 10 << 4]
+    # the same alignments as BAM (BGZF + binary records): identical reads
+    bam = tmp_path / "r.bam"
+    T.sam_to_bam(str(sam), str(bam))
+    hb = ctypes.c_void_p()
+    assert L.gt16_bam_read(str(bam).encode(), ix, 10, ctypes.byref(hb), err, 256) == 0, err.value
+    rb = T.capi_mod.Reads()
+    L.gt16_sam_reads(hb, ctypes.byref(rb))
+    assert L.gt16_sam_total_alignments(hb) == 8 and rb.n_reads == 3 and rb.n_bases == r.n_bases and rb.n_cigar_ops == r.n_cigar_ops
+    for field, ct, n in (("start", ctypes.c_uint32, 3), ("reverse", ctypes.c_uint8, 3), ("length", ctypes.c_uint32, 3),
+                         ("seq_off", ctypes.c_uint64, 3), ("cigar_off", ctypes.c_uint64, 3), ("n_cigar", ctypes.c_uint32, 3),
+                         ("bases", ctypes.c_uint8, 30), ("quals", ctypes.c_uint8, 30), ("cigar", ctypes.c_uint32, int(r.n_cigar_ops))):
+        a = np.ctypeslib.as_array(ctypes.cast(getattr(r, field), ctypes.POINTER(ct)), (n,))
+        b = np.ctypeslib.as_array(ctypes.cast(getattr(rb, field), ctypes.POINTER(ct)), (n,))
+        assert np.array_equal(a, b), field
+    L.gt16_sam_free(hb)
+    assert L.gt16_bam_read(str(sam).encode(), ix, 10, ctypes.byref(hb), err, 256) == -5        # a SAM file is not a BAM file
     L.gt16_sam_free(h)
     L.gt16_index_free(ix)
     p = T.capi_mod.PileupParams()

@@ -76,3 +76,62 @@ def test_caller_output_from_our_snapshot_equals_the_reference_pipelines(built, n
         r = subprocess.run([exe, idx, mine], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
         assert r.returncode == 0, r.stderr[-2000:]
         assert T.compare_txt(open(mine + ".txt", "rb").read(), T.golden_txt(name)) == 0
+
+
+def _decoded_equal(a, b):
+    ok = ~a["invalid"]
+    assert np.array_equal(a["invalid"], b["invalid"]) and np.array_equal(a["overflow"][ok], b["overflow"][ok])
+    for k in ("W", "F", "R"):
+        assert np.array_equal(a[k][ok], b[k][ok]), k
+    for k in ("ins", "dele"):
+        assert {p: v for p, v in a[k].items() if ok[p]} == {p: v for p, v in b[k].items() if ok[p]}, k
+
+
+def test_bam_input_and_several_files(tmp_path):
+    """-b: the same alignments as BAM (BGZF inflated with zlib, records as bam_read1 hands them over); and two input
+    files (-s first half, -b second half) processed in order, like the reference's loop over its inputs
+    (bam2snapshot.cpp:263-293).  The reference reads the very same BAM (its samtools layer) on the way."""
+    for exe in (T.REF_MKINDEX, T.REF_BAM2SNAPSHOT, T.READSIM):
+        if not os.path.exists(exe):
+            pytest.skip("%s not built" % os.path.relpath(exe, T.ROOT))
+    pre = str(tmp_path / "p")
+    subprocess.run([T.READSIM, "--out", pre, "--contigs", "chrA:300000,chrB:100000", "--depth", "20", "--seed", "5"], check=True,
+                   stderr=subprocess.DEVNULL)
+    subprocess.run([T.REF_MKINDEX, pre + ".fa", pre + ".index"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    T.sam_to_bam(pre + ".sam", pre + ".bam")
+    lines = open(pre + ".sam").read().split("\n")
+    head = [l for l in lines if l.startswith("@")]
+    body = [l for l in lines if l and not l.startswith("@")]
+    open(pre + ".1.sam", "w").write("\n".join(head + body[:len(body) // 2]) + "\n")
+    open(pre + ".2.sam", "w").write("\n".join(head + body[len(body) // 2:]) + "\n")
+    T.sam_to_bam(pre + ".2.sam", pre + ".2.bam")
+    subprocess.run([T.REF_BAM2SNAPSHOT, "-i", pre + ".index", "-b", pre + ".bam", "-o", pre + ".ref"], check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    ref = T.decode_snapshot(pre + ".ref.snapshot")
+    for tag, args in (("bam", ["-b", pre + ".bam"]), ("two", ["-s", pre + ".1.sam", "-b", pre + ".2.bam"])):
+        r = subprocess.run([B2S, "-i", pre + ".index"] + args + ["-o", pre + "." + tag], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.count("Processing ") == len(args) // 2
+        _decoded_equal(ref, T.decode_snapshot(pre + "." + tag + ".snapshot"))
+
+
+def test_deep_tile_with_more_indel_events_than_the_shared_memory_list(tmp_path):
+    """an 8,000x hotspot over planted indels: the tile reports far more than 2,048 indel events, is left out by the first
+    launch and done by the second with its event list in global memory -- same decoded snapshot as the reference's"""
+    for exe in (T.REF_MKINDEX, T.REF_BAM2SNAPSHOT, T.READSIM):
+        if not os.path.exists(exe):
+            pytest.skip("%s not built" % os.path.relpath(exe, T.ROOT))
+    pre = str(tmp_path / "p")
+    subprocess.run([T.READSIM, "--out", pre, "--contigs", "chrA:60000", "--depth", "10", "--indel-rate", "1e-2", "--hotspots", "1:300:8000",
+                    "--seed", "3"], check=True, stderr=subprocess.DEVNULL)
+    subprocess.run([T.REF_MKINDEX, pre + ".fa", pre + ".index"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([T.REF_BAM2SNAPSHOT, "-i", pre + ".index", "-s", pre + ".sam", "-o", pre + ".ref"], check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    r = subprocess.run([B2S, "-i", pre + ".index", "-s", pre + ".sam", "-o", pre + ".mine"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    import re
+    m = re.search(r"\((\d+) deep tiles in a second launch\)", r.stdout)
+    assert m and int(m.group(1)) >= 1, r.stdout
+    ref, got = T.decode_snapshot(pre + ".ref.snapshot"), T.decode_snapshot(pre + ".mine.snapshot")
+    assert max(sum(h + l for _, _, h, l in v) for v in got["ins"].values()) + max(sum(h + l for _, h, l in v) for v in got["dele"].values()) > 2048
+    _decoded_equal(ref, got)

@@ -11,6 +11,6 @@ F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false 
 nvcc $F "$@" -x cu -c ${KSRC:-16gt_b200/csrc/gt16_kernels.cu} -I 16gt_b200/csrc -o $out/k_$name.o
 nvcc $F "$@" -x cu -c ${CSRC:-16gt_b200/csrc/gt16_capi.cu} -I 16gt_b200/csrc -o $out/c_$name.o
 nvcc -shared -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a $out/k_$name.o $out/c_$name.o 16gt_b200/build/gt16_host_io.o 16gt_b200/build/gt16_pileup.o 16gt_b200/build/gt16_sam.o \
-  -o $out/libgt16_$name.so -cudart static -lpthread -ldl -lrt
+  -o $out/libgt16_$name.so -cudart static -lpthread -ldl -lrt -lz
 rm -f $out/k_$name.o $out/c_$name.o
 echo built $out/libgt16_$name.so
