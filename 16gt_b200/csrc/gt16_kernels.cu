@@ -339,10 +339,13 @@ k_stream_tma(const uint64_t *__restrict__ counters, const uint32_t *__restrict__
   drain(qtail - qhead);
 }
 
+static cudaError_t configure_stream_runs();     // (defined behind k_stream_runs)
 // function attributes are per device: called once per context, with its device current
 cudaError_t configure_kernels() {
   constexpr int R = GT16_STREAM_ROWS;
   cudaError_t e = cudaFuncSetAttribute(k_stream_tma<false, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmemT<false, R>));
+  if (e != cudaSuccess) return e;
+  e = configure_stream_runs();
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_stream_tma<true, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StreamSmemT<true, R>));
 }
@@ -501,11 +504,210 @@ __global__ void __launch_bounds__(256) k_stream_exact(SnapView V, DevSiteMap M, 
   if ((threadIdx.x & 31) == 0 && i < n) mask[i >> 5] = word;
 }
 
+// ---- region lists through the TMA ring ----------------------------------------------------------------------------
+// The streaming kernel for the targets of an exome (and any other list of regions) when the decision bitmaps allow the
+// shortcut tests: persistent CTAs, tiles of kRunTile PROCESSED sites.  A tile is a handful of runs of consecutive
+// positions -- the parts of the (seven or eight) regions it covers -- so a producer warp (one per stage), one lane per run, works out
+// where each run lies (per-tile cursor + the region arrays), issues its bulk copies (counters incl. one look-ahead
+// entry, reference words, invalid-bitmap words: sources rounded out to 16 bytes) into the stage's slabs and writes the
+// run table {first site, first position, where its data starts in the slabs} beside them; the sixteen consumer warps
+// then do what k_stream_tma's rows do (settle by mask tests, park the rest, one ballot per row, flag words written as
+// zeros), addressing shared memory through the run table.  A tile with more runs than the table holds (a list of tiny
+// regions) is not staged: its sites are read straight from global memory.
+constexpr int kRunTile = 2048, kRunWarps = 16, kRunStages = 4, kRunThreads = (kRunWarps + kRunStages) * 32, kRunParts = 16;
+constexpr int kRunCSlab = kRunTile + 4 * kRunParts, kRunRSlab = kRunTile / 16 + 8 * kRunParts, kRunBSlab = kRunTile / 32 + 8 * kRunParts;
+struct RunPart { uint32_t siteFirst, pA, cOff, rOff, bOff, wA, bA, pad; };
+struct RunSmem {
+  uint64_t counters[kRunStages][kRunCSlab];
+  uint32_t ref[kRunStages][kRunRSlab];
+  uint32_t bm[kRunStages][kRunBSlab];
+  RunPart part[kRunStages][kRunParts];
+  uint32_t nParts[kRunStages];                           // 0: the tile is not staged (too many runs)
+  uint2 queue[kRunWarps][64];                            // parked sites: {bit index, position}
+  uint64_t full[kRunStages];                             // the tile's bytes have landed (producer's expect-tx + arrive)
+  uint64_t empty[kRunStages];                            // every consumer warp has left the stage (kRunWarps arrivals)
+};
+static_assert(sizeof(RunSmem) <= 100 * 1024, "two CTAs per SM");
+static_assert(kRunTile % kCursorTile == 0 && (kRunCSlab % 2) == 0 && (kRunRSlab % 4) == 0 && (kRunBSlab % 4) == 0, "slab alignment");
+
+__global__ void __launch_bounds__(kRunThreads, 2)
+k_stream_runs(SnapView V, DevSiteMap M, uint64_t first, uint32_t n, DecisionTables D, uint32_t altBound,
+              uint32_t *__restrict__ mask, uint32_t *errWord) {
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  RunSmem &S = *reinterpret_cast<RunSmem *>(smemRaw);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t nTiles = (n + kRunTile - 1) / kRunTile;
+  if (tid == 0) {
+    for (int k = 0; k < kRunStages; ++k) { mbar_init(&S.full[k], 1); mbar_init(&S.empty[k], kRunWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= kRunWarps) {
+    // ---------------- producer warps, one per stage (working out a tile's runs is a chain of dependent loads: four of them
+    // overlap theirs): lane k stages run k of the tile
+    const uint32_t stage = warp - kRunWarps;
+    uint32_t round = 0;
+    for (uint32_t tile = blockIdx.x + stage * gridDim.x; tile < nTiles; tile += kRunStages * gridDim.x, ++round) {
+      // the stage's previous tile has been read by all consumer warps (a parked wait, not a poll: the producers must not take
+      // issue slots from the consumers)
+      if (round) mbar_wait(&S.empty[stage], (round - 1) & 1u);
+      const uint64_t i0 = first + (uint64_t) tile * kRunTile;
+      const uint32_t done = tile * (uint32_t) kRunTile, cnt = n - done < (uint32_t) kRunTile ? n - done : (uint32_t) kRunTile;
+      const uint32_t r0 = M.m.tileReg[i0 / kCursorTile], rHi = M.m.tileReg[(i0 + cnt - 1) / kCursorTile + 1];
+      const uint32_t nr = rHi - r0 + 1;
+      uint32_t bytes = 0;
+      if (nr <= (uint32_t) kRunParts) {
+        // this lane's run: the part of region r0 + lane inside [i0, i0 + cnt)
+        uint32_t nSites = 0, pA = 0, sFirst = cnt;
+        if (lane < nr) {
+          const uint64_t a = M.m.regFirst[r0 + lane], b = M.m.regFirst[r0 + lane + 1];
+          const uint64_t sA = a > i0 ? a : i0, sB = b < i0 + cnt ? b : i0 + cnt;
+          if (sB > sA) { nSites = (uint32_t) (sB - sA); sFirst = (uint32_t) (sA - i0); pA = M.m.regStart[r0 + lane] + (uint32_t) (sA - a); }
+        }
+        // sources rounded out to 16 bytes: counters from an even entry (+ the look-ahead entry), words in fours
+        const uint32_t e0 = pA & ~1u, entries = nSites ? ((pA - e0) + nSites + 2u) & ~1u : 0u;
+        const uint32_t wA = (pA >> 4) & ~3u, words = nSites ? ((((pA + nSites - 1u) >> 4) + 1u - wA) + 3u) & ~3u : 0u;
+        const uint32_t bA = (pA >> 5) & ~3u, bwords = (nSites && V.invalid) ? ((((pA + nSites - 1u) >> 5) + 1u - bA) + 3u) & ~3u : 0u;
+        uint32_t cAt = entries, rAt = words, bAt = bwords;    // exclusive prefix sums over the lanes: where the run's data goes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t c1 = __shfl_up_sync(0xffffffffu, cAt, o), r1 = __shfl_up_sync(0xffffffffu, rAt, o), b1 = __shfl_up_sync(0xffffffffu, bAt, o);
+          if ((int) lane >= o) { cAt += c1; rAt += r1; bAt += b1; }
+        }
+        cAt -= entries; rAt -= words; bAt -= bwords;
+        if (lane < (uint32_t) kRunParts) {
+          RunPart P; P.siteFirst = sFirst; P.pA = pA; P.cOff = cAt + (pA - e0); P.rOff = rAt; P.bOff = bAt; P.wA = wA; P.bA = bA; P.pad = 0;
+          S.part[stage][lane] = P;
+        }
+        bytes = entries * 8u + words * 4u + bwords * 4u;
+        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+        if (lane == 0) S.nParts[stage] = nr;
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(&S.full[stage], total);               // arrives, too: the phase completes when the bytes have landed
+        __syncwarp();
+        if (nSites) {
+          bulk_g2s(&S.counters[stage][cAt], V.counters + e0, entries * 8u, &S.full[stage]);
+          bulk_g2s(&S.ref[stage][rAt], V.packedRef + wA, words * 4u, &S.full[stage]);
+          if (bwords) bulk_g2s(&S.bm[stage][bAt], V.invalid + bA, bwords * 4u, &S.full[stage]);
+        }
+      } else {
+        if (lane == 0) { S.nParts[stage] = 0; mbar_expect_tx(&S.full[stage], 0); }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps
+  uint2 *q = S.queue[warp];
+  uint32_t qhead = 0, qtail = 0;
+  auto drain = [&](uint32_t count) {                        // lanes < count settle one parked site each (as in k_stream_tma)
+    if (lane < count) {
+      const uint2 e = q[(qhead + lane) & 63u];
+      const uint32_t p = e.y;
+      const uint2 c = __ldg(reinterpret_cast<const uint2 *>(V.counters + p));
+      const uint32_t nx = __ldg(reinterpret_cast<const uint32_t *>(V.counters + p + 1));
+      const uint32_t ref = (p >> 4) < V.refWords ? (__ldg(V.packedRef + (p >> 4)) >> (30u - ((p & 15u) << 1))) & 3u : 0u;
+      bool flag;
+      if ((nx & 0xE000E000u) >= 0xC000E000u) flag = true;
+      else if ((c.x & 0xC000C000u) != 0xC000C000u) flag = compact_needs_exact<true>(D, nullptr, c.x, c.y, ref);
+      else {
+        flag = false;
+        const uint8_t *rec = ovf_record(V, ovf_region(V, p), c.y);
+        if (!rec) atomicOr(errWord, kErrBadSnapshot);
+        else {
+          const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(rec));
+          const uint2 hi = __ldg(reinterpret_cast<const uint2 *>(rec + 16));
+          const uint32_t Wv[4] = {lo.x & 0xFFFFu, lo.x >> 16, lo.y & 0xFFFFu, lo.y >> 16};
+          const uint32_t Fv[4] = {lo.z & 0xFFFFu, lo.z >> 16, lo.w & 0xFFFFu, lo.w >> 16};
+          const uint32_t Rv[4] = {hi.x & 0xFFFFu, hi.x >> 16, hi.y & 0xFFFFu, hi.y >> 16};
+          uint32_t wr[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const uint32_t w = (Fv[b] | Rv[b]) ? Wv[b] : 0u, role = (uint32_t) b ^ ref;
+            if (role == 0) wr[0] = w; else if (role == 1) wr[1] = w; else if (role == 2) wr[2] = w; else wr[3] = w;
+          }
+          flag = lookup_needs_exact(D, wr[0], wr[2], wr[1], wr[3]);
+        }
+      }
+      if (flag) atomicOr(mask + (e.x >> 5), 1u << (e.x & 31));
+    }
+    qhead += count;
+  };
+  const uint32_t ltMask = (1u << lane) - 1u;
+  constexpr int kRows = kRunTile / (kRunWarps * 32);        // 32-site rows per warp and tile
+  uint32_t stage = 0, parity = 0;
+  for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    mbar_wait(&S.full[stage], parity);
+    const uint64_t i0 = first + (uint64_t) tile * kRunTile;
+    const uint32_t done = tile * (uint32_t) kRunTile, cnt = n - done < (uint32_t) kRunTile ? n - done : (uint32_t) kRunTile;
+    const uint32_t nParts = S.nParts[stage];
+    if (lane < (uint32_t) kRows && (warp * kRows + lane) * 32u < cnt) mask[(done >> 5) + warp * kRows + lane] = 0u;
+    uint32_t k = 0;                                         // run of the lane's current site (its sites ascend)
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const uint32_t s = warp * (32 * kRows) + 32 * r + lane;
+      bool park = false;
+      uint32_t p = 0;
+      if (s < cnt) {
+        uint32_t x, y, nx, ref;
+        bool invalidBit;
+        if (nParts) {
+          while (k + 1 < nParts && S.part[stage][k + 1].siteFirst <= s) ++k;
+          const RunPart P = S.part[stage][k];
+          const uint32_t d = s - P.siteFirst;
+          p = P.pA + d;
+          const uint2 c = reinterpret_cast<const uint2 *>(S.counters[stage])[P.cOff + d];
+          x = c.x; y = c.y;
+          nx = reinterpret_cast<const uint2 *>(S.counters[stage])[P.cOff + d + 1].x;
+          ref = (S.ref[stage][P.rOff + ((p >> 4) - P.wA)] >> (30u - ((p & 15u) << 1))) & 3u;
+          invalidBit = V.invalid ? (S.bm[stage][P.bOff + ((p >> 5) - P.bA)] >> (31u - (p & 31u))) & 1u : false;
+        } else {                                           // tile of many tiny regions: straight from global memory
+          p = pos_of_cursor(M.m, i0 + s);
+          const uint2 c = __ldg(reinterpret_cast<const uint2 *>(V.counters + p));
+          x = c.x; y = c.y;
+          nx = __ldg(reinterpret_cast<const uint32_t *>(V.counters + p + 1));
+          ref = (p >> 4) < V.refWords ? (__ldg(V.packedRef + (p >> 4)) >> (30u - ((p & 15u) << 1))) & 3u : 0u;
+          invalidBit = V.invalid ? (__ldg(V.invalid + (p >> 5)) >> (31u - (p & 31u))) & 1u : false;
+        }
+        const bool isRef1 = ((x >> 14) & 3u) == ref, live1 = (y & 0xFFFFu) != 0;
+        const bool tinyAlt = ((x & 0x3FFF0000u) <= altBound) & ((x & 0x3C00u) == 0);
+        const bool special = ((x & 0xC000C000u) == 0xC000C000u) | ((nx & 0xE000E000u) >= 0xC000E000u);
+        const bool settled = (y == 0) | (isRef1 & live1 & ((y < 0x10000u) | tinyAlt));
+        park = (special | !settled) & !invalidBit;
+      }
+      const uint32_t cw = __ballot_sync(0xffffffffu, park);
+      if (cw) {
+        if ((cw >> lane) & 1u) q[(qtail + __popc(cw & ltMask)) & 63u] = make_uint2(done + s, p);
+        qtail += __popc(cw);
+        __syncwarp();
+        if (qtail - qhead >= 32u) { drain(32); __syncwarp(); }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&S.empty[stage])) : "memory");
+    if (++stage == (uint32_t) kRunStages) { stage = 0; parity ^= 1u; }
+  }
+  __syncwarp();
+  drain(qtail - qhead);
+}
+
+static cudaError_t configure_stream_runs() {
+  return cudaFuncSetAttribute(k_stream_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RunSmem));
+}
+
 void launch_stream(const SnapView &V, const DevSiteMap &M, uint64_t first, uint32_t n, bool useTables,
                    const DecisionTables &D, uint32_t shortcutAlt, const EvalParams &P, uint32_t *mask, uint32_t *errWord,
                    cudaStream_t s) {
   if (!n) return;
-  if (useTables) k_stream_regions<<<(n + kRegTile - 1) / kRegTile, kRegThreads, 0, s>>>(V, M, first, n, D, shortcutAlt << 16, mask, errWord);
+  if (useTables && shortcutAlt && M.m.tileReg && first % kRunTile == 0 && !getenv("GT16_NO_RUNS")) {
+    // a region list, the shortcut tests allowed: runs of positions through the TMA ring, two persistent CTAs per SM
+    const uint32_t nTiles = (n + kRunTile - 1) / kRunTile;
+    static int numSMs = 0;
+    if (!numSMs) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev); }
+    unsigned grid = nTiles < (uint32_t) numSMs * 2u ? nTiles : (unsigned) numSMs * 2u;
+    k_stream_runs<<<grid, kRunThreads, sizeof(RunSmem), s>>>(V, M, first, n, D, shortcutAlt << 16, mask, errWord);
+  } else if (useTables) k_stream_regions<<<(n + kRegTile - 1) / kRegTile, kRegThreads, 0, s>>>(V, M, first, n, D, shortcutAlt << 16, mask, errWord);
   else k_stream_exact<<<(n + 255) / 256, 256, 0, s>>>(V, M, first, n, P, mask, errWord);
 }
 
