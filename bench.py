@@ -562,7 +562,7 @@ def main():
         "gpu_launches": launches,
         "device_ms_per_step_rank0": parts["ms_total_device"],
         "device_ms_breakdown_rank0": {k: parts[k] for k in ("ms_stream", "ms_eval", "ms_scan", "ms_candidates", "ms_d2h")},
-        "roofline": {"bound": "hbm", "kernel": ("k_stream_regions (decode + 16-genotype classification of every target site, region list staged in shared memory), rank 0's launches"
+        "roofline": {"bound": "hbm", "kernel": ("k_stream_runs (decode + 16-genotype classification of every target site; the targets' runs of positions staged through a TMA ring), rank 0's launches"
                                                 if region else "k_stream_tma (decode + 16-genotype classification of every site), rank 0's launch"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
