@@ -915,11 +915,17 @@ __global__ void __launch_bounds__(kEvalThreads, GT16_EVAL_BLOCKS) k_eval_mask(Sn
   const uint32_t warpsTotal = gridDim.x * (kEvalThreads / 32), nChunks = (nWords + 31) / 32;
   uint32_t head = 0, tail = 0, seen = 0;
   uint32_t slotNext = 0, slotEnd = 0;                   // the warp's reserved entries of part[]: [slotNext, slotEnd)
-  for (uint32_t c = blockIdx.x * (kEvalThreads / 32) + warp; c < nChunks; c += warpsTotal) {
+  // plain loads: the words are cleared by atomics of this very launch, but a word is read by exactly one lane and only
+  // bits that lane has queued are ever cleared -- so the word of the warp's NEXT chunk may be fetched one chunk ahead
+  uint32_t c = blockIdx.x * (kEvalThreads / 32) + warp;
+  uint32_t bitsAhead = (c < nChunks && c * 32 + lane < nWords) ? siteMask[wordBegin + c * 32 + lane] : 0u;
+  for (; c < nChunks; c += warpsTotal) {
     const uint32_t wi = c * 32 + lane;
-    // plain load: the words are cleared by atomics of this very launch (other warps' sites never share a word with ours
-    // before it has been read: a word is read by exactly one lane, and only bits it has queued are cleared)
-    uint32_t bits = wi < nWords ? siteMask[wordBegin + wi] : 0u;
+    uint32_t bits = bitsAhead;
+    {
+      const uint32_t cn = c + warpsTotal;
+      bitsAhead = (cn < nChunks && cn * 32 + lane < nWords) ? siteMask[wordBegin + cn * 32 + lane] : 0u;
+    }
     seen += __popc(bits);
     uint32_t any = __ballot_sync(0xffffffffu, bits != 0);
     while (any) {                                       // one bit per lane and round
