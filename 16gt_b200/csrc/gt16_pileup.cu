@@ -98,11 +98,13 @@ __device__ void pile_read(const PileArgs &A, PileSmem &S, PileEvent *ev, uint32_
   const uint32_t *ops = A.cigar + A.cigarOff[r];
   const uint8_t *sq = A.bases + A.seqOff[r];
   const uint32_t trimHead = A.trim, tailFrom = readLength - A.trim;      // unsigned, like the reference (:564)
+  const uint64_t tileEnd64 = (uint64_t) tileLo + kPileTile;               // (the last tile of a genome close to 2^32 positions)
+  const uint32_t tileEnd = tileEnd64 < A.L ? (uint32_t) tileEnd64 : A.L;
   uint32_t gpos = A.start[r], rpos = 0, trimmedHead = 0;
   uint32_t insLen = 0, insStart = 0, delLen = 0, delPos = 0;
   bool delActive = false;
   auto emit = [&](uint32_t pos, uint32_t kind, uint32_t len, bool hq, uint64_t seq) {   // lane 0
-    if (pos < tileLo || pos >= tileLo + (uint32_t) kPileTile || pos >= A.L) return;
+    if (pos < tileLo || pos >= tileEnd) return;
     const uint32_t at = atomicAdd(&S.nEvents, 1u);
     if (at >= evCap) return;                                   // counted: the tile goes to the second launch
     PileEvent e;
@@ -153,10 +155,10 @@ __device__ void pile_read(const PileArgs &A, PileSmem &S, PileEvent *ev, uint32_
       flush_deletion((uint32_t) (sq[rpos] >> 2));
       commit();
       // does the run touch the tile?
-      if (gpos < tileLo + (uint32_t) kPileTile && gpos + n > tileLo) {
+      if (gpos < tileEnd && gpos + n > tileLo) {
         const uint32_t k0 = gpos < tileLo ? tileLo - gpos : 0u;
         uint32_t k1 = n;
-        if (gpos + n > tileLo + (uint32_t) kPileTile) k1 = tileLo + (uint32_t) kPileTile - gpos;
+        if (gpos + n > tileEnd) k1 = tileEnd - gpos;
         const uint32_t strandOff = A.order[r] >> 31 ? 4u : 8u;                  // F (forward read) or R: see below
         for (uint32_t k = k0 + lane; k < k1; k += 32) {
           const uint32_t p = gpos + k;
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(kPileThreads, 1) k_pileup(PileArgs A) {
   const uint32_t tileLo = tile * (uint32_t) kPileTile;
   PileEvent *ev = A.tileList ? A.heavyList + A.heavyOff[blockIdx.x] : S.ev;
   const uint32_t evCap = A.tileList ? (uint32_t) (A.heavyOff[blockIdx.x + 1] - A.heavyOff[blockIdx.x]) : (uint32_t) kPileEvents;
-  const uint32_t tileHi = tileLo + (uint32_t) kPileTile < A.L ? tileLo + (uint32_t) kPileTile : A.L;
+  const uint32_t tileHi = (uint64_t) tileLo + kPileTile < A.L ? tileLo + (uint32_t) kPileTile : A.L;
   // reads with start in (tileLo - maxSpan, tileHi)
   uint64_t rLo, rHi;
   {
