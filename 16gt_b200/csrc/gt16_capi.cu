@@ -518,7 +518,14 @@ static int stage_threads() {                              // GT16_STAGE_THREADS,
 // it asked for (the buffers only grow, so this happens at most once per context and workload).
 // (The floor also covers the side-buffer entries the evaluator's warps reserve in chunks of 8 and leave unused: at most 7
 // per warp of its grid, 33,152 in all.)
-static uint32_t record_bound(uint64_t segSites) { return (uint32_t) std::min<uint64_t>(segSites / 128 + 65536, 0x7FFFFFFFull / 12); }
+static uint32_t record_bound(uint64_t segSites) {
+  uint64_t per = 128, floor = 65536;
+  if (const char *e = getenv("GT16_RECORD_BOUND")) {      // test hook "sites per record:floor": a tiny bound exercises the repeat
+    unsigned long a = 0, b = 0;
+    if (sscanf(e, "%lu:%lu", &a, &b) == 2 && a >= 1) { per = a; floor = b; }
+  }
+  return (uint32_t) std::min<uint64_t>(segSites / per + floor, 0x7FFFFFFFull / 12);
+}
 static const int kRetryLargerBuffers = 1;             // internal return code of call_common
 static const uint32_t kSegBatchesDefault = 2;         // batches per segment of a host-fed range (GT16_SEG_BATCHES overrides)
 

@@ -1052,7 +1052,7 @@ __global__ void __launch_bounds__(256) k_rank(const uint32_t *__restrict__ mask,
       const uint32_t blk = w / kScanBlock;
       const uint32_t r = chunkOffsets[blk >> 10] + blockOffsets[blk] + c + __popc(mask[firstWord + w] & ((1u << (site & 31)) - 1u));
       rankOf[j] = r;
-      list[r] = j;
+      if (r < cap) list[r] = j;        // (more candidates than the buffers hold: the call is repeated with larger ones)
     }
   }
 }

@@ -93,3 +93,34 @@ def test_batch_boundary_neighbourhood(gpu_caller, tmp_path):
         assert sum(s.called for s in st) == want_n
         T.compare_txt(open(out + ".txt", "rb").read(), open(out + ".oracle.txt", "rb").read())
         os.remove(out + ".snapshot")
+
+
+@pytest.mark.parametrize("mode", ["host", "resident", "device_nowait"])
+def test_more_candidates_than_the_record_bound(tmp_path, monkeypatch, mode):
+    """Record buffers are sized by a bound; a call that finds more candidates is repeated once with buffers of the size it
+    asked for (GT16_RECORD_BOUND shrinks the bound so that the small stress config overflows it): same .txt."""
+    import ctypes
+    monkeypatch.setenv("GT16_RECORD_BOUND", "1000000:24")
+    name = "stress_small"
+    idx, out, region = T.regenerate(name, tmp_path)
+    rows = T.manifest()[name]["rows"]
+    assert rows > 100
+    with T.Caller(0) as c:
+        inp = T.LoadedInput(idx, out + ".snapshot", region)
+        try:
+            if mode == "device_nowait":
+                L = c.L
+                dev, calls, st, host = ctypes.c_void_p(), ctypes.c_void_p(), T.Stats(), ctypes.c_void_p()
+                c.check(L.gt16_snapshot_upload(c.ctx, ctypes.byref(inp.view), ctypes.byref(dev)))
+                c.check(L.gt16_call_sites_device_nowait(c.ctx, dev, None, 0, 0, inp.total_sites, ctypes.byref(calls), ctypes.byref(st)))
+                c.check(L.gt16_dev_calls_wait(c.ctx, calls, ctypes.byref(st)))
+                assert st.called == rows == L.gt16_dev_calls_count(calls)
+                c.check(L.gt16_dev_calls_fetch(c.ctx, calls, ctypes.byref(host)))
+                assert L.gt16_write_txt((out + ".txt").encode(), inp.ix, L.gt16_calls_data(host), L.gt16_calls_count(host), 0, None) == 0
+                L.gt16_calls_free(host); L.gt16_dev_calls_free(calls); L.gt16_snapshot_release(c.ctx, dev)
+            else:
+                st = T.call_to_txt(c, inp, out + ".txt", resident=(mode == "resident"))
+                assert sum(x.called for x in st) == rows
+        finally:
+            inp.close()
+    assert T.compare_txt(open(out + ".txt", "rb").read(), T.golden_txt(name)) <= 2
