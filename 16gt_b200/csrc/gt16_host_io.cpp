@@ -157,6 +157,8 @@ int gt16_snapshot_read_ex(const char *path, int flags, uint32_t pos_lo, uint32_t
   int rc = GT16_OK;
   uint8_t hdr[4 + 5 * 16];
   uint64_t start[5], len[5];
+  uint64_t fileSize = 0;                    // sizes read from a damaged file are checked against it before anything is allocated
+  { struct stat st; if (fstat(fileno(f), &st) == 0) fileSize = (uint64_t) st.st_size; }
   do {
     if (!read_at(f, 0, hdr, sizeof(hdr))) { set_err(err, errLen, "%s: short header", path); rc = GT16_EIO; break; }
     for (int i = 0; i < 5; ++i) { memcpy(&start[i], hdr + 4 + 16 * i, 8); memcpy(&len[i], hdr + 12 + 16 * i, 8); }
@@ -167,6 +169,7 @@ int gt16_snapshot_read_ex(const char *path, int flags, uint32_t pos_lo, uint32_t
     memcpy(&hs->textLength, head + 1, 4);
     const uint32_t L = hs->textLength;
     if (!L) { set_err(err, errLen, "%s: empty snapshot", path); rc = GT16_EDATA; break; }
+    if ((mode & 1) && (uint64_t) L * 8 > fileSize) { set_err(err, errLen, "%s: truncated counters", path); rc = GT16_EIO; break; }
     // the window of counters kept in memory (a shard of a sharded genome reads and page-locks its own part only)
     const uint32_t wLo = pos_lo < L ? pos_lo : 0, wHi = pos_hi > L || pos_hi <= wLo ? L : pos_hi;
     const size_t W = (size_t) wHi - wLo;
@@ -182,7 +185,7 @@ int gt16_snapshot_read_ex(const char *path, int flags, uint32_t pos_lo, uint32_t
       // the records stay as the producer wrote them (12 bytes each, ascending positions): they are expanded in HBM, not
       // here -- a whole-genome array of zeros for an exome's worth of counters would cost 8 B per genome position of host
       // memory and of host-link traffic
-      if (len[1] < 5 || (len[1] - 5) % 12) { set_err(err, errLen, "%s: bad sparse counter subfile", path); rc = GT16_EDATA; break; }
+      if (len[1] < 5 || (len[1] - 5) % 12 || len[1] > fileSize) { set_err(err, errLen, "%s: bad sparse counter subfile", path); rc = GT16_EDATA; break; }
       hs->nSparse = (len[1] - 5) / 12;
       const size_t bytes = (size_t) hs->nSparse * 12;
       const bool mappedRecords = !pinned && !getenv("GT16_NO_MMAP") && bytes && hs->sparse.map_file(path, start[1] + 5, bytes);
@@ -228,6 +231,7 @@ int gt16_snapshot_read_ex(const char *path, int flags, uint32_t pos_lo, uint32_t
         // always holds there; anything else is not a snapshot the reference could have written (its reader would skip the
         // records of a limit-0 region and mis-parse the rest, :313)
         if (sz > lim) { bad = true; break; }
+        if ((uint64_t) sz * 32 > fileSize) { ok = false; break; }
         hs->ovfSize.push_back(sz);
         if (lim == 0) continue;                       // SnapshotHandler.cpp:313
         tmp[r].resize((size_t) sz * 32);
@@ -259,6 +263,7 @@ int gt16_snapshot_read_ex(const char *path, int flags, uint32_t pos_lo, uint32_t
     uint32_t curPtr; uint64_t capacity;
     memcpy(&curPtr, ph, 4); memcpy(&capacity, ph + 4, 8);
     if (curPtr > capacity) { set_err(err, errLen, "%s: pool pointer beyond capacity", path); rc = GT16_EDATA; break; }
+    if (curPtr > fileSize) { set_err(err, errLen, "%s: truncated pool", path); rc = GT16_EIO; break; }
     hs->poolBytes = curPtr;
     if (!hs->pool.alloc((size_t) curPtr + 16, pinned != 0)) { set_err(err, errLen, "Memory Allocation Failed!"); rc = GT16_EIO; break; }
     if (curPtr && fread(hs->pool.p, 1, curPtr, f) != curPtr) { set_err(err, errLen, "%s: truncated pool", path); rc = GT16_EIO; break; }

@@ -254,16 +254,25 @@ int gt16_bam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold
   int32_t lText = 0, nRef = 0;
   if (!R.get(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) return fail("not a BAM file");
   if (!R.get(&lText, 4) || lText < 0) return fail("truncated BAM header");
-  { std::vector<char> text((size_t) lText + 1); if (lText && !R.get(text.data(), (size_t) lText)) return fail("truncated BAM header"); }
+  // sizes in a damaged file may say anything: nothing is allocated ahead of the bytes that are really there
+  {
+    std::vector<char> text(1u << 16);
+    for (size_t left = (size_t) lText; left;) {
+      const size_t k = std::min(left, text.size());
+      if (!R.get(text.data(), k)) return fail("truncated BAM header");
+      left -= k;
+    }
+  }
   if (!R.get(&nRef, 4) || nRef < 0) return fail("truncated BAM header");
-  std::vector<int> chrId((size_t) nRef, 0);                     // 0: not looked up yet (chrIdMap, bam2snapshot.cpp:157-158)
-  std::vector<std::string> names((size_t) nRef);
+  std::vector<int> chrId;                                       // 0: not looked up yet (chrIdMap, bam2snapshot.cpp:157-158)
+  std::vector<std::string> names;
   for (int32_t r = 0; r < nRef; ++r) {
     int32_t lName = 0, lRef = 0;
     if (!R.get(&lName, 4) || lName <= 0 || lName > (1 << 16)) return fail("bad reference name in the BAM header");
     std::vector<char> nm((size_t) lName);
     if (!R.get(nm.data(), (size_t) lName) || !R.get(&lRef, 4)) return fail("truncated BAM header");
-    names[r] = std::string(nm.data());
+    names.push_back(std::string(nm.data(), strnlen(nm.data(), (size_t) lName)));
+    chrId.push_back(0);
   }
   gt16_sam *S = new gt16_sam();
   const uint32_t L = gt16_index_length(ix);
@@ -273,8 +282,13 @@ int gt16_bam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold
     int32_t blockSize = 0;
     if (!R.get(&blockSize, 4)) { if (R.bad) { delete S; return fail("corrupt BGZF stream"); } break; }
     if (blockSize < 32) { delete S; return fail("bad alignment record"); }
-    rec.resize((size_t) blockSize);
-    if (!R.get(rec.data(), (size_t) blockSize)) { delete S; return fail("truncated alignment record"); }
+    rec.clear();
+    for (size_t left = (size_t) blockSize; left;) {             // in steps: a damaged size does not reserve 2 GB
+      const size_t k = std::min<size_t>(left, 1u << 20), at = rec.size();
+      rec.resize(at + k);
+      if (!R.get(rec.data() + at, k)) { delete S; return fail("truncated alignment record"); }
+      left -= k;
+    }
     S->total++;
     int32_t tid, pos, lSeq;
     memcpy(&tid, &rec[0], 4); memcpy(&pos, &rec[4], 4);

@@ -280,3 +280,121 @@ def test_sam_reader_filters(tmp_path):
     p = T.capi_mod.PileupParams()
     L.gt16_pileup_default_params(ctypes.byref(p))
     assert list(p.weight_map)[9:22] == [0, 0, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4] and (p.trim_size, p.indel_weight_threshold, p.n_overflow_regions) == (5, 1, 16)
+
+
+def test_sam_and_bam_readers_survive_damaged_input(tmp_path):
+    """Mutated SAM lines and cut / corrupted BAM files: the readers return (reads or an error code), they never crash and
+    every read they hand on is self-consistent (lengths, offsets, positions inside the genome)."""
+    import random
+    idx, out, region = T.regenerate("wgs_small", tmp_path)
+    L = T.capi()
+    err = ctypes.create_string_buffer(256)
+    ix = ctypes.c_void_p()
+    assert L.gt16_index_read(idx.encode(), ctypes.byref(ix), err, 256) == 0
+    glen = L.gt16_index_length(ix)
+    rng = random.Random(5)
+    good = ["r%d\t%d\tchrA\t%d\t60\t%s\t*\t0\t0\t%s\t%s" % (i, rng.choice([0, 16]), rng.randrange(1, 170000), cg, "ACGTN"[i % 5] * 12, "I" * 12)
+            for i, cg in enumerate(["12M", "3S9M", "4M2I6M", "5M3D7M", "6M100N6M", "2H12M", "1M1I1M1I1M1I1M1I1M1I1M1I"] * 6)]
+
+    def check(h):
+        r = T.capi_mod.Reads()
+        L.gt16_sam_reads(h, ctypes.byref(r))
+        n = int(r.n_reads)
+        if n:
+            start = np.ctypeslib.as_array(ctypes.cast(r.start, ctypes.POINTER(ctypes.c_uint32)), (n,))
+            length = np.ctypeslib.as_array(ctypes.cast(r.length, ctypes.POINTER(ctypes.c_uint32)), (n,)).astype(np.int64)
+            so = np.ctypeslib.as_array(ctypes.cast(r.seq_off, ctypes.POINTER(ctypes.c_uint64)), (n,)).astype(np.int64)
+            co = np.ctypeslib.as_array(ctypes.cast(r.cigar_off, ctypes.POINTER(ctypes.c_uint64)), (n,)).astype(np.int64)
+            nc = np.ctypeslib.as_array(ctypes.cast(r.n_cigar, ctypes.POINTER(ctypes.c_uint32)), (n,)).astype(np.int64)
+            assert (start < glen).all() and (length > 0).all() and (nc > 0).all()
+            assert so[0] == 0 and (so[1:] == so[:-1] + length[:-1]).all() and so[-1] + length[-1] == r.n_bases
+            assert co[0] == 0 and (co[1:] == co[:-1] + nc[:-1]).all() and co[-1] + nc[-1] == r.n_cigar_ops
+            bases = np.ctypeslib.as_array(ctypes.cast(r.bases, ctypes.POINTER(ctypes.c_uint8)), (int(r.n_bases),))
+            assert bases.max() <= 3
+        return n
+
+    junk = ["\t", "*", "999999999999999999999", "-1", "M", "0M", "12", "chrZ", "", "\t\t\t", "12X", "268435456M", "\xff"]
+    sam = tmp_path / "m.sam"
+    kept = 0
+    for trial in range(60):
+        lines = []
+        for ln in good:
+            f = ln.split("\t")
+            for _ in range(rng.randrange(0, 3)):
+                f[rng.randrange(len(f))] = rng.choice(junk)
+            if trial == 59 and len(lines) == 7:
+                f[5] = "\x00"                     # a NUL cuts the line short: fewer than 11 fields
+            lines.append("\t".join(f))
+        with open(sam, "w", encoding="latin-1") as fh:
+            fh.write("@SQ\tSN:chrA\tLN:180000\n" + "\n".join(lines) + ("\n" if trial & 1 else ""))
+        h = ctypes.c_void_p()
+        rc = L.gt16_sam_read(str(sam).encode(), ix, 10, ctypes.byref(h), err, 256)
+        assert rc in (0, -5), rc                 # -5: a line with fewer than 11 fields
+        if rc == 0:
+            kept += check(h)
+            L.gt16_sam_free(h)
+        assert (rc == -5) == (trial == 59)
+    assert kept > 500
+    # BAM: cut at every few bytes, and single bytes overwritten
+    with open(sam, "w") as fh:
+        fh.write("@SQ\tSN:chrA\tLN:180000\n@SQ\tSN:chrB\tLN:70000\n" + "\n".join(good) + "\n")
+    bam = tmp_path / "m.bam"
+    T.sam_to_bam(str(sam), str(bam))
+    blob = open(bam, "rb").read()
+    hurt = tmp_path / "hurt.bam"
+    outcomes = set()
+    for trial in range(120):
+        b = bytearray(blob)
+        if trial < 60:
+            b = b[:rng.randrange(0, len(b))]
+        else:
+            for _ in range(rng.randrange(1, 4)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        open(hurt, "wb").write(bytes(b))
+        h = ctypes.c_void_p()
+        rc = L.gt16_bam_read(str(hurt).encode(), ix, 10, ctypes.byref(h), err, 256)
+        outcomes.add(rc)
+        assert rc in (0, -5), rc
+        if rc == 0:
+            check(h)
+            L.gt16_sam_free(h)
+    assert -5 in outcomes
+    L.gt16_index_free(ix)
+
+
+@pytest.mark.parametrize("name", ["stress_small", "exome_small"])
+def test_snapshot_reader_survives_damaged_containers(tmp_path, name, monkeypatch):
+    """Cut and overwritten snapshot containers (dense and sparse), mapped and read: an error code or a view, no crash, and
+    nothing allocated by a size only the damaged bytes vouch for."""
+    import random
+    idx, out, region = T.regenerate(name, tmp_path)
+    L = T.capi()
+    blob = open(out + ".snapshot", "rb").read()
+    rng = random.Random(11)
+    hurt = str(tmp_path / "hurt.snapshot")
+    err = ctypes.create_string_buffer(256)
+    outcomes = set()
+    for trial in range(80):
+        b = bytearray(blob)
+        if trial % 2:
+            b = b[:rng.randrange(0, len(b))]
+        else:
+            for _ in range(rng.randrange(1, 4)):
+                at = rng.randrange(0, 4096) if rng.random() < 0.7 else rng.randrange(len(b))     # mostly the header page
+                b[at] = rng.randrange(256)
+        open(hurt, "wb").write(bytes(b))
+        for flags, nommap in ((0, False), (0, True), (2, False)):
+            if nommap:
+                monkeypatch.setenv("GT16_NO_MMAP", "1")
+            else:
+                monkeypatch.delenv("GT16_NO_MMAP", raising=False)
+            hs = ctypes.c_void_p()
+            rc = L.gt16_snapshot_read_ex(hurt.encode(), flags, 0, 0xFFFFFFFF, ctypes.byref(hs), err, 256)
+            outcomes.add(rc)
+            assert rc in (0, -4, -5), (trial, rc, err.value)          # GT16_EIO, GT16_EDATA
+            if rc == 0:
+                v = T.capi_mod.View()
+                L.gt16_snapshot_view_of(hs, ctypes.byref(v))
+                assert v.text_length > 0
+                L.gt16_snapshot_free(hs)
+    assert 0 in outcomes and (-4 in outcomes or -5 in outcomes)
