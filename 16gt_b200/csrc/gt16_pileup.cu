@@ -401,13 +401,30 @@ extern "C" int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint3
   auto ms_since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
   const uint64_t n = reads->n_reads;
   const uint32_t L = text_length;
+  if (n >= 0x7FFFFFFFull) return gt16_pileup_set_error(ctx, GT16_EINVAL, "too many reads for one call");
+  // the kernel indexes bases[] and cigar[] by what the read records say: they are checked here, once, on the host
+  for (uint64_t i = 0; i < n; ++i) {
+    bool ok = reads->start[i] < L && reads->n_cigar[i] >= 1 && reads->length[i] >= 1 &&
+              reads->cigar_off[i] <= reads->n_cigar_ops && reads->n_cigar[i] <= reads->n_cigar_ops - reads->cigar_off[i] &&
+              reads->seq_off[i] <= reads->n_bases && reads->length[i] <= reads->n_bases - reads->seq_off[i];
+    uint64_t query = 0;
+    for (uint32_t c = 0; ok && c < reads->n_cigar[i]; ++c) {
+      const uint32_t v = reads->cigar[reads->cigar_off[i] + c], op = v & 15u;
+      if (op > 8) ok = false;
+      if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) query += v >> 4;
+    }
+    if (!ok || query > reads->length[i]) {
+      char msg[160];
+      snprintf(msg, sizeof(msg), "read %llu: start, CIGAR or sequence range outside the arrays (or a CIGAR longer than the read)", (unsigned long long) i);
+      return gt16_pileup_set_error(ctx, GT16_EINVAL, msg);
+    }
+  }
   // ---- sort the reads by start (stable: the input order decides which pattern appears first), pack what the kernel reads
   std::vector<uint64_t> order(n);
   for (uint64_t i = 0; i < n; ++i) order[i] = i;
   bool sorted = true;
   for (uint64_t i = 1; i < n && sorted; ++i) sorted = reads->start[i - 1] <= reads->start[i];
   if (!sorted) std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return reads->start[a] < reads->start[b]; });
-  if (n >= 0x7FFFFFFFull) return gt16_pileup_set_error(ctx, GT16_EINVAL, "too many reads for one call");
   std::vector<uint32_t> hStart(n), hLen(n), hOrder(n), hNCig(n);
   std::vector<uint64_t> hSeq(n), hCig(n);
   uint32_t maxSpan = 1;

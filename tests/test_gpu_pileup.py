@@ -135,3 +135,58 @@ def test_deep_tile_with_more_indel_events_than_the_shared_memory_list(tmp_path):
     ref, got = T.decode_snapshot(pre + ".ref.snapshot"), T.decode_snapshot(pre + ".mine.snapshot")
     assert max(sum(h + l for _, _, h, l in v) for v in got["ins"].values()) + max(sum(h + l for _, h, l in v) for v in got["dele"].values()) > 2048
     _decoded_equal(ref, got)
+
+
+def test_read_records_are_checked_before_the_kernel_indexes_by_them():
+    """gt16_build_snapshot straight through the C ABI: hand-made read records give the expected totals, and records that
+    point outside the arrays (or whose CIGAR is longer than the read) are refused with GT16_EINVAL, not run."""
+    import ctypes
+    L = T.capi()
+    M = T.capi_mod
+    glen = 6000
+    # read 0: forward, 20M at 100; read 1: reverse, 8M2I10M at 3000 (trim 5 at both ends of each)
+    start = np.array([100, 3000], np.uint32); rev = np.array([0, 1], np.uint8); length = np.array([20, 20], np.uint32)
+    seq_off = np.array([0, 20], np.uint64); cig_off = np.array([0, 1], np.uint64); n_cig = np.array([1, 3], np.uint32)
+    bases = np.tile(np.array([0, 1, 2, 3], np.uint8), 10); quals = np.full(40, 30, np.uint8)
+    cigar = np.array([20 << 4, 8 << 4, (2 << 4) | 1, 10 << 4], np.uint32)
+
+    def reads_of(**over):
+        a = dict(start=start, rev=rev, length=length, seq_off=seq_off, cig_off=cig_off, n_cig=n_cig, bases=bases, quals=quals, cigar=cigar)
+        a.update(over)
+        r = M.Reads()
+        r.n_reads = len(a["start"]); r.n_bases = len(a["bases"]); r.n_cigar_ops = len(a["cigar"])
+        for f, k in (("start", "start"), ("reverse", "rev"), ("length", "length"), ("seq_off", "seq_off"), ("cigar_off", "cig_off"),
+                     ("n_cigar", "n_cig"), ("bases", "bases"), ("quals", "quals"), ("cigar", "cigar")):
+            setattr(r, f, a[k].ctypes.data)
+        return r, a                       # the arrays stay alive with the struct
+
+    p = M.PileupParams()
+    L.gt16_pileup_default_params(ctypes.byref(p))
+    with T.Caller(0) as c:
+        r, keep = reads_of()
+        b = M.BuiltSnapshot()
+        c.check(L.gt16_build_snapshot(c.ctx, ctypes.byref(r), glen, ctypes.byref(p), ctypes.byref(b)))
+        cnt = np.ctypeslib.as_array(ctypes.cast(b.view.counters, ctypes.POINTER(ctypes.c_uint64)), (glen,)).copy()
+        covered = np.nonzero(cnt)[0]
+        # 10 applied bases of read 0 (positions 105..114); read 1: bases 5..7 before the insertion, 10..14 after it; its
+        # insertion makes position 3008 overflow-type, which is a non-zero counter as well
+        assert list(covered) == list(range(105, 115)) + list(range(3005, 3008)) + list(range(3008, 3013)), covered
+        assert b.view.overflow_size and b.aligned_bases == 40
+        L.gt16_built_snapshot_free(ctypes.byref(b))
+        bad = [dict(start=np.array([100, glen], np.uint32)),                              # a read starting behind the genome
+               dict(seq_off=np.array([0, 21], np.uint64)),                                # bases beyond the array
+               dict(seq_off=np.array([0, 2 ** 63], np.uint64)),
+               dict(cig_off=np.array([0, 2], np.uint64)),                                 # CIGAR operations beyond the array
+               dict(n_cig=np.array([1, 0], np.uint32)),                                   # no CIGAR
+               dict(length=np.array([20, 0], np.uint32)),                                 # no bases
+               dict(cigar=np.array([20 << 4, 9 << 4, (2 << 4) | 1, 10 << 4], np.uint32)),   # CIGAR longer than the read
+               dict(cigar=np.array([20 << 4, 8 << 4, (2 << 4) | 9, 10 << 4], np.uint32))]   # unknown operation
+        for over in bad:
+            r, keep = reads_of(**over)
+            rc = L.gt16_build_snapshot(c.ctx, ctypes.byref(r), glen, ctypes.byref(p), ctypes.byref(b))
+            assert rc == -1, (over, rc)
+            assert b"read 1" in L.gt16_last_error(c.ctx)
+        # and the context is still good for a correct call
+        r, keep = reads_of()
+        c.check(L.gt16_build_snapshot(c.ctx, ctypes.byref(r), glen, ctypes.byref(p), ctypes.byref(b)))
+        L.gt16_built_snapshot_free(ctypes.byref(b))
