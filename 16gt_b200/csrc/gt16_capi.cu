@@ -115,6 +115,10 @@ struct gt16_ctx {
   std::vector<cudaEvent_t> evPool[kCallRing];
   int evCur = 0;
   std::shared_ptr<PinPool> pins = std::make_shared<PinPool>();
+  DevBuf opIn, opOut;                     // operator seam: device scratch, ...
+  void *opPin = nullptr;                  // ... its two page-locked slots ...
+  size_t opPinCap = 0;
+  cudaEvent_t opEv[2] = {nullptr, nullptr};   // ... and the events that say a slot's chunk has been copied
   void *stagePin = nullptr;               // page-locked ring for callers whose counters live in pageable memory
   cudaEvent_t stageEv[32] = {nullptr};    // slot k's last copy has left the ring
 };
@@ -191,12 +195,6 @@ static EvalParams eval_params(const gt16_ctx *ctx) { return eval_params(ctx, ctx
 
 // scratch of the operator seam: freed on every return path
 namespace {
-struct DevScratch {
-  void *p = nullptr;
-  ~DevScratch() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-  template <class T> T *as() const { return (T *) p; }
-};
 struct EventPair {
   cudaEvent_t a = nullptr, b = nullptr;
   ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
@@ -309,6 +307,9 @@ void gt16_ctx_destroy(gt16_ctx *ctx) {
                     &ctx->sCounters, &ctx->sInvalid, &ctx->sOvf, &ctx->sOvfBase, &ctx->sPool, &ctx->sRef, &ctx->sSparse}) b->release();
   for (auto &pool : ctx->evPool) for (auto e : pool) cudaEventDestroy(e);
   if (ctx->stagePin) cudaFreeHost(ctx->stagePin);
+  ctx->opIn.release(); ctx->opOut.release();
+  if (ctx->opPin) cudaFreeHost(ctx->opPin);
+  for (auto e : ctx->opEv) if (e) cudaEventDestroy(e);
   for (auto e : ctx->stageEv) if (e) cudaEventDestroy(e);
   for (cudaStream_t st : {ctx->compute, ctx->copy, ctx->d2h, ctx->aux}) if (st) cudaStreamDestroy(st);
   if (ctx->sparseCopied) cudaEventDestroy(ctx->sparseCopied);
@@ -419,6 +420,44 @@ int gt16_setup_times(const gt16_ctx *ctx, float *prefill_ms, float *decision_ms)
 }
 
 // ---- operator seam ------------------------------------------------------------------------
+// The reference calls these once per batch of up to 8,388,608 sites with its array-of-structures buffers
+// (VariantCaller.cpp:620-707).  The sites go through in chunks: worker threads gather a chunk's fields out of the
+// caller's strides into one of two page-locked slots while the previous chunk is copied and computed; device and
+// page-locked scratch belong to the context and only grow, so a loop over batches allocates once.
+}  // extern "C"
+static uint32_t op_chunk_sites() {                        // GT16_OP_CHUNK: test hook (a small chunk exercises the ring)
+  uint32_t n = 1u << 18;
+  if (const char *e = getenv("GT16_OP_CHUNK")) { long v = atol(e); if (v >= 1 && v <= (1l << 22)) n = (uint32_t) v; }
+  return n;
+}
+static cudaError_t op_prepare(gt16_ctx *ctx, size_t slotBytes, size_t devIn, size_t devOut) {
+  if (2 * slotBytes > ctx->opPinCap) {
+    if (ctx->opPin) cudaFreeHost(ctx->opPin);
+    ctx->opPin = nullptr; ctx->opPinCap = 0;
+    cudaError_t e = cudaHostAlloc(&ctx->opPin, 2 * slotBytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return e;
+    ctx->opPinCap = 2 * slotBytes;
+  }
+  for (int k = 0; k < 2; ++k)
+    if (!ctx->opEv[k]) { cudaError_t e = cudaEventCreateWithFlags(&ctx->opEv[k], cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+  cudaError_t e = ctx->opIn.ensure(devIn);
+  return e != cudaSuccess ? e : ctx->opOut.ensure(devOut);
+}
+template <class F>
+static void op_parallel(uint32_t n, F f) {                // f(lo, hi) over [0, n) on a few threads
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::max(1u, std::min(8u, nt ? nt : 4u));
+  if (n < (1u << 15)) nt = 1;
+  if (nt == 1) { f(0u, n); return; }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t) {
+    const uint32_t lo = (uint32_t) ((uint64_t) n * t / nt), hi = (uint32_t) ((uint64_t) n * (t + 1) / nt);
+    th.emplace_back([=]() { f(lo, hi); });
+  }
+  for (auto &x : th) x.join();
+}
+extern "C" {
+
 int gt16_compute_genotype_likelihood(gt16_ctx *ctx, const void *w, size_t in_stride, const void *ref_char,
                                      size_t ref_stride, double *lh, uint32_t n, double balance, double unbalance) {
   if (!ctx || !w || !ref_char || !lh || in_stride < 24 || ref_stride < 1) return GT16_EINVAL;
@@ -427,21 +466,37 @@ int gt16_compute_genotype_likelihood(gt16_ctx *ctx, const void *w, size_t in_str
   CU(cudaSetDevice(ctx->device));
   // the call's own error rates go straight into the kernel parameters: the context's (which the fused path and its
   // decision bitmaps were configured with) are not touched
-  // only W[0..5] and refChar are read by the operator: gather them on the host side of the copy
-  std::vector<uint32_t> wbuf((size_t) n * 6);
-  std::vector<uint8_t> rbuf(n);
-  for (uint32_t i = 0; i < n; ++i) {
-    memcpy(&wbuf[(size_t) i * 6], (const char *) w + (size_t) i * in_stride, 24);
-    rbuf[i] = *((const uint8_t *) ref_char + (size_t) i * ref_stride);
+  const uint32_t chunk = std::min(op_chunk_sites(), n);
+  const size_t slotBytes = (size_t) chunk * 25;           // only W[0..5] and refChar are read by the operator
+  CU(op_prepare(ctx, slotBytes, slotBytes, (size_t) chunk * 128));
+  uint8_t *dIn = (uint8_t *) ctx->opIn.p;
+  double *dL = (double *) ctx->opOut.p;
+  const EvalParams P = eval_params(ctx, balance, unbalance);
+  // chunk k + 1 is gathered while chunk k is on the device; a copy into pageable `lh` returns when it is done
+  auto gather = [&](uint32_t k) -> cudaError_t {
+    const uint32_t a = k * chunk, m = std::min(chunk, n - a);
+    uint8_t *pin = (uint8_t *) ctx->opPin + (size_t) (k & 1) * slotBytes;
+    if (k >= 2) { cudaError_t e = cudaEventSynchronize(ctx->opEv[k & 1]); if (e != cudaSuccess) return e; }   // the slot's previous chunk has left it
+    op_parallel(m, [=](uint32_t lo, uint32_t hi) {
+      for (uint32_t i = lo; i < hi; ++i) {
+        memcpy(pin + (size_t) i * 24, (const char *) w + (size_t) (a + i) * in_stride, 24);
+        pin[(size_t) chunk * 24 + i] = *((const uint8_t *) ref_char + (size_t) (a + i) * ref_stride);
+      }
+    });
+    return cudaSuccess;
+  };
+  const uint32_t nChunks = (n + chunk - 1) / chunk;
+  CU(gather(0));
+  for (uint32_t k = 0; k < nChunks; ++k) {
+    const uint32_t a = k * chunk, m = std::min(chunk, n - a);
+    const uint8_t *pin = (const uint8_t *) ctx->opPin + (size_t) (k & 1) * slotBytes;
+    CU(cudaMemcpyAsync(dIn, pin, (size_t) chunk * 24 + m, cudaMemcpyHostToDevice, ctx->compute));
+    CU(cudaEventRecord(ctx->opEv[k & 1], ctx->compute));
+    launch_op_likelihood(P, dIn, 24, dIn + (size_t) chunk * 24, 1, dL, m, ctx->compute);
+    ctx->launches++;
+    if (k + 1 < nChunks) CU(gather(k + 1));
+    CU(cudaMemcpyAsync(lh + (size_t) a * 16, dL, (size_t) m * 128, cudaMemcpyDeviceToHost, ctx->compute));
   }
-  DevScratch sW, sR, sL;
-  CU(sW.alloc(wbuf.size() * 4)); CU(sR.alloc(n)); CU(sL.alloc((size_t) n * 128));
-  uint32_t *dW = sW.as<uint32_t>(); uint8_t *dR = sR.as<uint8_t>(); double *dL = sL.as<double>();
-  CU(cudaMemcpyAsync(dW, wbuf.data(), wbuf.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
-  CU(cudaMemcpyAsync(dR, rbuf.data(), n, cudaMemcpyHostToDevice, ctx->compute));
-  launch_op_likelihood(eval_params(ctx, balance, unbalance), (const uint8_t *) dW, 24, dR, 1, dL, n, ctx->compute);
-  ctx->launches++;
-  CU(cudaMemcpyAsync(lh, dL, (size_t) n * 128, cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
   CU(cudaGetLastError());
   return GT16_OK;
@@ -453,26 +508,47 @@ int gt16_compute_genotype(gt16_ctx *ctx, const unsigned char *ref_char, const do
   if (!n) return GT16_OK;
   CU(cudaSetDevice(ctx->device));
   const size_t dStride = 160;   // pD, genotype(+pad), flh[16], bestD, secondD
-  DevScratch sR, sL, sI;
-  CU(sR.alloc(n)); CU(sL.alloc((size_t) n * 128)); CU(sI.alloc((size_t) n * dStride));
-  uint8_t *dR = sR.as<uint8_t>(), *dI = sI.as<uint8_t>(); double *dL = sL.as<double>();
-  CU(cudaMemcpyAsync(dR, ref_char, n, cudaMemcpyHostToDevice, ctx->compute));
-  CU(cudaMemcpyAsync(dL, lh, (size_t) n * 128, cudaMemcpyHostToDevice, ctx->compute));
-  CU(cudaMemsetAsync(dI, 0, (size_t) n * dStride, ctx->compute));
-  launch_op_genotype(eval_params(ctx), dR, dL, dI, dStride, n, ctx->compute);
-  ctx->launches++;
-  std::vector<uint8_t> hI((size_t) n * dStride);
-  CU(cudaMemcpyAsync(hI.data(), dI, hI.size(), cudaMemcpyDeviceToHost, ctx->compute));
+  const uint32_t chunk = std::min(op_chunk_sites(), n);
+  const size_t slotBytes = (size_t) chunk * dStride;
+  CU(op_prepare(ctx, slotBytes, (size_t) chunk * 129, slotBytes));
+  uint8_t *dR = (uint8_t *) ctx->opIn.p + (size_t) chunk * 128, *dI = (uint8_t *) ctx->opOut.p;
+  double *dL = (double *) ctx->opIn.p;
+  const EvalParams P = eval_params(ctx);
+  // scatter into SnpCallingInfo (SNP_Meta.h:115-125); chunk k - 1 is scattered while chunk k is on the device
+  auto scatter = [&](uint32_t a, uint32_t m, const uint8_t *pin) {
+    op_parallel(m, [=](uint32_t lo, uint32_t hi) {
+      for (uint32_t i = lo; i < hi; ++i) {
+        char *d = (char *) info + (size_t) (a + i) * info_stride;
+        const uint8_t *s = pin + (size_t) i * dStride;
+        memcpy(d + 0, s + 0, 8);                  // pD
+        memcpy(d + 8, s + 8, 4);                  // genotype (secondGenotype @12 untouched)
+        memcpy(d + 16, s + 16, 128);              // flh
+        memcpy(d + 144, s + 144, 16);             // bestD, secondD (rfProb/rfMode untouched)
+      }
+    });
+  };
+  const uint32_t nChunks = (n + chunk - 1) / chunk;
+  uint32_t prevA = 0, prevM = 0;
+  for (uint32_t k = 0; k < nChunks; ++k) {
+    const uint32_t a = k * chunk, m = std::min(chunk, n - a);
+    uint8_t *pin = (uint8_t *) ctx->opPin + (size_t) (k & 1) * slotBytes;
+    CU(cudaMemcpyAsync(dR, ref_char + a, m, cudaMemcpyHostToDevice, ctx->compute));
+    CU(cudaMemcpyAsync(dL, lh + (size_t) a * 16, (size_t) m * 128, cudaMemcpyHostToDevice, ctx->compute));
+    CU(cudaMemsetAsync(dI, 0, (size_t) m * dStride, ctx->compute));
+    launch_op_genotype(P, dR, dL, dI, dStride, m, ctx->compute);
+    ctx->launches++;
+    // slot k & 1 was scattered (chunk k - 2) before chunk k - 1 was issued: it is free
+    CU(cudaMemcpyAsync(pin, dI, (size_t) m * dStride, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaEventRecord(ctx->opEv[k & 1], ctx->compute));
+    if (k >= 1) {
+      CU(cudaEventSynchronize(ctx->opEv[(k - 1) & 1]));
+      scatter(prevA, prevM, (const uint8_t *) ctx->opPin + (size_t) ((k - 1) & 1) * slotBytes);
+    }
+    prevA = a; prevM = m;
+  }
   CU(cudaStreamSynchronize(ctx->compute));
   CU(cudaGetLastError());
-  for (uint32_t i = 0; i < n; ++i) {          // scatter into SnpCallingInfo (SNP_Meta.h:115-125)
-    char *d = (char *) info + (size_t) i * info_stride;
-    const uint8_t *s = &hI[(size_t) i * dStride];
-    memcpy(d + 0, s + 0, 8);                  // pD
-    memcpy(d + 8, s + 8, 4);                  // genotype (secondGenotype @12 untouched)
-    memcpy(d + 16, s + 16, 128);              // flh
-    memcpy(d + 144, s + 144, 16);             // bestD, secondD (rfProb/rfMode untouched)
-  }
+  scatter(prevA, prevM, (const uint8_t *) ctx->opPin + (size_t) ((nChunks - 1) & 1) * slotBytes);
   return GT16_OK;
 }
 
@@ -481,20 +557,38 @@ int gt16_compute_bias(gt16_ctx *ctx, const void *w, const void *f, const void *r
   if (!ctx || !w || !f || !r || !sb || !bqb || stride < 16) return GT16_EINVAL;
   if (!n) return GT16_OK;
   CU(cudaSetDevice(ctx->device));
-  std::vector<uint32_t> buf((size_t) n * 12);
-  for (uint32_t i = 0; i < n; ++i) {
-    memcpy(&buf[(size_t) i * 12 + 0], (const char *) w + (size_t) i * stride, 16);
-    memcpy(&buf[(size_t) i * 12 + 4], (const char *) f + (size_t) i * stride, 16);
-    memcpy(&buf[(size_t) i * 12 + 8], (const char *) r + (size_t) i * stride, 16);
+  const uint32_t chunk = std::min(op_chunk_sites(), n);
+  const size_t slotBytes = (size_t) chunk * 48;           // W, F, R of a site side by side
+  CU(op_prepare(ctx, slotBytes, slotBytes, (size_t) chunk * 32));
+  uint8_t *d = (uint8_t *) ctx->opIn.p;
+  float *dS = (float *) ctx->opOut.p, *dB = dS + (size_t) chunk * 4;
+  const EvalParams P = eval_params(ctx);
+  auto gather = [&](uint32_t k) -> cudaError_t {
+    const uint32_t a = k * chunk, m = std::min(chunk, n - a);
+    uint8_t *pin = (uint8_t *) ctx->opPin + (size_t) (k & 1) * slotBytes;
+    if (k >= 2) { cudaError_t e = cudaEventSynchronize(ctx->opEv[k & 1]); if (e != cudaSuccess) return e; }
+    op_parallel(m, [=](uint32_t lo, uint32_t hi) {
+      for (uint32_t i = lo; i < hi; ++i) {
+        memcpy(pin + (size_t) i * 48 + 0, (const char *) w + (size_t) (a + i) * stride, 16);
+        memcpy(pin + (size_t) i * 48 + 16, (const char *) f + (size_t) (a + i) * stride, 16);
+        memcpy(pin + (size_t) i * 48 + 32, (const char *) r + (size_t) (a + i) * stride, 16);
+      }
+    });
+    return cudaSuccess;
+  };
+  const uint32_t nChunks = (n + chunk - 1) / chunk;
+  CU(gather(0));
+  for (uint32_t k = 0; k < nChunks; ++k) {
+    const uint32_t a = k * chunk, m = std::min(chunk, n - a);
+    const uint8_t *pin = (const uint8_t *) ctx->opPin + (size_t) (k & 1) * slotBytes;
+    CU(cudaMemcpyAsync(d, pin, (size_t) m * 48, cudaMemcpyHostToDevice, ctx->compute));
+    CU(cudaEventRecord(ctx->opEv[k & 1], ctx->compute));
+    launch_op_bias(P, d, d + 16, d + 32, 48, m, dS, dB, ctx->compute);
+    ctx->launches++;
+    if (k + 1 < nChunks) CU(gather(k + 1));
+    CU(cudaMemcpyAsync(sb + (size_t) a * 4, dS, (size_t) m * 16, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaMemcpyAsync(bqb + (size_t) a * 4, dB, (size_t) m * 16, cudaMemcpyDeviceToHost, ctx->compute));
   }
-  DevScratch sD, sS, sB;
-  CU(sD.alloc(buf.size() * 4)); CU(sS.alloc((size_t) n * 16)); CU(sB.alloc((size_t) n * 16));
-  uint8_t *d = sD.as<uint8_t>(); float *dS = sS.as<float>(), *dB = sB.as<float>();
-  CU(cudaMemcpyAsync(d, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
-  launch_op_bias(eval_params(ctx), d, d + 16, d + 32, 48, n, dS, dB, ctx->compute);
-  ctx->launches++;
-  CU(cudaMemcpyAsync(sb, dS, (size_t) n * 16, cudaMemcpyDeviceToHost, ctx->compute));
-  CU(cudaMemcpyAsync(bqb, dB, (size_t) n * 16, cudaMemcpyDeviceToHost, ctx->compute));
   CU(cudaStreamSynchronize(ctx->compute));
   CU(cudaGetLastError());
   return GT16_OK;

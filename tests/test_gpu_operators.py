@@ -86,6 +86,28 @@ def test_bias_operator_matches_reference(gpu_caller):
     assert np.array_equal(bqb.view(np.uint32), g["bqb"].view(np.uint32))
 
 
+@pytest.mark.parametrize("chunk,reps", [("700", 1), ("", 60)])
+def test_operator_seam_in_chunks(gpu_caller, monkeypatch, chunk, reps):
+    """The seam moves the sites through a two-slot page-locked ring in chunks (GT16_OP_CHUNK shrinks them so that 6,000
+    sites make 9 chunks with a ragged last one; 360,000 sites take two default chunks and the gather threads): results
+    equal to the reference's whatever the chunking."""
+    if chunk:
+        monkeypatch.setenv("GT16_OP_CHUNK", chunk)
+    g0 = np.load(os.path.join(T.GOLDEN, "operator_vectors.npz"))
+    g = {k: np.concatenate([g0[k]] * reps) for k in ("W", "ref", "lh", "flh", "pD", "bestD", "secondD", "genotype", "bias_W", "bias_F", "bias_R", "sb", "bqb")}
+    lh, flh, pD, best, second, gt = run_operator_seam(gpu_caller, g)
+    assert np.array_equal(gt, g["genotype"])
+    for got, name in ((lh, "lh"), (flh, "flh"), (pD, "pD"), (best, "bestD"), (second, "secondD")):
+        log_close(got, g[name])
+    m = len(g["bias_W"])
+    W, F, R = (np.ascontiguousarray(g[x]) for x in ("bias_W", "bias_F", "bias_R"))
+    sb = np.zeros((m, 4), dtype=np.float32); bqb = np.zeros((m, 4), dtype=np.float32)
+    gpu_caller.check(gpu_caller.L.gt16_compute_bias(gpu_caller.ctx, W.ctypes.data, F.ctypes.data, R.ctypes.data, 16, m,
+                                                    sb.ctypes.data, bqb.ctypes.data))
+    assert np.array_equal(sb.view(np.uint32), g["sb"].view(np.uint32))
+    assert np.array_equal(bqb.view(np.uint32), g["bqb"].view(np.uint32))
+
+
 def test_custom_prior_and_genotype_table(gpu_caller):
     """copySnpPriorToGPU / copyGenotypeTableToGPU are honoured (flat prior -> argmax of the likelihood)"""
     L = gpu_caller.L
