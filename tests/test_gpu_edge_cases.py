@@ -95,13 +95,14 @@ def test_batch_boundary_neighbourhood(gpu_caller, tmp_path):
         os.remove(out + ".snapshot")
 
 
-@pytest.mark.parametrize("mode", ["host", "resident", "device_nowait"])
-def test_more_candidates_than_the_record_bound(tmp_path, monkeypatch, mode):
+@pytest.mark.parametrize("name,mode", [("stress_small", "host"), ("stress_small", "resident"), ("stress_small", "device_nowait"),
+                                       ("two_batch", "host"), ("two_batch", "resident")])       # two_batch: several segments
+def test_more_candidates_than_the_record_bound(tmp_path, monkeypatch, name, mode):
     """Record buffers are sized by a bound; a call that finds more candidates is repeated once with buffers of the size it
     asked for (GT16_RECORD_BOUND shrinks the bound so that the small stress config overflows it): same .txt."""
     import ctypes
     monkeypatch.setenv("GT16_RECORD_BOUND", "1000000:24")
-    name = "stress_small"
+    monkeypatch.setenv("GT16_SEG_BATCHES", "1")
     idx, out, region = T.regenerate(name, tmp_path)
     rows = T.manifest()[name]["rows"]
     assert rows > 100
