@@ -13,6 +13,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <utility>
 #include <zlib.h>
 #include <vector>
 #include "../../include/gt16.h"
@@ -27,10 +28,20 @@ void set_err(char *err, size_t n, const char *fmt, ...) {
 }
 }  // namespace
 
+// vectors whose resize() leaves new elements unset (every one is written right after): growing a 150 MB array of bases
+// does not zero it first
+template <class T>
+struct DefaultInit : std::allocator<T> {
+  template <class U> struct rebind { using other = DefaultInit<U>; };
+  template <class U> void construct(U *p) noexcept { ::new ((void *) p) U; }
+  template <class U, class... A> void construct(U *p, A &&... a) { ::new ((void *) p) U(std::forward<A>(a)...); }
+};
+template <class T> using Vec = std::vector<T, DefaultInit<T> >;
+
 struct gt16_sam {
-  std::vector<uint32_t> start, length, nCigar, cigar;
-  std::vector<uint8_t> reverse, bases, quals;
-  std::vector<uint64_t> seqOff, cigarOff;
+  Vec<uint32_t> start, length, nCigar, cigar;
+  Vec<uint8_t> reverse, bases, quals;
+  Vec<uint64_t> seqOff, cigarOff;
   uint64_t total = 0;
 };
 
@@ -169,6 +180,11 @@ int gt16_sam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold
     std::vector<uint32_t> ops;
     std::string line;
     gt16_sam &P = part[t];
+    {                                                  // about half of a SAM file's bytes are SEQ and QUAL
+      const size_t slice = cut[t + 1] - cut[t];
+      P.bases.reserve(slice / 2); P.quals.reserve(slice / 2);
+      for (auto *v : {&P.start, &P.length, &P.nCigar}) v->reserve(slice / 160);
+    }
     for (size_t a = cut[t]; a < cut[t + 1];) {
       const char *nl = (const char *) memchr(data + a, '\n', cut[t + 1] - a);
       size_t b = nl ? (size_t) (nl - data) : cut[t + 1];
@@ -184,24 +200,30 @@ int gt16_sam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold
   for (auto &x : th) x.join();
   munmap((void *) data, size);
   for (unsigned t = 0; t < nt; ++t) if (!ok[t]) { delete S; set_err(err, errLen, "%s: alignment line with fewer than 11 fields", path); return GT16_EDATA; }
-  size_t nr = 0, nb = 0, nc = 0;
-  for (unsigned t = 0; t < nt; ++t) { nr += part[t].start.size(); nb += part[t].bases.size(); nc += part[t].cigar.size(); }
-  S->start.reserve(nr); S->reverse.reserve(nr); S->length.reserve(nr); S->seqOff.reserve(nr); S->cigarOff.reserve(nr); S->nCigar.reserve(nr);
-  S->bases.reserve(nb); S->quals.reserve(nb); S->cigar.reserve(nc);
+  if (nt == 1) { *S = std::move(part[0]); *out = S; return GT16_OK; }
+  // the lists are joined in file order: every thread copies its own list to its place in the whole
+  std::vector<size_t> r0(nt + 1, 0), b0(nt + 1, 0), c0(nt + 1, 0);
   for (unsigned t = 0; t < nt; ++t) {
-    const gt16_sam &P = part[t];
-    const uint64_t b0 = S->bases.size(), c0 = S->cigar.size();
-    S->total += P.total;
-    S->start.insert(S->start.end(), P.start.begin(), P.start.end());
-    S->reverse.insert(S->reverse.end(), P.reverse.begin(), P.reverse.end());
-    S->length.insert(S->length.end(), P.length.begin(), P.length.end());
-    S->nCigar.insert(S->nCigar.end(), P.nCigar.begin(), P.nCigar.end());
-    for (size_t i = 0; i < P.seqOff.size(); ++i) { S->seqOff.push_back(b0 + P.seqOff[i]); S->cigarOff.push_back(c0 + P.cigarOff[i]); }
-    S->bases.insert(S->bases.end(), P.bases.begin(), P.bases.end());
-    S->quals.insert(S->quals.end(), P.quals.begin(), P.quals.end());
-    S->cigar.insert(S->cigar.end(), P.cigar.begin(), P.cigar.end());
-    part[t] = gt16_sam();
+    r0[t + 1] = r0[t] + part[t].start.size(); b0[t + 1] = b0[t] + part[t].bases.size(); c0[t + 1] = c0[t] + part[t].cigar.size();
+    S->total += part[t].total;
   }
+  const size_t nr = r0[nt], nb = b0[nt], nc = c0[nt];
+  S->start.resize(nr); S->reverse.resize(nr); S->length.resize(nr); S->seqOff.resize(nr); S->cigarOff.resize(nr); S->nCigar.resize(nr);
+  S->bases.resize(nb); S->quals.resize(nb); S->cigar.resize(nc);
+  th.clear();
+  for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() {
+    gt16_sam &P = part[t];
+    const size_t n = P.start.size();
+    if (n) {
+      memcpy(&S->start[r0[t]], P.start.data(), n * 4); memcpy(&S->reverse[r0[t]], P.reverse.data(), n);
+      memcpy(&S->length[r0[t]], P.length.data(), n * 4); memcpy(&S->nCigar[r0[t]], P.nCigar.data(), n * 4);
+      for (size_t i = 0; i < n; ++i) { S->seqOff[r0[t] + i] = b0[t] + P.seqOff[i]; S->cigarOff[r0[t] + i] = c0[t] + P.cigarOff[i]; }
+    }
+    if (!P.bases.empty()) { memcpy(&S->bases[b0[t]], P.bases.data(), P.bases.size()); memcpy(&S->quals[b0[t]], P.quals.data(), P.quals.size()); }
+    if (!P.cigar.empty()) memcpy(&S->cigar[c0[t]], P.cigar.data(), P.cigar.size() * 4);
+    P = gt16_sam();
+  });
+  for (auto &x : th) x.join();
   *out = S;
   return GT16_OK;
 }
