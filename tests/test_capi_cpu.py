@@ -398,3 +398,44 @@ def test_snapshot_reader_survives_damaged_containers(tmp_path, name, monkeypatch
                 assert v.text_length > 0
                 L.gt16_snapshot_free(hs)
     assert 0 in outcomes and (-4 in outcomes or -5 in outcomes)
+
+
+def test_sam_slices_joined_in_file_order(tmp_path):
+    """A SAM file of more than 4 MB is parsed in slices by several threads and the lists are joined in parallel: the
+    reads equal those of the serial BAM reader on the same alignments, in the same order."""
+    import random
+    idx, out, region = T.regenerate("wgs_small", tmp_path)
+    L = T.capi()
+    err = ctypes.create_string_buffer(256)
+    ix = ctypes.c_void_p()
+    assert L.gt16_index_read(idx.encode(), ctypes.byref(ix), err, 256) == 0
+    rng = random.Random(3)
+    sam = tmp_path / "big.sam"
+    cigars = ["100M", "10S90M", "40M3I57M", "50M2D50M", "30M1I20M4D49M", "95M5S"]
+    with open(sam, "w") as f:
+        f.write("@SQ\tSN:chrA\tLN:180000\n@SQ\tSN:chrB\tLN:70000\n")
+        for i in range(22000):
+            seq = "".join(rng.choice("ACGT") for _ in range(100))
+            qual = "".join(chr(33 + rng.randrange(2, 41)) for _ in range(100))
+            contig, span = ("chrA", 179000) if i % 3 else ("chrB", 69000)
+            f.write("r%d\t%d\t%s\t%d\t%d\t%s\t*\t0\t0\t%s\t%s\n" % (i, rng.choice([0, 16, 0x400]), contig, rng.randrange(1, span),
+                                                                    rng.choice([0, 20, 60]), cigars[i % len(cigars)], seq, qual))
+    assert os.path.getsize(sam) > (4 << 20)
+    bam = tmp_path / "big.bam"
+    T.sam_to_bam(str(sam), str(bam))
+    hs, hb = ctypes.c_void_p(), ctypes.c_void_p()
+    assert L.gt16_sam_read(str(sam).encode(), ix, 10, ctypes.byref(hs), err, 256) == 0, err.value
+    assert L.gt16_bam_read(str(bam).encode(), ix, 10, ctypes.byref(hb), err, 256) == 0, err.value
+    rs, rb = T.capi_mod.Reads(), T.capi_mod.Reads()
+    L.gt16_sam_reads(hs, ctypes.byref(rs)); L.gt16_sam_reads(hb, ctypes.byref(rb))
+    n = int(rs.n_reads)
+    assert n > 5000 and n == rb.n_reads and rs.n_bases == rb.n_bases and rs.n_cigar_ops == rb.n_cigar_ops
+    assert L.gt16_sam_total_alignments(hs) == L.gt16_sam_total_alignments(hb) == 22000
+    for field, ct, k in (("start", ctypes.c_uint32, n), ("reverse", ctypes.c_uint8, n), ("length", ctypes.c_uint32, n),
+                         ("seq_off", ctypes.c_uint64, n), ("cigar_off", ctypes.c_uint64, n), ("n_cigar", ctypes.c_uint32, n),
+                         ("bases", ctypes.c_uint8, int(rs.n_bases)), ("quals", ctypes.c_uint8, int(rs.n_bases)),
+                         ("cigar", ctypes.c_uint32, int(rs.n_cigar_ops))):
+        a = np.ctypeslib.as_array(ctypes.cast(getattr(rs, field), ctypes.POINTER(ct)), (k,))
+        b = np.ctypeslib.as_array(ctypes.cast(getattr(rb, field), ctypes.POINTER(ct)), (k,))
+        assert np.array_equal(a, b), field
+    L.gt16_sam_free(hs); L.gt16_sam_free(hb); L.gt16_index_free(ix)
