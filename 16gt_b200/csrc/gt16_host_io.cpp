@@ -131,6 +131,11 @@ struct gt16_index {
   std::vector<std::string> names;          // annotation[i].text
   struct Tr { uint32_t startPos; uint16_t chrID; uint32_t correction; };
   std::vector<Tr> translate;               // HSP.translate
+  // gt16_index_locate_id is called once per read by the SAM / BAM readers: when the table is laid out the way the index
+  // builder writes it (a chromosome's entries side by side, in ascending order) the entry is found by bisection
+  std::vector<uint32_t> chrLo, chrHi;      // translate[chrLo[id] .. chrHi[id]) belong to chromosome id
+  std::vector<uint32_t> chrBegin;          // chromosome position (1-based) at which entry k begins: startPos - correction
+  bool bisect = false;
   bool pinned = false;                     // packed[] is page-locked (gt16_index_pin)
 };
 
@@ -337,6 +342,33 @@ int gt16_index_read(const char *prefix, gt16_index **out, char *err, size_t errL
     }
     fclose(f);
     if (!ok || ix->translate.empty()) { set_err(err, errLen, "%s.tra: truncated", prefix); rc = GT16_EDATA; break; }
+    {
+      // bisection gives the scan's answer when (a) a chromosome's entries are contiguous, (b) they begin at ascending
+      // chromosome positions and (c) the chromosome positions between two entries' beginnings are at least as many as
+      // the first one's bases (removed stretches only ever add to the gap): then no earlier entry can match a position
+      // at or behind a later entry's beginning
+      const size_t n = ix->translate.size();
+      unsigned maxId = 0;
+      for (const auto &t : ix->translate) maxId = std::max<unsigned>(maxId, t.chrID);
+      ix->chrLo.assign(maxId + 1, 0); ix->chrHi.assign(maxId + 1, 0); ix->chrBegin.resize(n);
+      std::vector<char> seen(maxId + 1, 0);
+      bool good = true;
+      for (size_t k = 0; k < n && good; ++k) {
+        const gt16_index::Tr &t = ix->translate[k];
+        ix->chrBegin[k] = t.startPos - t.correction;
+        if (k && ix->translate[k - 1].chrID == t.chrID) {
+          const gt16_index::Tr &q = ix->translate[k - 1];
+          good = t.startPos >= q.startPos && ix->chrBegin[k] >= ix->chrBegin[k - 1] &&
+                 ix->chrBegin[k] - ix->chrBegin[k - 1] >= t.startPos - q.startPos;
+        } else {
+          if (seen[t.chrID]) good = false;
+          seen[t.chrID] = 1;
+          ix->chrLo[t.chrID] = (uint32_t) k;
+        }
+        ix->chrHi[t.chrID] = (uint32_t) k + 1;
+      }
+      ix->bisect = good;
+    }
     // .pac: 4 bases / byte, first base in bits 7..6; trailing byte = length % 4
     // read straight into the word array (parallel pread), then swap each word's bytes in place: base 0 of a word
     // ends up in bits 31..30
@@ -415,6 +447,16 @@ int gt16_index_sequence_id(const gt16_index *ix, const char *chrName) {
 int gt16_index_locate_id(const gt16_index *ix, int chrID, uint32_t chrPos, uint32_t *amb) {
   if (!ix || !amb || chrID < 1) return -1;
   // getAmbPos: the concatenated position whose translation is (chrID, chrPos)
+  if (ix->bisect && (size_t) chrID < ix->chrLo.size() && ix->chrHi[chrID] > ix->chrLo[chrID]) {
+    const uint32_t *b = ix->chrBegin.data();
+    const size_t k = (size_t) (std::upper_bound(b + ix->chrLo[chrID], b + ix->chrHi[chrID], chrPos) - b);
+    if (k == ix->chrLo[chrID]) return -1;                      // in front of the chromosome's first entry
+    const gt16_index::Tr &t = ix->translate[k - 1];
+    const uint32_t a = chrPos + t.correction;
+    const uint64_t next = k < ix->translate.size() ? ix->translate[k].startPos : (uint64_t) ix->length;
+    if (a >= t.startPos && (uint64_t) a < next && a < ix->length) { *amb = a; return 0; }
+    return -1;
+  }
   for (size_t k = 0; k < ix->translate.size(); ++k) {
     const gt16_index::Tr &t = ix->translate[k];
     if ((int) t.chrID != chrID) continue;

@@ -10,6 +10,8 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <algorithm>
+#include <atomic>
+#include <future>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -232,12 +234,126 @@ int gt16_sam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold
 // BGZF is a series of gzip members; zlib inflates them one after the other.  The decompressed stream: "BAM\1", header
 // text, reference names, then the alignment records bamToAlignment looks at (SAM specification, section 4.2).
 namespace {
+// A BGZF file is a series of independent gzip members of at most 64 KB, each with its total size in a "BC" extra field:
+// the members of a batch (up to 256 MB of output) are inflated by all the host's threads at once while the batch before
+// it is being parsed.  A gzip stream without the fields (a BAM written by something else than bgzf) goes through one
+// streaming inflate instead.
+struct BgzfBatch {
+  Vec<uint8_t> data;
+  bool corruptBehind = false;      // the stream is damaged right behind these bytes
+};
+struct BgzfBlock { size_t off, size, out; uint32_t isize; };
+
 struct BgzfReader {
+  bool eof = false, bad = false, open = false;
+  // streaming
   FILE *f = nullptr;
   z_stream z;
   std::vector<uint8_t> in;
-  bool eof = false, bad = false, open = false;
+  // member by member, in parallel
+  const uint8_t *map = nullptr;
+  size_t mapSize = 0, nextOff = 0;
+  bool parallel = false, scanBad = false;
+  BgzfBatch cur;
+  size_t curPos = 0;
+  std::future<BgzfBatch> ahead;
+  static const size_t kBatchBytes = (size_t) 256 << 20;
+
+  // total size of the member at `o` when it carries a BC field and lies inside the file, else 0
+  static size_t member_size(const uint8_t *m, size_t size, size_t o) {
+    if (o + 18 > size || m[o] != 0x1f || m[o + 1] != 0x8b || m[o + 2] != 8 || !(m[o + 3] & 4)) return 0;
+    const size_t xlen = (size_t) m[o + 10] | ((size_t) m[o + 11] << 8);
+    if (o + 12 + xlen > size) return 0;
+    for (size_t s = o + 12; s + 4 <= o + 12 + xlen;) {
+      const size_t slen = (size_t) m[s + 2] | ((size_t) m[s + 3] << 8);
+      if (m[s] == 'B' && m[s + 1] == 'C' && slen == 2 && s + 6 <= o + 12 + xlen) {
+        const size_t total = ((size_t) m[s + 4] | ((size_t) m[s + 5] << 8)) + 1;
+        return total >= 12 + xlen + 8 && o + total <= size ? total : 0;
+      }
+      s += 4 + slen;
+    }
+    return 0;
+  }
+  // the members of the next batch, from nextOff on
+  std::vector<BgzfBlock> scan() {
+    std::vector<BgzfBlock> blocks;
+    size_t out = 0;
+    while (nextOff < mapSize && out < kBatchBytes) {
+      const size_t total = member_size(map, mapSize, nextOff);
+      uint32_t isize = 0;
+      if (total) memcpy(&isize, map + nextOff + total - 4, 4);
+      if (!total || isize > 65536u) { scanBad = true; break; }
+      blocks.push_back(BgzfBlock{nextOff, total, out, isize});
+      out += isize;
+      nextOff += total;
+    }
+    return blocks;
+  }
+  static BgzfBatch inflate_batch(const uint8_t *m, std::vector<BgzfBlock> blocks, bool corruptBehind) {
+    BgzfBatch B;
+    B.corruptBehind = corruptBehind;
+    const size_t total = blocks.empty() ? 0 : blocks.back().out + blocks.back().isize;
+    B.data.resize(total);
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = std::max(1u, std::min(32u, nt ? nt : 4u));
+    if (blocks.size() < 64) nt = 1;
+    std::atomic<size_t> next(0), firstBad(blocks.size());
+    auto work = [&]() {
+      z_stream zs;
+      memset(&zs, 0, sizeof(zs));
+      if (inflateInit2(&zs, 15 + 16) != Z_OK) { firstBad = 0; return; }
+      for (;;) {
+        const size_t k0 = next.fetch_add(16);
+        if (k0 >= blocks.size()) break;
+        for (size_t k = k0; k < std::min(blocks.size(), k0 + 16); ++k) {
+          const BgzfBlock &b = blocks[k];
+          zs.next_in = (Bytef *) (m + b.off); zs.avail_in = (uInt) b.size;
+          zs.next_out = B.data.data() + b.out; zs.avail_out = b.isize;
+          const int rc = inflate(&zs, Z_FINISH);                   // the gzip wrapper checks CRC32 and ISIZE
+          if (rc != Z_STREAM_END || zs.avail_out != 0) { size_t seen = firstBad.load(); while (k < seen && !firstBad.compare_exchange_weak(seen, k)) {} }
+          inflateReset(&zs);
+        }
+      }
+      inflateEnd(&zs);
+    };
+    if (nt == 1) work();
+    else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; ++t) th.emplace_back(work);
+      for (auto &x : th) x.join();
+    }
+    if (firstBad.load() < blocks.size()) {                          // bytes up to the first damaged member are good
+      B.data.resize(blocks[firstBad.load()].out);
+      B.corruptBehind = true;
+    }
+    return B;
+  }
+  void launch_ahead() {
+    if (scanBad || nextOff >= mapSize) return;
+    std::vector<BgzfBlock> blocks = scan();
+    if (blocks.empty() && !scanBad) return;
+    ahead = std::async(std::launch::async, inflate_batch, map, std::move(blocks), scanBad);
+  }
+
   bool start(const char *path) {
+    int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) == 0 && st.st_size > 0) {
+      void *m = mmap(nullptr, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m != MAP_FAILED) {
+        map = (const uint8_t *) m; mapSize = (size_t) st.st_size;
+        if (member_size(map, mapSize, 0)) {
+          ::close(fd);
+          madvise(m, mapSize, MADV_SEQUENTIAL);
+          parallel = true; open = true;
+          launch_ahead();
+          return true;
+        }
+        munmap(m, mapSize); map = nullptr;
+      }
+    }
+    ::close(fd);
     f = fopen(path, "rb");
     if (!f) return false;
     in.resize(1u << 20);
@@ -248,6 +364,23 @@ struct BgzfReader {
   }
   // exactly n bytes, false at a clean end of file (with none read) or on error (bad set)
   bool get(void *dst, size_t n) {
+    if (parallel) {
+      size_t done = 0;
+      while (done < n) {
+        if (curPos == cur.data.size()) {
+          if (cur.corruptBehind) { bad = true; return false; }
+          if (!ahead.valid()) { if (done) bad = true; return false; }
+          cur = ahead.get();
+          curPos = 0;
+          launch_ahead();
+          continue;
+        }
+        const size_t k = std::min(n - done, cur.data.size() - curPos);
+        memcpy((char *) dst + done, cur.data.data() + curPos, k);
+        done += k; curPos += k;
+      }
+      return true;
+    }
     z.next_out = (Bytef *) dst;
     z.avail_out = (uInt) n;
     while (z.avail_out) {
@@ -263,7 +396,12 @@ struct BgzfReader {
     }
     return true;
   }
-  ~BgzfReader() { if (open) inflateEnd(&z); if (f) fclose(f); }
+  ~BgzfReader() {
+    if (ahead.valid()) ahead.wait();
+    if (parallel) { if (map) munmap((void *) map, mapSize); }
+    else if (open) inflateEnd(&z);
+    if (f) fclose(f);
+  }
 };
 }  // namespace
 

@@ -439,3 +439,56 @@ def test_sam_slices_joined_in_file_order(tmp_path):
         b = np.ctypeslib.as_array(ctypes.cast(getattr(rb, field), ctypes.POINTER(ct)), (k,))
         assert np.array_equal(a, b), field
     L.gt16_sam_free(hs); L.gt16_sam_free(hb); L.gt16_index_free(ix)
+
+
+def test_coordinate_translation_with_removed_stretches(tmp_path):
+    """gt16_index_locate (getAmbPos, indexFunction.cpp) finds a read's translate entry by bisection: same answers as the
+    reference's scan over the whole table, on a table with removed stretches inside the chromosomes -- and on a table
+    whose entries are out of order, where the scan itself is used."""
+    import random
+    import shutil
+    idx, out, region = T.regenerate("wgs_small", tmp_path)
+    L = T.capi()
+    head = open(idx + ".tra").read().split("\n")
+    tl, ns, removed, grid = (int(x) for x in head[0].split())
+    assert (tl, ns, removed) == (250000, 2, 0)
+    # (startPos, chrID, correction): chrA loses 1,000 positions before amb 50,000 and 500 before amb 120,000; chrB (from amb
+    # 180,000) loses 250 before amb 200,000
+    entries = [(0, 1, 0xFFFFFFFF), (50000, 1, 0xFFFFFFFF - 1000), (120000, 1, 0xFFFFFFFF - 1500),
+               (180000, 2, 179999), (200000, 2, 179999 - 250)]
+
+    def scan(table, chr_id, pos):                      # the reference's rule, entry by entry
+        for k, (sp, c, corr) in enumerate(table):
+            if c != chr_id:
+                continue
+            a = (pos + corr) & 0xFFFFFFFF
+            nxt = table[k + 1][0] if k + 1 < len(table) else tl
+            if sp <= a < nxt and a < tl:
+                return a
+        return None
+
+    rng = random.Random(2)
+    for label, table in (("ordered", entries), ("shuffled", [entries[3], entries[0], entries[1], entries[4], entries[2]])):
+        pre = str(tmp_path / ("idx_" + label))
+        for ext in (".pac", ".ann"):
+            shutil.copy(idx + ext, pre + ext)
+        with open(pre + ".tra", "w") as f:
+            f.write("%d %d %d %d\n" % (tl, ns, len(table) - ns, grid))
+            f.write("\n".join(head[1:1 + grid]) + "\n")
+            for sp, c, corr in table:
+                f.write("%d %d %d\n" % (sp, c, corr))
+        err = ctypes.create_string_buffer(256)
+        ix = ctypes.c_void_p()
+        assert L.gt16_index_read(pre.encode(), ctypes.byref(ix), err, 256) == 0, err.value
+        amb = ctypes.c_uint32()
+        probes = [(c, p) for c in (1, 2) for p in (0, 1, 2, 49999, 50000, 50001, 51000, 51001, 119999, 121499, 121500, 121501, 181500, 181501,
+                                                    19999, 20000, 20001, 20250, 20251, 70000, 70250, 70251, 0xFFFFFFFF)]
+        probes += [(rng.choice([1, 2, 3]), rng.randrange(0, 200000)) for _ in range(20000)]
+        hits = 0
+        for c, p in probes:
+            rc = L.gt16_index_locate_id(ix, c, p, ctypes.byref(amb))
+            want = scan(table, c, p)
+            assert (rc == 0) == (want is not None) and (want is None or amb.value == want), (label, c, p, rc, amb.value, want)
+            hits += rc == 0
+        assert hits > 5000
+        L.gt16_index_free(ix)
