@@ -149,6 +149,42 @@ static bool parse_alignment(char *line, const gt16_index *ix, uint32_t L, uint32
   return true;
 }
 
+// Lists parsed by different threads, joined in order: every list is copied to its place in the whole by some thread.
+static void join_parts(std::vector<gt16_sam> &part, gt16_sam *S) {
+  const size_t np = part.size();
+  if (np == 1) { *S = std::move(part[0]); return; }
+  std::vector<size_t> r0(np + 1, 0), b0(np + 1, 0), c0(np + 1, 0);
+  for (size_t t = 0; t < np; ++t) {
+    r0[t + 1] = r0[t] + part[t].start.size(); b0[t + 1] = b0[t] + part[t].bases.size(); c0[t + 1] = c0[t] + part[t].cigar.size();
+    S->total += part[t].total;
+  }
+  const size_t nr = r0[np], nb = b0[np], nc = c0[np];
+  S->start.resize(nr); S->reverse.resize(nr); S->length.resize(nr); S->seqOff.resize(nr); S->cigarOff.resize(nr); S->nCigar.resize(nr);
+  S->bases.resize(nb); S->quals.resize(nb); S->cigar.resize(nc);
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = (unsigned) std::max<size_t>(1, std::min<size_t>(std::min(16u, nt ? nt : 4u), np));
+  std::atomic<size_t> next(0);
+  auto work = [&]() {
+    for (;;) {
+      const size_t t = next.fetch_add(1);
+      if (t >= np) break;
+      gt16_sam &P = part[t];
+      const size_t n = P.start.size();
+      if (n) {
+        memcpy(&S->start[r0[t]], P.start.data(), n * 4); memcpy(&S->reverse[r0[t]], P.reverse.data(), n);
+        memcpy(&S->length[r0[t]], P.length.data(), n * 4); memcpy(&S->nCigar[r0[t]], P.nCigar.data(), n * 4);
+        for (size_t i = 0; i < n; ++i) { S->seqOff[r0[t] + i] = b0[t] + P.seqOff[i]; S->cigarOff[r0[t] + i] = c0[t] + P.cigarOff[i]; }
+      }
+      if (!P.bases.empty()) { memcpy(&S->bases[b0[t]], P.bases.data(), P.bases.size()); memcpy(&S->quals[b0[t]], P.quals.data(), P.quals.size()); }
+      if (!P.cigar.empty()) memcpy(&S->cigar[c0[t]], P.cigar.data(), P.cigar.size() * 4);
+      P = gt16_sam();
+    }
+  };
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t) th.emplace_back(work);
+  for (auto &x : th) x.join();
+}
+
 // The file is mapped and cut into slices at line ends; worker threads parse their slices into lists of their own, which
 // are then joined in file order (the order of the reads decides which of two indel patterns is listed first).
 int gt16_sam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold, gt16_sam **out, char *err, size_t errLen) {
@@ -202,30 +238,7 @@ int gt16_sam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold
   for (auto &x : th) x.join();
   munmap((void *) data, size);
   for (unsigned t = 0; t < nt; ++t) if (!ok[t]) { delete S; set_err(err, errLen, "%s: alignment line with fewer than 11 fields", path); return GT16_EDATA; }
-  if (nt == 1) { *S = std::move(part[0]); *out = S; return GT16_OK; }
-  // the lists are joined in file order: every thread copies its own list to its place in the whole
-  std::vector<size_t> r0(nt + 1, 0), b0(nt + 1, 0), c0(nt + 1, 0);
-  for (unsigned t = 0; t < nt; ++t) {
-    r0[t + 1] = r0[t] + part[t].start.size(); b0[t + 1] = b0[t] + part[t].bases.size(); c0[t + 1] = c0[t] + part[t].cigar.size();
-    S->total += part[t].total;
-  }
-  const size_t nr = r0[nt], nb = b0[nt], nc = c0[nt];
-  S->start.resize(nr); S->reverse.resize(nr); S->length.resize(nr); S->seqOff.resize(nr); S->cigarOff.resize(nr); S->nCigar.resize(nr);
-  S->bases.resize(nb); S->quals.resize(nb); S->cigar.resize(nc);
-  th.clear();
-  for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() {
-    gt16_sam &P = part[t];
-    const size_t n = P.start.size();
-    if (n) {
-      memcpy(&S->start[r0[t]], P.start.data(), n * 4); memcpy(&S->reverse[r0[t]], P.reverse.data(), n);
-      memcpy(&S->length[r0[t]], P.length.data(), n * 4); memcpy(&S->nCigar[r0[t]], P.nCigar.data(), n * 4);
-      for (size_t i = 0; i < n; ++i) { S->seqOff[r0[t] + i] = b0[t] + P.seqOff[i]; S->cigarOff[r0[t] + i] = c0[t] + P.cigarOff[i]; }
-    }
-    if (!P.bases.empty()) { memcpy(&S->bases[b0[t]], P.bases.data(), P.bases.size()); memcpy(&S->quals[b0[t]], P.quals.data(), P.quals.size()); }
-    if (!P.cigar.empty()) memcpy(&S->cigar[c0[t]], P.cigar.data(), P.cigar.size() * 4);
-    P = gt16_sam();
-  });
-  for (auto &x : th) x.join();
+  join_parts(part, S);
   *out = S;
   return GT16_OK;
 }
@@ -257,7 +270,7 @@ struct BgzfReader {
   BgzfBatch cur;
   size_t curPos = 0;
   std::future<BgzfBatch> ahead;
-  static const size_t kBatchBytes = (size_t) 256 << 20;
+  size_t batchBytes = (size_t) 256 << 20;              // GT16_BGZF_BATCH: test hook (small batches: records straddle them)
 
   // total size of the member at `o` when it carries a BC field and lies inside the file, else 0
   static size_t member_size(const uint8_t *m, size_t size, size_t o) {
@@ -278,7 +291,7 @@ struct BgzfReader {
   std::vector<BgzfBlock> scan() {
     std::vector<BgzfBlock> blocks;
     size_t out = 0;
-    while (nextOff < mapSize && out < kBatchBytes) {
+    while (nextOff < mapSize && out < batchBytes) {
       const size_t total = member_size(map, mapSize, nextOff);
       uint32_t isize = 0;
       if (total) memcpy(&isize, map + nextOff + total - 4, 4);
@@ -347,6 +360,7 @@ struct BgzfReader {
           ::close(fd);
           madvise(m, mapSize, MADV_SEQUENTIAL);
           parallel = true; open = true;
+          if (const char *e = getenv("GT16_BGZF_BATCH")) { const long v = atol(e); if (v >= 1) batchBytes = (size_t) v; }
           launch_ahead();
           return true;
         }
@@ -360,6 +374,20 @@ struct BgzfReader {
     memset(&z, 0, sizeof(z));
     if (inflateInit2(&z, 15 + 16) != Z_OK) return false;      // gzip wrapper
     open = true;
+    return true;
+  }
+  // (parallel mode) the unread rest of the current batch, else the whole next batch; false at the end of the file or
+  // at a damaged member (bad set).  The bytes stay where they are until the next call.
+  bool span(const uint8_t **p, size_t *n) {
+    while (curPos == cur.data.size()) {
+      if (cur.corruptBehind) { bad = true; return false; }
+      if (!ahead.valid()) return false;
+      cur = ahead.get();
+      curPos = 0;
+      launch_ahead();
+    }
+    *p = cur.data.data() + curPos; *n = cur.data.size() - curPos;
+    curPos = cur.data.size();
     return true;
   }
   // exactly n bytes, false at a clean end of file (with none read) or on error (bad set)
@@ -405,6 +433,56 @@ struct BgzfReader {
 };
 }  // namespace
 
+// One alignment record (without its block_size field) into S the way bamToAlignment / updateSnapshotForFile see it;
+// false when the record's own sizes do not fit into it.
+struct BamRecordParser {
+  const gt16_index *ix;
+  uint32_t L, mapqThreshold;
+  const int *chrId;                  // reference id of the BAM -> chromosome id of the index (chrIdMap, bam2snapshot.cpp:157-158), -1: none
+  int32_t nRef;
+  bool operator()(const uint8_t *rec, size_t size, gt16_sam *S) const {
+    static const uint8_t code[16] = {0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 2};   // bamcode2snpcode, bam2snapshot.h:52-58
+    S->total++;
+    int32_t tid, pos, lSeq;
+    memcpy(&tid, &rec[0], 4); memcpy(&pos, &rec[4], 4);
+    const uint32_t lName = rec[8], mapq = rec[9];
+    uint16_t nCig, flag;
+    memcpy(&nCig, &rec[12], 2); memcpy(&flag, &rec[14], 2); memcpy(&lSeq, &rec[16], 4);
+    const size_t need = 32 + (size_t) lName + (size_t) nCig * 4 + ((size_t) (lSeq > 0 ? lSeq : 0) + 1) / 2 + (size_t) (lSeq > 0 ? lSeq : 0);
+    if (need > size) return false;
+    if (mapq < mapqThreshold) return true;                                        // bam2snapshot.cpp:84-87
+    if (tid < 0 || tid >= nRef || pos < 0 || pos == INT32_MAX) return true;       // :91-94
+    if (flag & 0x400) return true;                                                // :171-174
+    if (lSeq <= 0) return true;                                                   // :181
+    const uint8_t *cig = &rec[32 + lName], *seq = cig + (size_t) nCig * 4, *qual = seq + ((size_t) lSeq + 1) / 2;
+    size_t fromCigar = 0;
+    for (uint32_t c = 0; c < nCig; ++c) {
+      uint32_t v; memcpy(&v, cig + 4 * c, 4);
+      const uint32_t op = v & 15u;
+      if (op == 0 || op == 1 || op == 4) fromCigar += v >> 4;                     // getLenFromCigar (:55-77)
+    }
+    if (!nCig || fromCigar != (size_t) lSeq) return true;                         // :181-188
+    uint32_t amb;
+    if (chrId[tid] < 1 || gt16_index_locate_id(ix, chrId[tid], (uint32_t) pos + 1, &amb) != 0 || amb >= L) return true;
+    S->start.push_back(amb);
+    S->reverse.push_back((flag & 16) ? 1 : 0);
+    S->length.push_back((uint32_t) lSeq);
+    S->seqOff.push_back(S->bases.size());
+    S->cigarOff.push_back(S->cigar.size());
+    S->nCigar.push_back(nCig);
+    const size_t c0 = S->cigar.size();
+    S->cigar.resize(c0 + nCig);
+    memcpy(S->cigar.data() + c0, cig, (size_t) nCig * 4);
+    const size_t at = S->bases.size();
+    S->bases.resize(at + (size_t) lSeq); S->quals.resize(at + (size_t) lSeq);
+    uint8_t *bo = S->bases.data() + at;
+    for (int32_t k = 0; k + 1 < lSeq; k += 2) { const uint8_t b = seq[k >> 1]; bo[k] = code[b >> 4]; bo[k + 1] = code[b & 15u]; }   // bam1_seqi
+    if (lSeq & 1) bo[lSeq - 1] = code[seq[(lSeq - 1) >> 1] >> 4];
+    memcpy(S->quals.data() + at, qual, (size_t) lSeq);
+    return true;
+  }
+};
+
 int gt16_bam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold, gt16_sam **out, char *err, size_t errLen) {
   if (!path || !ix || !out) return GT16_EINVAL;
   BgzfReader R;
@@ -434,58 +512,95 @@ int gt16_bam_read(const char *path, const gt16_index *ix, uint32_t mapqThreshold
     names.push_back(std::string(nm.data(), strnlen(nm.data(), (size_t) lName)));
     chrId.push_back(0);
   }
+  for (int32_t r = 0; r < nRef; ++r) { const int id = gt16_index_sequence_id(ix, names[r].c_str()); chrId[r] = id < 1 ? -1 : id; }
+  const BamRecordParser parse{ix, gt16_index_length(ix), mapqThreshold, chrId.data(), nRef};
   gt16_sam *S = new gt16_sam();
-  const uint32_t L = gt16_index_length(ix);
-  static const uint8_t code[16] = {0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 2};   // bamcode2snpcode, bam2snapshot.h:52-58
-  std::vector<uint8_t> rec;
-  for (;;) {
-    int32_t blockSize = 0;
-    if (!R.get(&blockSize, 4)) { if (R.bad) { delete S; return fail("corrupt BGZF stream"); } break; }
-    if (blockSize < 32) { delete S; return fail("bad alignment record"); }
-    rec.clear();
-    for (size_t left = (size_t) blockSize; left;) {             // in steps: a damaged size does not reserve 2 GB
-      const size_t k = std::min<size_t>(left, 1u << 20), at = rec.size();
-      rec.resize(at + k);
-      if (!R.get(rec.data() + at, k)) { delete S; return fail("truncated alignment record"); }
-      left -= k;
+  if (!R.parallel) {                                            // one streaming inflate: record after record
+    std::vector<uint8_t> rec;
+    for (;;) {
+      int32_t blockSize = 0;
+      if (!R.get(&blockSize, 4)) { if (R.bad) { delete S; return fail("corrupt BGZF stream"); } break; }
+      if (blockSize < 32) { delete S; return fail("bad alignment record"); }
+      rec.clear();
+      for (size_t left = (size_t) blockSize; left;) {           // in steps: a damaged size does not reserve 2 GB
+        const size_t k = std::min<size_t>(left, 1u << 20), at = rec.size();
+        rec.resize(at + k);
+        if (!R.get(rec.data() + at, k)) { delete S; return fail("truncated alignment record"); }
+        left -= k;
+      }
+      if (!parse(rec.data(), rec.size(), S)) { delete S; return fail("bad alignment record"); }
     }
-    S->total++;
-    int32_t tid, pos, lSeq;
-    memcpy(&tid, &rec[0], 4); memcpy(&pos, &rec[4], 4);
-    const uint32_t lName = rec[8], mapq = rec[9];
-    uint16_t nCig, flag;
-    memcpy(&nCig, &rec[12], 2); memcpy(&flag, &rec[14], 2); memcpy(&lSeq, &rec[16], 4);
-    const size_t need = 32 + (size_t) lName + (size_t) nCig * 4 + ((size_t) (lSeq > 0 ? lSeq : 0) + 1) / 2 + (size_t) (lSeq > 0 ? lSeq : 0);
-    if (need > rec.size()) { delete S; return fail("bad alignment record"); }
-    if (mapq < mapqThreshold) continue;                                           // bam2snapshot.cpp:84-87
-    if (tid < 0 || tid >= nRef || pos < 0 || pos == INT32_MAX) continue;          // :91-94
-    if (flag & 0x400) continue;                                                   // :171-174
-    if (lSeq <= 0) continue;                                                      // :181
-    const uint8_t *cig = &rec[32 + lName], *seq = cig + (size_t) nCig * 4, *qual = seq + ((size_t) lSeq + 1) / 2;
-    size_t fromCigar = 0;
-    for (uint32_t c = 0; c < nCig; ++c) {
-      uint32_t v; memcpy(&v, cig + 4 * c, 4);
-      const uint32_t op = v & 15u;
-      if (op == 0 || op == 1 || op == 4) fromCigar += v >> 4;                     // getLenFromCigar (:55-77)
-    }
-    if (!nCig || fromCigar != (size_t) lSeq) continue;                            // :181-188
-    if (!chrId[tid]) { const int id = gt16_index_sequence_id(ix, names[tid].c_str()); chrId[tid] = id < 1 ? -1 : id; }
-    uint32_t amb;
-    if (chrId[tid] < 1 || gt16_index_locate_id(ix, chrId[tid], (uint32_t) pos + 1, &amb) != 0 || amb >= L) continue;
-    S->start.push_back(amb);
-    S->reverse.push_back((flag & 16) ? 1 : 0);
-    S->length.push_back((uint32_t) lSeq);
-    S->seqOff.push_back(S->bases.size());
-    S->cigarOff.push_back(S->cigar.size());
-    S->nCigar.push_back(nCig);
-    for (uint32_t c = 0; c < nCig; ++c) { uint32_t v; memcpy(&v, cig + 4 * c, 4); S->cigar.push_back(v); }
-    const size_t at = S->bases.size();
-    S->bases.resize(at + (size_t) lSeq); S->quals.resize(at + (size_t) lSeq);
-    for (int32_t k = 0; k < lSeq; ++k) {
-      S->bases[at + k] = code[(seq[k >> 1] >> ((~k & 1) << 2)) & 15u];            // bam1_seqi
-      S->quals[at + k] = qual[k];
-    }
+    *out = S;
+    return GT16_OK;
   }
+  // BGZF: what a batch of members inflates to is cut at record boundaries (a hop from size field to size field) and the
+  // records are parsed by several threads into lists of their own, joined in file order at the end; a record that
+  // straddles two batches is put together in `carry`
+  std::vector<gt16_sam> parts;
+  Vec<uint8_t> carry;
+  std::vector<size_t> starts;
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::max(1u, std::min(16u, nt ? nt : 4u));
+  const uint8_t *p = nullptr;
+  size_t n = 0;
+  bool malformed = false;
+  while (!malformed && R.span(&p, &n)) {
+    size_t pos = 0;
+    if (!carry.empty()) {                                       // finish the record the last batch ended in
+      while (carry.size() < 4 && pos < n) carry.push_back(p[pos++]);
+      if (carry.size() < 4) continue;
+      int32_t blockSize;
+      memcpy(&blockSize, carry.data(), 4);
+      if (blockSize < 32) { malformed = true; break; }
+      const size_t want = 4 + (size_t) blockSize, take = std::min(want - carry.size(), n - pos);
+      carry.insert(carry.end(), p + pos, p + pos + take);
+      pos += take;
+      if (carry.size() < want) continue;
+      parts.emplace_back();
+      if (!parse(carry.data() + 4, (size_t) blockSize, &parts.back())) { malformed = true; break; }
+      carry.clear();
+    }
+    starts.clear();
+    while (pos + 4 <= n) {
+      int32_t blockSize;
+      memcpy(&blockSize, p + pos, 4);
+      if (blockSize < 32) { malformed = true; break; }
+      if (pos + 4 + (size_t) blockSize > n) break;
+      starts.push_back(pos);
+      pos += 4 + (size_t) blockSize;
+    }
+    if (malformed) break;
+    carry.assign(p + pos, p + n);
+    const unsigned use = starts.size() < 4096 ? 1u : nt;
+    const size_t first = parts.size();
+    parts.resize(first + use);
+    std::vector<char> ok(use, 1);
+    auto work = [&](unsigned t) {
+      const size_t lo = starts.size() * t / use, hi = starts.size() * (t + 1) / use;
+      gt16_sam &P = parts[first + t];
+      if (hi > lo) {
+        const size_t bytes = (hi < starts.size() ? starts[hi] : pos) - starts[lo];
+        P.bases.reserve(bytes * 2 / 3); P.quals.reserve(bytes * 2 / 3);
+        for (auto *v : {&P.start, &P.length, &P.nCigar}) v->reserve(hi - lo);
+      }
+      for (size_t k = lo; k < hi; ++k) {
+        int32_t blockSize;
+        memcpy(&blockSize, p + starts[k], 4);
+        if (!parse(p + starts[k] + 4, (size_t) blockSize, &P)) { ok[t] = 0; return; }
+      }
+    };
+    if (use == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < use; ++t) th.emplace_back(work, t);
+      for (auto &x : th) x.join();
+    }
+    for (char c : ok) if (!c) malformed = true;
+  }
+  if (malformed) { delete S; return fail("bad alignment record"); }
+  if (R.bad) { delete S; return fail("corrupt BGZF stream"); }
+  if (!carry.empty()) { delete S; return fail("truncated alignment record"); }
+  if (!parts.empty()) join_parts(parts, S);
   *out = S;
   return GT16_OK;
 }

@@ -400,9 +400,13 @@ def test_snapshot_reader_survives_damaged_containers(tmp_path, name, monkeypatch
     assert 0 in outcomes and (-4 in outcomes or -5 in outcomes)
 
 
-def test_sam_slices_joined_in_file_order(tmp_path):
-    """A SAM file of more than 4 MB is parsed in slices by several threads and the lists are joined in parallel: the
-    reads equal those of the serial BAM reader on the same alignments, in the same order."""
+@pytest.mark.parametrize("bgzf_batch", ["", "100000"])
+def test_sam_slices_joined_in_file_order(tmp_path, monkeypatch, bgzf_batch):
+    """A SAM file of more than 4 MB is parsed in slices by several threads and the lists are joined in parallel; the BAM
+    reader inflates BGZF members batch by batch and parses each batch's records on several threads (GT16_BGZF_BATCH
+    shrinks the batches to two members, so that most of them end inside a record): the same reads, in the same order."""
+    if bgzf_batch:
+        monkeypatch.setenv("GT16_BGZF_BATCH", bgzf_batch)
     import random
     idx, out, region = T.regenerate("wgs_small", tmp_path)
     L = T.capi()
