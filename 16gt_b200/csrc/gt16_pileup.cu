@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <thread>
@@ -402,60 +403,90 @@ extern "C" int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint3
   const uint64_t n = reads->n_reads;
   const uint32_t L = text_length;
   if (n >= 0x7FFFFFFFull) return gt16_pileup_set_error(ctx, GT16_EINVAL, "too many reads for one call");
+  unsigned nThreads = std::thread::hardware_concurrency();
+  nThreads = std::max(1u, std::min(16u, nThreads ? nThreads : 4u));
+  auto parallel = [&](uint64_t count, const std::function<void(unsigned, uint64_t, uint64_t)> &f) {    // f(slice, lo, hi)
+    const unsigned nt = count < (1u << 16) ? 1u : nThreads;
+    if (nt == 1) { f(0, 0, count); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() { f(t, count * t / nt, count * (t + 1) / nt); });
+    for (auto &x : th) x.join();
+  };
   // the kernel indexes bases[] and cigar[] by what the read records say: they are checked here, once, on the host
-  for (uint64_t i = 0; i < n; ++i) {
-    bool ok = reads->start[i] < L && reads->n_cigar[i] >= 1 && reads->length[i] >= 1 &&
-              reads->cigar_off[i] <= reads->n_cigar_ops && reads->n_cigar[i] <= reads->n_cigar_ops - reads->cigar_off[i] &&
-              reads->seq_off[i] <= reads->n_bases && reads->length[i] <= reads->n_bases - reads->seq_off[i];
-    uint64_t query = 0;
-    for (uint32_t c = 0; ok && c < reads->n_cigar[i]; ++c) {
-      const uint32_t v = reads->cigar[reads->cigar_off[i] + c], op = v & 15u;
-      if (op > 8) ok = false;
-      if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) query += v >> 4;
-    }
-    if (!ok || query > reads->length[i]) {
+  {
+    std::vector<uint64_t> firstBad(nThreads, UINT64_MAX);
+    parallel(n, [&](unsigned t, uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) {
+        bool ok = reads->start[i] < L && reads->n_cigar[i] >= 1 && reads->length[i] >= 1 &&
+                  reads->cigar_off[i] <= reads->n_cigar_ops && reads->n_cigar[i] <= reads->n_cigar_ops - reads->cigar_off[i] &&
+                  reads->seq_off[i] <= reads->n_bases && reads->length[i] <= reads->n_bases - reads->seq_off[i];
+        uint64_t query = 0;
+        for (uint32_t c = 0; ok && c < reads->n_cigar[i]; ++c) {
+          const uint32_t v = reads->cigar[reads->cigar_off[i] + c], op = v & 15u;
+          if (op > 8) ok = false;
+          if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) query += v >> 4;
+        }
+        if (!ok || query > reads->length[i]) { firstBad[t] = i; return; }
+      }
+    });
+    const uint64_t bad = *std::min_element(firstBad.begin(), firstBad.end());
+    if (bad != UINT64_MAX) {
       char msg[160];
-      snprintf(msg, sizeof(msg), "read %llu: start, CIGAR or sequence range outside the arrays (or a CIGAR longer than the read)", (unsigned long long) i);
+      snprintf(msg, sizeof(msg), "read %llu: start, CIGAR or sequence range outside the arrays (or a CIGAR longer than the read)", (unsigned long long) bad);
       return gt16_pileup_set_error(ctx, GT16_EINVAL, msg);
     }
   }
   // ---- sort the reads by start (stable: the input order decides which pattern appears first), pack what the kernel reads
-  std::vector<uint64_t> order(n);
-  for (uint64_t i = 0; i < n; ++i) order[i] = i;
+  std::vector<uint32_t> order(n);
+  for (uint64_t i = 0; i < n; ++i) order[i] = (uint32_t) i;
   bool sorted = true;
   for (uint64_t i = 1; i < n && sorted; ++i) sorted = reads->start[i - 1] <= reads->start[i];
-  if (!sorted) std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return reads->start[a] < reads->start[b]; });
+  if (!sorted) {                                  // coordinate-sorted input never gets here; several files side by side do
+    std::vector<uint32_t> other(n);
+    std::vector<uint64_t> count(65537);
+    for (int pass = 0; pass < 2; ++pass) {        // stable radix sort on the two halves of the start position
+      const int shift = 16 * pass;
+      std::fill(count.begin(), count.end(), 0);
+      for (uint64_t k = 0; k < n; ++k) count[((reads->start[order[k]] >> shift) & 0xFFFFu) + 1]++;
+      for (int d = 0; d < 65536; ++d) count[d + 1] += count[d];
+      for (uint64_t k = 0; k < n; ++k) other[count[(reads->start[order[k]] >> shift) & 0xFFFFu]++] = order[k];
+      order.swap(other);
+    }
+  }
   std::vector<uint32_t> hStart(n), hLen(n), hOrder(n), hNCig(n);
   std::vector<uint64_t> hSeq(n), hCig(n);
   uint32_t maxSpan = 1;
-  for (uint64_t k = 0; k < n; ++k) {
-    const uint64_t i = order[k];
-    hStart[k] = reads->start[i]; hLen[k] = reads->length[i]; hNCig[k] = reads->n_cigar[i];
-    hSeq[k] = reads->seq_off[i]; hCig[k] = reads->cigar_off[i];
-    // bit 31: the read lies on the forward strand (its bases count as posStrandCount)
-    hOrder[k] = (uint32_t) i | (reads->reverse[i] ? 0u : 0x80000000u);
-    uint64_t span = 0;
-    for (uint32_t c = 0; c < reads->n_cigar[i]; ++c) {
-      const uint32_t op = reads->cigar[reads->cigar_off[i] + c] & 15u, len = reads->cigar[reads->cigar_off[i] + c] >> 4;
-      if (op == 0 || op == 2 || op == 7 || op == 8) span += len;
-    }
-    maxSpan = (uint32_t) std::max<uint64_t>(maxSpan, std::min<uint64_t>(span + 1, 0x7FFFFFFFull));
+  {
+    std::vector<uint32_t> spanOf(nThreads, 1);
+    parallel(n, [&](unsigned t, uint64_t lo, uint64_t hi) {
+      uint32_t mine = 1;
+      for (uint64_t k = lo; k < hi; ++k) {
+        const uint64_t i = order[k];
+        hStart[k] = reads->start[i]; hLen[k] = reads->length[i]; hNCig[k] = reads->n_cigar[i];
+        hSeq[k] = reads->seq_off[i]; hCig[k] = reads->cigar_off[i];
+        // bit 31: the read lies on the forward strand (its bases count as posStrandCount)
+        hOrder[k] = (uint32_t) i | (reads->reverse[i] ? 0u : 0x80000000u);
+        uint64_t span = 0;
+        for (uint32_t c = 0; c < reads->n_cigar[i]; ++c) {
+          const uint32_t op = reads->cigar[reads->cigar_off[i] + c] & 15u, len = reads->cigar[reads->cigar_off[i] + c] >> 4;
+          if (op == 0 || op == 2 || op == 7 || op == 8) span += len;
+        }
+        mine = (uint32_t) std::max<uint64_t>(mine, std::min<uint64_t>(span + 1, 0x7FFFFFFFull));
+      }
+      spanOf[t] = mine;
+    });
+    maxSpan = *std::max_element(spanOf.begin(), spanOf.end());
   }
   // base | weight << 2 per base (weightMap of the ini, bam2snapshot.cpp:352-363; quality correction :478-481)
   const uint64_t nBases = reads->n_bases;
-  std::vector<uint8_t> hBases(nBases);
+  std::unique_ptr<uint8_t[]> hBases(new uint8_t[nBases ? nBases : 1]);       // not zeroed: every byte is written below
   {
     uint8_t lut[256];                                // quality byte -> weight << 2 (0xFF = absent = negative = 0)
     for (int q = 0; q < 256; ++q) lut[q] = (uint8_t) (params->weight_map[q >= 128 ? 0 : q > 40 ? 40 : q] << 2);
-    unsigned nt = std::thread::hardware_concurrency();
-    nt = std::max(1u, std::min(16u, nt ? nt : 4u));
-    if (nBases < (1u << 22)) nt = 1;
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() {
-      const uint64_t a = nBases * t / nt, b = nBases * (t + 1) / nt;
-      for (uint64_t k = a; k < b; ++k) hBases[k] = (uint8_t) ((reads->bases[k] & 3u) | lut[reads->quals[k]]);
+    uint8_t *dst = hBases.get();
+    parallel(nBases, [&](unsigned, uint64_t lo, uint64_t hi) {
+      for (uint64_t k = lo; k < hi; ++k) dst[k] = (uint8_t) ((reads->bases[k] & 3u) | lut[reads->quals[k]]);
     });
-    for (auto &x : th) x.join();
   }
   const float msPack = ms_since(clock0);
   clock0 = std::chrono::steady_clock::now();
@@ -464,7 +495,7 @@ extern "C" int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint3
   Dev<uint8_t> dBases, dOvf, dPool;
   PCU(dStart.put(hStart.data(), n)); PCU(dLen.put(hLen.data(), n)); PCU(dOrder.put(hOrder.data(), n));
   PCU(dNCig.put(hNCig.data(), n)); PCU(dSeq.put(hSeq.data(), n)); PCU(dCig.put(hCig.data(), n));
-  PCU(dCigar.put(reads->cigar, reads->n_cigar_ops)); PCU(dBases.put(hBases.data(), nBases));
+  PCU(dCigar.put(reads->cigar, reads->n_cigar_ops)); PCU(dBases.put(hBases.get(), nBases));
   const uint32_t nReg = params->n_overflow_regions, regLen = L / nReg;
   const size_t words = ((size_t) L + 31) >> 5;
   PCU(dCounters.alloc((size_t) L + 1)); PCU(dInvalid.alloc(words + 1));
