@@ -14,6 +14,8 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
+#include <mutex>
+#include <condition_variable>
 #include <string>
 #include <thread>
 #include <vector>
@@ -490,10 +492,22 @@ namespace {
 // of the double, round-half-even): the scaled value is computed in 80-bit arithmetic (relative error < 2^-60), and
 // whenever it lies within 1e-7 of a rounding boundary -- where that error could matter, exact ties included --
 // the field is handed to snprintf.  tests/test_capi_cpu.py compares both on millions of values.
+// 10^k = m * 2^e with a 64-bit mantissa (top bit set), correctly rounded: taken from strtold, whose x87 format has just
+// that mantissa.  A double's 53 bits times the mantissa is a 128-bit integer whose error against the exact scaled value
+// is below 2^-63 relative: an integer part of five digits and a fraction good to ~2^-46.
 struct Pow10 {
-  long double p[701];                                         // 10^(k-350), correctly rounded
-  Pow10() { char b[16]; for (int k = 0; k <= 700; ++k) { snprintf(b, sizeof(b), "1e%d", k - 350); p[k] = strtold(b, nullptr); } }
-  long double operator()(int k) const { return p[k + 350]; }
+  uint64_t m[701];
+  int e[701];
+  Pow10() {
+    char b[16];
+    for (int k = 0; k <= 700; ++k) {
+      snprintf(b, sizeof(b), "1e%d", k - 350);
+      int ex;
+      const long double f = frexpl(strtold(b, nullptr), &ex);        // in [0.5, 1)
+      m[k] = (uint64_t) ldexpl(f, 64);
+      e[k] = ex - 64;
+    }
+  }
 };
 const Pow10 kPow10;
 
@@ -504,21 +518,43 @@ inline char *put_u32(char *o, uint32_t v) {
   return o;
 }
 
+// |v| = m * 2^e2 with the top bit of m set (v finite, not zero)
+inline void split_double(double v, uint64_t *m, int *e2) {
+  uint64_t bits;
+  memcpy(&bits, &v, 8);
+  const uint64_t frac = bits & ((1ull << 52) - 1);
+  const int be = (int) ((bits >> 52) & 0x7FF);
+  if (be) { *m = (frac | (1ull << 52)) << 11; *e2 = be - 1075 - 11; }
+  else { const int lz = __builtin_clzll(frac); *m = frac << lz; *e2 = -1074 - lz; }
+}
+const uint64_t kHalf = 1ull << 63, kTieBand = 1ull << 41;      // fractions within 2.4e-7 of one half go to snprintf
+
 // "%.4e" of v followed by a tab; returns the end of the output
 inline char *fmt_e4(char *o, double v) {
   if (v == 0.0 && !std::signbit(v)) { memcpy(o, "0.0000e+00\t", 11); return o + 11; }
   if (v == 1.0) { memcpy(o, "1.0000e+00\t", 11); return o + 11; }
   const double a = fabs(v);
   if (!(a > 0.0) || !(a <= DBL_MAX)) return o + snprintf(o, 40, "%.4e\t", v);      // -0, inf, nan
+  uint64_t m;
   int e2;
-  frexp(a, &e2);
-  int e = (int) floor((e2 - 1) * 0.30102999566398120);          // floor(log10 a) or one less
-  long double sc = (long double) a * kPow10(4 - e);
-  if (sc >= 100000.0L) { ++e; sc = (long double) a * kPow10(4 - e); }
-  if (sc < 10000.0L || sc >= 100000.0L) return o + snprintf(o, 40, "%.4e\t", v);
-  const long double fl = floorl(sc), fr = sc - fl;
-  if (fr > 0.4999999L && fr < 0.5000001L) return o + snprintf(o, 40, "%.4e\t", v);
-  uint32_t d = (uint32_t) fl + (fr > 0.5L ? 1u : 0u);
+  split_double(a, &m, &e2);
+  // a lies in [2^(e2+63), 2^(e2+64)): floor(log10 a) is this estimate or one more
+  int e = (int) (((int64_t) (e2 + 63) * 1292913986ll) >> 32);                     // log10(2) * 2^32
+  uint64_t fl = 0, fr = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int k = 4 - e + 350;
+    if (k < 0 || k > 700) return o + snprintf(o, 40, "%.4e\t", v);
+    const unsigned __int128 P = (unsigned __int128) m * kPow10.m[k];
+    const int s = -(e2 + kPow10.e[k]);                                            // a * 10^(4-e) = P / 2^s
+    if (s <= 64 || s >= 128) return o + snprintf(o, 40, "%.4e\t", v);
+    fl = (uint64_t) (P >> s);
+    fr = (uint64_t) ((P << (128 - s)) >> 64);
+    if (fl < 100000u) break;
+    ++e;
+  }
+  if (fl < 10000u || fl >= 100000u) return o + snprintf(o, 40, "%.4e\t", v);
+  if ((fr > kHalf ? fr - kHalf : kHalf - fr) < kTieBand) return o + snprintf(o, 40, "%.4e\t", v);
+  uint32_t d = (uint32_t) fl + (fr > kHalf ? 1u : 0u);
   if (d >= 100000u) { d = 10000u; ++e; }                         // 9.99996 -> 1.0000e+01
   if (std::signbit(v)) *o++ = '-';
   o[0] = (char) ('0' + d / 10000u); o[1] = '.';
@@ -536,10 +572,21 @@ inline char *fmt_e4(char *o, double v) {
 inline char *fmt_f4(char *o, double v) {
   const double a = fabs(v);
   if (!(a < 4.0e5)) return o + snprintf(o, 64, "%.4f\t", v);     // large, inf, nan
-  const long double sc = (long double) a * 10000.0L;
-  const long double fl = floorl(sc), fr = sc - fl;
-  if (fr > 0.4999999L && fr < 0.5000001L) return o + snprintf(o, 64, "%.4f\t", v);
-  const uint64_t d = (uint64_t) fl + (fr > 0.5L ? 1u : 0u);
+  uint64_t d = 0;
+  if (a > 0.0) {
+    uint64_t m;
+    int e2;
+    split_double(a, &m, &e2);
+    const unsigned __int128 P = (unsigned __int128) m * (10000ull << 50);          // 10^4, exactly
+    const int s = -(e2 - 50);                                                      // a * 10^4 = P / 2^s, s >= 96 here
+    if (s < 65) return o + snprintf(o, 64, "%.4f\t", v);
+    if (s <= 128) {
+      const uint64_t fl = s == 128 ? 0 : (uint64_t) (P >> s);
+      const uint64_t fr = s == 128 ? (uint64_t) (P >> 64) : (uint64_t) ((P << (128 - s)) >> 64);
+      if ((fr > kHalf ? fr - kHalf : kHalf - fr) < kTieBand) return o + snprintf(o, 64, "%.4f\t", v);
+      d = fl + (fr > kHalf ? 1u : 0u);
+    }                                                                              // else below 0.00005 by far: 0.0000
+  }
   if (std::signbit(v)) *o++ = '-';
   o = put_u32(o, (uint32_t) (d / 10000u));
   const uint32_t f = (uint32_t) (d % 10000u);
@@ -633,35 +680,87 @@ int gt16_write_txt(const char *path, const gt16_index *ix, const gt16_called_sit
           "totalHQ\ttotalLQ\n", f);
   }
   float lq = carry ? carry[0] : 0.0f, rq = carry ? carry[1] : 0.0f;
-  const unsigned nt = n < 2048 ? 1u : io_threads();
-  const uint64_t per = (n + nt - 1) / (nt ? nt : 1);
-  // values in force at the start of each worker's range
-  std::vector<float> lq0(nt, 0.f), rq0(nt, 0.f);
-  for (unsigned t = 0; t < nt; ++t) {
-    lq0[t] = lq; rq0[t] = rq;
-    const uint64_t a = std::min<uint64_t>(n, t * per), b = std::min<uint64_t>(n, a + per);
+  // Blocks of 1,024 rows (~0.7 MB of text) are formatted by worker threads into buffers out of a small pool and written
+  // by this thread in order while later blocks are being formatted: the text stays in cache-sized buffers that are used
+  // over and over (a string per worker holding its whole share page-faulted 0.7 GB per million rows, with all threads
+  // queueing for the address space).
+  const uint64_t kBlockRows = 1024;
+  const uint64_t nBlocks = (n + kBlockRows - 1) / kBlockRows;
+  const unsigned nt = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(io_threads(), nBlocks));
+  // values in force at the start of each block
+  std::vector<float> lq0(nBlocks, 0.f), rq0(nBlocks, 0.f);
+  for (uint64_t blk = 0; blk < nBlocks; ++blk) {
+    lq0[blk] = lq; rq0[blk] = rq;
+    const uint64_t a = blk * kBlockRows, b = std::min<uint64_t>(n, a + kBlockRows);
     for (uint64_t k = a; k < b; ++k) if (sites[k].rq_assigned) { lq = sites[k].lq; rq = sites[k].rq; }
   }
-  std::vector<std::string> parts(nt);
-  auto work = [&](unsigned t) {
-    const uint64_t a = std::min<uint64_t>(n, t * per), b = std::min<uint64_t>(n, a + per);
-    std::string &out = parts[t];
-    out.reserve((size_t) (b - a) * 720);
-    float l = lq0[t], r = rq0[t];
+  bool bad = false;
+  auto format_block = [&](uint64_t blk, std::string &out) {
+    const uint64_t a = blk * kBlockRows, b = std::min<uint64_t>(n, a + kBlockRows);
+    float l = lq0[blk], r = rq0[blk];
     for (uint64_t k = a; k < b; ++k) {
       if (sites[k].rq_assigned) { l = sites[k].lq; r = sites[k].rq; }   // else: previous row's values survive
       format_row(out, ix, sites[k], l, r);
     }
   };
-  if (nt == 1) work(0);
-  else {
+  if (nt == 1) {
+    std::string out;
+    out.reserve((size_t) std::min<uint64_t>(n, kBlockRows) * 760);
+    for (uint64_t blk = 0; blk < nBlocks; ++blk) {
+      out.clear();
+      format_block(blk, out);
+      if (!out.empty() && fwrite(out.data(), 1, out.size(), f) != out.size()) bad = true;
+    }
+  } else {
+    const uint64_t window = 4ull * nt;                  // blocks formatted ahead of the one being written
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<std::string> done(nBlocks);
+    std::vector<char> ready(nBlocks, 0);
+    std::vector<std::string> pool;
+    uint64_t next = 0, written = 0;
+    auto work = [&]() {
+      std::string out;
+      for (;;) {
+        uint64_t blk;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          blk = next++;
+          if (blk >= nBlocks) return;
+          cv.wait(lk, [&] { return blk < written + window; });
+          if (!pool.empty()) { out.swap(pool.back()); pool.pop_back(); }
+        }
+        out.clear();
+        if (out.capacity() < kBlockRows * 760) out.reserve(kBlockRows * 760);
+        format_block(blk, out);
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          done[blk].swap(out);
+          ready[blk] = 1;
+        }
+        cv.notify_all();
+      }
+    };
     std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work);
+    std::string cur;
+    for (uint64_t blk = 0; blk < nBlocks; ++blk) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return ready[blk] != 0; });
+        cur.swap(done[blk]);
+      }
+      if (!cur.empty() && fwrite(cur.data(), 1, cur.size(), f) != cur.size()) bad = true;
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        pool.emplace_back();
+        pool.back().swap(cur);
+        ++written;
+      }
+      cv.notify_all();
+    }
     for (auto &x : th) x.join();
   }
-  bool bad = false;
-  for (unsigned t = 0; t < nt; ++t)
-    if (!parts[t].empty() && fwrite(parts[t].data(), 1, parts[t].size(), f) != parts[t].size()) bad = true;
   if (carry) { carry[0] = lq; carry[1] = rq; }
   if (ferror(f)) bad = true;
   if (fclose(f) != 0 || bad) return GT16_EIO;

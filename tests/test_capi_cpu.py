@@ -496,3 +496,49 @@ def test_coordinate_translation_with_removed_stretches(tmp_path):
             hits += rc == 0
         assert hits > 5000
         L.gt16_index_free(ix)
+
+
+def test_txt_emitter_blocks_equal_row_by_row_calls(tmp_path):
+    """gt16_write_txt formats blocks of rows on worker threads and writes them in order; the LQ/RQ values that survive from
+    row to row are carried across blocks and calls.  One call for 50,000 rows must write the very bytes that appending
+    them in pieces of a few hundred rows (the single-threaded path) writes."""
+    idx, out, region = T.regenerate("wgs_small", tmp_path)
+    L = T.capi()
+    M = T.capi_mod
+    err = ctypes.create_string_buffer(256)
+    ix = ctypes.c_void_p()
+    assert L.gt16_index_read(idx.encode(), ctypes.byref(ix), err, 256) == 0
+    n = 50000
+    rng = np.random.default_rng(7)
+    r = np.zeros(n, dtype=M.CALLED_SITE_DTYPE)
+    r["amb"] = np.sort(rng.integers(0, 250000, n)).astype(np.uint32)
+    r["ref"] = rng.integers(0, 4, n); r["genotype"] = rng.integers(0, 16, n); r["rq_assigned"] = rng.integers(0, 2, n)
+    r["is_indel"] = rng.choice([0, 0, 0, 2, 3], n)
+    for f in ("W", "F", "R"):
+        r[f] = rng.integers(0, 70000, (n, 6))
+    r["lh"] = 10.0 ** rng.uniform(-320, 0, (n, 16)); r["flh"] = 10.0 ** rng.uniform(-320, 0, (n, 16))
+    r["lh"][rng.random((n, 16)) < 0.1] = 0.0
+    r["pD"] = 10.0 ** rng.uniform(-300, 0, n); r["bestD"] = rng.uniform(0, 1, n); r["secondD"] = rng.uniform(0, 1, n)
+    r["sb"] = rng.uniform(0, 1, (n, 3, 4)); r["bqb"] = rng.uniform(0, 1, (n, 3, 4))
+    for f in ("rpb", "lgc", "rgc", "asc", "lq", "rq"):
+        r[f] = rng.uniform(0, 3, n)
+    r["polyrun"] = rng.integers(1, 100, n); r["total_hq"] = rng.integers(0, 100, n); r["total_lq"] = rng.integers(0, 100, n)
+    for k in (0, 1):
+        r["indel"]["type"][:, k] = rng.choice([ord("*"), ord("I"), ord("D")], n)
+        r["indel"]["len"][:, k] = rng.integers(1, 40, n)
+        r["indel"]["hq"][:, k] = rng.integers(0, 500, n); r["indel"]["lq"][:, k] = rng.integers(0, 500, n)
+        r["indel"]["seq"][:, k, :] = rng.integers(0, 256, (n, 64))
+    whole, pieces = str(tmp_path / "whole.txt").encode(), str(tmp_path / "pieces.txt").encode()
+    c1 = (ctypes.c_float * 2)(0.25, 0.75)
+    assert L.gt16_write_txt(whole, ix, r.ctypes.data, n, 0, c1) == 0
+    c2 = (ctypes.c_float * 2)(0.25, 0.75)
+    at = 0
+    while at < n:
+        m = min(int(rng.integers(1, 900)), n - at)
+        assert L.gt16_write_txt(pieces, ix, r[at:].ctypes.data, m, 1 if at else 0, c2) == 0
+        at += m
+    a, b = open(whole, "rb").read(), open(pieces, "rb").read()
+    assert a == b and a.count(b"\n") == n + 1 and (c1[0], c1[1]) == (c2[0], c2[1])
+    row = a.split(b"\n")[1].split(b"\t")
+    assert len(row) == 98
+    L.gt16_index_free(ix)
