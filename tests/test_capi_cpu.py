@@ -150,7 +150,7 @@ def test_region_index_builder_matches_reference(tmp_path):
 
 
 def test_fast_number_formatting_equals_printf():
-    """The .txt emitter formats "%.4e" / "%.4f" fields itself (80-bit scaling, snprintf whenever the value lies close
+    """The .txt emitter formats "%.4e" / "%.4f" fields itself (128-bit integer scaling, snprintf whenever the value lies close
     to a rounding boundary): every byte must be what libc's printf writes -- random bit patterns over all exponents,
     subnormals, values next to d.dddd5 boundaries and next to powers of ten, exact ties of the fixed format."""
     import math, random, struct
