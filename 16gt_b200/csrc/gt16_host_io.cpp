@@ -489,8 +489,8 @@ namespace {
 // ---- number formatting -------------------------------------------------------------------------------------
 // A row holds ~60 "%.4e" fields; through snprintf they cost more than everything else the drop-in does on the
 // host after the GPU is done.  fmt_e4 / fmt_f4 produce the very bytes glibc's printf produces (exact decimal value
-// of the double, round-half-even): the scaled value is computed in 80-bit arithmetic (relative error < 2^-60), and
-// whenever it lies within 1e-7 of a rounding boundary -- where that error could matter, exact ties included --
+// of the double, round-half-even): the scaled value is a 128-bit integer product (relative error < 2^-63), and
+// whenever its fraction lies within 2.4e-7 of one half -- where that error could matter, exact ties included --
 // the field is handed to snprintf.  tests/test_capi_cpu.py compares both on millions of values.
 // 10^k = m * 2^e with a 64-bit mantissa (top bit set), correctly rounded: taken from strtold, whose x87 format has just
 // that mantissa.  A double's 53 bits times the mantissa is a 128-bit integer whose error against the exact scaled value
