@@ -623,7 +623,19 @@ int gt16_snapshot_write(const char *path, const gt16_snapshot_view *v, char *err
   const size_t page = (size_t) sysconf(_SC_PAGE_SIZE);
   // populated positions (isLowPopulation, bam2snapshot.cpp:527-561): overflow-type, or any non-zero field
   size_t populated = 0;
-  for (uint32_t p = 0; p < L; ++p) if (v->counters[p]) ++populated;
+  {
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = L < (1u << 24) ? 1u : std::max(1u, std::min(16u, nt ? nt : 4u));
+    std::vector<size_t> cnt(nt, 0);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() {
+      size_t c = 0;
+      for (uint64_t p = (uint64_t) L * t / nt, e = (uint64_t) L * (t + 1) / nt; p < e; ++p) c += v->counters[p] != 0;
+      cnt[t] = c;
+    });
+    for (auto &x : th) x.join();
+    for (size_t c : cnt) populated += c;
+  }
   const bool sparse = (double) populated / L < 0.1;
   std::vector<uint32_t> keep;                       // sparse: positions within 100 of a populated one (writeHeader :103-122)
   if (sparse) {
