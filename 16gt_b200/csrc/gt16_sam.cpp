@@ -321,7 +321,8 @@ struct BgzfReader {
         for (size_t k = k0; k < std::min(blocks.size(), k0 + 16); ++k) {
           const BgzfBlock &b = blocks[k];
           zs.next_in = (Bytef *) (m + b.off); zs.avail_in = (uInt) b.size;
-          zs.next_out = B.data.data() + b.out; zs.avail_out = b.isize;
+          Bytef none;                                              // an empty member (the end-of-file marker) still needs a place to write to
+          zs.next_out = b.isize ? B.data.data() + b.out : &none; zs.avail_out = b.isize;
           const int rc = inflate(&zs, Z_FINISH);                   // the gzip wrapper checks CRC32 and ISIZE
           if (rc != Z_STREAM_END || zs.avail_out != 0) { size_t seen = firstBad.load(); while (k < seen && !firstBad.compare_exchange_weak(seen, k)) {} }
           inflateReset(&zs);

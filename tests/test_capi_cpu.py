@@ -400,7 +400,7 @@ def test_snapshot_reader_survives_damaged_containers(tmp_path, name, monkeypatch
     assert 0 in outcomes and (-4 in outcomes or -5 in outcomes)
 
 
-@pytest.mark.parametrize("bgzf_batch", ["", "100000"])
+@pytest.mark.parametrize("bgzf_batch", ["", "100000", "1"])          # "1": one member per batch, the empty end-of-file member alone in the last
 def test_sam_slices_joined_in_file_order(tmp_path, monkeypatch, bgzf_batch):
     """A SAM file of more than 4 MB is parsed in slices by several threads and the lists are joined in parallel; the BAM
     reader inflates BGZF members batch by batch and parses each batch's records on several threads (GT16_BGZF_BATCH
