@@ -304,7 +304,9 @@ typedef struct gt16_built_snapshot {
 /* updateSnpCounterForReads over all reads + readFilesForOverflow (bam2snapshot.cpp:221-330; SNP.cpp:438-891,893-1688):
  * per-position base counters, overflow promotion, invalid bits, pooled insertion / deletion patterns, built on the GPU
  * as one histogram pass (gt16_pileup.cu).  The decoded content equals the reference producer's; slot order, array
- * indices and pool offsets -- which depend on the order in which the reference's threads get there -- need not. */
+ * indices and pool offsets -- which depend on the order in which the reference's threads get there -- need not.
+ * The read records are checked first (start inside the genome, CIGAR and sequence ranges inside the arrays, operations
+ * 0..8, no CIGAR longer than its read): GT16_EINVAL names the first read that fails. */
 int gt16_build_snapshot(gt16_ctx *ctx, const gt16_reads *reads, uint32_t text_length, const gt16_pileup_params *params,
                         gt16_built_snapshot *out);
 void gt16_built_snapshot_free(gt16_built_snapshot *s);
